@@ -1,0 +1,270 @@
+"""ctypes binding of libevx_b200.so (the C ABI declared in include/evoxels_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.
+Tensors are passed as raw device pointers together with the current CUDA stream of the
+tensor's device; nothing here allocates except through torch's caching allocator.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libevx_b200.so")
+
+BC_CODES = {"periodic": 0, "neumann": 1, "dirichlet": 2}
+FFT_AUTO, FFT_CUFFT, FFT_NATIVE = 0, 1, 2
+
+_c_void_p, _c_int, _c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+_dptr = ctypes.POINTER(ctypes.c_double)
+_iptr = ctypes.POINTER(ctypes.c_int)
+
+# name -> argtypes; every function returns int unless listed in _RESTYPES
+_STENCIL_ARGS = [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _dptr, _c_double,
+                 _c_double, _iptr, _dptr, _c_void_p, _c_void_p, _c_void_p]
+_AC_ARGS = [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_double, _c_void_p,
+            _c_void_p, _c_double, _c_int, _c_int, _c_int, _dptr, _c_double, _c_double,
+            _c_double, _c_double, _c_double, _iptr, _dptr, _c_void_p, _c_void_p, _c_void_p]
+_PAD_ARGS = [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _iptr, _dptr, _c_void_p]
+_PST_ARGS = [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _dptr, _c_int, _c_void_p]
+_APPLY_ARGS = [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _dptr, _c_double,
+               _c_double, _c_int, _c_void_p]
+_STEP_ARGS = [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _dptr, _c_double,
+              _c_double, _c_double, _c_double, _c_void_p]
+_FILTER_ARGS = [_c_void_p, _c_int, _c_int, _c_int, _dptr, _c_double, _c_double, _c_int,
+                _c_double, _c_void_p]
+
+SIGNATURES = {
+    "evx_version": [],
+    "evx_strerror": [_c_int],
+    "evx_launch_count": [],
+    "evx_ch_rhs_f32": _STENCIL_ARGS, "evx_ch_rhs_f64": _STENCIL_ARGS,
+    "evx_ac_stage_f32": _AC_ARGS, "evx_ac_stage_f64": _AC_ARGS,
+    "evx_pad_ghost_f32": _PAD_ARGS, "evx_pad_ghost_f64": _PAD_ARGS,
+    "evx_padded_stencil_f32": _PST_ARGS, "evx_padded_stencil_f64": _PST_ARGS,
+    "evx_imex_plan_create": [ctypes.POINTER(_c_void_p), _c_int, _c_int, _c_int, _c_int, _c_int],
+    "evx_imex_plan_destroy": [_c_void_p],
+    "evx_imex_plan_backend": [_c_void_p],
+    "evx_imex_plan_workspace_bytes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t)],
+    "evx_imex_apply_f32": _APPLY_ARGS, "evx_imex_apply_f64": _APPLY_ARGS,
+    "evx_ch_imex_step_f32": _STEP_ARGS, "evx_ch_imex_step_f64": _STEP_ARGS,
+    "evx_spectral_filter_c64": _FILTER_ARGS, "evx_spectral_filter_c128": _FILTER_ARGS,
+}
+_RESTYPES = {"evx_strerror": ctypes.c_char_p, "evx_launch_count": ctypes.c_ulonglong}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load libevx_b200.so and bind every symbol of the header.  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found. Build it with `python -m evoxels_b200.build` "
+            "(needs nvcc); evoxels_b200 has no CPU or pure-PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the .so is stale
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, _c_int)
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = load_library().evx_strerror(code).decode()
+        raise NativeLibraryError(f"{what} failed with code {code}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load_library().evx_launch_count())
+
+
+# --------------------------------------------------------------------------------------
+# argument marshalling
+# --------------------------------------------------------------------------------------
+def _suffix(t: torch.Tensor) -> str:
+    if t.dtype == torch.float32:
+        return "f32"
+    if t.dtype == torch.float64:
+        return "f64"
+    raise TypeError(f"evoxels_b200 kernels take float32/float64 fields, got {t.dtype}")
+
+
+def require_cuda(*tensors):
+    """The product has no CPU path - refuse anything that is not a CUDA tensor."""
+    for t in tensors:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise RuntimeError(
+                "evoxels_b200 has no CPU path: hot-path operators accept CUDA tensors only "
+                f"(got {type(t).__name__} on "
+                f"{getattr(t, 'device', 'host')}).")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _h3(spacing: Sequence[float]):
+    return (ctypes.c_double * 3)(*[float(s) for s in spacing])
+
+
+def bc_to_c(bc):
+    """((kind, values),)*3 -> (int[3], double[6])."""
+    kinds = (ctypes.c_int * 3)(*[BC_CODES[k] for k, _ in bc])
+    vals = []
+    for _, v in bc:
+        vals += [float(v[0]), float(v[1])] if v is not None else [0.0, 0.0]
+    return kinds, (ctypes.c_double * 6)(*vals)
+
+
+def _field3(t: torch.Tensor) -> torch.Tensor:
+    if t.dim() != 3 or not t.is_contiguous():
+        raise ValueError("expected a contiguous [nx,ny,nz] tensor")
+    return t
+
+
+# --------------------------------------------------------------------------------------
+# thin typed wrappers (one per C entry point)
+# --------------------------------------------------------------------------------------
+def ch_rhs(c, out, spacing, eps, D, bc, hom=None, halo_lo=None, halo_hi=None):
+    require_cuda(c, out, hom, halo_lo, halo_hi)
+    lib = load_library()
+    nx, ny, nz = _field3(c).shape
+    kinds, vals = bc_to_c(bc)
+    with torch.cuda.device(c.device):
+        check(getattr(lib, "evx_ch_rhs_" + _suffix(c))(
+            _ptr(c), _ptr(hom), _ptr(_field3(out)), nx, ny, nz, _h3(spacing), float(eps),
+            float(D), kinds, vals, _ptr(halo_lo), _ptr(halo_hi), _stream(c)), "evx_ch_rhs")
+    return out
+
+
+def ac_stage(phi, spacing, eps, gab, M, force, curvature, bc, *, pot=None, k_out=None,
+             base=None, y_out=None, alpha=0.0, acc_in=None, acc_out=None, beta=0.0,
+             halo_lo=None, halo_hi=None):
+    require_cuda(phi, pot, k_out, base, y_out, acc_in, acc_out, halo_lo, halo_hi)
+    lib = load_library()
+    nx, ny, nz = _field3(phi).shape
+    kinds, vals = bc_to_c(bc)
+    with torch.cuda.device(phi.device):
+        check(getattr(lib, "evx_ac_stage_" + _suffix(phi))(
+            _ptr(phi), _ptr(pot), _ptr(k_out), _ptr(base), _ptr(y_out), float(alpha),
+            _ptr(acc_in), _ptr(acc_out), float(beta), nx, ny, nz, _h3(spacing), float(eps),
+            float(gab), float(M), float(force), float(curvature), kinds, vals,
+            _ptr(halo_lo), _ptr(halo_hi), _stream(phi)), "evx_ac_stage")
+
+
+def pad_ghost(field, bc):
+    require_cuda(field)
+    lib = load_library()
+    nx, ny, nz = _field3(field).shape
+    out = torch.empty((nx + 2, ny + 2, nz + 2), dtype=field.dtype, device=field.device)
+    kinds, vals = bc_to_c(bc)
+    with torch.cuda.device(field.device):
+        check(getattr(lib, "evx_pad_ghost_" + _suffix(field))(
+            _ptr(field), _ptr(out), nx, ny, nz, kinds, vals, _stream(field)), "evx_pad_ghost")
+    return out
+
+
+def padded_stencil(padded, spacing, op):
+    require_cuda(padded)
+    lib = load_library()
+    px, py, pz = _field3(padded).shape
+    nx, ny, nz = px - 2, py - 2, pz - 2
+    out = torch.empty((nx, ny, nz), dtype=padded.dtype, device=padded.device)
+    with torch.cuda.device(padded.device):
+        check(getattr(lib, "evx_padded_stencil_" + _suffix(padded))(
+            _ptr(padded), _ptr(out), nx, ny, nz, _h3(spacing), int(op), _stream(padded)),
+            "evx_padded_stencil")
+    return out
+
+
+def spectral_filter(spec, shape, spacing, dt, coef, power, scale=1.0):
+    """In-place P(k) multiply of a cuFFT-layout half spectrum (complex64/128 tensor)."""
+    require_cuda(spec)
+    lib = load_library()
+    fn = lib.evx_spectral_filter_c64 if spec.dtype == torch.complex64 else lib.evx_spectral_filter_c128
+    nx, ny, nz = shape
+    with torch.cuda.device(spec.device):
+        check(fn(_ptr(spec), nx, ny, nz, _h3(spacing), float(dt), float(coef), int(power),
+                 float(scale), _stream(spec)), "evx_spectral_filter")
+    return spec
+
+
+class ImexPlan:
+    """Owns an evx_imex_plan and its torch-allocated scratch buffer."""
+
+    def __init__(self, shape, dtype=torch.float32, device="cuda", backend=FFT_AUTO):
+        self._handle = None
+        lib = load_library()
+        self.shape = tuple(int(n) for n in shape)
+        self.dtype = dtype
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("evoxels_b200 has no CPU path: ImexPlan needs a CUDA device")
+        handle = _c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.evx_imex_plan_create(ctypes.byref(handle), *self.shape,
+                                           1 if dtype == torch.float64 else 0, int(backend)),
+                  "evx_imex_plan_create")
+            self._handle = handle
+            nbytes = ctypes.c_size_t()
+            check(lib.evx_imex_plan_workspace_bytes(handle, ctypes.byref(nbytes)),
+                  "evx_imex_plan_workspace_bytes")
+            self.workspace = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8,
+                                         device=self.device)
+        self.backend = int(lib.evx_imex_plan_backend(handle))
+
+    @property
+    def backend_name(self):
+        return {FFT_CUFFT: "cufft", FFT_NATIVE: "native"}[self.backend]
+
+    def apply(self, u, r, out, spacing, dt, coef, power):
+        """out = u + irfftn(P * rfftn(r)); u may be None (out = update only)."""
+        require_cuda(u, r, out)
+        lib = load_library()
+        assert tuple(r.shape) == self.shape and r.dtype == self.dtype
+        with torch.cuda.device(self.device):
+            check(getattr(lib, "evx_imex_apply_" + _suffix(r))(
+                self._handle, _ptr(u), _ptr(_field3(r)), _ptr(_field3(out)),
+                _ptr(self.workspace), _h3(spacing), float(dt), float(coef), int(power),
+                _stream(r)), "evx_imex_apply")
+        return out
+
+    def ch_step(self, u, out, spacing, dt, eps, D, A, hom=None):
+        require_cuda(u, out, hom)
+        lib = load_library()
+        assert tuple(u.shape) == self.shape and u.dtype == self.dtype
+        with torch.cuda.device(self.device):
+            check(getattr(lib, "evx_ch_imex_step_" + _suffix(u))(
+                self._handle, _ptr(_field3(u)), _ptr(hom), _ptr(_field3(out)),
+                _ptr(self.workspace), _h3(spacing), float(dt), float(eps), float(D), float(A),
+                _stream(u)), "evx_ch_imex_step")
+        return out
+
+    def close(self):
+        if self._handle is not None and _lib is not None:
+            _lib.evx_imex_plan_destroy(self._handle)
+        self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

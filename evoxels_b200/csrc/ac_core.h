@@ -1,0 +1,269 @@
+// Fused two-phase Allen-Cahn right-hand side + explicit-stage update, one pass.
+//
+//   phi^ = clip(phi, 0, 1)
+//   k    = M * [ gab * ( curv * lap7(phi^) + (1-curv) * nlap19(phi^) - g(phi^)/2/eps )
+//                + 3/eps * phi^ (1-phi^) * force ]
+//   nlap19 = [ sum_a g_a^2 d_aa f + sum_{a<b} 1/2 g_a g_b d_ab f ] / |g|^2 ,  |g|^2<=1e-7 -> 1
+//
+// Replaces reference evoxels/problem_definition.py:421-447 (TwoPhaseAllenCahn.rhs),
+// fd_stencils.py:44-103 (centred gradients, laplace, normal_laplace) and the generic ghost
+// rules of boundary_conditions.py:33-59.  Ghost values (including the edge ghosts the
+// 19-point stencil touches) are produced on the fly: index map per axis (periodic wrap /
+// clamp to the inner cell) and the affine rule ghost = off + sgn * inner composed in the
+// reference's axis order x, then y, then z.
+//
+// A thread owns V contiguous z-values of one (y) row and marches along x keeping a
+// 3 planes x 3 rows x (V+2) window in registers; neighbouring rows/columns are re-read
+// through L1 (no shared memory, no barrier).
+#pragma once
+#include "evx_hd.h"
+
+namespace evx {
+
+template <typename T>
+struct AcParams {
+  const T* phi;      // [nx,ny,nz] raw
+  const T* pot;      // optional potential(clip(phi)) field
+  T* k_out;          // optional: k
+  const T* base;     // for y_out
+  T* y_out;          // optional: base + alpha*k
+  const T* acc_in;   // optional
+  T* acc_out;        // optional: acc_in + beta*k
+  T alpha, beta;
+  const T* halo_lo;  // optional [1,ny,nz] raw plane x=-1
+  const T* halo_hi;  // optional [1,ny,nz] raw plane x=nx
+  int nx, ny, nz, xchunk;
+  T ihx, ihy, ihz, ihx2, ihy2, ihz2, ih2sum;
+  T pot_scale, eps, gab, M, force, curv, omc, three_over_eps;
+  int bc_kind[3];
+  T ghost_off[3][2];
+  T ghost_sgn[3];
+};
+
+template <typename T, int V, int TY, int G>
+struct AcProgram {
+  static constexpr int TZ = G * V;
+  static constexpr int NTHREADS = TY * G;
+  static constexpr int W = V + 2;
+  using P = AcParams<T>;
+  using Vt = Vec<T, V>;
+
+  struct PlaneRef {
+    const T* ptr;
+    int side;   // -1: no x ghost rule, 0/1: apply the lo/hi rule of axis 0
+  };
+
+  EVX_HD static PlaneRef plane(const P& p, int q) {
+    const long long ps = (long long)p.ny * p.nz;
+    PlaneRef r;
+    r.side = -1;
+    if (q >= 0 && q < p.nx) { r.ptr = p.phi + q * ps; return r; }
+    if (q < 0) {
+      if (p.halo_lo) { r.ptr = p.halo_lo; return r; }
+      if (p.bc_kind[0] == BC_PERIODIC) { r.ptr = p.phi + wrap_index(q, p.nx) * ps; return r; }
+      r.ptr = p.phi; r.side = 0; return r;
+    }
+    if (p.halo_hi) { r.ptr = p.halo_hi; return r; }
+    if (p.bc_kind[0] == BC_PERIODIC) { r.ptr = p.phi + wrap_index(q, p.nx) * ps; return r; }
+    r.ptr = p.phi + (long long)(p.nx - 1) * ps; r.side = 1; return r;
+  }
+
+  struct Pos {
+    long long roff[3];   // element offset of rows y-1, y, y+1 (group start) in a plane
+    long long loff[3];   // same rows, element z0-1 (mapped)
+    long long hoff[3];   // same rows, element z0+V (mapped)
+    int yside[3];        // -1 or lo/hi side of the y rule to apply to that row
+    int zl_side, zr_side;
+  };
+
+  EVX_HD static T rule(const P& p, int axis, int side, T v) {
+    return side < 0 ? v : p.ghost_off[axis][side] + p.ghost_sgn[axis] * v;
+  }
+
+  // load the (V+2)-wide window of one row of one plane with all ghost rules applied
+  EVX_HD static void load_row(const P& p, const PlaneRef& pl, const Pos& ps, int j, T* w) {
+    const Vt c = vec_load<T, V>(pl.ptr + ps.roff[j]);
+    T l = pl.ptr[ps.loff[j]];
+    T h = pl.ptr[ps.hoff[j]];
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+      w[k + 1] = rule(p, 1, ps.yside[j], rule(p, 0, pl.side, clip01(c.v[k])));
+    l = rule(p, 1, ps.yside[j], rule(p, 0, pl.side, clip01(l)));
+    h = rule(p, 1, ps.yside[j], rule(p, 0, pl.side, clip01(h)));
+    w[0] = rule(p, 2, ps.zl_side, l);
+    w[V + 1] = rule(p, 2, ps.zr_side, h);
+  }
+
+  EVX_HD static void run(const P& p, int tid, int tile, int chunk) {
+    const int tiles_z = (p.nz + TZ - 1) / TZ;
+    const int y = (tile / tiles_z) * TY + tid / G;
+    const int z = (tile % tiles_z) * TZ + (tid % G) * V;
+    if (y >= p.ny || z + V > p.nz) return;
+    const int xa = chunk * p.xchunk;
+    const int xb = xa + p.xchunk < p.nx ? xa + p.xchunk : p.nx;
+    const bool per_y = p.bc_kind[1] == BC_PERIODIC, per_z = p.bc_kind[2] == BC_PERIODIC;
+
+    Pos ps;
+    {
+      const int zl = z - 1, zr = z + V;
+      const int zli = per_z ? wrap_index(zl, p.nz) : clamp_index(zl, 0, p.nz - 1);
+      const int zri = per_z ? wrap_index(zr, p.nz) : clamp_index(zr, 0, p.nz - 1);
+      ps.zl_side = (!per_z && zl < 0) ? 0 : -1;
+      ps.zr_side = (!per_z && zr >= p.nz) ? 1 : -1;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int yy = y + j - 1;
+        const int yi = per_y ? wrap_index(yy, p.ny) : clamp_index(yy, 0, p.ny - 1);
+        ps.yside[j] = (!per_y && yy < 0) ? 0 : ((!per_y && yy >= p.ny) ? 1 : -1);
+        ps.roff[j] = (long long)yi * p.nz + z;
+        ps.loff[j] = (long long)yi * p.nz + zli;
+        ps.hoff[j] = (long long)yi * p.nz + zri;
+      }
+    }
+
+    T f[3][3][W];
+    {
+      const PlaneRef a = plane(p, xa - 1), b = plane(p, xa);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        load_row(p, a, ps, j, f[1][j]);
+        load_row(p, b, ps, j, f[2][j]);
+      }
+    }
+    const long long plane_sz = (long long)p.ny * p.nz;
+    const long long ooff = (long long)y * p.nz + z;
+    for (int x = xa; x < xb; ++x) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          f[0][j][k] = f[1][j][k];
+          f[1][j][k] = f[2][j][k];
+        }
+      {
+        const PlaneRef nxt = plane(p, x + 1);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) load_row(p, nxt, ps, j, f[2][j]);
+      }
+      const long long o = (long long)x * plane_sz + ooff;
+      Vt potv = vec_splat<T, V>(T(0)), basev = potv, accv = potv;
+      if (p.pot) potv = vec_load<T, V>(p.pot + o);
+      if (p.y_out) basev = vec_load<T, V>(p.base + o);
+      if (p.acc_out && p.acc_in) accv = vec_load<T, V>(p.acc_in + o);
+      Vt kv;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const int k = e + 1;
+        const T C = f[1][1][k];
+        const T R = f[2][1][k], L = f[0][1][k];
+        const T Tp = f[1][2][k], B = f[1][0][k];
+        const T F = f[1][1][k + 1], Bk = f[1][1][k - 1];
+        const T lap = (R + L) * p.ihx2 + (Tp + B) * p.ihy2 + (F + Bk) * p.ihz2 -
+                      T(2) * C * p.ih2sum;
+        const T gx = T(0.5) * (R - L) * p.ihx;
+        const T gy = T(0.5) * (Tp - B) * p.ihy;
+        const T gz = T(0.5) * (F - Bk) * p.ihz;
+        const T mxy = f[2][2][k] + f[0][0][k] - f[0][2][k] - f[2][0][k];
+        const T mxz = f[2][1][k + 1] + f[0][1][k - 1] - f[0][1][k + 1] - f[2][1][k - 1];
+        const T myz = f[1][2][k + 1] + f[1][0][k - 1] - f[1][0][k + 1] - f[1][2][k - 1];
+        const T num = gx * gx * (R - T(2) * C + L) * p.ihx2 +
+                      gy * gy * (Tp - T(2) * C + B) * p.ihy2 +
+                      gz * gz * (F - T(2) * C + Bk) * p.ihz2 +
+                      T(0.5) * gx * gy * mxy * p.ihx * p.ihy +
+                      T(0.5) * gx * gz * mxz * p.ihx * p.ihz +
+                      T(0.5) * gy * gz * myz * p.ihy * p.ihz;
+        T n2 = gx * gx + gy * gy + gz * gz;
+        if (n2 <= T(1e-7)) n2 = T(1);
+        const T nl = num / n2;
+        const T pot = p.pot ? potv.v[e] : p.pot_scale * C * (T(1) - C) * (T(1) - T(2) * C);
+        const T df = p.gab * (p.curv * lap + p.omc * nl - pot / T(2) / p.eps) +
+                     p.three_over_eps * C * (T(1) - C) * p.force;
+        kv.v[e] = p.M * df;
+      }
+      if (p.k_out) vec_store<T, V>(p.k_out + o, kv);
+      if (p.y_out) {
+        Vt yv;
+#pragma unroll
+        for (int e = 0; e < V; ++e) yv.v[e] = basev.v[e] + p.alpha * kv.v[e];
+        vec_store<T, V>(p.y_out + o, yv);
+      }
+      if (p.acc_out) {
+        Vt av;
+#pragma unroll
+        for (int e = 0; e < V; ++e) av.v[e] = accv.v[e] + p.beta * kv.v[e];
+        vec_store<T, V>(p.acc_out + o, av);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// Generic ghost-layer fetch used by the pad kernel: value of the padded field at padded
+// coordinates (i,j,k) in [0,n+2)^3 (reference boundary_conditions.py:33-59).
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct PadParams {
+  const T* in;
+  T* out;
+  int nx, ny, nz;
+  int bc_kind[3];
+  T ghost_off[3][2];
+  T ghost_sgn[3];
+};
+
+template <typename T>
+EVX_HD T padded_value(const PadParams<T>& p, int i, int j, int k) {
+  const int n[3] = {p.nx, p.ny, p.nz};
+  int q[3] = {i - 1, j - 1, k - 1};
+  int side[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    side[a] = -1;
+    if (q[a] < 0 || q[a] >= n[a]) {
+      if (p.bc_kind[a] == BC_PERIODIC) {
+        q[a] = wrap_index(q[a], n[a]);
+      } else {
+        side[a] = q[a] < 0 ? 0 : 1;
+        q[a] = q[a] < 0 ? 0 : n[a] - 1;
+      }
+    }
+  }
+  T v = p.in[((long long)q[0] * p.ny + q[1]) * p.nz + q[2]];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    if (side[a] >= 0) v = p.ghost_off[a][side[a]] + p.ghost_sgn[a] * v;
+  return v;
+}
+
+// Stencils on an already padded field (reference fd_stencils.py:56-103): value at interior
+// voxel (x,y,z); g points at the padded array [nx+2,ny+2,nz+2].
+template <typename T>
+struct PaddedStencilParams {
+  const T* g;
+  T* out;
+  int nx, ny, nz, op;
+  T ihx, ihy, ihz, ihx2, ihy2, ihz2, ih2sum;
+};
+
+template <typename T>
+EVX_HD T padded_stencil_value(const PaddedStencilParams<T>& p, int x, int y, int z) {
+  const long long sy = p.nz + 2, sx = (long long)(p.ny + 2) * (p.nz + 2);
+  const T* c = p.g + (x + 1) * sx + (y + 1) * sy + (z + 1);
+  const T C = c[0], R = c[sx], L = c[-sx], Tp = c[sy], B = c[-sy], F = c[1], Bk = c[-1];
+  if (p.op == 0)
+    return (R + L) * p.ihx2 + (Tp + B) * p.ihy2 + (F + Bk) * p.ihz2 - T(2) * C * p.ih2sum;
+  const T gx = T(0.5) * (R - L) * p.ihx, gy = T(0.5) * (Tp - B) * p.ihy,
+          gz = T(0.5) * (F - Bk) * p.ihz;
+  T n2 = gx * gx + gy * gy + gz * gz;
+  if (p.op == 2) return n2;
+  const T mxy = c[sx + sy] + c[-sx - sy] - c[-sx + sy] - c[sx - sy];
+  const T mxz = c[sx + 1] + c[-sx - 1] - c[-sx + 1] - c[sx - 1];
+  const T myz = c[sy + 1] + c[-sy - 1] - c[-sy + 1] - c[sy - 1];
+  const T num = gx * gx * (R - T(2) * C + L) * p.ihx2 + gy * gy * (Tp - T(2) * C + B) * p.ihy2 +
+                gz * gz * (F - T(2) * C + Bk) * p.ihz2 + T(0.5) * gx * gy * mxy * p.ihx * p.ihy +
+                T(0.5) * gx * gz * mxz * p.ihx * p.ihz + T(0.5) * gy * gz * myz * p.ihy * p.ihz;
+  if (n2 <= T(1e-7)) n2 = T(1);
+  return num / n2;
+}
+
+}  // namespace evx

@@ -1,0 +1,63 @@
+// Host/device portability layer.
+//
+// Every kernel in this library is written as a "program": a struct with per-thread
+// register state (Regs), a shared-memory image (Smem) and phase functions that contain
+// no barrier.  On the GPU a thin __global__ wrapper runs the phases with __syncthreads()
+// between them.  The same phase functions compile as plain C++ so that tests/emu/ can
+// replay a thread block on the CPU (phase by phase, thread by thread) and compare the
+// index/halo/boundary logic against the oracle without a GPU.  The emulator is test
+// infrastructure; nothing in the shipped library executes on the host.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define EVX_HD __host__ __device__ __forceinline__
+#define EVX_D __device__ __forceinline__
+#else
+#define EVX_HD inline
+#define EVX_D inline
+#endif
+
+namespace evx {
+
+enum : int { BC_PERIODIC = 0, BC_NEUMANN = 1, BC_DIRICHLET = 2 };
+
+// V consecutive elements along the contiguous (z) axis; 16-byte aligned for
+// float x4 / double x2 so that loads and stores become single 128-bit accesses.
+template <typename T, int V>
+struct alignas(sizeof(T) * V >= 16 ? 16 : sizeof(T) * V) Vec {
+  T v[V];
+};
+
+template <typename T, int V>
+EVX_HD Vec<T, V> vec_load(const T* p) {
+  return *reinterpret_cast<const Vec<T, V>*>(p);
+}
+template <typename T, int V>
+EVX_HD void vec_store(T* p, const Vec<T, V>& x) {
+  *reinterpret_cast<Vec<T, V>*>(p) = x;
+}
+template <typename T, int V>
+EVX_HD Vec<T, V> vec_splat(T a) {
+  Vec<T, V> r;
+#pragma unroll
+  for (int k = 0; k < V; ++k) r.v[k] = a;
+  return r;
+}
+
+template <typename T>
+EVX_HD T clip01(T a) {
+  // torch.clip(c, 0, 1): min(max(c, 0), 1); NaN propagates in torch, here fmin/fmax
+  // would drop it, so keep the comparison form (NaN compares false -> passes through).
+  return a < T(0) ? T(0) : (a > T(1) ? T(1) : a);
+}
+
+EVX_HD int wrap_index(int i, int n) {
+  int m = i % n;
+  return m < 0 ? m + n : m;
+}
+EVX_HD int clamp_index(int i, int lo, int hi) { return i < lo ? lo : (i > hi ? hi : i); }
+
+}  // namespace evx

@@ -1,0 +1,53 @@
+// Plan object behind evx_imex_plan_* and declarations shared by spectral.cu / fft_native.cu.
+#pragma once
+#include <cufft.h>
+#include <cuda_runtime.h>
+#include "evx_hd.h"
+#include "../../include/evoxels_b200.h"
+
+namespace evx {
+
+struct FilterParams {
+  int n0, n1, n2;                       // extents (n2 is the halved, contiguous one)
+  float inv_len0, inv_len1, inv_len2;   // float(1/(n*h)) per axis
+  float dt, coef, scale;
+  int power;                            // 1: |k|^2, 2: |k|^4
+  double scale_d;
+};
+
+}  // namespace evx
+
+struct evx_imex_plan {
+  int nx = 0, ny = 0, nz = 0, is_f64 = 0, backend = 0;
+  int n[3] = {1, 1, 1};        // extents with size-1 axes squeezed to the front
+  int axis_of[3] = {-1, -1, -1};  // which original axis each squeezed axis is
+  int rank = 0;
+  size_t real_elems = 0, spec_elems = 0;
+  size_t real_bytes = 0, spec_bytes = 0, work_bytes = 0;
+  bool have_cufft = false;
+  cufftHandle fwd = 0, inv = 0;
+  // native back end
+  void* twiddles = nullptr;    // device table(s), owned
+  int spec_pitch = 0;          // complex elements per (x,y) row of the native spectrum
+};
+
+namespace evx {
+
+int plan_create(evx_imex_plan** out, int nx, int ny, int nz, int is_f64, int backend);
+int plan_destroy(evx_imex_plan* p);
+
+// fft_native.cu
+bool native_fft_supported(int nx, int ny, int nz);
+int native_plan_init(evx_imex_plan* p);
+void native_plan_free(evx_imex_plan* p);
+int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, void* workspace,
+                 const double* h, double dt, double coef, int power, cudaStream_t st);
+int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* out,
+                   void* workspace, const double* h, double dt, double eps, double D, double A,
+                   cudaStream_t st);
+
+__device__ __forceinline__ bool aligned16_dev(const void* p) {
+  return (reinterpret_cast<unsigned long long>(p) & 15ull) == 0;
+}
+
+}  // namespace evx

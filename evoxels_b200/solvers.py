@@ -1,0 +1,127 @@
+"""Time loop and field export around `step(t, u)`.
+
+Interface parity with evoxels/solvers.py: `BaseSolver` (:12-187) and
+`TimeDependentSolver` (:189-208) keep the dataclass fields
+`(vf, fieldnames, backend, problem_cls, timestepper_cls, step_fn, device)` and
+`solve(time_increment, frames, max_iters, problem_kwargs, jit, verbose, vtk_out,
+plot_bounds, colormap)`.  `backend` must be 'torch' (no JAX dispatch), `jit` is accepted
+and ignored: the step already is a handful of hand-written kernels, there is nothing to
+trace.  Live plotting (`verbose='plot'`) is host visualisation and not provided.
+"""
+from __future__ import annotations
+
+import sys
+import warnings
+from abc import ABC, abstractmethod
+from dataclasses import dataclass
+from timeit import default_timer as timer
+from typing import Any, Callable, Type
+
+import torch
+
+from .problem_definition import ODE
+from .timesteppers import TimeStepper
+from .voxelgrid import VoxelGridTorch
+
+
+@dataclass
+class BaseSolver(ABC):
+    vf: Any
+    fieldnames: str | list[str]
+    backend: str
+    problem_cls: Type[ODE] | None = None
+    timestepper_cls: Type[TimeStepper] | None = None
+    step_fn: Callable | None = None
+    device: str = "cuda"
+
+    def __post_init__(self):
+        if self.backend != "torch":
+            raise ValueError(f"Unsupported backend: {self.backend} "
+                             "(evoxels_b200 drives CUDA through torch only)")
+        self.vg = VoxelGridTorch(self.vf.grid_info(), precision=self.vf.precision,
+                                 device=self.device)
+        self.fieldnames = [self.fieldnames] if isinstance(self.fieldnames, str) \
+            else list(self.fieldnames)
+        self.problem = None
+        self.computation_time = None
+
+    # ---- set-up ----------------------------------------------------------------------
+    def _init_fields(self):
+        fields = [self.vg.init_scalar_field(self.vf.fields[n]) for n in self.fieldnames]
+        return self.vg.bc.trim_boundary_nodes(self.vg.concatenate(fields, 0))
+
+    def _init_stepper(self, time_increment, problem_kwargs, jit):
+        if self.step_fn is not None:
+            self.problem = None
+            return self.step_fn
+        if self.problem_cls is None or self.timestepper_cls is None:
+            raise ValueError("Either provide step_fn or both problem_cls and timestepper_cls")
+        self.problem = self.problem_cls(self.vg, **(problem_kwargs or {}))
+        return self.timestepper_cls(self.problem, time_increment).step
+
+    @abstractmethod
+    def _run_loop(self, u, step, time_increment, frames, max_iters, vtk_out, verbose,
+                  plot_bounds, colormap):
+        raise NotImplementedError
+
+    def solve(self, time_increment=0.1, frames=10, max_iters=100, problem_kwargs=None,
+              jit=True, verbose=True, vtk_out=False, plot_bounds=None, colormap="viridis"):
+        u = self._init_fields()
+        step = self._init_stepper(time_increment, problem_kwargs, jit)
+        if verbose == "plot":
+            warnings.warn("verbose='plot' is not available in evoxels_b200; printing stats only")
+        cuda = self.vg.device.type == "cuda"
+        if cuda:
+            torch.cuda.reset_peak_memory_stats(self.vg.device)
+            torch.cuda.synchronize(self.vg.device)
+        start = timer()
+        u = self._run_loop(u, step, time_increment, frames, max_iters, vtk_out, verbose,
+                           plot_bounds, colormap)
+        if cuda:
+            torch.cuda.synchronize(self.vg.device)
+        end = timer()
+        self.computation_time = end - start
+        if verbose:
+            per = self.computation_time / max(max_iters, 1)
+            print(f"Wall time: {self.computation_time:.4f} s after {max_iters} iterations "
+                  f"({per:.6f} s/iter)")
+            if cuda:
+                mb = 1024 ** 2
+                print(f"GPU-RAM (torch) current: {torch.cuda.memory_allocated(self.vg.device)/mb:.2f} MB "
+                      f"({torch.cuda.max_memory_allocated(self.vg.device)/mb:.2f} MB max)")
+
+    # ---- per-frame output --------------------------------------------------------------
+    def _export_fields(self, u_out):
+        for i, name in enumerate(self.fieldnames):
+            self.vf.set_field(name, self.vg.export_scalar_field_to_numpy(u_out[i:i + 1]))
+
+    def _handle_outputs(self, u, frame, time, vtk_out, verbose, plot_bounds, colormap):
+        # the reference pads and trims here (solvers.py:154-157), which is the identity
+        # on a cell-centred grid; export the state directly
+        u_out = u
+        nan_flag = torch.isnan(u_out).any()          # device-side reduction
+        self._export_fields(u_out)                   # D2H copy
+        if bool(nan_flag):
+            print(f"NaN detected in frame {frame} at time {time}. Aborting simulation.")
+            sys.exit(1)
+        if vtk_out:
+            prefix = self.problem_cls.__name__ if self.problem_cls else "custom"
+            self.vf.export_to_vtk(filename=f"{prefix}_{self.fieldnames[0]}_{frame:03d}.vtk",
+                                  field_names=self.fieldnames)
+
+
+@dataclass
+class TimeDependentSolver(BaseSolver):
+    def _run_loop(self, u, step, time_increment, frames, max_iters, vtk_out, verbose,
+                  plot_bounds, colormap):
+        every = max_iters // frames          # ZeroDivisionError if frames > max_iters, as upstream
+        frame = 0
+        for i in range(max_iters):
+            now = i * time_increment
+            if i % every == 0:
+                self._handle_outputs(u, frame, now, vtk_out, verbose, plot_bounds, colormap)
+                frame += 1
+            u = step(now, u)
+        self._handle_outputs(u, frame, max_iters * time_increment, vtk_out, verbose,
+                             plot_bounds, colormap)
+        return u

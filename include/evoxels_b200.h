@@ -1,0 +1,174 @@
+/* evoxels_b200 - C ABI of the B200-native hot path of daubners/evoxels.
+ *
+ * One shared library (libevx_b200.so, built for sm_100a) exports everything below with
+ * C linkage.  All data pointers are DEVICE pointers owned by the caller (PyTorch's caching
+ * allocator in the shipped host code); no call allocates device memory except
+ * evx_imex_plan_create (cuFFT plans, twiddle tables), no call synchronises the device,
+ * every call enqueues its work on `stream` (a cudaStream_t passed as void*).  Return value:
+ * 0 on success, > 0 a cudaError_t, < 0 one of EVX_ERR_* below; evx_strerror() names it.
+ * Calls are thread-safe for distinct streams/buffers/plans.
+ *
+ * Fields are C-contiguous [nx, ny, nz] with z fastest - exactly the reference's
+ * [C=1, Nx, Ny, Nz] tensors (evoxels/voxelgrid.py:126-130).  For x-slab decomposition `nx`
+ * is the local slab thickness and the optional halo pointers carry the neighbour's planes.
+ *
+ * Each entry point names the reference interface (file:line in daubners/evoxels) it
+ * replaces; INTEGRATION.md shows the binding a reference maintainer would add.
+ */
+#ifndef EVOXELS_B200_H
+#define EVOXELS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVX_VERSION 100  /* 0.1.0 */
+
+/* boundary-condition kinds per axis (evoxels/problem_definition.py:60-115) */
+#define EVX_BC_PERIODIC 0
+#define EVX_BC_NEUMANN 1
+#define EVX_BC_DIRICHLET 2
+
+/* error codes */
+#define EVX_OK 0
+#define EVX_ERR_ARG (-1)          /* null pointer / non-positive extent / bad enum      */
+#define EVX_ERR_UNSUPPORTED (-2)  /* valid in the reference, not implemented on device  */
+#define EVX_ERR_ALIGN (-3)        /* pointer not aligned as the entry point requires    */
+#define EVX_ERR_CUFFT (-1000)     /* -1000 - cufftResult                                */
+
+/* FFT back ends of an IMEX plan */
+#define EVX_FFT_AUTO 0
+#define EVX_FFT_CUFFT 1   /* cuFFT R2C/C2R + fused filter / add kernels (any extents)   */
+#define EVX_FFT_NATIVE 2  /* hand-written sm_100a pass kernels (power-of-two extents)   */
+
+int evx_version(void);
+const char* evx_strerror(int code);
+
+/* ---------------------------------------------------------------------------------
+ * Stencil layer
+ * ------------------------------------------------------------------------------- */
+
+/* Cahn-Hilliard right-hand side, fused: clip -> 7-pt Laplacian -> mu -> face-mobility
+ * flux -> divergence, ghost layers by index arithmetic.
+ * Replaces CahnHilliard.rhs (evoxels/problem_definition.py:328-371) incl. its calls to
+ * FDStencils.laplace/to_*_face/grad_*_face (evoxels/fd_stencils.py:20-42,62-75) and
+ * CellCenteredBCs.pad_* (evoxels/boundary_conditions.py:9-59).
+ *   c        raw concentration (clipped to [0,1] inside, like the reference)
+ *   hom      NULL -> default mu_hom 18/eps c(1-c)(1-2c); else a field holding mu_hom(clip(c))
+ *   rhs      output, must not alias c
+ *   h[3]     grid spacing;  bc_kind[3], bc_val[6]=(x_lo,x_hi,y_lo,y_hi,z_lo,z_hi) Dirichlet values
+ *   halo_lo  NULL, or [2,ny,nz] raw planes x=-2,-1 of the x-neighbour slab (then the x rule
+ *            of bc_kind is not applied on that side); halo_hi likewise planes x=nx,nx+1.
+ */
+int evx_ch_rhs_f32(const float* c, const float* hom, float* rhs, int nx, int ny, int nz,
+                   const double* h, double eps, double D, const int* bc_kind,
+                   const double* bc_val, const float* halo_lo, const float* halo_hi,
+                   void* stream);
+int evx_ch_rhs_f64(const double* c, const double* hom, double* rhs, int nx, int ny, int nz,
+                   const double* h, double eps, double D, const int* bc_kind,
+                   const double* bc_val, const double* halo_lo, const double* halo_hi,
+                   void* stream);
+
+/* Two-phase Allen-Cahn right-hand side k = rhs(phi), fused with the explicit-stage
+ * arithmetic of ForwardEuler / RungeKutta4:
+ *      k_out   = k                          (if k_out   != NULL)
+ *      y_out   = base + alpha * k           (if y_out   != NULL; base may equal phi)
+ *      acc_out = acc_in + beta * k          (if acc_out != NULL; acc_in NULL means 0)
+ * Replaces TwoPhaseAllenCahn.rhs (evoxels/problem_definition.py:421-447) with
+ * FDStencils.laplace / normal_laplace (evoxels/fd_stencils.py:44-103, 19-point footprint
+ * incl. the |grad|^2 <= 1e-7 guard), the generic ghost rules of CellCenteredBCs.pad_bc
+ * (evoxels/boundary_conditions.py:33-59, axis order x,y,z), ForwardEuler.step
+ * (evoxels/timesteppers.py:42-43) and the axpys of RungeKutta4.step (:56-61).
+ *   pot      NULL -> default potential 18/eps phi(1-phi)(1-2phi); else potential(clip(phi))
+ *   halo_lo  NULL or [1,ny,nz] raw plane x=-1 of the neighbour slab; halo_hi plane x=nx.
+ * Outputs must not alias phi (neighbouring threads read it).
+ */
+int evx_ac_stage_f32(const float* phi, const float* pot, float* k_out, const float* base,
+                     float* y_out, double alpha, const float* acc_in, float* acc_out,
+                     double beta, int nx, int ny, int nz, const double* h, double eps,
+                     double gab, double M, double force, double curvature,
+                     const int* bc_kind, const double* bc_val, const float* halo_lo,
+                     const float* halo_hi, void* stream);
+int evx_ac_stage_f64(const double* phi, const double* pot, double* k_out, const double* base,
+                     double* y_out, double alpha, const double* acc_in, double* acc_out,
+                     double beta, int nx, int ny, int nz, const double* h, double eps,
+                     double gab, double M, double force, double curvature,
+                     const int* bc_kind, const double* bc_val, const double* halo_lo,
+                     const double* halo_hi, void* stream);
+
+/* One ghost layer around a field: out[nx+2,ny+2,nz+2].
+ * Replaces CellCenteredBCs.pad_periodic / pad_dirichlet_periodic / pad_zero_flux_periodic /
+ * pad_bc (evoxels/boundary_conditions.py:9-59) and VoxelGridTorch.pad_periodic
+ * (evoxels/voxelgrid.py:194-195); edge/corner ghosts follow the reference's x,y,z order. */
+int evx_pad_ghost_f32(const float* in, float* out, int nx, int ny, int nz, const int* bc_kind,
+                      const double* bc_val, void* stream);
+int evx_pad_ghost_f64(const double* in, double* out, int nx, int ny, int nz, const int* bc_kind,
+                      const double* bc_val, void* stream);
+
+/* Stencils on an already ghost-padded field [nx+2,ny+2,nz+2] -> interior [nx,ny,nz]:
+ * op 0 = 7-pt Laplacian (fd_stencils.py:62-75), 1 = normal Laplacian (:77-103),
+ * 2 = |grad|^2 from centred differences (:56-60). */
+int evx_padded_stencil_f32(const float* padded, float* out, int nx, int ny, int nz,
+                           const double* h, int op, void* stream);
+int evx_padded_stencil_f64(const double* padded, double* out, int nx, int ny, int nz,
+                           const double* h, int op, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Spectral (semi-implicit) stage
+ * ------------------------------------------------------------------------------- */
+typedef struct evx_imex_plan evx_imex_plan;
+
+/* Plan for  out = u + irfftn( P(k) * rfftn(r) ),  P = dt / (1 + dt*coef*|k|^(2*power)),
+ * on a periodic [nx,ny,nz] grid.  Replaces PseudoSpectralIMEX.__post_init__/step
+ * (evoxels/timesteppers.py:75-89), VoxelGridTorch.rfftn/irfftn (evoxels/voxelgrid.py:
+ * 203-207) and the stored prefactor array built from VoxelGrid.rfft_k_squared
+ * (evoxels/voxelgrid.py:84-90,110-114): wavenumbers are recomputed on the fly in float32
+ * with the reference's rounding sequence, nothing of size O(N^3) is stored.
+ *   is_f64   0: float32 fields, 1: float64 fields (always cuFFT back end)
+ *   backend  EVX_FFT_AUTO / EVX_FFT_CUFFT / EVX_FFT_NATIVE (ERR_UNSUPPORTED if the extents
+ *            are not all powers of two in the supported range)                        */
+int evx_imex_plan_create(evx_imex_plan** plan, int nx, int ny, int nz, int is_f64, int backend);
+int evx_imex_plan_destroy(evx_imex_plan* plan);
+int evx_imex_plan_backend(const evx_imex_plan* plan);            /* EVX_FFT_CUFFT|NATIVE */
+/* bytes of caller-provided scratch every apply/step call needs (256-byte aligned) */
+int evx_imex_plan_workspace_bytes(const evx_imex_plan* plan, size_t* bytes);
+
+/* out = u + irfftn( P * rfftn(r) ).  `r` is preserved, `out` may alias `u` but not `r`;
+ * u == NULL gives the update alone (out = irfftn(P * rfftn(r))).
+ * CH: coef = 2*eps*D*A, power = 2 (problem_definition.py:303).  AC / reaction-diffusion:
+ * coef = M*gab or D*A, power = 1 (:198, :389). */
+int evx_imex_apply_f32(evx_imex_plan* plan, const float* u, const float* r, float* out,
+                       void* workspace, const double* h, double dt, double coef, int power,
+                       void* stream);
+int evx_imex_apply_f64(evx_imex_plan* plan, const double* u, const double* r, double* out,
+                       void* workspace, const double* h, double dt, double coef, int power,
+                       void* stream);
+
+/* One full Cahn-Hilliard IMEX step on a fully periodic grid:
+ *      out = u + irfftn( dt/(1 + dt*2*eps*D*A*|k|^4) * rfftn( CahnHilliard.rhs(u) ) )
+ * = PseudoSpectralIMEX.step o CahnHilliard.rhs (timesteppers.py:85-89,
+ * problem_definition.py:328-371).  `out` must not alias `u`. */
+int evx_ch_imex_step_f32(evx_imex_plan* plan, const float* u, const float* hom, float* out,
+                         void* workspace, const double* h, double dt, double eps, double D,
+                         double A, void* stream);
+int evx_ch_imex_step_f64(evx_imex_plan* plan, const double* u, const double* hom, double* out,
+                         void* workspace, const double* h, double dt, double eps, double D,
+                         double A, void* stream);
+
+/* The filter alone on a cuFFT-layout half spectrum [nx,ny,nz/2+1] (complex interleaved):
+ * spec *= scale * dt / (1 + dt*coef*|k|^(2*power)).  Exposed for tests and for callers
+ * that run their own transforms. */
+int evx_spectral_filter_c64(void* spec, int nx, int ny, int nz, const double* h, double dt,
+                            double coef, int power, double scale, void* stream);
+int evx_spectral_filter_c128(void* spec, int nx, int ny, int nz, const double* h, double dt,
+                             double coef, int power, double scale, void* stream);
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+unsigned long long evx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVOXELS_B200_H */

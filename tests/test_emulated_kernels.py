@@ -1,0 +1,153 @@
+"""CPU replay of the CUDA thread-block programs (tests/emu/emu_kernels.cpp compiles the
+very same *_core.h phase functions with g++) against the oracle.  Catches index / halo /
+boundary-rule mistakes without a GPU.  Test infrastructure only - the product never runs
+these on the host."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, rel_l2
+from oracle import evx_oracle as O
+
+KIND = {"periodic": 0, "neumann": 1, "dirichlet": 2}
+BCS = [("periodic",) * 3, ("neumann",) * 3,
+       (("dirichlet", (0.2, 0.6)), "neumann", "periodic"),
+       ("periodic", "neumann", ("dirichlet", (0.1, 0.9))),
+       (("dirichlet", (1, 2)), ("dirichlet", (3, 4)), ("dirichlet", (5, 6)))]
+SHAPES = [((12, 9, 8), (0.5, 1.0, 0.5)), ((7, 20, 68), (1.0, 1.0, 1.0)), ((16, 1, 1), (1, 1, 1)),
+          ((3, 33, 12), (1, 2, 1)), ((2, 2, 2), (1, 1, 1)), ((9, 8, 7), (1, 1, 1))]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(ROOT, "tests", "emu", "emu_kernels.cpp")
+    out = os.path.join(ROOT, "tests", "emu", "libevx_emu.so")
+    deps = [src] + [os.path.join(ROOT, "evoxels_b200", "csrc", f)
+                    for f in os.listdir(os.path.join(ROOT, "evoxels_b200", "csrc")) if f.endswith(".h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+                               "-o", out, src])
+    return ctypes.CDLL(out)
+
+
+def _bc(bc):
+    bc = O.normalize_bc(bc)
+    k = (ctypes.c_int * 3)(*[KIND[b[0]] for b in bc])
+    v = (ctypes.c_double * 6)(*sum([list(b[1]) if b[1] else [0.0, 0.0] for b in bc], []))
+    return k, v
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def emu_ch(lib, u, sp, eps, D, bc, xchunk, vec, hom=None, hlo=None, hhi=None):
+    f = lib.emu_ch_rhs_f32 if u.dtype == np.float32 else lib.emu_ch_rhs_f64
+    out = np.full_like(u, np.nan)
+    k, v = _bc(bc)
+    rc = f(_p(u), _p(hom), _p(out), *u.shape, (ctypes.c_double * 3)(*sp), ctypes.c_double(eps),
+           ctypes.c_double(D), k, v, _p(hlo), _p(hhi), xchunk, vec)
+    assert rc == 0
+    return out
+
+
+def emu_ac(lib, u, sp, kw, bc, xchunk, vec, alpha=0.0, beta=0.0, acc=None, hlo=None, hhi=None):
+    f = lib.emu_ac_stage_f32 if u.dtype == np.float32 else lib.emu_ac_stage_f64
+    k_, y_, a_ = (np.full_like(u, np.nan) for _ in range(3))
+    k, v = _bc(bc)
+    d = ctypes.c_double
+    rc = f(_p(u), None, _p(k_), _p(u), _p(y_), d(alpha), _p(acc), _p(a_), d(beta), *u.shape,
+           (ctypes.c_double * 3)(*sp), d(kw["eps"]), d(kw["gab"]), d(kw["M"]), d(kw["force"]),
+           d(kw["curvature"]), k, v, _p(hlo), _p(hhi), xchunk, vec)
+    assert rc == 0
+    return k_, y_, a_
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_ch_rhs_program(emu, dtype):
+    tol = 1e-12 if dtype == np.float64 else 2e-5
+    for shape, sp in SHAPES:
+        u = (-0.2 + 1.4 * np.random.default_rng(3).random(shape)).astype(dtype)
+        for bc in BCS:
+            ref = O.ch_rhs(torch.from_numpy(u)[None], sp, 2.5, 1.3, bc)[0].numpy()
+            for xchunk in (shape[0], 3):
+                for vec in (0, 1):
+                    if vec and shape[2] % (16 // np.dtype(dtype).itemsize):
+                        continue
+                    got = emu_ch(emu, u, sp, 2.5, 1.3, bc, xchunk, vec)
+                    assert rel_l2(got, ref) <= tol, (shape, bc, xchunk, vec)
+
+
+def test_ch_rhs_program_custom_potential_and_halos(emu):
+    u = (0.2 + 0.6 * np.random.default_rng(1).random((6, 10, 8)))
+    mu = lambda c: torch.log(c.clip(1e-4, 1 - 1e-4) / (1 - c.clip(1e-4, 1 - 1e-4))) + 2.5 * (1 - 2 * c)  # noqa: E731
+    ref = O.ch_rhs(torch.from_numpy(u)[None], (1, 1, 1), 3.0, 1.0, ("periodic",) * 3, mu)[0].numpy()
+    hom = mu(torch.from_numpy(u).clip(0, 1)).numpy()
+    assert rel_l2(emu_ch(emu, u, (1, 1, 1), 3.0, 1.0, ("periodic",) * 3, 4, 1, hom=hom), ref) <= 1e-12
+    # x-slab decomposition with 2-plane halos reproduces the single-domain result
+    u = (-0.2 + 1.4 * np.random.default_rng(2).random((12, 9, 8)))
+    for bc in [("periodic",) * 3, ("neumann", "periodic", "neumann"),
+               (("dirichlet", (0.2, 0.6)), "neumann", "periodic")]:
+        ref = O.ch_rhs(torch.from_numpy(u)[None], (1, 1, 1), 3.0, 1.0, bc)[0].numpy()
+        per = bc[0] == "periodic"
+        parts = []
+        for a, b in [(0, 5), (5, 12)]:
+            lo = np.ascontiguousarray(np.take(u, [a - 2, a - 1], axis=0, mode="wrap")) if (per or a > 0) else None
+            hi = np.ascontiguousarray(np.take(u, [b, b + 1], axis=0, mode="wrap")) if (per or b < 12) else None
+            parts.append(emu_ch(emu, np.ascontiguousarray(u[a:b]), (1, 1, 1), 3.0, 1.0, bc, 3, 1, hlo=lo, hhi=hi))
+        assert rel_l2(np.concatenate(parts), ref) <= 1e-12, bc
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_ac_stage_program(emu, dtype):
+    tol = 1e-12 if dtype == np.float64 else 3e-5
+    kw = dict(eps=3.0, gab=0.8, M=1.5, force=1.0, curvature=0.5)
+    for shape, sp in SHAPES:
+        u = (-0.2 + 1.4 * np.random.default_rng(3).random(shape)).astype(dtype)
+        acc = np.random.default_rng(4).random(shape).astype(dtype)
+        for bc in BCS:
+            ref = O.ac_rhs(torch.from_numpy(u)[None], sp, bc=bc, **kw)[0].numpy()
+            for vec in (0, 1):
+                if vec and shape[2] % (16 // np.dtype(dtype).itemsize):
+                    continue
+                k, y, a = emu_ac(emu, u, sp, kw, bc, 3, vec, alpha=0.05, beta=2.0, acc=acc)
+                assert rel_l2(k, ref) <= tol, (shape, bc, vec)
+                assert rel_l2(y, u + dtype(0.05) * ref) <= tol
+                assert rel_l2(a, acc + 2 * ref) <= tol
+
+
+def test_ac_stage_program_halos(emu):
+    kw = dict(eps=3.0, gab=0.8, M=1.5, force=1.0, curvature=0.5)
+    u = (-0.2 + 1.4 * np.random.default_rng(2).random((12, 9, 8)))
+    for bc in [("periodic",) * 3, ("neumann",) * 3, (("dirichlet", (0.2, 0.6)), "neumann", "periodic")]:
+        ref = O.ac_rhs(torch.from_numpy(u)[None], (1, 1, 1), bc=bc, **kw)[0].numpy()
+        per = bc[0] == "periodic"
+        parts = []
+        for a, b in [(0, 5), (5, 12)]:
+            lo = np.ascontiguousarray(np.take(u, [a - 1], axis=0, mode="wrap")) if (per or a > 0) else None
+            hi = np.ascontiguousarray(np.take(u, [b], axis=0, mode="wrap")) if (per or b < 12) else None
+            parts.append(emu_ac(emu, np.ascontiguousarray(u[a:b]), (1, 1, 1), kw, bc, 3, 1, hlo=lo, hhi=hi)[0])
+        assert rel_l2(np.concatenate(parts), ref) <= 1e-12, bc
+
+
+def test_pad_and_padded_stencils(emu):
+    for dtype in (np.float64, np.float32):
+        sfx = "f64" if dtype == np.float64 else "f32"
+        for shape in [(5, 4, 3), (2, 2, 2), (3, 1, 4)]:
+            u = np.random.default_rng(5).random(shape).astype(dtype)
+            for bc in BCS:
+                out = np.zeros(tuple(s + 2 for s in shape), dtype)
+                k, v = _bc(bc)
+                getattr(emu, "emu_pad_ghost_" + sfx)(_p(u), _p(out), *shape, k, v)
+                ref = O.ghost_pad(torch.from_numpy(u)[None], bc)[0].numpy()
+                assert np.abs(out - ref).max() <= 1e-6
+                h = (ctypes.c_double * 3)(0.5, 1.0, 0.25)
+                for op, fn in [(0, O.laplace7), (1, O.normal_laplace19)]:
+                    o2 = np.zeros(shape, dtype)
+                    getattr(emu, "emu_padded_stencil_" + sfx)(_p(ref), _p(o2), *shape, h, op)
+                    r2 = fn(torch.from_numpy(ref)[None], (0.5, 1.0, 0.25))[0].numpy()
+                    assert rel_l2(o2, r2) <= (1e-12 if dtype == np.float64 else 2e-4)
