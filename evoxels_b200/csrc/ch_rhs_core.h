@@ -17,9 +17,17 @@
 // y-z plane and marches along x through a chunk of planes.  Each thread owns V contiguous
 // z-values ("a group") of one row of the tile *extended by one ring* (the ring is needed
 // because rhs at the tile edge needs mu one cell outside the tile, and that mu needs c^
-// two cells outside).  x-neighbours live in registers (rolling window of 4 planes of c^,
-// 3 of mu); y/z-neighbours come from shared memory (2 plane slots of c^, 2 of mu).
+// two cells outside).  x-neighbours live in registers (rolling window of 3 planes of c^,
+// mu of the previous plane and the carried x-face term); y/z-neighbours come from shared memory (2 plane slots of c^, 2 of mu).
 // One barrier per plane.
+//
+// Arithmetic: the kernel is FP32-issue bound on B200 (about 45 flop/voxel against
+// 8 B/voxel), so the face terms are written as
+//      4 cf (1-cf) (mu_b - mu_a) = s (2 - s) (mu_b - mu_a),   s = c_a + c_b
+// with all metric factors folded into three constants D/(4 h_a^2); the x-face term is
+// carried to the next plane in a register and the z-face terms are shared inside a
+// thread's group, so each face is evaluated once per thread.  This reassociates the
+// reference's expression; the result differs by fp32 rounding only (tests: rel-L2 <= 5e-6).
 //
 // The footprint of rhs is the 25-point "diamond" |dx|+|dy|+|dz| <= 2, so tile corners of
 // the rings are never consumed (they hold don't-care values).
@@ -37,17 +45,16 @@ struct ChParams {
   const T* halo_hi;  // optional [2,ny,nz]: raw planes x=nx,nx+1
   int nx, ny, nz;
   int xchunk;        // planes per blockIdx.y
-  T ihx, ihy, ihz;   // 1/h
-  T ihx2, ihy2, ihz2, ih2sum;
   T pot_scale;       // 18/eps
-  T two_eps;         // 2*eps
-  T D;
+  // folded constants
+  T lx, ly, lz, l0;  // mu = g + lx (c_x+ + c_x-) + ly (..) + lz (..) + l0 c ; l_a = -2 eps / h_a^2
+  T fx, fy, fz;      // rhs = fx dFx + fy dFy + fz dFz ; f_a = D / (4 h_a^2)
   int bc_kind[3];
   T ghost_off[3][2];   // ghost = ghost_off + ghost_sgn * inner   (per axis, lo/hi side)
   T ghost_sgn[3];
 };
 
-template <typename T, int V, int TY, int G, bool HOM = false>
+template <typename T, int V, int TY, int G, bool HOM = false, bool GHOSTS = true>
 struct ChRhsProgram {
   static constexpr int TZ = G * V;
   static constexpr int RZ = V >= 2 ? 1 : 2; // ring groups per side: c^ is needed 2 cells out
@@ -67,41 +74,44 @@ struct ChRhsProgram {
   };
 
   struct Regs {
-    // position of this thread in the extended tile
-    int r, g;                 // row in [-1, TY], group in [-RZ, G+RZ-1]
-    bool has_pos;             // tid < NPOS
-    bool interior;            // produces an output value
+    int row, col;             // smem indices of the own position (row in s.c numbering)
+    bool has_pos, want_mu, interior, has_extra;
     bool gy_lo, gy_hi, gz_lo, gz_hi;   // neighbour in that direction is a non-periodic ghost
+    bool xlo_ghost, xhi_ghost;         // planes below 0 / above nx-1 are non-periodic ghosts
     long long off;            // element offset of this position inside a plane
     long long out_off;
-    // extra loader (two outermost rows)
-    bool has_extra;
-    int er, eg;               // smem row / col of the extra element
+    int er, ec;               // smem row / col of the extra element
     long long eoff;
-    // rolling windows
-    Vt cA, cB, cC, cD;        // c^ at planes p-2, p-1, p, p+1 (own position)
+    Vt cB, cC, cD;            // c^ at planes p-1, p, p+1 (own position)
     Vt hC, hD;                // hom at planes p, p+1
-    Vt mA, mB;                // mu at planes p-2, p-1
+    Vt mB;                    // mu at plane p-1
+    Vt fxm;                   // x-face term between planes p-2 and p-1
     Vt nxt, hnxt, enxt;       // raw prefetched plane p+2 (own / hom / extra rows)
-    Vt sN, sS;                // saved y-neighbours of c^(p-1)
-    T sL, sR;                 // saved z-neighbours of c^(p-1)
+    Vt sN, sS;                // y-neighbours of c^(p-1)
+    T sL, sR;                 // z-neighbours of c^(p-1)
     int xa, xb;               // chunk [xa, xb)
   };
 
   EVX_HD static int slot(int q) { return (q + 4) & 1; }
 
-  // pointer to plane q of the raw field (own slab, x-halo, or periodic image); null = ghost
+  // pointer to plane q of a field (own slab, x-halo, or periodic image); null = ghost plane
   EVX_HD static const T* plane(const P& p, const T* base, int q, bool use_halo) {
     const long long ps = (long long)p.ny * p.nz;
-    if (q >= 0 && q < p.nx) return base + q * ps;
-    if (q < 0) {
-      if (use_halo && p.halo_lo) return p.halo_lo + (q + 2) * ps;
-      if (p.bc_kind[0] == BC_PERIODIC && !p.halo_lo) return base + wrap_index(q, p.nx) * ps;
-      return nullptr;
+    if (q < 0 || q >= p.nx) {        // rare: chunk ends only
+      if (q < 0) {
+        if (use_halo && p.halo_lo) return p.halo_lo + (q + 2) * ps;
+        if (p.bc_kind[0] != BC_PERIODIC || p.halo_lo) return nullptr;
+      } else {
+        if (use_halo && p.halo_hi) return p.halo_hi + (q - p.nx) * ps;
+        if (p.bc_kind[0] != BC_PERIODIC || p.halo_hi) return nullptr;
+      }
+      q = wrap_index(q, p.nx);
     }
-    if (use_halo && p.halo_hi) return p.halo_hi + (q - p.nx) * ps;
-    if (p.bc_kind[0] == BC_PERIODIC && !p.halo_hi) return base + wrap_index(q, p.nx) * ps;
-    return nullptr;
+    return base + q * ps;
+  }
+
+  EVX_HD static bool is_ghost_plane(const Regs& t, const P& p, int q) {
+    return GHOSTS && ((q < 0 && t.xlo_ghost) || (q >= p.nx && t.xhi_ghost));
   }
 
   EVX_HD static Vt clipv(const Vt& a) {
@@ -123,6 +133,12 @@ struct ChRhsProgram {
     return vec_splat<T, V>(T(0));
   }
 
+  // 4 cf (1 - cf) (mb - ma) with cf = (ca + cb)/2
+  EVX_HD static T face(T ca, T cb, T ma, T mb) {
+    const T s = ca + cb;
+    return s * (T(2) - s) * (mb - ma);
+  }
+
   // ---- prologue: decode position, load planes xa-2, xa-1, xa, prefetch xa+1 ----------
   EVX_HD static void init(Regs& t, Smem& s, const P& p, int tid, int tile, int chunk) {
     const int tiles_z = (p.nz + TZ - 1) / TZ;
@@ -131,21 +147,25 @@ struct ChRhsProgram {
     t.xa = chunk * p.xchunk;
     t.xb = t.xa + p.xchunk < p.nx ? t.xa + p.xchunk : p.nx;
     t.has_pos = tid < NPOS;
-    t.r = tid / COLS - 1;
-    t.g = tid % COLS - RZ;
+    const int r = tid / COLS - 1;        // row in [-1, TY]
+    const int g = tid % COLS - RZ;       // group in [-RZ, G+RZ-1]
+    t.row = r + 2;
+    t.col = g + RZ;
     const bool per_y = p.bc_kind[1] == BC_PERIODIC, per_z = p.bc_kind[2] == BC_PERIODIC;
+    t.xlo_ghost = p.bc_kind[0] != BC_PERIODIC && !p.halo_lo;
+    t.xhi_ghost = p.bc_kind[0] != BC_PERIODIC && !p.halo_hi;
     {
-      const int y = y0 + t.r, z = z0 + t.g * V;
+      const int y = y0 + r, z = z0 + g * V;
       const int yi = per_y ? wrap_index(y, p.ny) : clamp_index(y, 0, p.ny - 1);
       const int zi = per_z ? wrap_index(z, p.nz) : clamp_index(z, 0, p.nz - V);
       t.off = (long long)yi * p.nz + zi;
-      t.interior = t.has_pos && t.r >= 0 && t.r < TY && t.g >= 0 && t.g < G && y < p.ny &&
-                   z + V <= p.nz;
+      t.want_mu = t.has_pos && g >= -1 && g <= G;
+      t.interior = t.has_pos && r >= 0 && r < TY && g >= 0 && g < G && y < p.ny && z + V <= p.nz;
       t.out_off = (long long)y * p.nz + z;
-      t.gy_lo = !per_y && y == 0;
-      t.gy_hi = !per_y && y == p.ny - 1;
-      t.gz_lo = !per_z && z == 0;
-      t.gz_hi = !per_z && z + V == p.nz;
+      t.gy_lo = GHOSTS && !per_y && y == 0;
+      t.gy_hi = GHOSTS && !per_y && y == p.ny - 1;
+      t.gz_lo = GHOSTS && !per_z && z == 0;
+      t.gz_hi = GHOSTS && !per_z && z + V == p.nz;
     }
     t.has_extra = tid < NEXTRA;
     {
@@ -156,13 +176,14 @@ struct ChRhsProgram {
       const int yi = per_y ? wrap_index(y, p.ny) : clamp_index(y, 0, p.ny - 1);
       const int zi = per_z ? wrap_index(z, p.nz) : clamp_index(z, 0, p.nz - V);
       t.er = rr + 2;
-      t.eg = eg + RZ;
+      t.ec = eg + RZ;
       t.eoff = (long long)yi * p.nz + zi;
     }
     const Vt zero = vec_splat<T, V>(T(0));
-    t.cA = t.cB = t.cC = t.cD = zero;
+    t.cB = t.cC = t.cD = zero;
     t.hC = t.hD = zero;
-    t.mA = t.mB = zero;
+    t.mB = zero;
+    t.fxm = zero;
     t.sN = t.sS = zero;
     t.sL = t.sR = T(0);
     t.nxt = t.hnxt = t.enxt = zero;
@@ -176,12 +197,12 @@ struct ChRhsProgram {
         t.hD = load_plane(p, p.hom, t.xa, t.off, false);
         t.hnxt = load_plane(p, p.hom, t.xa + 1, t.off, false);
       }
-      s.c[slot(t.xa - 1)][t.r + 2][t.g + RZ] = t.cC;
-      s.c[slot(t.xa)][t.r + 2][t.g + RZ] = t.cD;
+      s.c[slot(t.xa - 1)][t.row][t.col] = t.cC;
+      s.c[slot(t.xa)][t.row][t.col] = t.cD;
     }
     if (t.has_extra) {
-      s.c[slot(t.xa - 1)][t.er][t.eg] = clipv(load_plane(p, p.c, t.xa - 1, t.eoff, true));
-      s.c[slot(t.xa)][t.er][t.eg] = clipv(load_plane(p, p.c, t.xa, t.eoff, true));
+      s.c[slot(t.xa - 1)][t.er][t.ec] = clipv(load_plane(p, p.c, t.xa - 1, t.eoff, true));
+      s.c[slot(t.xa)][t.er][t.ec] = clipv(load_plane(p, p.c, t.xa, t.eoff, true));
       t.enxt = load_plane(p, p.c, t.xa + 1, t.eoff, true);
     }
   }
@@ -189,70 +210,95 @@ struct ChRhsProgram {
   // ---- phase A of plane p: mu(p) -> smem, then rhs(x = p-1) -> global ------------------
   EVX_HD static void phase_a(Regs& t, Smem& s, const P& p, int pl) {
     if (!t.has_pos) return;
-    const int row = t.r + 2, col = t.g + RZ;     // indices into s.c
-    const bool real_p = plane(p, p.c, pl, true) != nullptr;
-    const bool xm_ghost = plane(p, p.c, pl - 1, true) == nullptr;
-    const bool xp_ghost = plane(p, p.c, pl + 1, true) == nullptr;
+    const int row = t.row, col = t.col;
+    const T oy0 = p.ghost_off[1][0], oy1 = p.ghost_off[1][1], sy = p.ghost_sgn[1];
+    const T oz0 = p.ghost_off[2][0], oz1 = p.ghost_off[2][1], sz = p.ghost_sgn[2];
+    const T ox0 = p.ghost_off[0][0], ox1 = p.ghost_off[0][1], sx = p.ghost_sgn[0];
 
     // neighbours of c^(pl) in y and z (ghosts synthesised from the own value)
     Vt cN, cS;
     T cL, cR;
     {
       const int sl = slot(pl);
-      cS = t.gy_lo ? ghostv(t.cC, p.ghost_off[1][0], p.ghost_sgn[1]) : s.c[sl][row - 1][col];
-      cN = t.gy_hi ? ghostv(t.cC, p.ghost_off[1][1], p.ghost_sgn[1]) : s.c[sl][row + 1][col];
-      cL = t.gz_lo ? p.ghost_off[2][0] + p.ghost_sgn[2] * t.cC.v[0] : s.c[sl][row][col - 1].v[V - 1];
-      cR = t.gz_hi ? p.ghost_off[2][1] + p.ghost_sgn[2] * t.cC.v[V - 1] : s.c[sl][row][col + 1].v[0];
+      cS = s.c[sl][row - 1][col];
+      cN = s.c[sl][row + 1][col];
+      cL = s.c[sl][row][col - 1].v[V - 1];
+      cR = s.c[sl][row][col + 1].v[0];
+      if (GHOSTS) {
+        if (t.gy_lo) cS = ghostv(t.cC, oy0, sy);
+        if (t.gy_hi) cN = ghostv(t.cC, oy1, sy);
+        if (t.gz_lo) cL = oz0 + sz * t.cC.v[0];
+        if (t.gz_hi) cR = oz1 + sz * t.cC.v[V - 1];
+      }
     }
     Vt mC = vec_splat<T, V>(T(0));
-    if (real_p && t.g >= -1 && t.g <= G) {
-      const Vt cXm = xm_ghost ? ghostv(t.cC, p.ghost_off[0][0], p.ghost_sgn[0]) : t.cB;
-      const Vt cXp = xp_ghost ? ghostv(t.cC, p.ghost_off[0][1], p.ghost_sgn[0]) : t.cD;
+    if (t.want_mu && !is_ghost_plane(t, p, pl)) {
+      Vt cXm = t.cB, cXp = t.cD;
+      if (GHOSTS) {
+        if (is_ghost_plane(t, p, pl - 1)) cXm = ghostv(t.cC, ox0, sx);
+        if (is_ghost_plane(t, p, pl + 1)) cXp = ghostv(t.cC, ox1, sx);
+      }
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         const T c0 = t.cC.v[k];
         const T zl = k == 0 ? cL : t.cC.v[k - 1];
         const T zr = k == V - 1 ? cR : t.cC.v[k + 1];
-        const T lap = (cXp.v[k] + cXm.v[k]) * p.ihx2 + (cN.v[k] + cS.v[k]) * p.ihy2 +
-                      (zr + zl) * p.ihz2 - T(2) * c0 * p.ih2sum;
-        const T hom = HOM ? t.hC.v[k] : p.pot_scale * c0 * (T(1) - c0) * (T(1) - T(2) * c0);
-        mC.v[k] = hom - p.two_eps * lap;
+        const T hom = HOM ? t.hC.v[k] : p.pot_scale * (c0 * (T(1) - c0)) * (T(1) - T(2) * c0);
+        mC.v[k] = hom + p.lx * (cXp.v[k] + cXm.v[k]) + p.ly * (cN.v[k] + cS.v[k]) +
+                  p.lz * (zr + zl) + p.l0 * c0;
       }
     }
-    s.mu[pl & 1][t.r + 1][col] = mC;
+    s.mu[pl & 1][row - 1][col] = mC;
 
-    // rhs at plane x = pl-1: c^ window (cA,cB,cC) = (x-1,x,x+1), mu window (mA,mB,mC)
+    // x-face term between planes pl-1 and pl (carried to the next plane as "minus" face)
+    Vt fxp;
+#pragma unroll
+    for (int k = 0; k < V; ++k) fxp.v[k] = face(t.cB.v[k], t.cC.v[k], t.mB.v[k], mC.v[k]);
+
+    // rhs at plane x = pl-1: c^(x) = cB, mu(x) = mB; the x-faces are fxm (carried) and fxp
     const int x = pl - 1;
     if (t.interior && x >= t.xa && x < t.xb) {
       const int ms = x & 1;
-      const int mrow = t.r + 1;
-      const Vt mS = t.gy_lo ? ghostv(t.mB, p.ghost_off[1][0], p.ghost_sgn[1]) : s.mu[ms][mrow - 1][col];
-      const Vt mN = t.gy_hi ? ghostv(t.mB, p.ghost_off[1][1], p.ghost_sgn[1]) : s.mu[ms][mrow + 1][col];
-      const T mL = t.gz_lo ? p.ghost_off[2][0] + p.ghost_sgn[2] * t.mB.v[0] : s.mu[ms][mrow][col - 1].v[V - 1];
-      const T mR = t.gz_hi ? p.ghost_off[2][1] + p.ghost_sgn[2] * t.mB.v[V - 1] : s.mu[ms][mrow][col + 1].v[0];
-      const bool gxm = plane(p, p.c, x - 1, true) == nullptr;
-      const bool gxp = xp_ghost_of(p, x);
-      const Vt cXm = gxm ? ghostv(t.cB, p.ghost_off[0][0], p.ghost_sgn[0]) : t.cA;
-      const Vt cXp = gxp ? ghostv(t.cB, p.ghost_off[0][1], p.ghost_sgn[0]) : t.cC;
-      const Vt mXm = gxm ? ghostv(t.mB, p.ghost_off[0][0], p.ghost_sgn[0]) : t.mA;
-      const Vt mXp = gxp ? ghostv(t.mB, p.ghost_off[0][1], p.ghost_sgn[0]) : mC;
+      const int mrow = row - 1;
+      Vt mS = s.mu[ms][mrow - 1][col];
+      Vt mN = s.mu[ms][mrow + 1][col];
+      T mL = s.mu[ms][mrow][col - 1].v[V - 1];
+      T mR = s.mu[ms][mrow][col + 1].v[0];
+      Vt fxm = t.fxm;
+      if (GHOSTS) {
+        if (t.gy_lo) mS = ghostv(t.mB, oy0, sy);
+        if (t.gy_hi) mN = ghostv(t.mB, oy1, sy);
+        if (t.gz_lo) mL = oz0 + sz * t.mB.v[0];
+        if (t.gz_hi) mR = oz1 + sz * t.mB.v[V - 1];
+        if (is_ghost_plane(t, p, x - 1)) {
+#pragma unroll
+          for (int k = 0; k < V; ++k)
+            fxm.v[k] = face(ox0 + sx * t.cB.v[k], t.cB.v[k], ox0 + sx * t.mB.v[k], t.mB.v[k]);
+        }
+        if (is_ghost_plane(t, p, x + 1)) {
+#pragma unroll
+          for (int k = 0; k < V; ++k)
+            fxp.v[k] = face(t.cB.v[k], ox1 + sx * t.cB.v[k], t.mB.v[k], ox1 + sx * t.mB.v[k]);
+        }
+      }
+      // z-face terms: fz[k] is the face between elements k-1 and k of the group
+      T fz[V + 1];
+      fz[0] = face(t.sL, t.cB.v[0], mL, t.mB.v[0]);
+#pragma unroll
+      for (int k = 1; k < V; ++k) fz[k] = face(t.cB.v[k - 1], t.cB.v[k], t.mB.v[k - 1], t.mB.v[k]);
+      fz[V] = face(t.cB.v[V - 1], t.sR, t.mB.v[V - 1], mR);
       Vt o;
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         const T c0 = t.cB.v[k], m0 = t.mB.v[k];
-        const T czl = k == 0 ? t.sL : t.cB.v[k - 1];
-        const T czr = k == V - 1 ? t.sR : t.cB.v[k + 1];
-        const T mzl = k == 0 ? mL : t.mB.v[k - 1];
-        const T mzr = k == V - 1 ? mR : t.mB.v[k + 1];
-        T div = face_div(c0, m0, cXm.v[k], mXm.v[k], cXp.v[k], mXp.v[k], p.ihx);
-        div += face_div(c0, m0, t.sS.v[k], mS.v[k], t.sN.v[k], mN.v[k], p.ihy);
-        div += face_div(c0, m0, czl, mzl, czr, mzr, p.ihz);
-        o.v[k] = p.D * div;
+        const T fyp = face(c0, t.sN.v[k], m0, mN.v[k]);
+        const T fym = face(t.sS.v[k], c0, mS.v[k], m0);
+        o.v[k] = p.fx * (fxp.v[k] - fxm.v[k]) + p.fy * (fyp - fym) + p.fz * (fz[k + 1] - fz[k]);
       }
       vec_store<T, V>(p.out + (long long)x * p.ny * p.nz + t.out_off, o);
     }
     // roll the mu window and remember the y/z neighbours of c^(pl) for the next plane
-    t.mA = t.mB;
+    t.fxm = fxp;
     t.mB = mC;
     t.sN = cN;
     t.sS = cS;
@@ -260,22 +306,10 @@ struct ChRhsProgram {
     t.sR = cR;
   }
 
-  EVX_HD static bool xp_ghost_of(const P& p, int x) { return plane(p, p.c, x + 1, true) == nullptr; }
-
-  // divergence contribution of one axis: ( F(+1/2) - F(-1/2) ) / h
-  EVX_HD static T face_div(T c0, T m0, T cm, T mm, T cp, T mp, T ih) {
-    const T fp = T(0.5) * (cp + c0);
-    const T fm = T(0.5) * (c0 + cm);
-    const T Fp = fp * (T(1) - fp) * ((mp - m0) * ih);
-    const T Fm = fm * (T(1) - fm) * ((m0 - mm) * ih);
-    return (Fp - Fm) * ih;
-  }
-
   // ---- phase B of plane p (after the barrier): roll c^ window, publish plane p+2 -------
   EVX_HD static void phase_b(Regs& t, Smem& s, const P& p, int pl) {
     const bool more = pl + 3 <= t.xb + 1;     // plane pl+3 is still needed as a centre value
     if (t.has_pos) {
-      t.cA = t.cB;
       t.cB = t.cC;
       t.cC = t.cD;
       t.cD = clipv(t.nxt);
@@ -283,14 +317,14 @@ struct ChRhsProgram {
         t.hC = t.hD;
         t.hD = t.hnxt;
       }
-      s.c[slot(pl + 2)][t.r + 2][t.g + RZ] = t.cD;
+      s.c[slot(pl + 2)][t.row][t.col] = t.cD;
       if (more) {
         t.nxt = load_plane(p, p.c, pl + 3, t.off, true);
         if (HOM) t.hnxt = load_plane(p, p.hom, pl + 3, t.off, false);
       }
     }
     if (t.has_extra) {
-      s.c[slot(pl + 2)][t.er][t.eg] = clipv(t.enxt);
+      s.c[slot(pl + 2)][t.er][t.ec] = clipv(t.enxt);
       if (more) t.enxt = load_plane(p, p.c, pl + 3, t.eoff, true);
     }
   }

@@ -31,15 +31,13 @@ inline ChParams<T> make_ch_params(const T* c, const T* hom, T* out, int nx, int 
   ChParams<T> p;
   p.c = c; p.hom = hom; p.out = out; p.halo_lo = halo_lo; p.halo_hi = halo_hi;
   p.nx = nx; p.ny = ny; p.nz = nz; p.xchunk = xchunk;
-  // same rounding sequence as the reference: spacing -> T, then 1/h and 1/h^2 in T
-  // (voxelgrid.py:29-30), sum of the three 1/h^2 in T (fd_stencils.py:74)
-  const T hx = T(h[0]), hy = T(h[1]), hz = T(h[2]);
-  p.ihx = T(1) / hx; p.ihy = T(1) / hy; p.ihz = T(1) / hz;
-  p.ihx2 = T(1) / (hx * hx); p.ihy2 = T(1) / (hy * hy); p.ihz2 = T(1) / (hz * hz);
-  p.ih2sum = (p.ihx2 + p.ihy2) + p.ihz2;
+  // metric factors folded in double, rounded once to T (the kernel reassociates the
+  // reference's expression anyway; see ch_rhs_core.h)
+  const double ih2[3] = {1.0 / (h[0] * h[0]), 1.0 / (h[1] * h[1]), 1.0 / (h[2] * h[2])};
   p.pot_scale = T(18.0 / eps);
-  p.two_eps = T(2.0 * eps);
-  p.D = T(D);
+  p.lx = T(-2.0 * eps * ih2[0]); p.ly = T(-2.0 * eps * ih2[1]); p.lz = T(-2.0 * eps * ih2[2]);
+  p.l0 = T(4.0 * eps * (ih2[0] + ih2[1] + ih2[2]));
+  p.fx = T(0.25 * D * ih2[0]); p.fy = T(0.25 * D * ih2[1]); p.fz = T(0.25 * D * ih2[2]);
   fill_ghost_rules<T>(bc_kind, bc_val, p.bc_kind, p.ghost_off, p.ghost_sgn);
   return p;
 }

@@ -32,26 +32,34 @@ __device__ __forceinline__ float imex_prefactor(float k2, const FilterParams& f)
   return __fdiv_rn(f.dt, den);
 }
 
-// cuFFT layout: [n0, n1, n2/2+1] complex, contiguous.  One block strides over (i0,i1) rows.
+// cuFFT layout: [n0, n1, n2/2+1] complex, contiguous.  Each block owns ROWS consecutive
+// (i0,i1) rows and walks their elements with a flat index, one complex (8/16 B) per access.
 template <typename R>
-__global__ void __launch_bounds__(256) spectral_filter_kernel(R* __restrict__ spec,
-                                                              const FilterParams f) {
-  const int nh = f.n2 / 2 + 1;
+struct Cplx { R x, y; };
+
+template <typename R>
+__global__ void __launch_bounds__(256) spectral_filter_kernel(Cplx<R>* __restrict__ spec,
+                                                              const FilterParams f,
+                                                              int rows_per_block) {
+  const unsigned nh = (unsigned)(f.n2 / 2 + 1);
   const long long rows = (long long)f.n0 * f.n1;
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int i0 = (int)(row / f.n1), i1 = (int)(row % f.n1);
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  const long long nrow = rows - row0 < rows_per_block ? rows - row0 : rows_per_block;
+  const unsigned count = (unsigned)nrow * nh;
+  Cplx<R>* base = spec + row0 * nh;
+  for (unsigned e = threadIdx.x; e < count; e += blockDim.x) {
+    const unsigned r = e / nh, i2 = e - r * nh;
+    const long long row = row0 + r;
+    const int i0 = (int)(row / f.n1), i1 = (int)(row - (long long)i0 * f.n1);
     const float k0 = wavenumber(signed_freq(i0, f.n0), f.inv_len0);
     const float k1 = wavenumber(signed_freq(i1, f.n1), f.inv_len1);
-    const float k01 = __fadd_rn(__fmul_rn(k0, k0), __fmul_rn(k1, k1));
-    R* line = spec + row * nh * 2;
-    for (int i2 = threadIdx.x; i2 < nh; i2 += blockDim.x) {
-      const float k2v = wavenumber(i2, f.inv_len2);
-      const float ksq = __fadd_rn(k01, __fmul_rn(k2v, k2v));
-      const R w = (R)imex_prefactor(ksq, f) * (sizeof(R) == 8 ? (R)f.scale_d : (R)f.scale);
-      R re = line[2 * i2], im = line[2 * i2 + 1];
-      line[2 * i2] = re * w;
-      line[2 * i2 + 1] = im * w;
-    }
+    const float k2v = wavenumber((int)i2, f.inv_len2);
+    const float ksq = __fadd_rn(__fadd_rn(__fmul_rn(k0, k0), __fmul_rn(k1, k1)), __fmul_rn(k2v, k2v));
+    const R w = (R)imex_prefactor(ksq, f) * (sizeof(R) == 8 ? (R)f.scale_d : (R)f.scale);
+    Cplx<R> v = base[e];
+    v.x *= w;
+    v.y *= w;
+    base[e] = v;
   }
 }
 
@@ -94,8 +102,12 @@ static FilterParams make_filter(const int n[3], const double len_h[3], double dt
 template <typename R>
 static int launch_filter(R* spec, const FilterParams& f, cudaStream_t st) {
   const long long rows = (long long)f.n0 * f.n1;
-  const unsigned grid = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
-  spectral_filter_kernel<R><<<grid, 256, 0, st>>>(spec, f);
+  const int nh = f.n2 / 2 + 1;
+  int rpb = (int)((8192 + nh - 1) / nh);          // ~8k complex values per block
+  if (rpb < 1) rpb = 1;
+  const long long grid = (rows + rpb - 1) / rpb;
+  if (grid > 2147483647LL) return EVX_ERR_UNSUPPORTED;
+  spectral_filter_kernel<R><<<(unsigned)grid, 256, 0, st>>>((Cplx<R>*)spec, f, rpb);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -11,10 +11,11 @@ std::atomic<unsigned long long> g_launches{0};
 // ------------------------------------------------------------------------------------
 // Cahn-Hilliard rhs
 // ------------------------------------------------------------------------------------
-template <typename T, int V, int TY, int G, bool HOM>
-__global__ void __launch_bounds__(ChRhsProgram<T, V, TY, G, HOM>::NTHREADS, sizeof(T) == 4 ? 2 : 1)
+template <typename T, int V, int TY, int G, bool HOM, bool GHOSTS>
+__global__ void __launch_bounds__(ChRhsProgram<T, V, TY, G, HOM, GHOSTS>::NTHREADS,
+                                  sizeof(T) == 4 ? 2 : 1)
     ch_rhs_kernel(const ChParams<T> p) {
-  using Prog = ChRhsProgram<T, V, TY, G, HOM>;
+  using Prog = ChRhsProgram<T, V, TY, G, HOM, GHOSTS>;
   __shared__ typename Prog::Smem s;
   typename Prog::Regs t;
   Prog::init(t, s, p, threadIdx.x, blockIdx.x, blockIdx.y);
@@ -44,10 +45,15 @@ static int launch_ch(ChParams<T> p, cudaStream_t st) {
   const int chunks = (p.nx + p.xchunk - 1) / p.xchunk;
   if (tiles > 2147483647LL || chunks > 65535) return EVX_ERR_UNSUPPORTED;
   dim3 grid((unsigned)tiles, (unsigned)chunks);
-  if (p.hom)
-    ch_rhs_kernel<T, V, TY, G, true><<<grid, Prog::NTHREADS, 0, st>>>(p);
-  else
-    ch_rhs_kernel<T, V, TY, G, false><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  const bool ghosts = p.bc_kind[0] != BC_PERIODIC || p.bc_kind[1] != BC_PERIODIC ||
+                      p.bc_kind[2] != BC_PERIODIC;
+  if (p.hom) {   // user potential: rare, keep one (general) instantiation
+    ch_rhs_kernel<T, V, TY, G, true, true><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  } else if (ghosts) {
+    ch_rhs_kernel<T, V, TY, G, false, true><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  } else {
+    ch_rhs_kernel<T, V, TY, G, false, false><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  }
   count_launch();
   return (int)cudaGetLastError();
 }

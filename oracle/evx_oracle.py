@@ -27,6 +27,9 @@ norm; torch>=2.1 un-pinned in the reference's pyproject.toml:41-43, 2.11.0 insta
 is the same library call here as in the reference, so the FFT boundary is pinned by
 those fixtures too.
 
+All tensors are created on the CPU explicitly: the product mirrors the reference's global
+`torch.set_default_device(cuda)` side effect (voxelgrid.py:178), which must not leak in here.
+
 The operation structure (ghost-padded copies + strided slices, ~60 elementwise passes
 per Cahn-Hilliard step) deliberately follows the reference so that timing this module
 on the host cores is a fair stand-in for the reference's torch CPU path.
@@ -102,7 +105,7 @@ def _win(g: torch.Tensor, dx: int, dy: int, dz: int) -> torch.Tensor:
 # stencils
 # ----------------------------------------------------------------------------------
 def _inv_h(spacing, like: torch.Tensor):
-    h = torch.tensor([float(s) for s in spacing], dtype=like.dtype)
+    h = torch.tensor([float(s) for s in spacing], dtype=like.dtype, device=like.device)
     return 1.0 / h, 1.0 / h ** 2
 
 
@@ -219,9 +222,9 @@ def k_squared(shape: Sequence[int], spacing, mirrored_x: bool = False) -> torch.
     fftfreq(2*Nx) (cell_center convention, voxelgrid.py:116-118)."""
     nx, ny, nz = shape
     hx, hy, hz = (float(s) for s in spacing)
-    kx = 2 * math.pi * torch.fft.fftfreq(2 * nx if mirrored_x else nx, hx)
-    ky = 2 * math.pi * torch.fft.fftfreq(ny, hy)
-    kz = 2 * math.pi * torch.fft.rfftfreq(nz, hz)
+    kx = 2 * math.pi * torch.fft.fftfreq(2 * nx if mirrored_x else nx, hx, device="cpu")
+    ky = 2 * math.pi * torch.fft.fftfreq(ny, hy, device="cpu")
+    kz = 2 * math.pi * torch.fft.rfftfreq(nz, hz, device="cpu")
     KX, KY, KZ = torch.meshgrid(kx, ky, kz, indexing="ij")
     return KX ** 2 + KY ** 2 + KZ ** 2
 

@@ -11,9 +11,9 @@
 
 using namespace evx;
 
-template <typename T, int V, int TY, int G, bool HOM>
+template <typename T, int V, int TY, int G, bool HOM, bool GHOSTS>
 static void run_ch_(const ChParams<T>& p) {
-  using Prog = ChRhsProgram<T, V, TY, G, HOM>;
+  using Prog = ChRhsProgram<T, V, TY, G, HOM, GHOSTS>;
   const int tiles = ((p.ny + TY - 1) / TY) * ((p.nz + Prog::TZ - 1) / Prog::TZ);
   const int chunks = (p.nx + p.xchunk - 1) / p.xchunk;
   std::vector<typename Prog::Regs> regs(Prog::NTHREADS);
@@ -32,7 +32,11 @@ static void run_ch_(const ChParams<T>& p) {
 
 template <typename T, int V, int TY, int G>
 static void run_ch(const ChParams<T>& p) {
-  if (p.hom) run_ch_<T, V, TY, G, true>(p); else run_ch_<T, V, TY, G, false>(p);
+  const bool ghosts = p.bc_kind[0] != BC_PERIODIC || p.bc_kind[1] != BC_PERIODIC ||
+                      p.bc_kind[2] != BC_PERIODIC;
+  if (p.hom) run_ch_<T, V, TY, G, true, true>(p);
+  else if (ghosts) run_ch_<T, V, TY, G, false, true>(p);
+  else run_ch_<T, V, TY, G, false, false>(p);
 }
 
 template <typename T>

@@ -1,0 +1,286 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the golden fixtures.
+Needs a GPU: run with `pytest -m gpu` on the B200 box.
+
+Tolerances (north_star): fp32 state rel-L2 <= 1e-5 per step, <= 1e-4 after 1000 steps,
+mass conserved to fp32 rounding.  Stricter self-checks where the noise floor allows:
+rhs <= 5e-6, update <= 2e-5."""
+import ast
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from oracle import evx_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+import evoxels_b200 as evo  # noqa: E402
+from evoxels_b200 import _native  # noqa: E402
+from evoxels_b200.problem_definition import CahnHilliard, ReactionDiffusion, TwoPhaseAllenCahn  # noqa: E402
+from evoxels_b200.solvers import TimeDependentSolver  # noqa: E402
+from evoxels_b200.timesteppers import ForwardEuler, PseudoSpectralIMEX, RungeKutta4  # noqa: E402
+from evoxels_b200.voxelgrid import VoxelGridTorch  # noqa: E402
+
+RHS_TOL = {torch.float32: 5e-6, torch.float64: 1e-12}
+STEP_TOL = {torch.float32: 1e-5, torch.float64: 1e-9}   # fp64: k arrays are fp32 upstream
+
+
+def make_grid(shape, spacing, precision="float32"):
+    dom = tuple(float(n * h) for n, h in zip(shape, spacing))
+    vf = evo.VoxelFields(tuple(int(n) for n in shape), dom)
+    vf.precision = precision
+    return vf, VoxelGridTorch(vf.grid_info(), precision=precision, device="cuda")
+
+
+def quiet(fn, *a, **k):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return fn(*a, **k)
+
+
+CH_CASES = ["ch_readme16", "ch_odd_aniso", "ch_line16", "ch_pow2_small", "ch_neumann_x",
+            "ch_dirichlet_x", "ch_mixed_rhs_only", "ch_neumann3_rhs_only",
+            "ch_zdirichlet_rhs_only", "ch_odd_aniso_f64"]
+
+
+@pytest.mark.parametrize("name", CH_CASES)
+def test_ch_golden(cuda_device, name):
+    g = load_golden(name)
+    prec = "float64" if g["u0"].dtype == np.float64 else "float32"
+    vf, vg = make_grid(g["u0"].shape, g["spacing"], prec)
+    u = vg.init_scalar_field(g["u0"])
+    prob = quiet(CahnHilliard, vg, eps=g["eps"], D=g["D"], A=g["A"], bc=g["bc"])
+    rhs = prob.rhs(0.0, u)
+    assert rel_l2(rhs[0].cpu().numpy(), g["rhs"]) <= RHS_TOL[u.dtype]
+    if "padded" in g:
+        assert np.array_equal(prob.pad_bc(u)[0].cpu().numpy(), g["padded"])
+    if "step1" not in g:
+        return
+    ts = PseudoSpectralIMEX(prob, g["dt"])
+    v = u
+    u_before = u.clone()
+    for i in range(1, g["nsteps"] + 1):
+        v = ts.step(0.0, v)
+        if f"step{i}" in g:
+            assert rel_l2(v[0].cpu().numpy(), g[f"step{i}"]) <= STEP_TOL[u.dtype] * max(1, i ** 0.5)
+    assert torch.equal(u, u_before), "step must not mutate its input"
+    assert rel_l2(ts._fft_prefac.cpu().numpy(), g["prefac"]) <= 1e-6
+
+
+def test_ch_custom_mu_hom(cuda_device):
+    g = load_golden("ch_custom_mu")
+    vf, vg = make_grid(g["u0"].shape, g["spacing"])
+
+    def mu_log(c, lib=None):
+        cc = torch.clip(c, 1e-4, 1 - 1e-4)
+        return torch.log(cc / (1 - cc)) + 2.5 * (1 - 2 * c)
+
+    prob = CahnHilliard(vg, eps=g["eps"], D=g["D"], mu_hom=mu_log)
+    u = vg.init_scalar_field(g["u0"])
+    assert rel_l2(prob.rhs(0, u)[0].cpu().numpy(), g["rhs"]) <= 2e-5
+    out = PseudoSpectralIMEX(prob, g["dt"]).step(0, u)
+    assert rel_l2(out[0].cpu().numpy(), g["step1"]) <= 1e-5
+
+
+AC_CASES = ["ac_default_neumann", "ac_curv_force", "ac_periodic", "ac_mixed", "ac_line16",
+            "ac_flat_bulk"]
+
+
+@pytest.mark.parametrize("name", AC_CASES)
+def test_ac_golden(cuda_device, name):
+    g = load_golden(name)
+    vf, vg = make_grid(g["u0"].shape, g["spacing"])
+    prob = quiet(TwoPhaseAllenCahn, vg, eps=g["eps"], gab=g["gab"], M=g["M"], force=g["force"],
+                 curvature=g["curvature"], bc=g["bc"])
+    u = vg.init_scalar_field(g["u0"])
+    tol = 2e-5   # the normal-Laplacian quotient amplifies fp32 rounding (oracle floor 1.7e-7..2.6e-6)
+    assert rel_l2(prob.rhs(0, u)[0].cpu().numpy(), g["rhs"]) <= tol
+    assert rel_l2(ForwardEuler(prob, g["dt"]).step(0, u)[0].cpu().numpy(), g["euler1"]) <= 1e-5
+    assert rel_l2(RungeKutta4(prob, g["dt"]).step(0, u)[0].cpu().numpy(), g["rk4_1"]) <= 1e-5
+
+
+def test_ghost_rules_and_padded_stencils(cuda_device):
+    g = load_golden("ghost_and_stencils")
+    vf, vg = make_grid(g["f0"].shape, g["spacing"])
+    f = vg.init_scalar_field(g["f0"])
+    for i in range(g["n"]):
+        bc = ast.literal_eval(str(g[f"bc{i}"]))
+        prob = quiet(ReactionDiffusion, vg, D=1.0, bc=bc)
+        assert np.array_equal(prob.pad_bc(f)[0].cpu().numpy(), g[f"pad{i}"]), bc
+    pad = vg.bc.pad_bc(f, (("neumann", None),) * 3)
+    assert rel_l2(vg.laplace(pad)[0].cpu().numpy(), g["laplace"]) <= 5e-6
+    assert rel_l2(vg.normal_laplace(pad)[0].cpu().numpy(), g["normal_laplace"]) <= 5e-5
+    assert rel_l2(vg.gradient_norm_squared(pad)[0].cpu().numpy(), g["gradnorm2"]) <= 5e-6
+    for nm, fn in [("x_face", vg.to_x_face), ("y_face", vg.to_y_face), ("z_face", vg.to_z_face),
+                   ("gx_face", vg.grad_x_face), ("gy_face", vg.grad_y_face), ("gz_face", vg.grad_z_face)]:
+        assert rel_l2(fn(pad)[0].cpu().numpy(), g[nm]) <= 1e-6
+    assert rel_l2(vg.rfft_k_squared().cpu().numpy(), g["k2"]) <= 1e-7
+    # the reference's own known-answer array (tests/test_solvers.py:105-126)
+    vf2, vg2 = make_grid((2, 2, 2), (0.5, 0.5, 0.5))
+    a = np.arange(1, 9, dtype=np.float32).reshape(2, 2, 2)
+    prob = quiet(ReactionDiffusion, vg2, D=1.0, bc=(("dirichlet", (10.0, 20.0)), "neumann", "periodic"))
+    expected = np.pad(a, 1, mode="wrap")
+    expected[0] = 2.0 * 10.0 - expected[1]
+    expected[-1] = 2.0 * 20.0 - expected[-2]
+    expected[:, 0] = expected[:, 1]
+    expected[:, -1] = expected[:, -2]
+    assert np.allclose(prob.pad_bc(vg2.init_scalar_field(a))[0].cpu().numpy(), expected)
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 64), (33, 20, 18), (100, 100, 100), (48, 40, 132)])
+@pytest.mark.parametrize("bc", [("periodic",) * 3, ("neumann",) * 3,
+                                (("dirichlet", (0.2, 0.6)), "neumann", "periodic")])
+def test_ch_rhs_vs_live_oracle(cuda_device, shape, bc):
+    u = O.noise_field(shape, seed=3, lo=-0.1, amp=1.2)
+    ref = O.ch_rhs(u, (1.0, 0.5, 2.0), 3.0, 1.0, bc)
+    vf, vg = make_grid(shape, (1.0, 0.5, 2.0))
+    prob = quiet(CahnHilliard, vg, bc=bc)
+    got = prob.rhs(0, u.cuda())
+    assert rel_l2(got.cpu().numpy(), ref.numpy()) <= 5e-6
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 64), (33, 20, 18), (40, 36, 132)])
+@pytest.mark.parametrize("bc", [("neumann",) * 3, ("periodic",) * 3,
+                                (("dirichlet", (0.0, 1.0)), "neumann", "periodic")])
+def test_ac_vs_live_oracle(cuda_device, shape, bc):
+    u = O.noise_field(shape, seed=1, lo=0.0, amp=1.0)
+    orc = O.ACOracle(shape, (1.0, 1.0, 1.0), 0.05, bc=bc)
+    vf, vg = make_grid(shape, (1.0, 1.0, 1.0))
+    prob = quiet(TwoPhaseAllenCahn, vg, bc=bc)
+    ts = ForwardEuler(prob, 0.05)
+    v, w = u, u.cuda()
+    for _ in range(3):
+        v, w = orc.step(v), ts.step(0, w)
+    assert rel_l2(w.cpu().numpy(), v.numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("shape,backend", [((64, 64, 64), "cufft"), ((100, 100, 100), "cufft"),
+                                           ((33, 20, 18), "cufft"), ((128, 64, 256), "cufft"),
+                                           ((64, 64, 64), "auto"), ((128, 64, 256), "auto")])
+def test_ch_imex_step_vs_live_oracle(cuda_device, shape, backend):
+    u = O.noise_field(shape, seed=0)
+    orc = O.CHOracle(shape, (1.0, 1.0, 1.0), 0.1)
+    vf, vg = make_grid(shape, (1.0, 1.0, 1.0))
+    ts = PseudoSpectralIMEX(CahnHilliard(vg), 0.1, fft_backend=backend)
+    v, w = u, u.cuda()
+    for i in range(3):
+        v_new, w_new = orc.step(v), ts.step(0, w)
+        # update-level check is ~100x stricter than the state-level one
+        assert rel_l2((w_new - w).cpu().numpy(), (v_new - v).numpy()) <= 2e-5
+        assert rel_l2(w_new.cpu().numpy(), v_new.numpy()) <= 1e-5
+        v, w = v_new, w_new
+    m0, m1 = float(u.double().mean()), float(w.double().mean())
+    assert abs(m1 - m0) <= 2e-7 * abs(m0), "mass must be conserved to fp32 rounding"
+
+
+def test_ch_nonperiodic_x_imex(cuda_device):
+    for name in ("ch_neumann_x", "ch_dirichlet_x"):
+        g = load_golden(name)
+        vf, vg = make_grid(g["u0"].shape, g["spacing"])
+        prob = quiet(CahnHilliard, vg, eps=g["eps"], D=g["D"], A=g["A"], bc=g["bc"])
+        out = PseudoSpectralIMEX(prob, g["dt"]).step(0, vg.init_scalar_field(g["u0"]))
+        assert rel_l2(out[0].cpu().numpy(), g["step1"]) <= 1e-5
+
+
+def test_readme_config_1000_steps(cuda_device):
+    """README.md:98-115: 100^3, dt=0.1, 1000 steps, against the reference record."""
+    g = load_golden("ch_readme100_1000steps")
+    vf = evo.VoxelFields((100, 100, 100), (100, 100, 100))
+    u0 = 0.5 + 0.1 * np.random.default_rng(0).random((100, 100, 100)).astype(np.float32)
+    vf.add_field("c", u0)
+    vg = VoxelGridTorch(vf.grid_info(), device="cuda")
+    ts = PseudoSpectralIMEX(CahnHilliard(vg, eps=3.0, D=1.0), 0.1)
+    v = vg.init_scalar_field(u0)
+    for i in range(1, 1001):
+        v = ts.step(0, v)
+        if i in (1, 10, 100, 1000):
+            a = v[0].cpu().numpy()
+            tol = 1e-5 if i < 1000 else 1e-4
+            assert rel_l2(a[::4, ::4, ::4], g[f"sub{i}"]) <= tol, i
+            assert abs(a.astype(np.float64).mean() - g["mean0"]) <= 2e-7, "mass drift"
+
+
+def test_solver_drivers(cuda_device):
+    # seam test of the reference (tests/test_solvers.py:14-27)
+    vf = evo.VoxelFields((4, 4, 4))
+    vf.add_field("a", np.ones(vf.shape))
+    vf.add_field("b", np.zeros(vf.shape))
+    TimeDependentSolver(vf, ["a", "b"], backend="torch", step_fn=lambda t, u: u + 1,
+                        device="cuda").solve(frames=1, max_iters=1, verbose=False, jit=False)
+    assert np.allclose(vf.fields["a"], 2) and np.allclose(vf.fields["b"], 1)
+    # 1-D tanh equilibrium (tests/test_solvers.py:29-82), both drivers on CUDA
+    Nx = 16
+    vf = evo.VoxelFields((Nx, 1, 1), domain_size=(Nx, 1, 1))
+    phi = np.zeros((Nx, 1, 1), dtype=np.float32)
+    phi[: Nx // 2] = 1.0
+    vf.add_field("phi1", phi.copy())
+    vf.add_field("phi2", phi.copy())
+    eps = 3.0
+    evo.run_allen_cahn_solver(vf, "phi1", backend="torch", device="cuda", frames=1, max_iters=10,
+                              time_increment=0.5, eps=eps, jit=False, verbose=False)
+    evo.run_cahn_hilliard_solver(vf, "phi2", backend="torch", device="cuda", frames=1,
+                                 max_iters=10, time_increment=0.5, eps=eps, jit=True, verbose=False)
+    x = np.arange(Nx) + 0.5
+    ana = 0.5 - 0.5 * np.tanh(3 * (x - 0.5 * Nx) / 2 / eps)
+    assert np.linalg.norm(vf.fields["phi1"].squeeze() - ana) < 0.05
+    sel = (x > 5) & (x < 11)
+    assert np.linalg.norm(vf.fields["phi2"].squeeze()[sel] - ana[sel]) < 0.05
+
+
+def test_rhs_convergence_order(cuda_device):
+    """Spatial order 2 of CahnHilliard.rhs / TwoPhaseAllenCahn.rhs in float64, the check of
+    the reference's tests/test_rhs.py:10-37 (MMS on the unit cube)."""
+    import sympy as sp
+    import sympy.vector as spv
+    CS = spv.CoordSys3D("CS")
+    cases = [(CahnHilliard, dict(eps=3.0, D=1.0, A=0.25), 0.4 + 0.1 * sp.sin(2 * sp.pi * CS.x)),
+             (TwoPhaseAllenCahn, dict(eps=3.0, curvature=0.5, force=1),
+              0.5 + 0.3 * sp.cos(4 * sp.pi * CS.x) * sp.cos(2 * sp.pi * CS.y) * (CS.z ** 2 / 2 - CS.z ** 3 / 3))]
+    for cls, kw, fun in cases:
+        dx, err = [], []
+        for p in (3, 4, 5, 6):
+            n = 2 ** p
+            vf = evo.VoxelFields((n, n, n), (1, 1, 1))
+            vf.precision = "float64"
+            vg = VoxelGridTorch(vf.grid_info(), precision="float64", device="cuda")
+            grid = vf.meshgrid()
+            u = vg.init_scalar_field(sp.lambdify((CS.x, CS.y, CS.z), fun, "numpy")(*grid))
+            prob = cls(vg, **kw)
+            num = prob.rhs(0, u)[0].cpu().numpy()
+            exact = sp.lambdify((CS.x, CS.y, CS.z), prob.rhs_analytic(0, fun), "numpy")(*grid)
+            dx.append(vf.spacing[0])
+            err.append(np.linalg.norm(num - exact) / np.linalg.norm(exact))
+        slope = np.polyfit(np.log(dx), np.log(err), 1)[0]
+        assert abs(slope - 2) < 0.1, (cls.__name__, slope)
+
+
+def test_full_size_properties_512(cuda_device):
+    """BASELINE config 2 (512^3 fp32 periodic): size-independent properties - mass
+    conservation, translation equivariance of the step, determinism."""
+    n = 512
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    u = (0.5 + 0.1 * torch.rand((1, n, n, n), device="cuda", generator=gen))
+    vf, vg = make_grid((n, n, n), (1.0, 1.0, 1.0))
+    ts = PseudoSpectralIMEX(CahnHilliard(vg), 0.1)
+    v = ts.step(0, u)
+    assert abs(float(v.double().mean()) - float(u.double().mean())) <= 2e-7
+    assert torch.equal(v, ts.step(0, u))
+    shift = (5, 17, 64)
+    vs = ts.step(0, torch.roll(u, shift, (1, 2, 3)))
+    d = (torch.roll(v, shift, (1, 2, 3)) - vs)
+    assert float(d.norm() / v.norm()) <= 1e-6
+    r = CahnHilliard(vg).rhs(0, u)
+    assert abs(float(r.double().sum())) <= 1e-3 * float(r.double().abs().sum())
+
+
+def test_ch_step_512_vs_oracle(cuda_device):
+    """One step at 512^3 against the CPU oracle (needs ~6 GB host RAM, ~10 s)."""
+    n = 512
+    u = O.noise_field((n, n, n), seed=0)
+    ref = O.CHOracle((n, n, n), (1.0, 1.0, 1.0), 0.1).step(u)
+    vf, vg = make_grid((n, n, n), (1.0, 1.0, 1.0))
+    got = PseudoSpectralIMEX(CahnHilliard(vg), 0.1).step(0, u.cuda()).cpu()
+    assert rel_l2((got - u).numpy(), (ref - u).numpy()) <= 2e-5
+    assert rel_l2(got.numpy(), ref.numpy()) <= 1e-5
