@@ -61,10 +61,14 @@ struct ChRhsProgram {
   static constexpr int COLS = G + 2 * RZ;   // groups incl. the ring groups
   static constexpr int ROWS_MU = TY + 2;    // rows incl. one ring row each side
   static constexpr int ROWS_C = TY + 4;     // rows incl. two ring rows each side
-  static constexpr int NPOS = ROWS_MU * COLS;
+  // thread -> position: interior positions first (whole warps of interior threads run the
+  // full body), then the two ring rows (which also load the two outermost rows of c^), then
+  // the ring columns; ring warps skip the rhs part as a warp.
+  static constexpr int N_INT = TY * G;
+  static constexpr int N_RROW = 2 * G;
+  static constexpr int N_RCOL = 2 * RZ * (TY + 2);   // incl. the 4 ring corners (c^ only)
+  static constexpr int NPOS = N_INT + N_RROW + N_RCOL;
   static constexpr int NTHREADS = ((NPOS + 31) / 32) * 32;
-  static constexpr int NEXTRA = 2 * G;      // loaders of the two outermost rows of c^
-  static_assert(NEXTRA <= NTHREADS, "tile too flat");
   using Vt = Vec<T, V>;
   using P = ChParams<T>;
 
@@ -78,10 +82,14 @@ struct ChRhsProgram {
     bool has_pos, want_mu, interior, has_extra;
     bool gy_lo, gy_hi, gz_lo, gz_hi;   // neighbour in that direction is a non-periodic ghost
     bool xlo_ghost, xhi_ghost;         // planes below 0 / above nx-1 are non-periodic ghosts
-    long long off;            // element offset of this position inside a plane
-    long long out_off;
+    long long ps;             // plane stride ny*nz
+    const T* pn;              // own element of the next plane to prefetch (null: ghost plane)
+    const T* ph;              // same for the hom field
+    const T* pe;              // same for the extra (outermost-row) element
+    long long off, eoff;      // element offsets inside a plane (own / extra)
+    int qn;                   // index of the plane pn/ph/pe point into
+    T* po;                    // own output element of the next plane to write
     int er, ec;               // smem row / col of the extra element
-    long long eoff;
     Vt cB, cC, cD;            // c^ at planes p-1, p, p+1 (own position)
     Vt hC, hD;                // hom at planes p, p+1
     Vt mB;                    // mu at plane p-1
@@ -92,7 +100,6 @@ struct ChRhsProgram {
     int xa, xb;               // chunk [xa, xb)
   };
 
-  EVX_HD static int slot(int q) { return (q + 4) & 1; }
 
   // pointer to plane q of a field (own slab, x-halo, or periodic image); null = ghost plane
   EVX_HD static const T* plane(const P& p, const T* base, int q, bool use_halo) {
@@ -147,8 +154,20 @@ struct ChRhsProgram {
     t.xa = chunk * p.xchunk;
     t.xb = t.xa + p.xchunk < p.nx ? t.xa + p.xchunk : p.nx;
     t.has_pos = tid < NPOS;
-    const int r = tid / COLS - 1;        // row in [-1, TY]
-    const int g = tid % COLS - RZ;       // group in [-RZ, G+RZ-1]
+    int r, g;                            // row in [-1, TY], group in [-RZ, G+RZ-1]
+    if (tid < N_INT) {
+      r = tid / G;
+      g = tid % G;
+    } else if (tid < N_INT + N_RROW) {
+      const int j = tid - N_INT;
+      r = j < G ? -1 : TY;
+      g = j % G;
+    } else {
+      const int j = tid - N_INT - N_RROW;
+      const int side = j / (RZ * (TY + 2)), w = j % (RZ * (TY + 2));
+      r = w % (TY + 2) - 1;
+      g = side == 0 ? -1 - w / (TY + 2) : G + w / (TY + 2);
+    }
     t.row = r + 2;
     t.col = g + RZ;
     const bool per_y = p.bc_kind[1] == BC_PERIODIC, per_z = p.bc_kind[2] == BC_PERIODIC;
@@ -161,16 +180,17 @@ struct ChRhsProgram {
       t.off = (long long)yi * p.nz + zi;
       t.want_mu = t.has_pos && g >= -1 && g <= G;
       t.interior = t.has_pos && r >= 0 && r < TY && g >= 0 && g < G && y < p.ny && z + V <= p.nz;
-      t.out_off = (long long)y * p.nz + z;
+      t.po = p.out + (long long)t.xa * p.ny * p.nz + (long long)y * p.nz + z;
       t.gy_lo = GHOSTS && !per_y && y == 0;
       t.gy_hi = GHOSTS && !per_y && y == p.ny - 1;
       t.gz_lo = GHOSTS && !per_z && z == 0;
       t.gz_hi = GHOSTS && !per_z && z + V == p.nz;
     }
-    t.has_extra = tid < NEXTRA;
+    t.has_extra = tid >= N_INT && tid < N_INT + N_RROW;   // ring-row threads
     {
-      const int side = tid / G;                 // 0: row -2, 1: row TY+1
-      const int eg = tid % G;
+      const int j = tid - N_INT;
+      const int side = j < G ? 0 : 1;           // 0: row -2, 1: row TY+1
+      const int eg = (j < 0 ? 0 : j) % G;
       const int rr = side == 0 ? -2 : TY + 1;
       const int y = y0 + rr, z = z0 + eg * V;
       const int yi = per_y ? wrap_index(y, p.ny) : clamp_index(y, 0, p.ny - 1);
@@ -197,17 +217,46 @@ struct ChRhsProgram {
         t.hD = load_plane(p, p.hom, t.xa, t.off, false);
         t.hnxt = load_plane(p, p.hom, t.xa + 1, t.off, false);
       }
-      s.c[slot(t.xa - 1)][t.row][t.col] = t.cC;
-      s.c[slot(t.xa)][t.row][t.col] = t.cD;
+      s.c[0][t.row][t.col] = t.cC;     // slot = (plane - (xa-1)) & 1
+      s.c[1][t.row][t.col] = t.cD;
     }
     if (t.has_extra) {
-      s.c[slot(t.xa - 1)][t.er][t.ec] = clipv(load_plane(p, p.c, t.xa - 1, t.eoff, true));
-      s.c[slot(t.xa)][t.er][t.ec] = clipv(load_plane(p, p.c, t.xa, t.eoff, true));
+      s.c[0][t.er][t.ec] = clipv(load_plane(p, p.c, t.xa - 1, t.eoff, true));
+      s.c[1][t.er][t.ec] = clipv(load_plane(p, p.c, t.xa, t.eoff, true));
       t.enxt = load_plane(p, p.c, t.xa + 1, t.eoff, true);
+    }
+    t.ps = (long long)p.ny * p.nz;
+    t.qn = t.xa + 2;
+    resolve_next(t, p);
+  }
+
+  // pointers into plane t.qn (general path: slab ends, halos, periodic images, ghosts)
+  EVX_HD static void resolve_next(Regs& t, const P& p) {
+    const T* b = plane(p, p.c, t.qn, true);
+    t.pn = b ? b + t.off : nullptr;
+    t.pe = b ? b + t.eoff : nullptr;
+    if (HOM) {
+      const T* h = plane(p, p.hom, t.qn, false);
+      t.ph = h ? h + t.off : nullptr;
+    } else {
+      t.ph = nullptr;
+    }
+  }
+  EVX_HD static void advance_next(Regs& t, const P& p) {
+    ++t.qn;
+    if (t.qn >= 1 && t.qn < p.nx) {      // both planes inside the slab: plain stride
+      t.pn += t.ps;
+      t.pe += t.ps;
+      if (HOM) t.ph += t.ps;
+    } else {
+      resolve_next(t, p);
     }
   }
 
   // ---- phase A of plane p: mu(p) -> smem, then rhs(x = p-1) -> global ------------------
+  // PAR = (pl - (xa-1)) & 1 is the shared-memory slot of plane pl (static so that all
+  // shared-memory offsets are immediates)
+  template <int PAR>
   EVX_HD static void phase_a(Regs& t, Smem& s, const P& p, int pl) {
     if (!t.has_pos) return;
     const int row = t.row, col = t.col;
@@ -219,7 +268,7 @@ struct ChRhsProgram {
     Vt cN, cS;
     T cL, cR;
     {
-      const int sl = slot(pl);
+      constexpr int sl = PAR;
       cS = s.c[sl][row - 1][col];
       cN = s.c[sl][row + 1][col];
       cL = s.c[sl][row][col - 1].v[V - 1];
@@ -248,7 +297,7 @@ struct ChRhsProgram {
                   p.lz * (zr + zl) + p.l0 * c0;
       }
     }
-    s.mu[pl & 1][row - 1][col] = mC;
+    s.mu[PAR][row - 1][col] = mC;
 
     // x-face term between planes pl-1 and pl (carried to the next plane as "minus" face)
     Vt fxp;
@@ -257,8 +306,8 @@ struct ChRhsProgram {
 
     // rhs at plane x = pl-1: c^(x) = cB, mu(x) = mB; the x-faces are fxm (carried) and fxp
     const int x = pl - 1;
-    if (t.interior && x >= t.xa && x < t.xb) {
-      const int ms = x & 1;
+    if (t.interior && x >= t.xa) {
+      constexpr int ms = PAR ^ 1;
       const int mrow = row - 1;
       Vt mS = s.mu[ms][mrow - 1][col];
       Vt mN = s.mu[ms][mrow + 1][col];
@@ -295,7 +344,8 @@ struct ChRhsProgram {
         const T fym = face(t.sS.v[k], c0, mS.v[k], m0);
         o.v[k] = p.fx * (fxp.v[k] - fxm.v[k]) + p.fy * (fyp - fym) + p.fz * (fz[k + 1] - fz[k]);
       }
-      vec_store<T, V>(p.out + (long long)x * p.ny * p.nz + t.out_off, o);
+      vec_store<T, V>(t.po, o);
+      t.po += t.ps;
     }
     // roll the mu window and remember the y/z neighbours of c^(pl) for the next plane
     t.fxm = fxp;
@@ -307,8 +357,9 @@ struct ChRhsProgram {
   }
 
   // ---- phase B of plane p (after the barrier): roll c^ window, publish plane p+2 -------
+  template <int PAR>
   EVX_HD static void phase_b(Regs& t, Smem& s, const P& p, int pl) {
-    const bool more = pl + 3 <= t.xb + 1;     // plane pl+3 is still needed as a centre value
+    const bool more = t.qn <= t.xb + 1;       // plane qn = pl+3 is still needed as a centre value
     if (t.has_pos) {
       t.cB = t.cC;
       t.cC = t.cD;
@@ -317,16 +368,17 @@ struct ChRhsProgram {
         t.hC = t.hD;
         t.hD = t.hnxt;
       }
-      s.c[slot(pl + 2)][t.row][t.col] = t.cD;
+      s.c[PAR][t.row][t.col] = t.cD;
       if (more) {
-        t.nxt = load_plane(p, p.c, pl + 3, t.off, true);
-        if (HOM) t.hnxt = load_plane(p, p.hom, pl + 3, t.off, false);
+        if (t.pn) t.nxt = vec_load<T, V>(t.pn);
+        if (HOM && t.ph) t.hnxt = vec_load<T, V>(t.ph);
       }
     }
     if (t.has_extra) {
-      s.c[slot(pl + 2)][t.er][t.ec] = clipv(t.enxt);
-      if (more) t.enxt = load_plane(p, p.c, pl + 3, t.eoff, true);
+      s.c[PAR][t.er][t.ec] = clipv(t.enxt);
+      if (more && t.pe) t.enxt = vec_load<T, V>(t.pe);
     }
+    if (more) advance_next(t, p);
   }
 };
 

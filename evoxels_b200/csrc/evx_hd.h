@@ -47,12 +47,19 @@ EVX_HD Vec<T, V> vec_splat(T a) {
   return r;
 }
 
+// torch.clip(c, 0, 1).  On the device float uses the single-instruction saturate; a NaN
+// input becomes 0 there instead of propagating, which is harmless for the time steppers:
+// u+ = u + update keeps the NaN of u, so the solver's per-frame NaN abort still fires.
 template <typename T>
 EVX_HD T clip01(T a) {
-  // torch.clip(c, 0, 1): min(max(c, 0), 1); NaN propagates in torch, here fmin/fmax
-  // would drop it, so keep the comparison form (NaN compares false -> passes through).
   return a < T(0) ? T(0) : (a > T(1) ? T(1) : a);
 }
+#if defined(__CUDA_ARCH__)
+template <>
+EVX_HD float clip01<float>(float a) {
+  return __saturatef(a);
+}
+#endif
 
 EVX_HD int wrap_index(int i, int n) {
   int m = i % n;

@@ -17,7 +17,7 @@
 
 namespace evx {
 
-struct cf {
+struct alignas(8) cf {
   float x, y;
 };
 

@@ -1,18 +1,157 @@
-// Native sm_100a FFT back end of the IMEX plan (power-of-two extents).  Placeholder until
-// the pass kernels land: reports "unsupported" so that EVX_FFT_AUTO selects cuFFT.
+// Native sm_100a FFT back end of the IMEX plan: five hand-written passes
+//   ZFwd -> Y fwd -> X fwd*filter*X inv -> Y inv -> ZInv(+u)
+// over a pitched half spectrum (see fft_pass_core.h).  Power-of-two extents:
+// 8 <= nx, ny <= 2048, 16 <= nz <= 2048.
+#include <cmath>
+#include <vector>
 #include "evx_internal.h"
 #include "spectral_plan.h"
+#include "fft_pass_core.h"
 
 namespace evx {
 
-bool native_fft_supported(int, int, int) { return false; }
-int native_plan_init(evx_imex_plan*) { return EVX_ERR_UNSUPPORTED; }
+constexpr int kPitchAlign = 8;   // spectrum rows are padded to a multiple of 8 complex
+
+template <class Prog, class Params>
+__global__ void __launch_bounds__(Prog::NTHREADS, Prog::NTHREADS <= 512 ? 2 : 1) fft_pass_kernel(const Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf* smem = reinterpret_cast<cf*>(smem_raw);
+  typename Prog::Regs r;
+  Prog::init(r, p, threadIdx.x, (long long)blockIdx.x);
+#pragma unroll
+  for (int k = 0; k < Prog::NPHASES; ++k) {
+    if (k) __syncthreads();
+    Prog::phase(k, r, smem, p);
+  }
+}
+
+template <class Prog, class Params>
+static int launch_pass(const Params& p, long long blocks, cudaStream_t st) {
+  if (blocks < 1 || blocks > 2147483647LL) return EVX_ERR_UNSUPPORTED;
+  auto kern = fft_pass_kernel<Prog, Params>;
+  if (Prog::SMEM_BYTES > 48 * 1024) {
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)Prog::SMEM_BYTES);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+  }
+  kern<<<(unsigned)blocks, Prog::NTHREADS, Prog::SMEM_BYTES, st>>>(p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <int L>
+struct StridedCfg { static constexpr int KZ = L >= 2048 ? 4 : 8; };
+
+template <int MODE>
+static int launch_strided(int L, const StridedParams& p, cudaStream_t st) {
+#define EVX_CASE(N)                                                                   \
+  case N: {                                                                           \
+    constexpr int KZ = StridedCfg<N>::KZ;                                             \
+    return launch_pass<StridedPass<N, KZ, MODE>, StridedParams>(                      \
+        p, (p.ncols_total + KZ - 1) / KZ, st);                                        \
+  }
+  switch (L) {
+    EVX_CASE(8) EVX_CASE(16) EVX_CASE(32) EVX_CASE(64) EVX_CASE(128) EVX_CASE(256)
+    EVX_CASE(512) EVX_CASE(1024) EVX_CASE(2048)
+    default: return EVX_ERR_UNSUPPORTED;
+  }
+#undef EVX_CASE
+}
+
+template <bool INV>
+static int launch_z(int M, const ZParams& p, cudaStream_t st) {
+#define EVX_CASE(N, NL)                                                               \
+  case N: return launch_pass<ZPass<N, NL, INV>, ZParams>(p, (p.rows + NL - 1) / NL, st);
+  switch (M) {
+    EVX_CASE(8, 32) EVX_CASE(16, 32) EVX_CASE(32, 32) EVX_CASE(64, 32) EVX_CASE(128, 16)
+    EVX_CASE(256, 8) EVX_CASE(512, 4) EVX_CASE(1024, 2)
+    default: return EVX_ERR_UNSUPPORTED;
+  }
+#undef EVX_CASE
+}
+
+bool native_fft_supported(int nx, int ny, int nz) {
+  return is_pow2(nx) && is_pow2(ny) && is_pow2(nz) && nx >= 8 && nx <= 2048 && ny >= 8 &&
+         ny <= 2048 && nz >= 16 && nz <= 2048;
+}
+
+static void fill_roots(std::vector<cf>& w, size_t off, int n, int count) {
+  for (int m = 0; m < count; ++m) {
+    const double a = -2.0 * M_PI * (double)m / (double)n;
+    w[off + m] = cf{(float)std::cos(a), (float)std::sin(a)};
+  }
+}
+
+int native_plan_init(evx_imex_plan* p) {
+  const int M = p->nz / 2;
+  p->spec_pitch = ((M + 1 + kPitchAlign - 1) / kPitchAlign) * kPitchAlign;
+  p->spec_bytes = ((size_t)p->nx * p->ny * p->spec_pitch * sizeof(cf) + 255) & ~(size_t)255;
+  p->work_bytes = 0;
+  // tables: W_nx | W_ny | W_M | W_nz[0..M]
+  const size_t total = (size_t)p->nx + p->ny + M + (M + 1);
+  std::vector<cf> host(total);
+  fill_roots(host, 0, p->nx, p->nx);
+  fill_roots(host, p->nx, p->ny, p->ny);
+  fill_roots(host, (size_t)p->nx + p->ny, M, M);
+  fill_roots(host, (size_t)p->nx + p->ny + M, p->nz, M + 1);
+  cudaError_t e = cudaMalloc(&p->twiddles, total * sizeof(cf));
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpy(p->twiddles, host.data(), total * sizeof(cf), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(p->twiddles); p->twiddles = nullptr; return (int)e; }
+  return EVX_OK;
+}
+
 void native_plan_free(evx_imex_plan* p) {
   if (p && p->twiddles) { cudaFree(p->twiddles); p->twiddles = nullptr; }
 }
-int native_apply(evx_imex_plan*, const float*, const float*, float*, void*, const double*, double,
-                 double, int, cudaStream_t) { return EVX_ERR_UNSUPPORTED; }
-int native_ch_step(evx_imex_plan*, const float*, const float*, float*, void*, const double*,
-                   double, double, double, double, cudaStream_t) { return EVX_ERR_UNSUPPORTED; }
+
+int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, void* workspace,
+                 const double* h, double dt, double coef, int power, cudaStream_t st) {
+  const int nx = p->nx, ny = p->ny, nz = p->nz, M = nz / 2, P = p->spec_pitch;
+  cf* spec = reinterpret_cast<cf*>((char*)workspace + p->real_bytes);
+  const cf* twx = (const cf*)p->twiddles;
+  const cf* twy = twx + nx;
+  const cf* twz = twy + ny;
+  const cf* twr = twz + M;
+
+  ZParams zp;
+  zp.real_in = r; zp.real_out = nullptr; zp.spec = spec; zp.tw = twz; zp.twr = twr;
+  zp.rows = (long long)nx * ny; zp.nz = nz; zp.P = P;
+  int rc = launch_z<false>(M, zp, st);
+  if (rc) return rc;
+
+  StridedParams yp;
+  yp.data = spec; yp.tw = twy; yp.line_stride = P; yp.plane_stride = (long long)ny * P;
+  yp.P = P; yp.ncols_valid = M + 1; yp.ncols_total = (long long)nx * P;
+  yp.filt = FilterParams{};
+  if ((rc = launch_strided<PASS_FWD>(ny, yp, st))) return rc;
+
+  StridedParams xp = yp;
+  xp.tw = twx; xp.line_stride = (long long)ny * P; xp.plane_stride = P;
+  xp.ncols_total = (long long)ny * P;
+  const int n[3] = {nx, ny, nz};
+  xp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
+  if ((rc = launch_strided<PASS_XMID>(nx, xp, st))) return rc;
+
+  if ((rc = launch_strided<PASS_INV>(ny, yp, st))) return rc;
+
+  zp.real_in = u; zp.real_out = out;
+  return launch_z<true>(M, zp, st);
+}
+
+int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* out,
+                   void* workspace, const double* h, double dt, double eps, double D, double A,
+                   cudaStream_t st) {
+  const int per[3] = {BC_PERIODIC, BC_PERIODIC, BC_PERIODIC};
+  float* rhs = (float*)workspace;
+  int rc = ch_rhs_impl<float>(u, hom, rhs, p->nx, p->ny, p->nz, h, eps, D, per, nullptr, nullptr,
+                              nullptr, st);
+  if (rc) return rc;
+  return native_apply(p, u, rhs, out, workspace, h, dt, 2.0 * eps * D * A, 2, st);
+}
 
 }  // namespace evx

@@ -1,0 +1,264 @@
+// Pass programs of the native 3-D real FFT (host/device, barrier-free phases).
+//
+// Spectrum layout: S[nx][ny][P] complex64, P = pitch >= nz/2+1 (multiple of KZ), kz fastest.
+//   ZFwd   real line (nz) -> half spectrum line (nz/2+1): half-length complex FFT + untangle
+//   Strided<FWD|INV>   in-place complex FFT along y or x (line stride P or ny*P)
+//   Strided<XMID>      forward along x, multiply by P(k)/N, inverse along x, one pass
+//   ZInv   half spectrum line -> real line, fused  out = u + line
+// Together: out = u + irfftn(P * rfftn(r)) with 5 passes over the data instead of the
+// 6 transform passes + filter + add of a library FFT (reference timesteppers.py:85-89).
+#pragma once
+#include "fft_core.h"
+#include "spectral_math.h"
+
+namespace evx {
+
+EVX_HD int smem_pad(int i) { return i + (i >> 3); }
+constexpr int smem_padded_len(int n) { return n + (n >> 3) + 1; }
+
+enum : int { PASS_FWD = 0, PASS_INV = 1, PASS_XMID = 2 };
+
+// ------------------------------------------------------------------------------------
+// strided passes (y and x)
+// ------------------------------------------------------------------------------------
+struct StridedParams {
+  cf* data;
+  const cf* tw;            // W_L table
+  long long line_stride;   // elements between consecutive points of a line
+  long long plane_stride;  // elements between column groups: base(c) = (c / P) * plane_stride + c % P
+  int P;                   // pitch (columns per group)
+  int ncols_valid;         // columns kz < ncols_valid carry data (nz/2+1)
+  long long ncols_total;   // number of columns incl. pitch padding (groups * P)
+  FilterParams filt;       // XMID only; n0 = L (this axis), n1 = the other strided axis, n2 = nz
+};
+
+template <int L, int KZ, int MODE>
+struct StridedPass {
+  static constexpr int T = L / 8;
+  static constexpr int NTHREADS = T * KZ;
+  static constexpr int S = num_stages(L);
+  static constexpr int NPHASES = MODE == PASS_XMID ? 2 * S - 1 : S;
+  static constexpr int LP = smem_padded_len(L);
+  static constexpr size_t SMEM_BYTES = (S > 1 ? 2 : 0) * (size_t)LP * KZ * sizeof(cf);
+
+  struct Regs {
+    cf v[8];
+    int t, cl;
+    bool valid;
+    long long base;
+    int kz, kother;
+  };
+
+  EVX_HD static cf* buf(cf* smem, int which) { return smem + (size_t)which * LP * KZ; }
+
+  EVX_HD static void init(Regs& r, const StridedParams& p, int tid, long long block) {
+    r.cl = tid % KZ;
+    r.t = tid / KZ;
+    const long long c = block * KZ + r.cl;
+    const long long grp = c / p.P;
+    r.kz = (int)(c - grp * p.P);
+    r.kother = (int)grp;
+    r.valid = c < p.ncols_total && r.kz < p.ncols_valid;
+    r.base = grp * p.plane_stride + r.kz;
+  }
+
+  template <int DIR>
+  EVX_HD static void write_stage(Regs& r, cf* b, int s) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      b[(size_t)smem_pad(line_stage_out_index<L>(s, r.t, e)) * KZ + r.cl] = r.v[e];
+  }
+  EVX_HD static void read_natural(Regs& r, const cf* b) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r.v[e] = b[(size_t)smem_pad(r.t + e * T) * KZ + r.cl];
+  }
+  EVX_HD static void load_global(Regs& r, const StridedParams& p) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      r.v[e] = r.valid ? p.data[r.base + (long long)(r.t + e * T) * p.line_stride] : cf{0.f, 0.f};
+  }
+  EVX_HD static void store_global(Regs& r, const StridedParams& p) {
+    if (!r.valid) return;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) p.data[r.base + (long long)(r.t + e * T) * p.line_stride] = r.v[e];
+  }
+  EVX_HD static void apply_filter(Regs& r, const StridedParams& p) {
+    const FilterParams& f = p.filt;
+    const float k1 = wavenumber(signed_freq(r.kother, f.n1), f.inv_len1);
+    const float k2 = wavenumber(r.kz, f.inv_len2);
+    const float k1sq = fmul_rn(k1, k1), k2sq = fmul_rn(k2, k2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float k0 = wavenumber(signed_freq(r.t + e * T, f.n0), f.inv_len0);
+      // reference order: (kx^2 + ky^2) + kz^2; this pass runs along x
+      const float ksq = fadd_rn(fadd_rn(fmul_rn(k0, k0), k1sq), k2sq);
+      const float w = imex_prefactor(ksq, f) * f.scale;
+      r.v[e] = cscale(r.v[e], w);
+    }
+  }
+
+  // transform step q of the pass: FWD/INV: stage q; XMID: q < S forward stage q, else inverse q-S
+  template <int DIRSEL>
+  EVX_HD static void compute(Regs& r, const StridedParams& p, int stage) {
+    line_stage_compute<L, DIRSEL>(stage, r.v, r.t, p.tw);
+  }
+
+  EVX_HD static void phase(int k, Regs& r, cf* smem, const StridedParams& p) {
+    if (MODE == PASS_FWD || MODE == PASS_INV) {
+      if (k == 0) load_global(r, p); else read_natural(r, buf(smem, (k - 1) & 1));
+      if (MODE == PASS_FWD) compute<-1>(r, p, k); else compute<+1>(r, p, k);
+      if (k == S - 1) store_global(r, p);
+      else if (MODE == PASS_FWD) write_stage<-1>(r, buf(smem, k & 1), k);
+      else write_stage<+1>(r, buf(smem, k & 1), k);
+    } else {
+      // XMID: phases 0..S-2 forward stages, phase S-1: last forward + filter + first inverse,
+      // phases S..2S-2 remaining inverse stages
+      if (k == 0) load_global(r, p); else read_natural(r, buf(smem, (k - 1) & 1));
+      if (k < S - 1) {
+        compute<-1>(r, p, k);
+        write_stage<-1>(r, buf(smem, k & 1), k);
+      } else if (k == S - 1) {
+        compute<-1>(r, p, S - 1);
+        apply_filter(r, p);
+        compute<+1>(r, p, 0);
+        if (S == 1) store_global(r, p); else write_stage<+1>(r, buf(smem, k & 1), 0);
+      } else {
+        const int s = k - (S - 1);
+        compute<+1>(r, p, s);
+        if (s == S - 1) store_global(r, p); else write_stage<+1>(r, buf(smem, k & 1), s);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// z passes (contiguous axis, real <-> half spectrum)
+// ------------------------------------------------------------------------------------
+struct ZParams {
+  const float* real_in;    // ZFwd: r [rows][nz]            ZInv: u (may be null: out = update)
+  float* real_out;         // ZInv: out [rows][nz]
+  cf* spec;                // [rows][P]
+  const cf* tw;            // W_M table, M = nz/2
+  const cf* twr;           // W_nz[k], k = 0..M (untangle roots)
+  long long rows;          // nx*ny
+  int nz, P;
+};
+
+template <int M, int NL, bool INVERSE>
+struct ZPass {
+  static constexpr int T = M / 8;
+  static constexpr int NTHREADS = T * NL;
+  static constexpr int S = num_stages(M);
+  static constexpr int NPHASES = S + 1;
+  static constexpr int LP = smem_padded_len(M + 1);
+  static constexpr size_t SMEM_BYTES = 2 * (size_t)LP * NL * sizeof(cf);
+
+  struct Regs {
+    cf v[8];
+    int t, l;
+    bool valid;
+    long long row;
+  };
+
+  EVX_HD static cf* buf(cf* smem, int which, int l) { return smem + ((size_t)which * NL + l) * LP; }
+
+  EVX_HD static void init(Regs& r, const ZParams& p, int tid, long long block) {
+    r.t = tid % T;
+    r.l = tid / T;
+    r.row = block * NL + r.l;
+    r.valid = r.row < p.rows;
+  }
+
+  EVX_HD static void write_stage(Regs& r, cf* b, int s) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) b[smem_pad(line_stage_out_index<M>(s, r.t, e))] = r.v[e];
+  }
+  EVX_HD static void read_natural(Regs& r, const cf* b) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r.v[e] = b[smem_pad(r.t + e * T)];
+  }
+
+  // X[k] from Z[k], Z[M-k]  (forward untangle)
+  EVX_HD static cf untangle_fwd(cf zk, cf zmk, cf w) {
+    const cf a = cadd(zk, cconj(zmk));              // 2 E[k]
+    const cf b = csub(zk, cconj(zmk));              // 2 i O[k]
+    const cf o = cf{b.y, -b.x};                     // -i * b = 2 O[k]
+    const cf wo = cmul(w, o);
+    return cf{0.5f * (a.x + wo.x), 0.5f * (a.y + wo.y)};
+  }
+  // Z'[k] from X[k], X[M-k]  (inverse; unnormalised: ifft_M(Z') = N x)
+  EVX_HD static cf untangle_inv(cf xk, cf xmk, cf w) {
+    const cf a = cadd(xk, cconj(xmk));              // 2 E[k]
+    const cf b = csub(xk, cconj(xmk));
+    const cf wo = cmul(cconj(w), b);                // 2 O[k]
+    return cf{a.x - wo.y, a.y + wo.x};              // a + i * wo
+  }
+
+  EVX_HD static void phase(int k, Regs& r, cf* smem, const ZParams& p) {
+    if (!INVERSE) {
+      if (k < S) {
+        if (k == 0) {
+          const cf* line = reinterpret_cast<const cf*>(p.real_in + r.row * p.nz);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r.v[e] = r.valid ? line[r.t + e * T] : cf{0.f, 0.f};
+        } else {
+          read_natural(r, buf(smem, (k - 1) & 1, r.l));
+        }
+        line_stage_compute<M, -1>(k, r.v, r.t, p.tw);
+        write_stage(r, buf(smem, k & 1, r.l), k);     // last stage lands in natural order
+      } else {
+        const cf* z = buf(smem, (S - 1) & 1, r.l);
+        if (!r.valid) return;
+        cf* out = p.spec + r.row * p.P;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int kk = r.t + e * T;
+          const cf zk = z[smem_pad(kk)];
+          const cf zmk = z[smem_pad(kk == 0 ? 0 : M - kk)];
+          out[kk] = untangle_fwd(zk, zmk, p.twr[kk]);
+        }
+        if (r.t == 0) {
+          const cf z0 = z[smem_pad(0)];
+          out[M] = cf{z0.x - z0.y, 0.f};
+        }
+      }
+    } else {
+      if (k == 0) {
+        cf* x = buf(smem, 1, r.l);
+        const cf* in = p.spec + r.row * p.P;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int kk = r.t + e * T;
+          x[smem_pad(kk)] = r.valid ? in[kk] : cf{0.f, 0.f};
+        }
+        if (r.t == 0) x[smem_pad(M)] = r.valid ? in[M] : cf{0.f, 0.f};
+      } else {
+        const int s = k - 1;
+        if (s == 0) {
+          const cf* x = buf(smem, 1, r.l);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int kk = r.t + e * T;
+            r.v[e] = untangle_inv(x[smem_pad(kk)], x[smem_pad(M - kk)], p.twr[kk]);
+          }
+        } else {
+          read_natural(r, buf(smem, (s - 1) & 1, r.l));
+        }
+        line_stage_compute<M, +1>(s, r.v, r.t, p.tw);
+        if (s < S - 1) {
+          write_stage(r, buf(smem, s & 1, r.l), s);
+        } else if (r.valid) {
+          cf* out = reinterpret_cast<cf*>(p.real_out + r.row * p.nz);
+          const cf* u = p.real_in ? reinterpret_cast<const cf*>(p.real_in + r.row * p.nz) : nullptr;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int m = r.t + e * T;
+            out[m] = u ? cadd(r.v[e], u[m]) : r.v[e];
+          }
+        }
+      }
+    }
+  }
+};
+
+}  // namespace evx

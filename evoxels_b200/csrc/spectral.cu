@@ -8,29 +8,9 @@
 #include <new>
 #include "evx_internal.h"
 #include "spectral_plan.h"
+#include "spectral_math.h"
 
 namespace evx {
-
-// ------------------------------------------------------------------------------------
-// wavenumber arithmetic, float32 with the reference's rounding sequence
-//   freq = float(idx) * float(1/(n*d))          torch.fft.fftfreq / rfftfreq
-//   k    = float(2*pi) * freq                   voxelgrid.py:84-90
-//   k2   = (kx*kx + ky*ky) + kz*kz              voxelgrid.py:110-114
-//   P    = dt / (1 + dt * (coef * k2^power))    problem_definition.py:303, timesteppers.py:77
-// The reference keeps all of this in float32 even for float64 fields.
-// __f*_rn intrinsics keep nvcc from contracting mul+add into fma, so P is bit-identical
-// to the reference's stored prefactor array.
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ float wavenumber(int idx, float inv_len) {
-  return __fmul_rn(6.283185307179586f, __fmul_rn((float)idx, inv_len));
-}
-__device__ __forceinline__ int signed_freq(int i, int n) { return i < (n + 1) / 2 ? i : i - n; }
-
-__device__ __forceinline__ float imex_prefactor(float k2, const FilterParams& f) {
-  const float kp = f.power == 2 ? __fmul_rn(k2, k2) : k2;
-  const float den = __fadd_rn(1.0f, __fmul_rn(f.dt, __fmul_rn(f.coef, kp)));
-  return __fdiv_rn(f.dt, den);
-}
 
 // cuFFT layout: [n0, n1, n2/2+1] complex, contiguous.  Each block owns ROWS consecutive
 // (i0,i1) rows and walks their elements with a flat index, one complex (8/16 B) per access.
@@ -82,21 +62,6 @@ __global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ u,
   } else {
     for (long long i = t0; i < n; i += stride) out[i] = u[i] + upd[i];
   }
-}
-
-static FilterParams make_filter(const int n[3], const double len_h[3], double dt, double coef,
-                                int power, double scale) {
-  FilterParams f;
-  f.n0 = n[0]; f.n1 = n[1]; f.n2 = n[2];
-  f.inv_len0 = (float)(1.0 / (n[0] * len_h[0]));
-  f.inv_len1 = (float)(1.0 / (n[1] * len_h[1]));
-  f.inv_len2 = (float)(1.0 / (n[2] * len_h[2]));
-  f.dt = (float)dt;
-  f.coef = (float)coef;
-  f.power = power;
-  f.scale = (float)scale;
-  f.scale_d = scale;
-  return f;
 }
 
 template <typename R>

@@ -3,19 +3,8 @@
 #include <cufft.h>
 #include <cuda_runtime.h>
 #include "evx_hd.h"
+#include "spectral_math.h"
 #include "../../include/evoxels_b200.h"
-
-namespace evx {
-
-struct FilterParams {
-  int n0, n1, n2;                       // extents (n2 is the halved, contiguous one)
-  float inv_len0, inv_len1, inv_len2;   // float(1/(n*h)) per axis
-  float dt, coef, scale;
-  int power;                            // 1: |k|^2, 2: |k|^4
-  double scale_d;
-};
-
-}  // namespace evx
 
 struct evx_imex_plan {
   int nx = 0, ny = 0, nz = 0, is_f64 = 0, backend = 0;

@@ -1,6 +1,7 @@
 // CUDA wrappers + C-ABI launchers for the stencil layer (see include/evoxels_b200.h).
 // Kernel bodies live in ch_rhs_core.h / ac_core.h as barrier-free phase functions.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "evx_internal.h"
 #include "evx_params.h"
 
@@ -13,17 +14,22 @@ std::atomic<unsigned long long> g_launches{0};
 // ------------------------------------------------------------------------------------
 template <typename T, int V, int TY, int G, bool HOM, bool GHOSTS>
 __global__ void __launch_bounds__(ChRhsProgram<T, V, TY, G, HOM, GHOSTS>::NTHREADS,
-                                  sizeof(T) == 4 ? 2 : 1)
+                                  (sizeof(T) == 4 && TY <= 16) ? 2 : 1)
     ch_rhs_kernel(const ChParams<T> p) {
   using Prog = ChRhsProgram<T, V, TY, G, HOM, GHOSTS>;
   __shared__ typename Prog::Smem s;
   typename Prog::Regs t;
   Prog::init(t, s, p, threadIdx.x, blockIdx.x, blockIdx.y);
   __syncthreads();
-  for (int pl = t.xa - 1; pl <= t.xb; ++pl) {
-    Prog::phase_a(t, s, p, pl);
+  for (int pl = t.xa - 1; pl <= t.xb; pl += 2) {
+    Prog::template phase_a<0>(t, s, p, pl);
     __syncthreads();
-    Prog::phase_b(t, s, p, pl);
+    Prog::template phase_b<0>(t, s, p, pl);
+    if (pl + 1 <= t.xb) {          // uniform across the block
+      Prog::template phase_a<1>(t, s, p, pl + 1);
+      __syncthreads();
+      Prog::template phase_b<1>(t, s, p, pl + 1);
+    }
   }
 }
 
@@ -74,7 +80,13 @@ int ch_rhs_impl(const T* c, const T* hom, T* rhs, int nx, int ny, int nz, const 
   constexpr int VW = 16 / (int)sizeof(T);
   const bool vec = nz % VW == 0 && aligned16(c) && aligned16(rhs) && aligned16(hom) &&
                    aligned16(halo_lo) && aligned16(halo_hi);
-  if (vec) return launch_ch<T, VW, 16, 16>(p, st);
+  if (vec) {
+    // tile height: 14 rows x 16 groups = 7 interior warps + 2 ring warps = 288 threads
+    static const int tile = [] { const char* e = getenv("EVX_CH_TILE"); return e ? atoi(e) : 14; }();
+    if (tile == 16) return launch_ch<T, VW, 16, 16>(p, st);
+    if (tile == 30) return launch_ch<T, VW, 30, 16>(p, st);
+    return launch_ch<T, VW, 14, 16>(p, st);
+  }
   return launch_ch<T, 1, 8, 32>(p, st);
 }
 

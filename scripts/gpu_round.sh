@@ -8,6 +8,7 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt 2>&1
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tee $OUT/smoke.log | tail -5
 echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider 2>&1 | tee $OUT/pytest_gpu.log | tail -40
+echo "== kernels"; for t in 14 16 30; do EVX_CH_TILE=$t timeout 300 python scripts/bench_kernels.py 512 2>&1 | tail -1 | tee -a $OUT/kernels.jsonl | cut -c1-700; done
 echo "== bench"; timeout 600 python bench.py --steps 20 --warmup 3 2>$OUT/bench.err | tee $OUT/bench.json | cut -c1-1500
 tail -5 $OUT/bench.err
 echo "== ncu launch list"

@@ -22,9 +22,13 @@ static void run_ch_(const ChParams<T>& p) {
     for (int tile = 0; tile < tiles; ++tile) {
       std::memset(s, 0, sizeof(*s));
       for (int t = 0; t < Prog::NTHREADS; ++t) Prog::init(regs[t], *s, p, t, tile, chunk);
-      for (int pl = regs[0].xa - 1; pl <= regs[0].xb; ++pl) {
-        for (int t = 0; t < Prog::NTHREADS; ++t) Prog::phase_a(regs[t], *s, p, pl);
-        for (int t = 0; t < Prog::NTHREADS; ++t) Prog::phase_b(regs[t], *s, p, pl);
+      for (int pl = regs[0].xa - 1; pl <= regs[0].xb; pl += 2) {
+        for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_a<0>(regs[t], *s, p, pl);
+        for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_b<0>(regs[t], *s, p, pl);
+        if (pl + 1 <= regs[0].xb) {
+          for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_a<1>(regs[t], *s, p, pl + 1);
+          for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_b<1>(regs[t], *s, p, pl + 1);
+        }
       }
     }
   delete s;
@@ -47,7 +51,9 @@ static int emu_ch(const T* c, const T* hom, T* out, int nx, int ny, int nz, cons
   constexpr int VW = 16 / sizeof(T);
   if (vec) {
     if (nz % VW) return -1;
-    run_ch<T, VW, 16, 16>(p);
+    if (vec == 16) run_ch<T, VW, 16, 16>(p);
+    else if (vec == 30) run_ch<T, VW, 30, 16>(p);
+    else run_ch<T, VW, 14, 16>(p);
   } else {
     run_ch<T, 1, 8, 32>(p);
   }
@@ -131,5 +137,118 @@ int emu_ch_rhs_f64(const double* c, const double* hom, double* out, int nx, int 
                    const double* h, double eps, double D, const int* bck, const double* bcv,
                    const double* hlo, const double* hhi, int xchunk, int vec) {
   return emu_ch<double>(c, hom, out, nx, ny, nz, h, eps, D, bck, bcv, hlo, hhi, xchunk, vec);
+}
+}
+
+// =====================================================================================
+// native FFT passes
+// =====================================================================================
+#include <cmath>
+#include "../../evoxels_b200/csrc/fft_pass_core.h"
+
+static std::vector<cf> make_roots(int n, int count) {   // exp(-2 pi i m / n), m < count
+  std::vector<cf> w(count);
+  for (int m = 0; m < count; ++m) {
+    const double a = -2.0 * M_PI * (double)m / (double)n;
+    w[m] = cf{(float)std::cos(a), (float)std::sin(a)};
+  }
+  return w;
+}
+
+template <int L, int KZ, int MODE>
+static void run_strided(const StridedParams& p) {
+  using Prog = StridedPass<L, KZ, MODE>;
+  const long long blocks = (p.ncols_total + KZ - 1) / KZ;
+  std::vector<typename Prog::Regs> regs(Prog::NTHREADS);
+  std::vector<cf> smem(Prog::SMEM_BYTES / sizeof(cf) + 1);
+  for (long long b = 0; b < blocks; ++b) {
+    for (int t = 0; t < Prog::NTHREADS; ++t) Prog::init(regs[t], p, t, b);
+    for (int k = 0; k < Prog::NPHASES; ++k)
+      for (int t = 0; t < Prog::NTHREADS; ++t) Prog::phase(k, regs[t], smem.data(), p);
+  }
+}
+
+template <int KZ, int MODE>
+static int dispatch_strided(int L, const StridedParams& p) {
+  switch (L) {
+    case 8: run_strided<8, KZ, MODE>(p); return 0;
+    case 16: run_strided<16, KZ, MODE>(p); return 0;
+    case 32: run_strided<32, KZ, MODE>(p); return 0;
+    case 64: run_strided<64, KZ, MODE>(p); return 0;
+    case 128: run_strided<128, KZ, MODE>(p); return 0;
+    case 256: run_strided<256, KZ, MODE>(p); return 0;
+    case 512: run_strided<512, KZ, MODE>(p); return 0;
+    case 1024: run_strided<1024, KZ, MODE>(p); return 0;
+    default: return -1;
+  }
+}
+
+template <int M, int NL, bool INV>
+static void run_z(const ZParams& p) {
+  using Prog = ZPass<M, NL, INV>;
+  const long long blocks = (p.rows + NL - 1) / NL;
+  std::vector<typename Prog::Regs> regs(Prog::NTHREADS);
+  std::vector<cf> smem(Prog::SMEM_BYTES / sizeof(cf) + 1);
+  for (long long b = 0; b < blocks; ++b) {
+    for (int t = 0; t < Prog::NTHREADS; ++t) Prog::init(regs[t], p, t, b);
+    for (int k = 0; k < Prog::NPHASES; ++k)
+      for (int t = 0; t < Prog::NTHREADS; ++t) Prog::phase(k, regs[t], smem.data(), p);
+  }
+}
+
+template <bool INV>
+static int dispatch_z(int M, const ZParams& p) {
+  switch (M) {
+    case 8: run_z<8, 4, INV>(p); return 0;
+    case 16: run_z<16, 4, INV>(p); return 0;
+    case 32: run_z<32, 4, INV>(p); return 0;
+    case 64: run_z<64, 4, INV>(p); return 0;
+    case 128: run_z<128, 4, INV>(p); return 0;
+    case 256: run_z<256, 8, INV>(p); return 0;
+    case 512: run_z<512, 2, INV>(p); return 0;
+    default: return -1;
+  }
+}
+
+extern "C" {
+
+// out = u + irfftn(P * rfftn(r)) through the five native passes; spec is scratch
+// [nx*ny*P] complex with P = roundup(nz/2+1, 8).  mode: 0 full, 1 forward only (spec out),
+int emu_native_apply(const float* u, const float* r, float* out, float* spec_out, int nx, int ny,
+                     int nz, const double* h, double dt, double coef, int power) {
+  constexpr int KZ = 8;
+  const int M = nz / 2, P = ((M + 1 + KZ - 1) / KZ) * KZ;
+  std::vector<cf> spec((size_t)nx * ny * P, cf{0.f, 0.f});
+  auto twx = make_roots(nx, nx), twy = make_roots(ny, ny), twz = make_roots(M, M),
+       twr = make_roots(nz, M + 1);
+  ZParams zp;
+  zp.real_in = r; zp.real_out = nullptr; zp.spec = spec.data(); zp.tw = twz.data();
+  zp.twr = twr.data(); zp.rows = (long long)nx * ny; zp.nz = nz; zp.P = P;
+  if (dispatch_z<false>(M, zp)) return -1;
+  StridedParams sp;
+  sp.data = spec.data(); sp.P = P; sp.ncols_valid = M + 1;
+  // y pass: columns (x, kz), line stride P, group stride ny*P
+  sp.tw = twy.data(); sp.line_stride = P; sp.plane_stride = (long long)ny * P;
+  sp.ncols_total = (long long)nx * P;
+  if (dispatch_strided<KZ, PASS_FWD>(ny, sp)) return -2;
+  if (spec_out) {   // forward-only check: finish x forward and return the spectrum
+    sp.tw = twx.data(); sp.line_stride = (long long)ny * P; sp.plane_stride = P;
+    sp.ncols_total = (long long)ny * P;
+    if (dispatch_strided<KZ, PASS_FWD>(nx, sp)) return -3;
+    for (size_t i = 0; i < spec.size(); ++i) { spec_out[2 * i] = spec[i].x; spec_out[2 * i + 1] = spec[i].y; }
+    return P;
+  }
+  // x pass: forward, filter, inverse
+  const int n[3] = {nx, ny, nz};
+  sp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
+  sp.tw = twx.data(); sp.line_stride = (long long)ny * P; sp.plane_stride = P;
+  sp.ncols_total = (long long)ny * P;
+  if (dispatch_strided<KZ, PASS_XMID>(nx, sp)) return -3;
+  sp.tw = twy.data(); sp.line_stride = P; sp.plane_stride = (long long)ny * P;
+  sp.ncols_total = (long long)nx * P;
+  if (dispatch_strided<KZ, PASS_INV>(ny, sp)) return -4;
+  zp.real_in = u; zp.real_out = out;
+  if (dispatch_z<true>(M, zp)) return -5;
+  return 0;
 }
 }

@@ -61,7 +61,7 @@ def test_ch_golden(cuda_device, name):
     ts = PseudoSpectralIMEX(prob, g["dt"])
     v = u
     u_before = u.clone()
-    for i in range(1, g["nsteps"] + 1):
+    for i in range(1, g.get("nsteps", 1) + 1):
         v = ts.step(0.0, v)
         if f"step{i}" in g:
             assert rel_l2(v[0].cpu().numpy(), g[f"step{i}"]) <= STEP_TOL[u.dtype] * max(1, i ** 0.5)
@@ -158,7 +158,8 @@ def test_ac_vs_live_oracle(cuda_device, shape, bc):
 
 @pytest.mark.parametrize("shape,backend", [((64, 64, 64), "cufft"), ((100, 100, 100), "cufft"),
                                            ((33, 20, 18), "cufft"), ((128, 64, 256), "cufft"),
-                                           ((64, 64, 64), "auto"), ((128, 64, 256), "auto")])
+                                           ((64, 64, 64), "native"), ((128, 64, 256), "native"),
+                                           ((256, 256, 256), "native")])
 def test_ch_imex_step_vs_live_oracle(cuda_device, shape, backend):
     u = O.noise_field(shape, seed=0)
     orc = O.CHOracle(shape, (1.0, 1.0, 1.0), 0.1)
@@ -173,6 +174,37 @@ def test_ch_imex_step_vs_live_oracle(cuda_device, shape, backend):
         v, w = v_new, w_new
     m0, m1 = float(u.double().mean()), float(w.double().mean())
     assert abs(m1 - m0) <= 2e-7 * abs(m0), "mass must be conserved to fp32 rounding"
+
+
+@pytest.mark.parametrize("shape", [(8, 8, 16), (16, 32, 64), (64, 8, 32), (8, 128, 16), (32, 16, 128),
+                                   (256, 64, 32), (64, 512, 64), (1024, 16, 32), (16, 16, 2048),
+                                   (32, 2048, 16), (2048, 8, 16), (128, 128, 128)])
+def test_native_fft_backend_matches_cufft_backend(cuda_device, shape):
+    """The hand-written five-pass FFT path against the cuFFT path on identical inputs
+    (both are checked against the oracle elsewhere; this sweeps every line length)."""
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    r = torch.randn(shape, device="cuda", generator=gen)
+    u = torch.rand(shape, device="cuda", generator=gen)
+    sp = (1.0, 0.5, 2.0)
+    outs = {}
+    for name, code in (("cufft", _native.FFT_CUFFT), ("native", _native.FFT_NATIVE)):
+        plan = _native.ImexPlan(shape, torch.float32, "cuda", code)
+        assert plan.backend_name == name
+        out = torch.empty_like(u)
+        plan.apply(u, r, out, sp, 0.1, 1.5, 2)
+        upd = torch.empty_like(u)
+        plan.apply(None, r, upd, sp, 0.1, 1.5, 2)
+        assert torch.allclose(out, u + upd, rtol=0, atol=1e-6)
+        outs[name] = (out - u).double()
+    assert float((outs["native"] - outs["cufft"]).norm() / outs["cufft"].norm()) <= 2e-6
+
+
+def test_native_fft_unsupported_sizes_fall_back(cuda_device):
+    assert _native.ImexPlan((100, 100, 100), torch.float32, "cuda").backend_name == "cufft"
+    assert _native.ImexPlan((64, 64, 64), torch.float32, "cuda").backend_name == "native"
+    assert _native.ImexPlan((64, 64, 64), torch.float64, "cuda").backend_name == "cufft"
+    with pytest.raises(_native.NativeLibraryError):
+        _native.ImexPlan((100, 64, 64), torch.float32, "cuda", _native.FFT_NATIVE)
 
 
 def test_ch_nonperiodic_x_imex(cuda_device):
