@@ -16,6 +16,18 @@ namespace evx {
 EVX_HD int smem_pad(int i) { return i + (i >> 3); }
 constexpr int smem_padded_len(int n) { return n + (n >> 3) + 1; }
 
+// Shared-memory index map of the z passes (lines are contiguous, lanes run along a line).
+// For M >= 128 an XOR swizzle of the low four index bits makes every Stockham write pattern
+// (strides 2/4/8 and the run-of-Ns patterns of later stages) and the natural-order reads
+// conflict-free for 64-bit accesses (searched exhaustively); short lines keep
+// the additive padding.
+template <int M>
+EVX_HD int zline_idx(int i) {
+  return M >= 128 ? (i ^ ((i >> 3) & 15) ^ ((i >> 4) & 3)) : i + (i >> 3);
+}
+template <int M>
+constexpr int zline_len() { return M >= 128 ? M + 16 : smem_padded_len(M + 1); }
+
 enum : int { PASS_FWD = 0, PASS_INV = 1, PASS_XMID = 2 };
 
 // ------------------------------------------------------------------------------------
@@ -86,13 +98,12 @@ struct StridedPass {
     const FilterParams& f = p.filt;
     const float k1 = wavenumber(signed_freq(r.kother, f.n1), f.inv_len1);
     const float k2 = wavenumber(r.kz, f.inv_len2);
-    const float k1sq = fmul_rn(k1, k1), k2sq = fmul_rn(k2, k2);
+    const float k12 = k1 * k1 + k2 * k2;
+    const float s0 = 6.283185307179586f * f.inv_len0;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float k0 = wavenumber(signed_freq(r.t + e * T, f.n0), f.inv_len0);
-      // reference order: (kx^2 + ky^2) + kz^2; this pass runs along x
-      const float ksq = fadd_rn(fadd_rn(fmul_rn(k0, k0), k1sq), k2sq);
-      const float w = imex_prefactor(ksq, f) * f.scale;
+      const float k0 = s0 * (float)signed_freq(r.t + e * T, f.n0);
+      const float w = imex_prefactor_fast(k0 * k0 + k12, f) * f.scale;
       r.v[e] = cscale(r.v[e], w);
     }
   }
@@ -150,11 +161,12 @@ struct ZPass {
   static constexpr int NTHREADS = T * NL;
   static constexpr int S = num_stages(M);
   static constexpr int NPHASES = S + 1;
-  static constexpr int LP = smem_padded_len(M + 1);
+  static constexpr int LP = zline_len<M>();
   static constexpr size_t SMEM_BYTES = 2 * (size_t)LP * NL * sizeof(cf);
 
   struct Regs {
     cf v[8];
+    cf u[INVERSE ? 8 : 1];   // ZInv: the u values added at the end, fetched up front
     int t, l;
     bool valid;
     long long row;
@@ -171,11 +183,11 @@ struct ZPass {
 
   EVX_HD static void write_stage(Regs& r, cf* b, int s) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) b[smem_pad(line_stage_out_index<M>(s, r.t, e))] = r.v[e];
+    for (int e = 0; e < 8; ++e) b[zline_idx<M>(line_stage_out_index<M>(s, r.t, e))] = r.v[e];
   }
   EVX_HD static void read_natural(Regs& r, const cf* b) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) r.v[e] = b[smem_pad(r.t + e * T)];
+    for (int e = 0; e < 8; ++e) r.v[e] = b[zline_idx<M>(r.t + e * T)];
   }
 
   // X[k] from Z[k], Z[M-k]  (forward untangle)
@@ -213,12 +225,12 @@ struct ZPass {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int kk = r.t + e * T;
-          const cf zk = z[smem_pad(kk)];
-          const cf zmk = z[smem_pad(kk == 0 ? 0 : M - kk)];
+          const cf zk = z[zline_idx<M>(kk)];
+          const cf zmk = z[zline_idx<M>(kk == 0 ? 0 : M - kk)];
           out[kk] = untangle_fwd(zk, zmk, p.twr[kk]);
         }
         if (r.t == 0) {
-          const cf z0 = z[smem_pad(0)];
+          const cf z0 = z[zline_idx<M>(0)];
           out[M] = cf{z0.x - z0.y, 0.f};
         }
       }
@@ -229,9 +241,17 @@ struct ZPass {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int kk = r.t + e * T;
-          x[smem_pad(kk)] = r.valid ? in[kk] : cf{0.f, 0.f};
+          x[zline_idx<M>(kk)] = r.valid ? in[kk] : cf{0.f, 0.f};
         }
-        if (r.t == 0) x[smem_pad(M)] = r.valid ? in[M] : cf{0.f, 0.f};
+        if (r.t == 0) x[zline_idx<M>(M)] = r.valid ? in[M] : cf{0.f, 0.f};
+        if (p.real_in && r.valid) {
+          const cf* u = reinterpret_cast<const cf*>(p.real_in + r.row * p.nz);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r.u[e] = u[r.t + e * T];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r.u[e] = cf{0.f, 0.f};
+        }
       } else {
         const int s = k - 1;
         if (s == 0) {
@@ -239,7 +259,7 @@ struct ZPass {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int kk = r.t + e * T;
-            r.v[e] = untangle_inv(x[smem_pad(kk)], x[smem_pad(M - kk)], p.twr[kk]);
+            r.v[e] = untangle_inv(x[zline_idx<M>(kk)], x[zline_idx<M>(M - kk)], p.twr[kk]);
           }
         } else {
           read_natural(r, buf(smem, (s - 1) & 1, r.l));
@@ -249,12 +269,8 @@ struct ZPass {
           write_stage(r, buf(smem, s & 1, r.l), s);
         } else if (r.valid) {
           cf* out = reinterpret_cast<cf*>(p.real_out + r.row * p.nz);
-          const cf* u = p.real_in ? reinterpret_cast<const cf*>(p.real_in + r.row * p.nz) : nullptr;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int m = r.t + e * T;
-            out[m] = u ? cadd(r.v[e], u[m]) : r.v[e];
-          }
+          for (int e = 0; e < 8; ++e) out[r.t + e * T] = cadd(r.v[e], r.u[e]);
         }
       }
     }

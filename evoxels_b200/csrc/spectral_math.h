@@ -3,7 +3,8 @@
 //   freq = float(idx) * float(1/(n*d))          torch.fft.fftfreq / rfftfreq
 //   k    = float(2*pi) * freq                   evoxels/voxelgrid.py:84-90
 //   k2   = (kx*kx + ky*ky) + kz*kz              evoxels/voxelgrid.py:110-114
-//   P    = dt / (1 + dt * (coef * k2^power))    problem_definition.py:303, timesteppers.py:77
+//   P    = (1 / (1 + dt * (coef * k2^power))) * dt   problem_definition.py:303, timesteppers.py:77
+//          (torch evaluates `scalar / tensor` as tensor.reciprocal() * scalar)
 // The reference keeps all of this in float32 even for float64 fields.
 // On the device the *_rn intrinsics keep nvcc from contracting mul+add into fma, so P is
 // bit-identical to the reference's stored prefactor array.
@@ -23,11 +24,11 @@ struct FilterParams {
 #if defined(__CUDA_ARCH__)
 EVX_HD float fmul_rn(float a, float b) { return __fmul_rn(a, b); }
 EVX_HD float fadd_rn(float a, float b) { return __fadd_rn(a, b); }
-EVX_HD float fdiv_rn(float a, float b) { return __fdiv_rn(a, b); }
+EVX_HD float frcp_rn(float a) { return __frcp_rn(a); }
 #else
 EVX_HD float fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 EVX_HD float fadd_rn(float a, float b) { volatile float r = a + b; return r; }
-EVX_HD float fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+EVX_HD float frcp_rn(float a) { volatile float r = 1.0f / a; return r; }
 #endif
 
 EVX_HD float wavenumber(int idx, float inv_len) {
@@ -35,10 +36,23 @@ EVX_HD float wavenumber(int idx, float inv_len) {
 }
 EVX_HD int signed_freq(int i, int n) { return i < (n + 1) / 2 ? i : i - n; }
 
+// Same prefactor with the hardware reciprocal approximation (<= 1 ulp off the IEEE result):
+// used inside the native x pass, where the filter sits between two FFTs in an issue-bound
+// kernel.  The stand-alone filter kernel keeps the bit-exact sequence.
+EVX_HD float imex_prefactor_fast(float k2, const FilterParams& f) {
+  const float kp = f.power == 2 ? k2 * k2 : k2;
+  const float den = 1.0f + f.dt * (f.coef * kp);
+#if defined(__CUDA_ARCH__)
+  return __fdividef(f.dt, den);
+#else
+  return f.dt / den;
+#endif
+}
+
 EVX_HD float imex_prefactor(float k2, const FilterParams& f) {
   const float kp = f.power == 2 ? fmul_rn(k2, k2) : k2;
   const float den = fadd_rn(1.0f, fmul_rn(f.dt, fmul_rn(f.coef, kp)));
-  return fdiv_rn(f.dt, den);
+  return fmul_rn(frcp_rn(den), f.dt);
 }
 
 inline FilterParams make_filter(const int n[3], const double len_h[3], double dt, double coef,

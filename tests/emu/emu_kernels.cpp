@@ -206,6 +206,7 @@ static int dispatch_z(int M, const ZParams& p) {
     case 128: run_z<128, 4, INV>(p); return 0;
     case 256: run_z<256, 8, INV>(p); return 0;
     case 512: run_z<512, 2, INV>(p); return 0;
+    case 1024: run_z<1024, 2, INV>(p); return 0;
     default: return -1;
   }
 }
