@@ -170,7 +170,6 @@ def test_native_fft_pipeline(emu, shape):
     rc = emu.emu_native_apply(_p(u), _p(r), None, _p(spec), nx, ny, nz, h, d(0.1), d(1.5), 2)
     assert rc == P
     got = spec[:, :, :M + 1, 0] + 1j * spec[:, :, :M + 1, 1]
-    assert rel_l2(np.abs(got - np.fft.rfftn(r.astype(np.float64))), 0 * got.real + 1) / np.sqrt(got.size) < 1e-3
     assert np.linalg.norm(got - np.fft.rfftn(r.astype(np.float64))) / np.linalg.norm(got) < 5e-7
     out = np.zeros(shape, np.float32)
     assert emu.emu_native_apply(_p(u), _p(r), _p(out), None, nx, ny, nz, h, d(0.1), d(1.5), 2) == 0
