@@ -52,6 +52,12 @@ SIGNATURES = {
     "evx_imex_apply_f32": _APPLY_ARGS, "evx_imex_apply_f64": _APPLY_ARGS,
     "evx_ch_imex_step_f32": _STEP_ARGS, "evx_ch_imex_step_f64": _STEP_ARGS,
     "evx_spectral_filter_c64": _FILTER_ARGS, "evx_spectral_filter_c128": _FILTER_ARGS,
+    "evx_dist_plan_create": [ctypes.POINTER(_c_void_p), _c_int, _c_int, _c_int, _c_int, _c_int],
+    "evx_dist_plan_destroy": [_c_void_p],
+    "evx_dist_plan_sizes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t), _iptr],
+    "evx_dist_forward_f32": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
+    "evx_dist_middle_f32": [_c_void_p, _c_void_p, _dptr, _c_double, _c_double, _c_int, _c_void_p],
+    "evx_dist_backward_f32": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
 }
 _RESTYPES = {"evx_strerror": ctypes.c_char_p, "evx_launch_count": ctypes.c_ulonglong}
 
@@ -261,6 +267,65 @@ class ImexPlan:
     def close(self):
         if self._handle is not None and _lib is not None:
             _lib.evx_imex_plan_destroy(self._handle)
+        self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DistPlan:
+    """x-slab distributed spectral stage of one rank (evx_dist_plan_* in the header)."""
+
+    def __init__(self, global_shape, world, rank, device):
+        self._handle = None
+        lib = load_library()
+        self.shape = tuple(int(n) for n in global_shape)
+        self.world, self.rank = int(world), int(rank)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("evoxels_b200 has no CPU path: DistPlan needs a CUDA device")
+        handle = _c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.evx_dist_plan_create(ctypes.byref(handle), *self.shape, self.world, self.rank),
+                  "evx_dist_plan_create")
+            self._handle = handle
+            nbytes, pitch = ctypes.c_size_t(), ctypes.c_int()
+            check(lib.evx_dist_plan_sizes(handle, ctypes.byref(nbytes), ctypes.byref(pitch)),
+                  "evx_dist_plan_sizes")
+        self.pitch = int(pitch.value)
+        nx, ny, _ = self.shape
+        self.block_shape = (self.world, nx // self.world, ny // self.world, self.pitch)
+        assert nbytes.value == 8 * self.world * self.block_shape[1] * self.block_shape[2] * self.pitch
+
+    def new_buffer(self):
+        return torch.empty(self.block_shape, dtype=torch.complex64, device=self.device)
+
+    def forward(self, r_local, spec, send):
+        require_cuda(r_local, spec, send)
+        with torch.cuda.device(self.device):
+            check(load_library().evx_dist_forward_f32(self._handle, _ptr(_field3(r_local)), _ptr(spec),
+                                                      _ptr(send), _stream(r_local)), "evx_dist_forward")
+
+    def middle(self, recv, spacing, dt, coef, power):
+        require_cuda(recv)
+        with torch.cuda.device(self.device):
+            check(load_library().evx_dist_middle_f32(self._handle, _ptr(recv), _h3(spacing), float(dt),
+                                                     float(coef), int(power), _stream(recv)),
+                  "evx_dist_middle")
+
+    def backward(self, recv, spec, u_local, out_local):
+        require_cuda(recv, spec, u_local, out_local)
+        with torch.cuda.device(self.device):
+            check(load_library().evx_dist_backward_f32(self._handle, _ptr(recv), _ptr(spec),
+                                                       _ptr(u_local), _ptr(_field3(out_local)),
+                                                       _stream(recv)), "evx_dist_backward")
+
+    def close(self):
+        if self._handle is not None and _lib is not None:
+            _lib.evx_dist_plan_destroy(self._handle)
         self._handle = None
 
     def __del__(self):

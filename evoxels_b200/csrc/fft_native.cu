@@ -125,13 +125,15 @@ int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, v
   if (rc) return rc;
 
   StridedParams yp;
-  yp.data = spec; yp.tw = twy; yp.line_stride = P; yp.plane_stride = (long long)ny * P;
+  yp.in = spec; yp.out = spec; yp.tw = twy;
+  yp.src = yp.dst = plain_io(P, (long long)ny * P, ny);
   yp.P = P; yp.ncols_valid = M + 1; yp.ncols_total = (long long)nx * P;
+  yp.kother_offset = 0;
   yp.filt = FilterParams{};
   if ((rc = launch_strided<PASS_FWD>(ny, yp, st))) return rc;
 
   StridedParams xp = yp;
-  xp.tw = twx; xp.line_stride = (long long)ny * P; xp.plane_stride = P;
+  xp.tw = twx; xp.src = xp.dst = plain_io((long long)ny * P, P, nx);
   xp.ncols_total = (long long)ny * P;
   const int n[3] = {nx, ny, nz};
   xp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
@@ -154,4 +156,125 @@ int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* ou
   return native_apply(p, u, rhs, out, workspace, h, dt, 2.0 * eps * D * A, 2, st);
 }
 
+// ------------------------------------------------------------------------------------
+// x-slab distributed variant: the y passes write / read the all-to-all block layout
+// ------------------------------------------------------------------------------------
+struct DistPlan {
+  int nx, ny, nz, world, rank, nxl, nyl, P, M;
+  void* twiddles;
+};
+
+static const cf* tw_x(const DistPlan* p) { return (const cf*)p->twiddles; }
+static const cf* tw_y(const DistPlan* p) { return tw_x(p) + p->nx; }
+static const cf* tw_z(const DistPlan* p) { return tw_y(p) + p->ny; }
+static const cf* tw_r(const DistPlan* p) { return tw_z(p) + p->M; }
+
+int dist_plan_create(DistPlan** out, int nx, int ny, int nz, int world, int rank) {
+  if (!out || world < 1 || rank < 0 || rank >= world) return EVX_ERR_ARG;
+  if (!native_fft_supported(nx, ny, nz) || !is_pow2(world) || nx % world || ny % world)
+    return EVX_ERR_UNSUPPORTED;
+  DistPlan* p = new DistPlan();
+  p->nx = nx; p->ny = ny; p->nz = nz; p->world = world; p->rank = rank;
+  p->nxl = nx / world; p->nyl = ny / world; p->M = nz / 2;
+  p->P = ((p->M + 1 + kPitchAlign - 1) / kPitchAlign) * kPitchAlign;
+  const size_t total = (size_t)nx + ny + p->M + (p->M + 1);
+  std::vector<cf> host(total);
+  fill_roots(host, 0, nx, nx);
+  fill_roots(host, nx, ny, ny);
+  fill_roots(host, (size_t)nx + ny, p->M, p->M);
+  fill_roots(host, (size_t)nx + ny + p->M, nz, p->M + 1);
+  cudaError_t e = cudaMalloc(&p->twiddles, total * sizeof(cf));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(p->twiddles, host.data(), total * sizeof(cf), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { delete p; return (int)e; }
+  *out = p;
+  return EVX_OK;
+}
+
+// block layout [world][nxl][nyl][P] seen from local group xl: chunks nxl*nyl*P apart
+static StridedIO block_io(const DistPlan* p) {
+  return StridedIO{p->P, (long long)p->nyl * p->P, (long long)p->nxl * p->nyl * p->P, p->nyl};
+}
+
+int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, cudaStream_t st) {
+  ZParams zp;
+  zp.real_in = r_local; zp.real_out = nullptr; zp.spec = spec; zp.tw = tw_z(p); zp.twr = tw_r(p);
+  zp.rows = (long long)p->nxl * p->ny; zp.nz = p->nz; zp.P = p->P;
+  int rc = launch_z<false>(p->M, zp, st);
+  if (rc) return rc;
+  StridedParams yp;
+  yp.in = spec; yp.out = send; yp.tw = tw_y(p);
+  yp.src = plain_io(p->P, (long long)p->ny * p->P, p->ny);
+  yp.dst = block_io(p);
+  yp.P = p->P; yp.ncols_valid = p->M + 1; yp.ncols_total = (long long)p->nxl * p->P;
+  yp.kother_offset = 0; yp.filt = FilterParams{};
+  return launch_strided<PASS_FWD>(p->ny, yp, st);
+}
+
+int dist_middle(DistPlan* p, cf* recv, const double* h, double dt, double coef, int power,
+                cudaStream_t st) {
+  StridedParams xp;
+  xp.in = recv; xp.out = recv; xp.tw = tw_x(p);
+  xp.src = xp.dst = plain_io((long long)p->nyl * p->P, p->P, p->nx);
+  xp.P = p->P; xp.ncols_valid = p->M + 1; xp.ncols_total = (long long)p->nyl * p->P;
+  xp.kother_offset = p->rank * p->nyl;
+  const int n[3] = {p->nx, p->ny, p->nz};
+  xp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)p->nx * p->ny * p->nz));
+  return launch_strided<PASS_XMID>(p->nx, xp, st);
+}
+
+int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, float* out_local,
+                  cudaStream_t st) {
+  StridedParams yp;
+  yp.in = recv; yp.out = spec; yp.tw = tw_y(p);
+  yp.src = block_io(p);
+  yp.dst = plain_io(p->P, (long long)p->ny * p->P, p->ny);
+  yp.P = p->P; yp.ncols_valid = p->M + 1; yp.ncols_total = (long long)p->nxl * p->P;
+  yp.kother_offset = 0; yp.filt = FilterParams{};
+  int rc = launch_strided<PASS_INV>(p->ny, yp, st);
+  if (rc) return rc;
+  ZParams zp;
+  zp.real_in = u_local; zp.real_out = out_local; zp.spec = spec; zp.tw = tw_z(p); zp.twr = tw_r(p);
+  zp.rows = (long long)p->nxl * p->ny; zp.nz = p->nz; zp.P = p->P;
+  return launch_z<true>(p->M, zp, st);
+}
+
 }  // namespace evx
+
+using namespace evx;
+
+extern "C" {
+
+int evx_dist_plan_create(evx_dist_plan** plan, int nx, int ny, int nz, int world, int rank) {
+  return dist_plan_create((DistPlan**)plan, nx, ny, nz, world, rank);
+}
+int evx_dist_plan_destroy(evx_dist_plan* plan) {
+  DistPlan* p = (DistPlan*)plan;
+  if (p) { if (p->twiddles) cudaFree(p->twiddles); delete p; }
+  return EVX_OK;
+}
+int evx_dist_plan_sizes(const evx_dist_plan* plan, size_t* spec_bytes, int* pitch) {
+  const DistPlan* p = (const DistPlan*)plan;
+  if (!p || !spec_bytes) return EVX_ERR_ARG;
+  *spec_bytes = (size_t)p->nxl * p->ny * p->P * sizeof(cf);
+  if (pitch) *pitch = p->P;
+  return EVX_OK;
+}
+int evx_dist_forward_f32(evx_dist_plan* plan, const float* r_local, void* spec, void* send,
+                         void* stream) {
+  if (!plan || !r_local || !spec || !send || spec == send) return EVX_ERR_ARG;
+  return dist_forward((DistPlan*)plan, r_local, (cf*)spec, (cf*)send, (cudaStream_t)stream);
+}
+int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double dt, double coef,
+                        int power, void* stream) {
+  if (!plan || !recv || !h || (power != 1 && power != 2)) return EVX_ERR_ARG;
+  return dist_middle((DistPlan*)plan, (cf*)recv, h, dt, coef, power, (cudaStream_t)stream);
+}
+int evx_dist_backward_f32(evx_dist_plan* plan, const void* recv, void* spec, const float* u_local,
+                          float* out_local, void* stream) {
+  if (!plan || !recv || !spec || !out_local || recv == spec) return EVX_ERR_ARG;
+  return dist_backward((DistPlan*)plan, (const cf*)recv, (cf*)spec, u_local, out_local,
+                       (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -33,16 +33,39 @@ enum : int { PASS_FWD = 0, PASS_INV = 1, PASS_XMID = 2 };
 // ------------------------------------------------------------------------------------
 // strided passes (y and x)
 // ------------------------------------------------------------------------------------
+// Addressing of one side (input or output) of a strided pass.  Column c = grp * P + kz;
+// point idx of its line lives at
+//   grp * plane_stride + kz + (idx / split) * split_stride + (idx % split) * line_stride.
+// split == L (split_stride unused) is the plain layout; split = L / W writes / reads the
+// line in W chunks that are split_stride apart - the block layout of the slab<->pencil
+// all-to-all, so that no separate pack / unpack pass exists.
+struct StridedIO {
+  long long line_stride;
+  long long plane_stride;
+  long long split_stride;
+  int split;
+};
+
 struct StridedParams {
-  cf* data;
+  const cf* in;
+  cf* out;                 // may equal `in` when both sides use the same addressing
+  StridedIO src, dst;
   const cf* tw;            // W_L table
-  long long line_stride;   // elements between consecutive points of a line
-  long long plane_stride;  // elements between column groups: base(c) = (c / P) * plane_stride + c % P
   int P;                   // pitch (columns per group)
   int ncols_valid;         // columns kz < ncols_valid carry data (nz/2+1)
   long long ncols_total;   // number of columns incl. pitch padding (groups * P)
+  int kother_offset;       // XMID: global index of the first local column group (y-pencils)
   FilterParams filt;       // XMID only; n0 = L (this axis), n1 = the other strided axis, n2 = nz
 };
+
+inline StridedIO plain_io(long long line_stride, long long plane_stride, int L) {
+  return StridedIO{line_stride, plane_stride, 0, L};
+}
+
+EVX_HD long long strided_offset(const StridedIO& io, long long grp, int kz, int idx) {
+  const int hi = idx / io.split, lo = idx - hi * io.split;
+  return grp * io.plane_stride + kz + hi * io.split_stride + lo * io.line_stride;
+}
 
 template <int L, int KZ, int MODE>
 struct StridedPass {
@@ -57,7 +80,7 @@ struct StridedPass {
     cf v[8];
     int t, cl;
     bool valid;
-    long long base;
+    long long grp;
     int kz, kother;
   };
 
@@ -69,9 +92,9 @@ struct StridedPass {
     const long long c = block * KZ + r.cl;
     const long long grp = c / p.P;
     r.kz = (int)(c - grp * p.P);
-    r.kother = (int)grp;
+    r.kother = (int)grp + p.kother_offset;
+    r.grp = grp;
     r.valid = c < p.ncols_total && r.kz < p.ncols_valid;
-    r.base = grp * p.plane_stride + r.kz;
   }
 
   template <int DIR>
@@ -87,12 +110,12 @@ struct StridedPass {
   EVX_HD static void load_global(Regs& r, const StridedParams& p) {
 #pragma unroll
     for (int e = 0; e < 8; ++e)
-      r.v[e] = r.valid ? p.data[r.base + (long long)(r.t + e * T) * p.line_stride] : cf{0.f, 0.f};
+      r.v[e] = r.valid ? p.in[strided_offset(p.src, r.grp, r.kz, r.t + e * T)] : cf{0.f, 0.f};
   }
   EVX_HD static void store_global(Regs& r, const StridedParams& p) {
     if (!r.valid) return;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) p.data[r.base + (long long)(r.t + e * T) * p.line_stride] = r.v[e];
+    for (int e = 0; e < 8; ++e) p.out[strided_offset(p.dst, r.grp, r.kz, r.t + e * T)] = r.v[e];
   }
   EVX_HD static void apply_filter(Regs& r, const StridedParams& p) {
     const FilterParams& f = p.filt;

@@ -1,0 +1,209 @@
+"""x-slab multi-GPU execution of the hot path (one process per GPU, torch.distributed).
+
+The reference is single-device (no NCCL/MPI code exists upstream); this
+module is the multi-GPU form of the same step.  Rank r owns the planes
+x in [r*nx/W, (r+1)*nx/W) of every field (dim 0 of the [nx,ny,nz] tensor).
+
+* Stencil halos: 2 raw planes per side for the fused Cahn-Hilliard rhs, 1 for Allen-Cahn,
+  exchanged point-to-point with the ring neighbours (NCCL send/recv = NVLink P2P on one
+  box) and handed to the kernels as separate `halo_lo` / `halo_hi` buffers.
+* Spectral stage: local z and y passes, slab->pencil all-to-all, fused x pass, pencil->slab
+  all-to-all, local inverse y and z passes.  The y-pass kernels write / read the
+  all-to-all block layout directly (no pack / unpack kernels).
+
+All collective calls go through the small `Comm` adapter so that the orchestration (who
+sends which planes where, global wavenumber offsets, block layouts) can be tested on CPU
+with the gloo backend and a stand-in for the kernels (tests/test_distributed_cpu.py); the
+shipped `CudaOps` has no CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+from . import _native
+from .problem_definition import normalize_bc
+
+
+@dataclass
+class Slab:
+    """Geometry of one rank's x-slab."""
+    global_shape: tuple
+    world: int
+    rank: int
+
+    def __post_init__(self):
+        nx, ny, nz = self.global_shape
+        if nx % self.world or ny % self.world:
+            raise ValueError(f"x-slab decomposition needs world | nx and world | ny, got "
+                             f"{self.global_shape} on {self.world} ranks")
+        self.nxl = nx // self.world
+        self.nyl = ny // self.world
+        self.x0 = self.rank * self.nxl
+        self.local_shape = (self.nxl, ny, nz)
+
+    def take(self, global_field):
+        """Local part of a replicated [.., nx, ny, nz] tensor / array."""
+        return global_field[..., self.x0:self.x0 + self.nxl, :, :]
+
+
+class Comm:
+    """Thin adapter over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.backend = dist.get_backend(group) if dist.is_initialized() else "none"
+
+    def exchange_halos(self, u_local, width, periodic):
+        """Ring exchange of `width` boundary planes of a [nxl,ny,nz] tensor.  Returns
+        (halo_lo, halo_hi): the neighbour planes below / above the slab, or None at a
+        non-periodic domain end (or everywhere when world == 1 and the axis is periodic,
+        in which case the kernels wrap by index arithmetic)."""
+        W, r = self.world, self.rank
+        if W == 1:
+            return None, None
+        if u_local.shape[0] < width:
+            raise ValueError("slab thinner than the halo width")
+        has_lo = periodic or r > 0
+        has_hi = periodic or r < W - 1
+        lo, hi = (r - 1) % W, (r + 1) % W
+        first = u_local[:width].contiguous()
+        last = u_local[-width:].contiguous()
+        halo_lo = torch.empty_like(first) if has_lo else None
+        halo_hi = torch.empty_like(last) if has_hi else None
+        ops = []
+        # order matters when lo == hi (W == 2): each side posts "first planes" before "last
+        # planes", so the receiver takes the upper neighbour's first planes first
+        if has_lo:
+            ops.append(dist.P2POp(dist.isend, first, lo, self.group, tag=0))
+        if has_hi:
+            ops.append(dist.P2POp(dist.isend, last, hi, self.group, tag=1))
+        if has_hi:
+            ops.append(dist.P2POp(dist.irecv, halo_hi, hi, self.group, tag=0))
+        if has_lo:
+            ops.append(dist.P2POp(dist.irecv, halo_lo, lo, self.group, tag=1))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        return halo_lo, halo_hi
+
+    def all_to_all_blocks(self, send, recv):
+        """Block j of `send` ([W, ...]) goes to rank j; block i of `recv` comes from rank i."""
+        if self.world == 1:
+            recv.copy_(send)
+            return
+        if self.backend == "nccl":
+            # complex64 is not a NCCL dtype: exchange the float32 view
+            s = torch.view_as_real(send) if send.is_complex() else send
+            r = torch.view_as_real(recv) if recv.is_complex() else recv
+            dist.all_to_all_single(r, s, group=self.group)
+            return
+        ops = []
+        for peer in range(self.world):
+            if peer == self.rank:
+                recv[peer].copy_(send[peer])
+                continue
+            ops.append(dist.P2POp(dist.isend, send[peer].contiguous(), peer, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv[peer], peer, self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return t
+
+
+class CudaOps:
+    """The kernels behind one rank of the distributed step."""
+
+    def __init__(self, slab: Slab, spacing, device, spectral=True):
+        self.slab, self.spacing, self.device = slab, tuple(spacing), torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("evoxels_b200 has no CPU path: CudaOps needs a CUDA device")
+        if spectral:
+            self.plan = _native.DistPlan(slab.global_shape, slab.world, slab.rank, device)
+            self.spec = self.plan.new_buffer()
+            self.buf_a = self.plan.new_buffer()
+            self.buf_b = self.plan.new_buffer()
+
+    def new_field(self):
+        return torch.empty(self.slab.local_shape, dtype=torch.float32, device=self.device)
+
+    def ch_rhs(self, u, out, eps, D, bc, halo_lo, halo_hi):
+        _native.ch_rhs(u, out, self.spacing, eps, D, bc, halo_lo=halo_lo, halo_hi=halo_hi)
+
+    def ac_stage(self, phi, out, params, bc, dt, halo_lo, halo_hi):
+        _native.ac_stage(phi, self.spacing, params["eps"], params["gab"], params["M"],
+                         params["force"], params["curvature"], bc, base=phi, y_out=out, alpha=dt,
+                         halo_lo=halo_lo, halo_hi=halo_hi)
+
+    def spectral_forward(self, r):
+        self.plan.forward(r, self.spec, self.buf_a)
+        return self.buf_a
+
+    def spectral_middle(self, buf, dt, coef, power):
+        self.plan.middle(buf, self.spacing, dt, coef, power)
+
+    def spectral_backward(self, buf, u, out):
+        self.plan.backward(buf, self.spec, u, out)
+
+    def exchange_buffers(self):
+        return self.buf_a, self.buf_b
+
+
+class DistributedCahnHilliardIMEX:
+    """CahnHilliard + PseudoSpectralIMEX (fully periodic) on an x-slab decomposition.
+    `step(u_local) -> u_local_new`; same arithmetic as the single-GPU step."""
+
+    def __init__(self, global_shape, spacing, dt, eps=3.0, D=1.0, A=0.25, group=None,
+                 device=None, ops=None):
+        self.comm = Comm(group)
+        self.slab = Slab(tuple(global_shape), self.comm.world, self.comm.rank)
+        self.spacing, self.dt, self.eps, self.D, self.A = tuple(spacing), dt, eps, D, A
+        self.bc = normalize_bc(("periodic",) * 3)
+        self.ops = ops if ops is not None else CudaOps(self.slab, spacing, device or "cuda")
+        self.rhs = self.ops.new_field()
+
+    def step(self, u_local):
+        ops, comm = self.ops, self.comm
+        u_local = u_local.contiguous()
+        halo_lo, halo_hi = comm.exchange_halos(u_local, 2, periodic=True)
+        ops.ch_rhs(u_local, self.rhs, self.eps, self.D, self.bc, halo_lo, halo_hi)
+        a, b = ops.exchange_buffers()
+        send = ops.spectral_forward(self.rhs)            # fills `a`
+        comm.all_to_all_blocks(send, b)
+        ops.spectral_middle(b, self.dt, 2.0 * self.eps * self.D * self.A, 2)
+        comm.all_to_all_blocks(b, a)
+        out = ops.new_field()
+        ops.spectral_backward(a, u_local, out)
+        return out
+
+    def total_mass(self, u_local):
+        s = u_local.double().sum().reshape(1)
+        return float(self.comm.all_reduce_sum(s).item())
+
+
+class DistributedAllenCahnEuler:
+    """TwoPhaseAllenCahn + ForwardEuler on an x-slab decomposition (1-plane halos)."""
+
+    def __init__(self, global_shape, spacing, dt, eps=2.0, gab=1.0, M=1.0, force=0.0,
+                 curvature=0.01, bc=("neumann",) * 3, group=None, device=None, ops=None):
+        self.comm = Comm(group)
+        self.slab = Slab(tuple(global_shape), self.comm.world, self.comm.rank)
+        self.dt = dt
+        self.params = dict(eps=eps, gab=gab, M=M, force=force, curvature=curvature)
+        self.bc = normalize_bc(bc)
+        self.ops = ops if ops is not None else CudaOps(self.slab, spacing, device or "cuda",
+                                                       spectral=False)
+
+    def step(self, phi_local):
+        phi_local = phi_local.contiguous()
+        periodic = self.bc[0][0] == "periodic"
+        halo_lo, halo_hi = self.comm.exchange_halos(phi_local, 1, periodic=periodic)
+        out = torch.empty_like(phi_local)
+        self.ops.ac_stage(phi_local, out, self.params, self.bc, self.dt, halo_lo, halo_hi)
+        return out

@@ -165,6 +165,30 @@ int evx_spectral_filter_c64(void* spec, int nx, int ny, int nz, const double* h,
 int evx_spectral_filter_c128(void* spec, int nx, int ny, int nz, const double* h, double dt,
                              double coef, int power, double scale, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * x-slab distributed spectral stage (one process per GPU; rank owns x in [rank*nx/W, ...))
+ *
+ * The reference has no distributed code; this is the multi-GPU form of
+ * PseudoSpectralIMEX.step (evoxels/timesteppers.py:85-89).  Power-of-two extents, W | nx, W | ny.
+ * Buffers (all complex64, `*spec_bytes` bytes each, from evx_dist_plan_sizes):
+ *   spec  [nx/W][ny][P]      local half spectrum (P = pitch, returned in *pitch)
+ *   send / recv  [W][nx/W][ny/W][P]   all-to-all block layout: block j of `send` goes to rank j,
+ *                block i of `recv` came from rank i, so `recv` is [nx][ny/W][P] (y-pencils).
+ * Per step:  forward(r_local) -> all-to-all -> middle (x fwd * P(k)/N * x inv) -> all-to-all
+ *            -> backward(u_local) = out_local.  The y passes read / write the block layout
+ * directly, so there is no pack / unpack kernel around the collective.
+ * ------------------------------------------------------------------------------- */
+typedef struct evx_dist_plan evx_dist_plan;
+int evx_dist_plan_create(evx_dist_plan** plan, int nx, int ny, int nz, int world, int rank);
+int evx_dist_plan_destroy(evx_dist_plan* plan);
+int evx_dist_plan_sizes(const evx_dist_plan* plan, size_t* spec_bytes, int* pitch);
+int evx_dist_forward_f32(evx_dist_plan* plan, const float* r_local, void* spec, void* send,
+                         void* stream);
+int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double dt, double coef,
+                        int power, void* stream);
+int evx_dist_backward_f32(evx_dist_plan* plan, const void* recv, void* spec, const float* u_local,
+                          float* out_local, void* stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long evx_launch_count(void);
 

@@ -1,0 +1,126 @@
+"""Worker for tests/test_distributed_cpu.py: runs the distributed orchestration of
+evoxels_b200.distributed on `world` CPU processes (gloo) with a torch-CPU stand-in for the
+kernels, and compares every rank's slab with the single-domain oracle.
+
+The stand-in (`OracleOps`) is TEST CODE: it reproduces what the CUDA kernels compute for
+one rank (rhs from slab + halo planes; z/y transforms into the all-to-all block layout; x
+transform + filter with the global ky offset; inverse) using the oracle's arithmetic, so
+that slab geometry, halo routing, block ordering and global index offsets are verified
+without a GPU.  The shipped CudaOps has no CPU path.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import evx_oracle as O  # noqa: E402
+from evoxels_b200.distributed import (DistributedAllenCahnEuler, DistributedCahnHilliardIMEX,  # noqa: E402
+                                      Slab)
+
+
+class OracleOps:
+    def __init__(self, slab, spacing, dt, coef_power):
+        self.slab, self.spacing = slab, tuple(spacing)
+        nx, ny, nz = slab.global_shape
+        self.nzh = nz // 2 + 1
+        shape = (slab.world, slab.nxl, slab.nyl, self.nzh)
+        self.a = torch.zeros(shape, dtype=torch.complex64)
+        self.b = torch.zeros(shape, dtype=torch.complex64)
+
+    def new_field(self):
+        return torch.empty(self.slab.local_shape, dtype=torch.float32)
+
+    @staticmethod
+    def _extended(u, lo, hi, width):
+        parts = ([lo] if lo is not None else []) + [u] + ([hi] if hi is not None else [])
+        return torch.cat(parts, 0), (width if lo is not None else 0), (width if hi is not None else 0)
+
+    def ch_rhs(self, u, out, eps, D, bc, halo_lo, halo_hi):
+        ext, a, b = self._extended(u, halo_lo, halo_hi, 2)
+        # x rule of `bc` applies only where no halo was supplied (domain ends); with halos on
+        # both sides any x rule is fine because the footprint (radius 2) stays inside `ext`
+        r = O.ch_rhs(ext[None], self.spacing, eps, D, bc)[0]
+        out.copy_(r[a:r.shape[0] - b])
+
+    def ac_stage(self, phi, out, params, bc, dt, halo_lo, halo_hi):
+        ext, a, b = self._extended(phi, halo_lo, halo_hi, 1)
+        kw = dict(params)
+        r = O.ac_rhs(ext[None], self.spacing, bc=bc, **kw)[0]
+        out.copy_(phi + dt * r[a:r.shape[0] - b])
+
+    def exchange_buffers(self):
+        return self.a, self.b
+
+    def spectral_forward(self, r):
+        s = torch.fft.fft(torch.fft.rfft(r, dim=2), dim=1)            # [nxl, ny, nzh]
+        nyl = self.slab.nyl
+        for j in range(self.slab.world):
+            self.a[j] = s[:, j * nyl:(j + 1) * nyl, :]
+        return self.a
+
+    def spectral_middle(self, buf, dt, coef, power):
+        nx, ny, nz = self.slab.global_shape
+        pencils = buf.reshape(nx, self.slab.nyl, self.nzh)
+        k2 = O.k_squared((nx, ny, nz), self.spacing)
+        pref = O.imex_prefactor(-coef * k2 ** power, dt)
+        y0 = self.slab.rank * self.slab.nyl
+        f = torch.fft.fft(pencils, dim=0) * pref[:, y0:y0 + self.slab.nyl, :]
+        buf.copy_(torch.fft.ifft(f, dim=0).reshape(buf.shape))
+
+    def spectral_backward(self, buf, u, out):
+        s = torch.cat([buf[j] for j in range(self.slab.world)], dim=1)   # [nxl, ny, nzh]
+        upd = torch.fft.irfft(torch.fft.ifft(s, dim=1), n=self.slab.global_shape[2], dim=2)
+        out.copy_(u + upd)
+
+
+def run(rank, world, port, shape):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    spacing = (1.0, 0.5, 2.0)
+    slab = Slab(shape, world, rank)
+    u = O.noise_field(shape, seed=3, lo=-0.1, amp=1.2)[0]
+
+    # Cahn-Hilliard IMEX, 3 steps
+    ops = OracleOps(slab, spacing, 0.1, (1.5, 2))
+    stepper = DistributedCahnHilliardIMEX(shape, spacing, 0.1, ops=ops)
+    orc = O.CHOracle(shape, spacing, 0.1)
+    v, w = u[None], slab.take(u).clone()
+    m0 = stepper.total_mass(w)
+    for _ in range(3):
+        v, w = orc.step(v), stepper.step(w)
+    ref = slab.take(v[0])
+    err = float((w - ref).norm() / ref.norm())
+    assert err < 2e-6, f"CH rank {rank}: {err}"
+    assert abs(stepper.total_mass(w) - m0) < 1e-3 * abs(m0) * 1e-3
+    assert abs(m0 - float(u.double().sum())) < 1e-6 * abs(m0)
+
+    # Allen-Cahn Euler with three BC layouts along x
+    for bc in (("neumann",) * 3, ("periodic",) * 3, (("dirichlet", (0.0, 1.0)), "neumann", "periodic")):
+        phi = O.noise_field(shape, seed=1, lo=0.0, amp=1.0)[0]
+        ac = DistributedAllenCahnEuler(shape, spacing, 0.05, bc=bc,
+                                       ops=OracleOps(slab, spacing, 0.05, (1.0, 1)))
+        aorc = O.ACOracle(shape, spacing, 0.05, bc=bc)
+        v, w = phi[None], slab.take(phi).clone()
+        for _ in range(2):
+            v, w = aorc.step(v), ac.step(w)
+        ref = slab.take(v[0])
+        err = float((w - ref).norm() / ref.norm())
+        assert err < 1e-6, f"AC {bc} rank {rank}: {err}"
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    world = int(sys.argv[1])
+    port = int(sys.argv[2])
+    shape = tuple(int(x) for x in sys.argv[3].split("x"))
+    mp.spawn(run, args=(world, port, shape), nprocs=world, join=True)
+    print("OK")

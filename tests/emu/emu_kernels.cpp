@@ -227,13 +227,14 @@ int emu_native_apply(const float* u, const float* r, float* out, float* spec_out
   zp.twr = twr.data(); zp.rows = (long long)nx * ny; zp.nz = nz; zp.P = P;
   if (dispatch_z<false>(M, zp)) return -1;
   StridedParams sp;
-  sp.data = spec.data(); sp.P = P; sp.ncols_valid = M + 1;
+  sp.in = spec.data(); sp.out = spec.data(); sp.P = P; sp.ncols_valid = M + 1; sp.kother_offset = 0;
+  const StridedIO yio = plain_io(P, (long long)ny * P, ny), xio = plain_io((long long)ny * P, P, nx);
   // y pass: columns (x, kz), line stride P, group stride ny*P
-  sp.tw = twy.data(); sp.line_stride = P; sp.plane_stride = (long long)ny * P;
+  sp.tw = twy.data(); sp.src = sp.dst = yio;
   sp.ncols_total = (long long)nx * P;
   if (dispatch_strided<KZ, PASS_FWD>(ny, sp)) return -2;
   if (spec_out) {   // forward-only check: finish x forward and return the spectrum
-    sp.tw = twx.data(); sp.line_stride = (long long)ny * P; sp.plane_stride = P;
+    sp.tw = twx.data(); sp.src = sp.dst = xio;
     sp.ncols_total = (long long)ny * P;
     if (dispatch_strided<KZ, PASS_FWD>(nx, sp)) return -3;
     for (size_t i = 0; i < spec.size(); ++i) { spec_out[2 * i] = spec[i].x; spec_out[2 * i + 1] = spec[i].y; }
@@ -242,10 +243,10 @@ int emu_native_apply(const float* u, const float* r, float* out, float* spec_out
   // x pass: forward, filter, inverse
   const int n[3] = {nx, ny, nz};
   sp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
-  sp.tw = twx.data(); sp.line_stride = (long long)ny * P; sp.plane_stride = P;
+  sp.tw = twx.data(); sp.src = sp.dst = xio;
   sp.ncols_total = (long long)ny * P;
   if (dispatch_strided<KZ, PASS_XMID>(nx, sp)) return -3;
-  sp.tw = twy.data(); sp.line_stride = P; sp.plane_stride = (long long)ny * P;
+  sp.tw = twy.data(); sp.src = sp.dst = yio;
   sp.ncols_total = (long long)nx * P;
   if (dispatch_strided<KZ, PASS_INV>(ny, sp)) return -4;
   zp.real_in = u; zp.real_out = out;
