@@ -52,6 +52,12 @@ SIGNATURES = {
     "evx_imex_apply_f32": _APPLY_ARGS, "evx_imex_apply_f64": _APPLY_ARGS,
     "evx_ch_imex_step_f32": _STEP_ARGS, "evx_ch_imex_step_f64": _STEP_ARGS,
     "evx_spectral_filter_c64": _FILTER_ARGS, "evx_spectral_filter_c128": _FILTER_ARGS,
+    "evx_ch_mu_f32": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
+    "evx_ch_mu_f64": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
+    "evx_ch_adjoint_flux_f32": [_c_void_p] * 5 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
+    "evx_ch_adjoint_flux_f64": [_c_void_p] * 5 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
+    "evx_ch_adjoint_combine_f32": [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
+    "evx_ch_adjoint_combine_f64": [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
     "evx_dist_plan_create": [ctypes.POINTER(_c_void_p), _c_int, _c_int, _c_int, _c_int, _c_int],
     "evx_dist_plan_destroy": [_c_void_p],
     "evx_dist_plan_sizes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t), _iptr],
@@ -274,6 +280,29 @@ class ImexPlan:
             self.close()
         except Exception:
             pass
+
+
+def ch_rhs_vjp(u, w, spacing, eps, D, lam_in=None):
+    """Vector-Jacobian product of the periodic CH rhs at state `u` with cotangent `w`.
+    Returns (dL/du [+ lam_in], dL/deps as a 0-dim float64 CUDA tensor).  Three kernels."""
+    require_cuda(u, w, lam_in)
+    lib = load_library()
+    sfx = _suffix(u)
+    nx, ny, nz = _field3(u).shape
+    mu, z, m, lam = (torch.empty_like(u) for _ in range(4))
+    deps = torch.zeros((), dtype=torch.float64, device=u.device)
+    h = _h3(spacing)
+    with torch.cuda.device(u.device):
+        st = _stream(u)
+        check(getattr(lib, "evx_ch_mu_" + sfx)(_ptr(u), _ptr(mu), nx, ny, nz, h, float(eps), st),
+              "evx_ch_mu")
+        check(getattr(lib, "evx_ch_adjoint_flux_" + sfx)(_ptr(u), _ptr(mu), _ptr(_field3(w)), _ptr(z),
+                                                         _ptr(m), nx, ny, nz, h, float(D), st),
+              "evx_ch_adjoint_flux")
+        check(getattr(lib, "evx_ch_adjoint_combine_" + sfx)(_ptr(u), _ptr(z), _ptr(m), _ptr(lam_in),
+                                                            _ptr(lam), _ptr(deps), nx, ny, nz, h,
+                                                            float(eps), st), "evx_ch_adjoint_combine")
+    return lam, deps
 
 
 class DistPlan:

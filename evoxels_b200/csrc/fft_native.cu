@@ -193,7 +193,7 @@ int dist_plan_create(DistPlan** out, int nx, int ny, int nz, int world, int rank
 
 // block layout [world][nxl][nyl][P] seen from local group xl: chunks nxl*nyl*P apart
 static StridedIO block_io(const DistPlan* p) {
-  return StridedIO{p->P, (long long)p->nyl * p->P, (long long)p->nxl * p->nyl * p->P, p->nyl};
+  return StridedIO{p->P, (long long)p->nyl * p->P, (long long)p->nxl * p->nyl * p->P, ilog2(p->nyl)};
 }
 
 int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, cudaStream_t st) {

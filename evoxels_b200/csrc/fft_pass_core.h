@@ -35,7 +35,8 @@ enum : int { PASS_FWD = 0, PASS_INV = 1, PASS_XMID = 2 };
 // ------------------------------------------------------------------------------------
 // Addressing of one side (input or output) of a strided pass.  Column c = grp * P + kz;
 // point idx of its line lives at
-//   grp * plane_stride + kz + (idx / split) * split_stride + (idx % split) * line_stride.
+//   grp * plane_stride + kz + (idx / split) * split_stride + (idx % split) * line_stride,
+// split = 2^split_shift.
 // split == L (split_stride unused) is the plain layout; split = L / W writes / reads the
 // line in W chunks that are split_stride apart - the block layout of the slab<->pencil
 // all-to-all, so that no separate pack / unpack pass exists.
@@ -43,7 +44,7 @@ struct StridedIO {
   long long line_stride;
   long long plane_stride;
   long long split_stride;
-  int split;
+  int split_shift;         // split = 1 << split_shift (power of two)
 };
 
 struct StridedParams {
@@ -59,11 +60,11 @@ struct StridedParams {
 };
 
 inline StridedIO plain_io(long long line_stride, long long plane_stride, int L) {
-  return StridedIO{line_stride, plane_stride, 0, L};
+  return StridedIO{line_stride, plane_stride, 0, ilog2(L)};
 }
 
 EVX_HD long long strided_offset(const StridedIO& io, long long grp, int kz, int idx) {
-  const int hi = idx / io.split, lo = idx - hi * io.split;
+  const int hi = idx >> io.split_shift, lo = idx & ((1 << io.split_shift) - 1);
   return grp * io.plane_stride + kz + hi * io.split_stride + lo * io.line_stride;
 }
 

@@ -189,6 +189,34 @@ int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double
 int evx_dist_backward_f32(evx_dist_plan* plan, const void* recv, void* spec, const float* u_local,
                           float* out_local, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Adjoint of the Cahn-Hilliard right-hand side (fully periodic grids)
+ *
+ * Backward pass of CahnHilliard.rhs / PseudoSpectralIMEX.step for parameter estimation -
+ * the capability of evoxels/inversion.py:51-124 (JAX/diffrax there) behind a
+ * torch.autograd.Function here (evoxels_b200/autograd.py).  With w = dL/d(rhs):
+ *   evx_ch_mu            mu = (18/eps) p(c^) - 2 eps lap(c^),  c^ = clip(u,0,1)
+ *   evx_ch_adjoint_flux  z = D div( c_f(1-c_f) grad w ),
+ *                        m = -D/2 sum_faces (1 - 2 c_f) (dw)(dmu) / h^2
+ *   evx_ch_adjoint_combine  lam_out = [lam_in +] 1[0<=u<=1] ( g'(c^) z - 2 eps lap(z) + m ),
+ *                        *deps_acc += sum z ( -(18/eps^2) p(c^) - 2 lap(c^) )   (device double)
+ * ------------------------------------------------------------------------------- */
+int evx_ch_mu_f32(const float* u, float* mu, int nx, int ny, int nz, const double* h, double eps,
+                  void* stream);
+int evx_ch_mu_f64(const double* u, double* mu, int nx, int ny, int nz, const double* h, double eps,
+                  void* stream);
+int evx_ch_adjoint_flux_f32(const float* u, const float* mu, const float* w, float* z, float* m,
+                            int nx, int ny, int nz, const double* h, double D, void* stream);
+int evx_ch_adjoint_flux_f64(const double* u, const double* mu, const double* w, double* z,
+                            double* m, int nx, int ny, int nz, const double* h, double D,
+                            void* stream);
+int evx_ch_adjoint_combine_f32(const float* u, const float* z, const float* m,
+                               const float* lam_in, float* lam_out, double* deps_acc, int nx,
+                               int ny, int nz, const double* h, double eps, void* stream);
+int evx_ch_adjoint_combine_f64(const double* u, const double* z, const double* m,
+                               const double* lam_in, double* lam_out, double* deps_acc, int nx,
+                               int ny, int nz, const double* h, double eps, void* stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long evx_launch_count(void);
 

@@ -254,3 +254,35 @@ int emu_native_apply(const float* u, const float* r, float* out, float* spec_out
   return 0;
 }
 }
+
+// =====================================================================================
+// adjoint of the CH rhs
+// =====================================================================================
+#include "../../evoxels_b200/csrc/adjoint_core.h"
+
+extern "C" {
+// lam = dR/du^T w  and  *deps = dL/deps  for the periodic CH rhs (float64)
+int emu_ch_rhs_vjp_f64(const double* u, const double* w, double* lam, double* deps, int nx, int ny,
+                       int nz, const double* h, double eps, double D) {
+  const size_t n = (size_t)nx * ny * nz;
+  std::vector<double> mu(n), z(n), m(n);
+  AdjParams<double> p;
+  p.u = u; p.mu = mu.data(); p.w = w; p.z = z.data(); p.m = m.data(); p.lam_in = nullptr;
+  p.red = nullptr; p.nx = nx; p.ny = ny; p.nz = nz;
+  p.ihx2 = 1.0 / (h[0] * h[0]); p.ihy2 = 1.0 / (h[1] * h[1]); p.ihz2 = 1.0 / (h[2] * h[2]);
+  p.eps = eps; p.D = D;
+  auto idx = [&](int x, int y, int zz) { return ((size_t)x * ny + y) * nz + zz; };
+  for (int x = 0; x < nx; ++x) for (int y = 0; y < ny; ++y) for (int zz = 0; zz < nz; ++zz)
+    mu[idx(x, y, zz)] = adj_mu(p, x, y, zz);
+  for (int x = 0; x < nx; ++x) for (int y = 0; y < ny; ++y) for (int zz = 0; zz < nz; ++zz)
+    adj_flux(p, x, y, zz, z[idx(x, y, zz)], m[idx(x, y, zz)]);
+  double acc = 0.0;
+  for (int x = 0; x < nx; ++x) for (int y = 0; y < ny; ++y) for (int zz = 0; zz < nz; ++zz) {
+    double term;
+    lam[idx(x, y, zz)] = adj_combine(p, x, y, zz, term);
+    acc += term;
+  }
+  *deps = acc;
+  return 0;
+}
+}

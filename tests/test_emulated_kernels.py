@@ -177,3 +177,24 @@ def test_native_fft_pipeline(emu, shape):
     want = O.imex_step(torch.from_numpy(u)[None], torch.from_numpy(r)[None], pref)[0].numpy()
     assert rel_l2(out - u, want - u) < 2e-6
     assert rel_l2(out, want) < 1e-6
+
+
+def test_ch_rhs_adjoint_against_autograd(emu):
+    """The hand-written VJP of the periodic CH rhs (adjoint_core.h) against torch autograd
+    through the oracle, float64, values outside [0,1] included (clip mask)."""
+    for shape, sp in [((6, 5, 4), (1.0, 0.5, 2.0)), ((8, 8, 8), (1.0, 1.0, 1.0)), ((3, 1, 7), (1, 1, 1))]:
+        rng = np.random.default_rng(4)
+        u = (-0.2 + 1.4 * rng.random(shape))
+        w = rng.standard_normal(shape)
+        ut = torch.from_numpy(u)[None].requires_grad_(True)
+        D = torch.tensor(1.3, dtype=torch.float64, requires_grad=True)
+        eps = torch.tensor(2.5, dtype=torch.float64, requires_grad=True)
+        R = O.ch_rhs(ut, sp, eps, D)
+        gu, gD, ge = torch.autograd.grad((R * torch.from_numpy(w)[None]).sum(), (ut, D, eps))
+        lam = np.zeros(shape)
+        deps = ctypes.c_double(0.0)
+        emu.emu_ch_rhs_vjp_f64(_p(u), _p(w), _p(lam), ctypes.byref(deps), *shape,
+                               (ctypes.c_double * 3)(*sp), ctypes.c_double(2.5), ctypes.c_double(1.3))
+        assert rel_l2(lam, gu[0].numpy()) < 1e-12, shape
+        assert abs(deps.value - float(ge)) < 1e-10 * max(1.0, abs(float(ge))), shape
+        assert abs(float((R.detach()[0] * torch.from_numpy(w)).sum() / 1.3) - float(gD)) < 1e-10 * max(1.0, abs(float(gD)))
