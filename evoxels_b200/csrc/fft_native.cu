@@ -3,6 +3,7 @@
 // over a pitched half spectrum (see fft_pass_core.h).  Power-of-two extents:
 // 8 <= nx, ny <= 2048, 16 <= nz <= 2048.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "evx_internal.h"
 #include "spectral_plan.h"
@@ -46,11 +47,77 @@ static int launch_pass(const Params& p, long long blocks, cudaStream_t st) {
 template <int L>
 struct StridedCfg { static constexpr int KZ = L >= 2048 ? 4 : 8; };
 
+// persistent, software-pipelined form (see StridedPipe in fft_pass_core.h)
+template <class Pipe>
+__global__ void __launch_bounds__(Pipe::NTHREADS, Pipe::NTHREADS <= 512 ? 2 : 1)
+    fft_pipe_kernel(const StridedParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf* t0 = reinterpret_cast<cf*>(smem_raw);
+  cf* t1 = t0 + Pipe::BUF;
+  cf* c = t1 + Pipe::BUF;
+  const long long ntiles = Pipe::num_tiles(p);
+  long long tile = blockIdx.x;
+  if (tile < ntiles) Pipe::prefetch(threadIdx.x, p, tile, t0);
+  async_copy_commit();
+  typename Pipe::Regs r;
+  for (int par = 0; tile < ntiles; tile += gridDim.x, par ^= 1) {
+    cf* a = par ? t1 : t0;
+    cf* b = par ? t0 : t1;
+    async_copy_commit_and_wait();
+    __syncthreads();
+    Pipe::Base::init(r, p, threadIdx.x, tile);
+    Pipe::read_tile(r, a);
+    const long long next = tile + gridDim.x;
+    if (next < ntiles) Pipe::prefetch(threadIdx.x, p, next, b);
+    async_copy_commit();
+#pragma unroll
+    for (int k = 0; k < Pipe::NPHASES; ++k) {
+      if (k) __syncthreads();
+      Pipe::phase(k, r, a, c, p);
+    }
+  }
+}
+
+static int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+static bool use_pipeline() {
+  static const bool on = [] { const char* e = getenv("EVX_FFT_PIPE"); return !e || atoi(e) != 0; }();
+  return on;
+}
+
+template <class Pipe>
+static int launch_pipe(const StridedParams& p, cudaStream_t st) {
+  const long long ntiles = Pipe::num_tiles(p);
+  if (ntiles < 1) return EVX_ERR_UNSUPPORTED;
+  auto kern = fft_pipe_kernel<Pipe>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Pipe::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const long long resident = (long long)sm_count() * (Pipe::NTHREADS <= 512 ? 2 : 1);
+  const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);
+  kern<<<grid, Pipe::NTHREADS, Pipe::SMEM_BYTES, st>>>(p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 template <int MODE>
 static int launch_strided(int L, const StridedParams& p, cudaStream_t st) {
 #define EVX_CASE(N)                                                                   \
   case N: {                                                                           \
     constexpr int KZ = StridedCfg<N>::KZ;                                             \
+    if (N >= 64 && use_pipeline()) return launch_pipe<StridedPipe<N, KZ, MODE>>(p, st); \
     return launch_pass<StridedPass<N, KZ, MODE>, StridedParams>(                      \
         p, (p.ncols_total + KZ - 1) / KZ, st);                                        \
   }

@@ -167,6 +167,99 @@ struct StridedPass {
 };
 
 // ------------------------------------------------------------------------------------
+// Pipelined (persistent) form of the strided passes.
+//
+// A block walks tiles b, b + gridDim, ... and keeps THREE padded line buffers: while it
+// transforms tile i out of buffer A it has the asynchronous copy (cp.async / LDGSTS) of
+// tile i+1 in flight into buffer B; the stage exchanges alternate between the third buffer
+// C and A (A is free once every thread has picked up its stage-0 inputs).  Next tile: A and
+// B swap.  Memory latency is thereby hidden inside one block instead of relying on other
+// resident blocks, and two blocks (2 x 111 KB for L = 512) still fit an SM.
+// ------------------------------------------------------------------------------------
+EVX_HD void async_copy16(void* smem_dst, const void* gmem_src) {
+#if defined(__CUDA_ARCH__)
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
+  // host replay: the copy lands immediately (the destination buffer is not touched by
+  // anyone between issue and wait, see the buffer rotation above)
+  const float* s = reinterpret_cast<const float*>(gmem_src);
+  float* d = reinterpret_cast<float*>(smem_dst);
+  d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+#endif
+}
+EVX_HD void async_copy_commit_and_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+EVX_HD void async_copy_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+
+template <int L, int KZ, int MODE>
+struct StridedPipe {
+  using Base = StridedPass<L, KZ, MODE>;
+  using Regs = typename Base::Regs;
+  static constexpr int T = Base::T, S = Base::S, NTHREADS = Base::NTHREADS, NPHASES = Base::NPHASES;
+  static constexpr int LP = Base::LP;
+  static constexpr int BUF = LP * KZ;                       // cf elements per buffer
+  static constexpr size_t SMEM_BYTES = 3 * (size_t)BUF * sizeof(cf);
+  static constexpr int CHUNKS_PER_ROW = KZ * (int)sizeof(cf) / 16;
+  static constexpr int CHUNKS = L * CHUNKS_PER_ROW;
+  static_assert(KZ * sizeof(cf) % 16 == 0, "rows must be 16-byte multiples");
+
+  EVX_HD static long long num_tiles(const StridedParams& p) { return (p.ncols_total + KZ - 1) / KZ; }
+
+  // all threads: enqueue the copy of tile `tile` (dense [L][KZ] rows of KZ*8 bytes) into dst
+  EVX_HD static void prefetch(int tid, const StridedParams& p, long long tile, cf* dst) {
+    const long long c0 = tile * KZ;
+    const long long grp = c0 / p.P;
+    const int kz0 = (int)(c0 - grp * p.P);
+    for (int q = tid; q < CHUNKS; q += NTHREADS) {
+      const int row = q / CHUNKS_PER_ROW, part = q - row * CHUNKS_PER_ROW;
+      const cf* src = p.in + strided_offset(p.src, grp, kz0, row) + part * (16 / (int)sizeof(cf));
+      async_copy16(dst + (size_t)row * KZ + part * (16 / (int)sizeof(cf)), src);
+    }
+  }
+
+  EVX_HD static void read_tile(Regs& r, const cf* a) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r.v[e] = a[(size_t)(r.t + e * T) * KZ + r.cl];
+  }
+
+  // phase 0 is split around the prefetch of the next tile: `pick` then `phase(0, ..)`
+  EVX_HD static void phase(int k, Regs& r, cf* a, cf* c, const StridedParams& p) {
+    // exchange buffers alternate C, A, C, ...: phase k writes (k even ? C : A)
+    cf* wr = (k & 1) ? a : c;
+    const cf* rd = (k & 1) ? c : a;        // written by phase k-1
+    if (k > 0) Base::read_natural(r, rd);
+    if (MODE == PASS_FWD || MODE == PASS_INV) {
+      if (MODE == PASS_FWD) Base::template compute<-1>(r, p, k); else Base::template compute<+1>(r, p, k);
+      if (k == S - 1) Base::store_global(r, p);
+      else if (MODE == PASS_FWD) Base::template write_stage<-1>(r, wr, k);
+      else Base::template write_stage<+1>(r, wr, k);
+    } else {
+      if (k < S - 1) {
+        Base::template compute<-1>(r, p, k);
+        Base::template write_stage<-1>(r, wr, k);
+      } else if (k == S - 1) {
+        Base::template compute<-1>(r, p, S - 1);
+        Base::apply_filter(r, p);
+        Base::template compute<+1>(r, p, 0);
+        if (S == 1) Base::store_global(r, p); else Base::template write_stage<+1>(r, wr, 0);
+      } else {
+        const int s = k - (S - 1);
+        Base::template compute<+1>(r, p, s);
+        if (s == S - 1) Base::store_global(r, p); else Base::template write_stage<+1>(r, wr, s);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------
 // z passes (contiguous axis, real <-> half spectrum)
 // ------------------------------------------------------------------------------------
 struct ZParams {

@@ -168,8 +168,45 @@ static void run_strided(const StridedParams& p) {
   }
 }
 
+// persistent pipelined variant, replayed with `nblocks` resident blocks
+template <int L, int KZ, int MODE>
+static void run_pipe(const StridedParams& p, int nblocks) {
+  using Pipe = StridedPipe<L, KZ, MODE>;
+  const long long ntiles = Pipe::num_tiles(p);
+  std::vector<typename Pipe::Regs> regs(Pipe::NTHREADS);
+  std::vector<cf> smem(3 * (size_t)Pipe::BUF);
+  for (int blk = 0; blk < nblocks; ++blk) {
+    cf* t0 = smem.data(); cf* t1 = t0 + Pipe::BUF; cf* c = t1 + Pipe::BUF;
+    long long tile = blk;
+    if (tile < ntiles) for (int t = 0; t < Pipe::NTHREADS; ++t) Pipe::prefetch(t, p, tile, t0);
+    for (int par = 0; tile < ntiles; tile += nblocks, par ^= 1) {
+      cf* a = par ? t1 : t0; cf* b = par ? t0 : t1;
+      for (int t = 0; t < Pipe::NTHREADS; ++t) { Pipe::Base::init(regs[t], p, t, tile); Pipe::read_tile(regs[t], a); }
+      const long long next = tile + nblocks;
+      if (next < ntiles) for (int t = 0; t < Pipe::NTHREADS; ++t) Pipe::prefetch(t, p, next, b);
+      for (int k = 0; k < Pipe::NPHASES; ++k)
+        for (int t = 0; t < Pipe::NTHREADS; ++t) Pipe::phase(k, regs[t], a, c, p);
+    }
+  }
+}
+
+static int g_emu_pipe_blocks = 0;   // 0: one block per tile (StridedPass), >0: pipelined with that many blocks
+
 template <int KZ, int MODE>
 static int dispatch_strided(int L, const StridedParams& p) {
+  if (g_emu_pipe_blocks > 0) {
+    switch (L) {
+      case 8: run_pipe<8, KZ, MODE>(p, g_emu_pipe_blocks); return 0;
+      case 16: run_pipe<16, KZ, MODE>(p, g_emu_pipe_blocks); return 0;
+      case 32: run_pipe<32, KZ, MODE>(p, g_emu_pipe_blocks); return 0;
+      case 64: run_pipe<64, KZ, MODE>(p, g_emu_pipe_blocks); return 0;
+      case 128: run_pipe<128, KZ, MODE>(p, g_emu_pipe_blocks); return 0;
+      case 256: run_pipe<256, KZ, MODE>(p, g_emu_pipe_blocks); return 0;
+      case 512: run_pipe<512, KZ, MODE>(p, g_emu_pipe_blocks); return 0;
+      case 1024: run_pipe<1024, KZ, MODE>(p, g_emu_pipe_blocks); return 0;
+      default: return -1;
+    }
+  }
   switch (L) {
     case 8: run_strided<8, KZ, MODE>(p); return 0;
     case 16: run_strided<16, KZ, MODE>(p); return 0;
@@ -212,6 +249,8 @@ static int dispatch_z(int M, const ZParams& p) {
 }
 
 extern "C" {
+
+void emu_set_pipe_blocks(int n) { g_emu_pipe_blocks = n; }
 
 // out = u + irfftn(P * rfftn(r)) through the five native passes; spec is scratch
 // [nx*ny*P] complex with P = roundup(nz/2+1, 8).  mode: 0 full, 1 forward only (spec out),

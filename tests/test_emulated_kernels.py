@@ -153,10 +153,13 @@ def test_pad_and_padded_stencils(emu):
                     assert rel_l2(o2, r2) <= (1e-12 if dtype == np.float64 else 2e-4)
 
 
+@pytest.mark.parametrize("pipe_blocks", [0, 1, 3])
 @pytest.mark.parametrize("shape", [(8, 8, 16), (16, 32, 64), (32, 16, 128), (8, 8, 256), (64, 8, 32)])
-def test_native_fft_pipeline(emu, shape):
+def test_native_fft_pipeline(emu, shape, pipe_blocks):
     """Five-pass native FFT pipeline (ZFwd, Y, X fwd*filter*inv, Y inv, ZInv+u) replayed on
     the CPU: forward spectrum against numpy's rfftn, full update against the oracle."""
+    # pipe_blocks > 0: persistent software-pipelined strided passes with that many blocks
+    emu.emu_set_pipe_blocks(pipe_blocks)
     nx, ny, nz = shape
     rng = np.random.default_rng(0)
     r = rng.standard_normal(shape).astype(np.float32)
@@ -175,6 +178,7 @@ def test_native_fft_pipeline(emu, shape):
     assert emu.emu_native_apply(_p(u), _p(r), _p(out), None, nx, ny, nz, h, d(0.1), d(1.5), 2) == 0
     pref = O.imex_prefactor(O.ch_symbol(shape, sp, 3.0, 1.0, 0.25), 0.1)
     want = O.imex_step(torch.from_numpy(u)[None], torch.from_numpy(r)[None], pref)[0].numpy()
+    emu.emu_set_pipe_blocks(0)
     assert rel_l2(out - u, want - u) < 2e-6
     assert rel_l2(out, want) < 1e-6
 
