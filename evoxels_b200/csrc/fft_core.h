@@ -21,11 +21,54 @@ struct alignas(8) cf {
   float x, y;
 };
 
+// Complex arithmetic.  On sm_100a these are the packed-FP32 instructions of Blackwell
+// (PTX add/sub/mul/fma .f32x2 -> SASS FADD2 / FMUL2 / FFMA2): a complex add is ONE
+// instruction, a complex multiply two, and multiplication by +-i is an operand modifier
+// (half swap + per-half negate) that ptxas folds into the consuming instruction.  The host
+// replay uses the scalar expressions.
+#if defined(__CUDA_ARCH__)
+typedef unsigned long long cf_bits;
+EVX_D cf_bits cf_pack(float lo, float hi) {
+  cf_bits r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+EVX_D cf cf_unpack(cf_bits v) {
+  cf r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+EVX_D cf cadd(cf a, cf b) {
+  cf_bits r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cf_pack(a.x, a.y)), "l"(cf_pack(b.x, b.y)));
+  return cf_unpack(r);
+}
+EVX_D cf csub(cf a, cf b) {
+  cf_bits r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cf_pack(a.x, a.y)), "l"(cf_pack(b.x, b.y)));
+  return cf_unpack(r);
+}
+EVX_D cf cmul(cf a, cf b) {
+  cf_bits t, r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(t) : "l"(cf_pack(a.y, a.y)), "l"(cf_pack(b.y, b.x)));
+  const cf tt = cf_unpack(t);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(r)
+      : "l"(cf_pack(a.x, a.x)), "l"(cf_pack(b.x, b.y)), "l"(cf_pack(-tt.x, tt.y)));
+  return cf_unpack(r);
+}
+EVX_D cf cscale(cf a, float s) {
+  cf_bits r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cf_pack(a.x, a.y)), "l"(cf_pack(s, s)));
+  return cf_unpack(r);
+}
+#else
 EVX_HD cf cadd(cf a, cf b) { return {a.x + b.x, a.y + b.y}; }
 EVX_HD cf csub(cf a, cf b) { return {a.x - b.x, a.y - b.y}; }
 EVX_HD cf cmul(cf a, cf b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
-EVX_HD cf cconj(cf a) { return {a.x, -a.y}; }
 EVX_HD cf cscale(cf a, float s) { return {a.x * s, a.y * s}; }
+#endif
+EVX_HD cf cconj(cf a) { return {a.x, -a.y}; }
 // multiply by -i (DIR=-1) or +i (DIR=+1)
 template <int DIR>
 EVX_HD cf mul_dir_i(cf a) {
@@ -57,10 +100,11 @@ EVX_HD void dft8(cf* v) {
   cf a1 = cadd(v[1], v[5]), b1 = csub(v[1], v[5]);
   cf a2 = cadd(v[2], v[6]), b2 = csub(v[2], v[6]);
   cf a3 = cadd(v[3], v[7]), b3 = csub(v[3], v[7]);
-  // b_r *= w8^r : w8 = exp(DIR * 2 pi i / 8)
-  b1 = DIR < 0 ? cf{(b1.x + b1.y) * h, (b1.y - b1.x) * h} : cf{(b1.x - b1.y) * h, (b1.y + b1.x) * h};
+  // b_r *= w8^r, w8 = exp(DIR * 2 pi i / 8) = (1 + DIR*i)/sqrt2:
+  //   b w8 = h (b + (DIR*i) b),   b w8^3 = h ((DIR*i) b - b)
+  b1 = cscale(cadd(b1, mul_dir_i<DIR>(b1)), h);
   b2 = mul_dir_i<DIR>(b2);
-  b3 = DIR < 0 ? cf{(b3.y - b3.x) * h, -(b3.x + b3.y) * h} : cf{-(b3.x + b3.y) * h, (b3.x - b3.y) * h};
+  b3 = cscale(csub(mul_dir_i<DIR>(b3), b3), h);
   dft4<DIR>(a0, a1, a2, a3);
   dft4<DIR>(b0, b1, b2, b3);
   v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
@@ -163,6 +207,25 @@ EVX_HD int line_stage_out_index(int s, int t, int e) {
   const int jv = t + i * LP::T;
   const int Ns = LP::ns(s);
   return (jv / Ns) * Ns * R + jv % Ns + r * Ns;
+}
+
+// Decomposition of the Stockham output index into a per-thread base and a per-element
+// constant:  out_index(s, t, e) = stage_out_base(s, t) + stage_out_const(s, e)
+// (valid because Ns <= T for every stage, so jv = t + i*T splits cleanly).  With the
+// additive smem padding x + (x >> 3) the two parts never carry into each other's low
+// three bits, hence pad(base + c) = pad(base) + pad(c): every shared-memory access of a
+// stage is one address computation per thread plus compile-time immediates.
+template <int N>
+EVX_HD int stage_out_base(int s, int t) {
+  using LP = LinePlan<N>;
+  const int Ns = LP::ns(s), R = LP::radix(s);
+  return (t / Ns) * (Ns * R) + (t % Ns);
+}
+template <int N>
+EVX_HD constexpr int stage_out_const(int s, int e) {
+  using LP = LinePlan<N>;
+  const int R = LP::radix(s), Q = 8 / R;
+  return (e % Q) * LP::T * R + (e / Q) * LP::ns(s);
 }
 
 }  // namespace evx

@@ -113,7 +113,8 @@ static int launch_pipe(const StridedParams& p, cudaStream_t st) {
 }
 
 template <int MODE>
-static int launch_strided(int L, const StridedParams& p, cudaStream_t st) {
+static int launch_strided(int L, StridedParams p, cudaStream_t st) {
+  finalize_strided(p, L);
 #define EVX_CASE(N)                                                                   \
   case N: {                                                                           \
     constexpr int KZ = StridedCfg<N>::KZ;                                             \

@@ -57,6 +57,8 @@ struct StridedParams {
   long long ncols_total;   // number of columns incl. pitch padding (groups * P)
   int kother_offset;       // XMID: global index of the first local column group (y-pencils)
   FilterParams filt;       // XMID only; n0 = L (this axis), n1 = the other strided axis, n2 = nz
+  long long src_step[8];   // strided_step(src, e * L/8), filled by finalize_strided()
+  long long dst_step[8];
 };
 
 inline StridedIO plain_io(long long line_stride, long long plane_stride, int L) {
@@ -66,6 +68,23 @@ inline StridedIO plain_io(long long line_stride, long long plane_stride, int L) 
 EVX_HD long long strided_offset(const StridedIO& io, long long grp, int kz, int idx) {
   const int hi = idx >> io.split_shift, lo = idx & ((1 << io.split_shift) - 1);
   return grp * io.plane_stride + kz + hi * io.split_stride + lo * io.line_stride;
+}
+// strided_offset(io, grp, kz, t + c) = strided_base(io, grp, kz, t) + strided_step(io, c)
+// for c a multiple of T (T and split are powers of two, so one divides the other); the
+// step part is the same for all threads of a block.
+EVX_HD long long strided_base(const StridedIO& io, long long grp, int kz, int t) {
+  return strided_offset(io, grp, kz, t);
+}
+EVX_HD long long strided_step(const StridedIO& io, int c) {
+  const int hi = c >> io.split_shift, lo = c & ((1 << io.split_shift) - 1);
+  return hi * io.split_stride + lo * io.line_stride;
+}
+// host: tabulate the eight per-element steps of a pass over lines of length L
+inline void finalize_strided(StridedParams& p, int L) {
+  for (int e = 0; e < 8; ++e) {
+    p.src_step[e] = strided_step(p.src, e * (L / 8));
+    p.dst_step[e] = strided_step(p.dst, e * (L / 8));
+  }
 }
 
 template <int L, int KZ, int MODE>
@@ -82,6 +101,7 @@ struct StridedPass {
     int t, cl;
     bool valid;
     long long grp;
+    long long src_base, dst_base;
     int kz, kother;
   };
 
@@ -96,27 +116,32 @@ struct StridedPass {
     r.kother = (int)grp + p.kother_offset;
     r.grp = grp;
     r.valid = c < p.ncols_total && r.kz < p.ncols_valid;
+    r.src_base = strided_base(p.src, grp, r.kz, r.t);
+    r.dst_base = strided_base(p.dst, grp, r.kz, r.t);
   }
 
   template <int DIR>
   EVX_HD static void write_stage(Regs& r, cf* b, int s) {
+    cf* base = b + smem_pad(stage_out_base<L>(s, r.t)) * KZ + r.cl;
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      b[(size_t)smem_pad(line_stage_out_index<L>(s, r.t, e)) * KZ + r.cl] = r.v[e];
+    for (int e = 0; e < 8; ++e) base[smem_pad(stage_out_const<L>(s, e)) * KZ] = r.v[e];
   }
   EVX_HD static void read_natural(Regs& r, const cf* b) {
+    const cf* base = b + smem_pad(r.t) * KZ + r.cl;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) r.v[e] = b[(size_t)smem_pad(r.t + e * T) * KZ + r.cl];
+    for (int e = 0; e < 8; ++e) r.v[e] = base[smem_pad(e * T) * KZ];
   }
   EVX_HD static void load_global(Regs& r, const StridedParams& p) {
+    const cf* base = p.in + r.src_base;
 #pragma unroll
     for (int e = 0; e < 8; ++e)
-      r.v[e] = r.valid ? p.in[strided_offset(p.src, r.grp, r.kz, r.t + e * T)] : cf{0.f, 0.f};
+      r.v[e] = r.valid ? base[p.src_step[e]] : cf{0.f, 0.f};
   }
   EVX_HD static void store_global(Regs& r, const StridedParams& p) {
     if (!r.valid) return;
+    cf* base = p.out + r.dst_base;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) p.out[strided_offset(p.dst, r.grp, r.kz, r.t + e * T)] = r.v[e];
+    for (int e = 0; e < 8; ++e) base[p.dst_step[e]] = r.v[e];
   }
   EVX_HD static void apply_filter(Regs& r, const StridedParams& p) {
     const FilterParams& f = p.filt;
@@ -312,15 +337,14 @@ struct ZPass {
     const cf a = cadd(zk, cconj(zmk));              // 2 E[k]
     const cf b = csub(zk, cconj(zmk));              // 2 i O[k]
     const cf o = cf{b.y, -b.x};                     // -i * b = 2 O[k]
-    const cf wo = cmul(w, o);
-    return cf{0.5f * (a.x + wo.x), 0.5f * (a.y + wo.y)};
+    return cscale(cadd(a, cmul(w, o)), 0.5f);
   }
   // Z'[k] from X[k], X[M-k]  (inverse; unnormalised: ifft_M(Z') = N x)
   EVX_HD static cf untangle_inv(cf xk, cf xmk, cf w) {
     const cf a = cadd(xk, cconj(xmk));              // 2 E[k]
     const cf b = csub(xk, cconj(xmk));
     const cf wo = cmul(cconj(w), b);                // 2 O[k]
-    return cf{a.x - wo.y, a.y + wo.x};              // a + i * wo
+    return cadd(a, cf{-wo.y, wo.x});                // a + i * wo
   }
 
   EVX_HD static void phase(int k, Regs& r, cf* smem, const ZParams& p) {

@@ -193,7 +193,8 @@ static void run_pipe(const StridedParams& p, int nblocks) {
 static int g_emu_pipe_blocks = 0;   // 0: one block per tile (StridedPass), >0: pipelined with that many blocks
 
 template <int KZ, int MODE>
-static int dispatch_strided(int L, const StridedParams& p) {
+static int dispatch_strided(int L, StridedParams p) {
+  finalize_strided(p, L);
   if (g_emu_pipe_blocks > 0) {
     switch (L) {
       case 8: run_pipe<8, KZ, MODE>(p, g_emu_pipe_blocks); return 0;
