@@ -58,6 +58,7 @@ SIGNATURES = {
     "evx_ch_adjoint_flux_f64": [_c_void_p] * 5 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
     "evx_ch_adjoint_combine_f32": [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
     "evx_ch_adjoint_combine_f64": [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
+    "evx_debug_strided_copy": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "evx_dist_plan_create": [ctypes.POINTER(_c_void_p), _c_int, _c_int, _c_int, _c_int, _c_int],
     "evx_dist_plan_destroy": [_c_void_p],
     "evx_dist_plan_sizes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t), _iptr],

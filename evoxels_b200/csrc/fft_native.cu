@@ -14,7 +14,7 @@ namespace evx {
 constexpr int kPitchAlign = 8;   // spectrum rows are padded to a multiple of 8 complex
 
 template <class Prog, class Params>
-__global__ void __launch_bounds__(Prog::NTHREADS, Prog::NTHREADS <= 512 ? 2 : 1) fft_pass_kernel(const Params p) {
+__global__ void __launch_bounds__(Prog::NTHREADS, Prog::NTHREADS <= 256 ? 4 : (Prog::NTHREADS <= 512 ? 2 : 1)) fft_pass_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf* smem = reinterpret_cast<cf*>(smem_raw);
   typename Prog::Regs r;
@@ -307,11 +307,33 @@ int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, f
   return launch_z<true>(p->M, zp, st);
 }
 
+// access-pattern probe: the load/store pattern of a strided pass without the transform
+int debug_strided_copy(cf* data, int nx, int ny, int P, int along_x, int kz_cols, cudaStream_t st) {
+  StridedParams p;
+  p.in = data; p.out = data; p.tw = nullptr; p.P = P; p.ncols_valid = P; p.kother_offset = 0;
+  p.filt = FilterParams{};
+  int L;
+  if (along_x) { p.src = p.dst = plain_io((long long)ny * P, P, nx); p.ncols_total = (long long)ny * P; L = nx; }
+  else { p.src = p.dst = plain_io(P, (long long)ny * P, ny); p.ncols_total = (long long)nx * P; L = ny; }
+  if (L != 512) return EVX_ERR_UNSUPPORTED;
+  finalize_strided(p, L);
+  switch (kz_cols) {
+    case 4: return launch_pass<StridedPass<512, 4, PASS_COPY>, StridedParams>(p, (p.ncols_total + 3) / 4, st);
+    case 8: return launch_pass<StridedPass<512, 8, PASS_COPY>, StridedParams>(p, (p.ncols_total + 7) / 8, st);
+    case 16: return launch_pass<StridedPass<512, 16, PASS_COPY>, StridedParams>(p, (p.ncols_total + 15) / 16, st);
+    default: return EVX_ERR_ARG;
+  }
+}
+
 }  // namespace evx
 
 using namespace evx;
 
 extern "C" {
+
+int evx_debug_strided_copy(void* data, int nx, int ny, int P, int along_x, int kz_cols, void* stream) {
+  return debug_strided_copy((cf*)data, nx, ny, P, along_x, kz_cols, (cudaStream_t)stream);
+}
 
 int evx_dist_plan_create(evx_dist_plan** plan, int nx, int ny, int nz, int world, int rank) {
   return dist_plan_create((DistPlan**)plan, nx, ny, nz, world, rank);

@@ -28,7 +28,7 @@ EVX_HD int zline_idx(int i) {
 template <int M>
 constexpr int zline_len() { return M >= 128 ? M + 16 : smem_padded_len(M + 1); }
 
-enum : int { PASS_FWD = 0, PASS_INV = 1, PASS_XMID = 2 };
+enum : int { PASS_FWD = 0, PASS_INV = 1, PASS_XMID = 2, PASS_COPY = 3 };   // COPY: access-pattern probe
 
 // ------------------------------------------------------------------------------------
 // strided passes (y and x)
@@ -92,9 +92,10 @@ struct StridedPass {
   static constexpr int T = L / 8;
   static constexpr int NTHREADS = T * KZ;
   static constexpr int S = num_stages(L);
-  static constexpr int NPHASES = MODE == PASS_XMID ? 2 * S - 1 : S;
+  static constexpr int NPHASES = MODE == PASS_XMID ? 2 * S - 1 : (MODE == PASS_COPY ? 1 : S);
   static constexpr int LP = smem_padded_len(L);
-  static constexpr size_t SMEM_BYTES = (S > 1 ? 2 : 0) * (size_t)LP * KZ * sizeof(cf);
+  static constexpr size_t SMEM_BYTES =
+      (S > 1 && MODE != PASS_COPY ? 2 : 0) * (size_t)LP * KZ * sizeof(cf);
 
   struct Regs {
     cf v[8];
@@ -164,7 +165,10 @@ struct StridedPass {
   }
 
   EVX_HD static void phase(int k, Regs& r, cf* smem, const StridedParams& p) {
-    if (MODE == PASS_FWD || MODE == PASS_INV) {
+    if (MODE == PASS_COPY) {
+      load_global(r, p);
+      store_global(r, p);
+    } else if (MODE == PASS_FWD || MODE == PASS_INV) {
       if (k == 0) load_global(r, p); else read_natural(r, buf(smem, (k - 1) & 1));
       if (MODE == PASS_FWD) compute<-1>(r, p, k); else compute<+1>(r, p, k);
       if (k == S - 1) store_global(r, p);

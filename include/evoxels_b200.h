@@ -217,6 +217,10 @@ int evx_ch_adjoint_combine_f64(const double* u, const double* z, const double* m
                                const double* lam_in, double* lam_out, double* deps_acc, int nx,
                                int ny, int nz, const double* h, double eps, void* stream);
 
+/* measurement aid: the global load/store pattern of a strided FFT pass (512-point lines, tiles
+ * of kz_cols columns) without the transform - the bandwidth ceiling of that access pattern */
+int evx_debug_strided_copy(void* data, int nx, int ny, int P, int along_x, int kz_cols, void* stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long evx_launch_count(void);
 

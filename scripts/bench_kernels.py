@@ -38,6 +38,17 @@ for name, code in (("cufft", _native.FFT_CUFFT), ("native", _native.FFT_NATIVE))
         del plan
     except Exception as exc:
         res[f"imex_apply_{name}_ms"] = str(exc)
+if n == 512:
+    lib = _native.load_library()
+    P = 264
+    spec = torch.zeros((n, n, P), dtype=torch.complex64, device=dev)
+    import ctypes
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for along_x in (0, 1):
+        for kz in (4, 8, 16):
+            ms = timed(lambda: lib.evx_debug_strided_copy(ctypes.c_void_p(spec.data_ptr()), n, n, P, along_x, kz, st))
+            res[f"probe_copy_{'x' if along_x else 'y'}_kz{kz}_ms"] = round(ms, 4)
+    del spec
 ms = timed(lambda: out.copy_(u))
 res["copy_ms"] = ms; res["copy_GBs"] = 8 * n**3 / ms / 1e6
 print(json.dumps(res))
