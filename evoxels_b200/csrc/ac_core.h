@@ -17,6 +17,7 @@
 // through L1 (no shared memory, no barrier).
 #pragma once
 #include "evx_hd.h"
+#include "packed_f32.h"
 
 namespace evx {
 
@@ -35,10 +36,78 @@ struct AcParams {
   int nx, ny, nz, xchunk;
   T ihx, ihy, ihz, ihx2, ihy2, ihz2, ih2sum;
   T pot_scale, eps, gab, M, force, curv, omc, three_over_eps;
+  T hihx, hihy, hihz;        // 0.5 / h
+  T hxy, hxz, hyz;           // 0.5 / (h_a h_b)
+  T neg_inv_2eps, force3;    // -1/(2 eps),  3/eps * force
   int bc_kind[3];
   T ghost_off[3][2];
   T ghost_sgn[3];
 };
+
+// ------------------------------------------------------------------------------------
+// Lane types of the Allen-Cahn arithmetic: one value, or a pair of neighbouring z values
+// (float pairs use the packed FADD2/FMUL2/FFMA2 path on the device).
+// ------------------------------------------------------------------------------------
+template <typename T, int LW>
+struct AcLane;
+
+template <typename T>
+struct AcLane<T, 1> {
+  T a;
+  EVX_HD static AcLane load(const T* w, int k) { return AcLane{w[k]}; }
+  EVX_HD void store(T* w, int k) const { w[k] = a; }
+  EVX_HD static AcLane add(AcLane x, AcLane y) { return AcLane{x.a + y.a}; }
+  EVX_HD static AcLane sub(AcLane x, AcLane y) { return AcLane{x.a - y.a}; }
+  EVX_HD static AcLane mul(AcLane x, AcLane y) { return AcLane{x.a * y.a}; }
+  EVX_HD static AcLane fma(AcLane x, AcLane y, AcLane z) { return AcLane{x.a * y.a + z.a}; }
+  EVX_HD static AcLane muls(AcLane x, T s) { return AcLane{x.a * s}; }
+  EVX_HD static AcLane fmas(AcLane x, T s, AcLane z) { return AcLane{x.a * s + z.a}; }
+  EVX_HD static AcLane rsubs(T s, AcLane x) { return AcLane{s - x.a}; }
+  EVX_HD static AcLane guarded_div(AcLane n, AcLane d) {
+    return AcLane{n.a / (d.a <= T(1e-7) ? T(1) : d.a)};
+  }
+};
+
+template <typename T>
+struct AcLane<T, 2> {
+  T a, b;
+  EVX_HD static AcLane load(const T* w, int k) { return AcLane{w[k], w[k + 1]}; }
+  EVX_HD void store(T* w, int k) const { w[k] = a; w[k + 1] = b; }
+  EVX_HD static AcLane add(AcLane x, AcLane y) { return AcLane{x.a + y.a, x.b + y.b}; }
+  EVX_HD static AcLane sub(AcLane x, AcLane y) { return AcLane{x.a - y.a, x.b - y.b}; }
+  EVX_HD static AcLane mul(AcLane x, AcLane y) { return AcLane{x.a * y.a, x.b * y.b}; }
+  EVX_HD static AcLane fma(AcLane x, AcLane y, AcLane z) {
+    return AcLane{x.a * y.a + z.a, x.b * y.b + z.b};
+  }
+  EVX_HD static AcLane muls(AcLane x, T s) { return AcLane{x.a * s, x.b * s}; }
+  EVX_HD static AcLane fmas(AcLane x, T s, AcLane z) { return AcLane{x.a * s + z.a, x.b * s + z.b}; }
+  EVX_HD static AcLane rsubs(T s, AcLane x) { return AcLane{s - x.a, s - x.b}; }
+  EVX_HD static AcLane guarded_div(AcLane n, AcLane d) {
+    return AcLane{n.a / (d.a <= T(1e-7) ? T(1) : d.a), n.b / (d.b <= T(1e-7) ? T(1) : d.b)};
+  }
+};
+
+#if defined(__CUDA_ARCH__)
+template <>
+struct AcLane<float, 2> {
+  f2 v;
+  EVX_D static AcLane load(const float* w, int k) { return AcLane{f2{w[k], w[k + 1]}}; }
+  EVX_D void store(float* w, int k) const { w[k] = v.a; w[k + 1] = v.b; }
+  EVX_D static AcLane add(AcLane x, AcLane y) { return AcLane{f2_add(x.v, y.v)}; }
+  EVX_D static AcLane sub(AcLane x, AcLane y) { return AcLane{f2_sub(x.v, y.v)}; }
+  EVX_D static AcLane mul(AcLane x, AcLane y) { return AcLane{f2_mul(x.v, y.v)}; }
+  EVX_D static AcLane fma(AcLane x, AcLane y, AcLane z) { return AcLane{f2_fma(x.v, y.v, z.v)}; }
+  EVX_D static AcLane muls(AcLane x, float s) { return AcLane{f2_mul(x.v, f2_splat(s))}; }
+  EVX_D static AcLane fmas(AcLane x, float s, AcLane z) { return AcLane{f2_fma(x.v, f2_splat(s), z.v)}; }
+  EVX_D static AcLane rsubs(float s, AcLane x) { return AcLane{f2_sub(f2_splat(s), x.v)}; }
+  EVX_D static AcLane guarded_div(AcLane n, AcLane d) {
+    // hardware reciprocal (<= 2 ulp); the reference divides exactly, the difference is far
+    // below the test tolerances
+    const float da = d.v.a <= 1e-7f ? 1.0f : d.v.a, db = d.v.b <= 1e-7f ? 1.0f : d.v.b;
+    return AcLane{f2{__fdividef(n.v.a, da), __fdividef(n.v.b, db)}};
+  }
+};
+#endif
 
 template <typename T, int V, int TY, int G>
 struct AcProgram {
@@ -94,6 +163,101 @@ struct AcProgram {
     w[V + 1] = rule(p, 2, ps.zr_side, h);
   }
 
+  // ---- lane arithmetic: a "lane" is one value (scalar path) or an aligned/shifted pair of
+  // neighbouring z values (packed path; FADD2/FMUL2/FFMA2 on sm_100a for float) -------------
+  // one plane of the rolling window: 3 rows x (V+2) values
+  struct Plane {
+    T w[3][W];
+  };
+
+  template <typename L>
+  EVX_HD static L at(const T* w, int k) { return L::load(w, k); }
+
+  // the right-hand side for the lanes starting at window index k (element e = k-1)
+  template <typename L>
+  EVX_HD static L rhs_lanes(const P& p, const Plane& fm, const Plane& fc, const Plane& fp, int k,
+                            const T* potv, int e) {
+    const L C = at<L>(fc.w[1], k);
+    const L R = at<L>(fp.w[1], k), Lf = at<L>(fm.w[1], k);
+    const L Tp = at<L>(fc.w[2], k), B = at<L>(fc.w[0], k);
+    const L F = at<L>(fc.w[1], k + 1), Bk = at<L>(fc.w[1], k - 1);
+    const L two_c = L::add(C, C);
+    const L dxx = L::sub(L::add(R, Lf), two_c), dyy = L::sub(L::add(Tp, B), two_c),
+            dzz = L::sub(L::add(F, Bk), two_c);
+    // lap = dxx/hx^2 + dyy/hy^2 + dzz/hz^2
+    const L lap = L::fmas(dxx, p.ihx2, L::fmas(dyy, p.ihy2, L::muls(dzz, p.ihz2)));
+    const L gx = L::muls(L::sub(R, Lf), p.hihx), gy = L::muls(L::sub(Tp, B), p.hihy),
+            gz = L::muls(L::sub(F, Bk), p.hihz);
+    const L mxy = L::sub(L::add(at<L>(fp.w[2], k), at<L>(fm.w[0], k)),
+                         L::add(at<L>(fm.w[2], k), at<L>(fp.w[0], k)));
+    const L mxz = L::sub(L::add(at<L>(fp.w[1], k + 1), at<L>(fm.w[1], k - 1)),
+                         L::add(at<L>(fm.w[1], k + 1), at<L>(fp.w[1], k - 1)));
+    const L myz = L::sub(L::add(at<L>(fc.w[2], k + 1), at<L>(fc.w[0], k - 1)),
+                         L::add(at<L>(fc.w[0], k + 1), at<L>(fc.w[2], k - 1)));
+    const L gxx = L::mul(gx, gx), gyy = L::mul(gy, gy), gzz = L::mul(gz, gz);
+    // num = sum_a g_a^2 d_aa / h_a^2 + sum_{a<b} 1/2 g_a g_b d_ab / (h_a h_b)
+    L num = L::mul(gxx, L::muls(dxx, p.ihx2));
+    num = L::fma(gyy, L::muls(dyy, p.ihy2), num);
+    num = L::fma(gzz, L::muls(dzz, p.ihz2), num);
+    num = L::fma(L::mul(gx, gy), L::muls(mxy, p.hxy), num);
+    num = L::fma(L::mul(gx, gz), L::muls(mxz, p.hxz), num);
+    num = L::fma(L::mul(gy, gz), L::muls(myz, p.hyz), num);
+    const L n2 = L::add(L::add(gxx, gyy), gzz);
+    const L nl = L::guarded_div(num, n2);
+    const L one_m_c = L::rsubs(T(1), C);
+    const L cc = L::mul(C, one_m_c);                                  // c (1 - c)
+    L pot;
+    if (p.pot) pot = L::load(potv, e);
+    else pot = L::muls(L::mul(cc, L::rsubs(T(1), two_c)), p.pot_scale);
+    // df = gab (curv lap + (1-curv) nl - pot/(2 eps)) + 3/eps c(1-c) force
+    L inner = L::fmas(lap, p.curv, L::fmas(nl, p.omc, L::muls(pot, p.neg_inv_2eps)));
+    const L df = L::fmas(inner, p.gab, L::muls(cc, p.force3));
+    return L::muls(df, p.M);
+  }
+
+  EVX_HD static PlaneRef plane_of(const P& p, int q) { return plane(p, q); }
+
+  EVX_HD static void load_plane(const P& p, const PlaneRef& pl, const Pos& ps, bool plain, Plane& f) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (plain && pl.side < 0) {        // no ghost rule touches this thread: clip only
+        const Vt c = vec_load<T, V>(pl.ptr + ps.roff[j]);
+#pragma unroll
+        for (int k = 0; k < V; ++k) f.w[j][k + 1] = clip01(c.v[k]);
+        f.w[j][0] = clip01(pl.ptr[ps.loff[j]]);
+        f.w[j][V + 1] = clip01(pl.ptr[ps.hoff[j]]);
+      } else {
+        load_row(p, pl, ps, j, f.w[j]);
+      }
+    }
+  }
+
+  // one output plane x: window planes (fm, fc, fp) = (x-1, x, x+1)
+  EVX_HD static void emit(const P& p, const Plane& fm, const Plane& fc, const Plane& fp, long long o) {
+    Vt potv = vec_splat<T, V>(T(0)), basev = potv, accv = potv;
+    if (p.pot) potv = vec_load<T, V>(p.pot + o);
+    if (p.y_out) basev = vec_load<T, V>(p.base + o);
+    if (p.acc_out && p.acc_in) accv = vec_load<T, V>(p.acc_in + o);
+    Vt kv;
+    constexpr int LW = (V % 2 == 0) ? 2 : 1;
+    using L = AcLane<T, LW>;
+#pragma unroll
+    for (int e = 0; e < V; e += LW) rhs_lanes<L>(p, fm, fc, fp, e + 1, potv.v, e).store(kv.v, e);
+    if (p.k_out) vec_store<T, V>(p.k_out + o, kv);
+    if (p.y_out) {
+      Vt yv;
+#pragma unroll
+      for (int e = 0; e < V; ++e) yv.v[e] = basev.v[e] + p.alpha * kv.v[e];
+      vec_store<T, V>(p.y_out + o, yv);
+    }
+    if (p.acc_out) {
+      Vt av;
+#pragma unroll
+      for (int e = 0; e < V; ++e) av.v[e] = accv.v[e] + p.beta * kv.v[e];
+      vec_store<T, V>(p.acc_out + o, av);
+    }
+  }
+
   EVX_HD static void run(const P& p, int tid, int tile, int chunk) {
     const int tiles_z = (p.nz + TZ - 1) / TZ;
     const int y = (tile / tiles_z) * TY + tid / G;
@@ -104,95 +268,45 @@ struct AcProgram {
     const bool per_y = p.bc_kind[1] == BC_PERIODIC, per_z = p.bc_kind[2] == BC_PERIODIC;
 
     Pos ps;
+    bool plain = true;
     {
       const int zl = z - 1, zr = z + V;
       const int zli = per_z ? wrap_index(zl, p.nz) : clamp_index(zl, 0, p.nz - 1);
       const int zri = per_z ? wrap_index(zr, p.nz) : clamp_index(zr, 0, p.nz - 1);
       ps.zl_side = (!per_z && zl < 0) ? 0 : -1;
       ps.zr_side = (!per_z && zr >= p.nz) ? 1 : -1;
+      plain = ps.zl_side < 0 && ps.zr_side < 0;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const int yy = y + j - 1;
         const int yi = per_y ? wrap_index(yy, p.ny) : clamp_index(yy, 0, p.ny - 1);
         ps.yside[j] = (!per_y && yy < 0) ? 0 : ((!per_y && yy >= p.ny) ? 1 : -1);
+        plain = plain && ps.yside[j] < 0;
         ps.roff[j] = (long long)yi * p.nz + z;
         ps.loff[j] = (long long)yi * p.nz + zli;
         ps.hoff[j] = (long long)yi * p.nz + zri;
       }
     }
 
-    T f[3][3][W];
-    {
-      const PlaneRef a = plane(p, xa - 1), b = plane(p, xa);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        load_row(p, a, ps, j, f[1][j]);
-        load_row(p, b, ps, j, f[2][j]);
-      }
-    }
+    // rolling window of three planes; the loop is unrolled by three so that the planes
+    // rotate by renaming instead of by register moves
+    Plane f0, f1, f2;
+    load_plane(p, plane(p, xa - 1), ps, plain, f0);
+    load_plane(p, plane(p, xa), ps, plain, f1);
     const long long plane_sz = (long long)p.ny * p.nz;
-    const long long ooff = (long long)y * p.nz + z;
-    for (int x = xa; x < xb; ++x) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int k = 0; k < W; ++k) {
-          f[0][j][k] = f[1][j][k];
-          f[1][j][k] = f[2][j][k];
-        }
-      {
-        const PlaneRef nxt = plane(p, x + 1);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) load_row(p, nxt, ps, j, f[2][j]);
+    long long o = (long long)xa * plane_sz + (long long)y * p.nz + z;
+    for (int x = xa; x < xb; x += 3) {
+      load_plane(p, plane(p, x + 1), ps, plain, f2);
+      emit(p, f0, f1, f2, o);
+      if (x + 1 < xb) {
+        load_plane(p, plane(p, x + 2), ps, plain, f0);
+        emit(p, f1, f2, f0, o + plane_sz);
       }
-      const long long o = (long long)x * plane_sz + ooff;
-      Vt potv = vec_splat<T, V>(T(0)), basev = potv, accv = potv;
-      if (p.pot) potv = vec_load<T, V>(p.pot + o);
-      if (p.y_out) basev = vec_load<T, V>(p.base + o);
-      if (p.acc_out && p.acc_in) accv = vec_load<T, V>(p.acc_in + o);
-      Vt kv;
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const int k = e + 1;
-        const T C = f[1][1][k];
-        const T R = f[2][1][k], L = f[0][1][k];
-        const T Tp = f[1][2][k], B = f[1][0][k];
-        const T F = f[1][1][k + 1], Bk = f[1][1][k - 1];
-        const T lap = (R + L) * p.ihx2 + (Tp + B) * p.ihy2 + (F + Bk) * p.ihz2 -
-                      T(2) * C * p.ih2sum;
-        const T gx = T(0.5) * (R - L) * p.ihx;
-        const T gy = T(0.5) * (Tp - B) * p.ihy;
-        const T gz = T(0.5) * (F - Bk) * p.ihz;
-        const T mxy = f[2][2][k] + f[0][0][k] - f[0][2][k] - f[2][0][k];
-        const T mxz = f[2][1][k + 1] + f[0][1][k - 1] - f[0][1][k + 1] - f[2][1][k - 1];
-        const T myz = f[1][2][k + 1] + f[1][0][k - 1] - f[1][0][k + 1] - f[1][2][k - 1];
-        const T num = gx * gx * (R - T(2) * C + L) * p.ihx2 +
-                      gy * gy * (Tp - T(2) * C + B) * p.ihy2 +
-                      gz * gz * (F - T(2) * C + Bk) * p.ihz2 +
-                      T(0.5) * gx * gy * mxy * p.ihx * p.ihy +
-                      T(0.5) * gx * gz * mxz * p.ihx * p.ihz +
-                      T(0.5) * gy * gz * myz * p.ihy * p.ihz;
-        T n2 = gx * gx + gy * gy + gz * gz;
-        if (n2 <= T(1e-7)) n2 = T(1);
-        const T nl = num / n2;
-        const T pot = p.pot ? potv.v[e] : p.pot_scale * C * (T(1) - C) * (T(1) - T(2) * C);
-        const T df = p.gab * (p.curv * lap + p.omc * nl - pot / T(2) / p.eps) +
-                     p.three_over_eps * C * (T(1) - C) * p.force;
-        kv.v[e] = p.M * df;
+      if (x + 2 < xb) {
+        load_plane(p, plane(p, x + 3), ps, plain, f1);
+        emit(p, f2, f0, f1, o + 2 * plane_sz);
       }
-      if (p.k_out) vec_store<T, V>(p.k_out + o, kv);
-      if (p.y_out) {
-        Vt yv;
-#pragma unroll
-        for (int e = 0; e < V; ++e) yv.v[e] = basev.v[e] + p.alpha * kv.v[e];
-        vec_store<T, V>(p.y_out + o, yv);
-      }
-      if (p.acc_out) {
-        Vt av;
-#pragma unroll
-        for (int e = 0; e < V; ++e) av.v[e] = accv.v[e] + p.beta * kv.v[e];
-        vec_store<T, V>(p.acc_out + o, av);
-      }
+      o += 3 * plane_sz;
     }
   }
 };

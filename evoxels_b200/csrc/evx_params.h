@@ -66,6 +66,9 @@ inline AcParams<T> make_ac_params(const T* phi, const T* pot, T* k_out, const T*
   fill_metric<T>(p, h);
   p.pot_scale = T(18.0 / eps); p.eps = T(eps); p.gab = T(gab); p.M = T(M); p.force = T(force);
   p.curv = T(curvature); p.omc = T(1.0 - curvature); p.three_over_eps = T(3.0 / eps);
+  p.hihx = T(0.5 / h[0]); p.hihy = T(0.5 / h[1]); p.hihz = T(0.5 / h[2]);
+  p.hxy = T(0.5 / (h[0] * h[1])); p.hxz = T(0.5 / (h[0] * h[2])); p.hyz = T(0.5 / (h[1] * h[2]));
+  p.neg_inv_2eps = T(-0.5 / eps); p.force3 = T(3.0 / eps * force);
   fill_ghost_rules<T>(bc_kind, bc_val, p.bc_kind, p.ghost_off, p.ghost_sgn);
   return p;
 }

@@ -44,8 +44,15 @@ static int launch_pass(const Params& p, long long blocks, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
-template <int L>
-struct StridedCfg { static constexpr int KZ = L >= 2048 ? 4 : 8; };
+// Columns per tile.  The x pass walks lines whose points are ny*P elements (~1 MB) apart:
+// measured with the access-pattern probe (evx_debug_strided_copy, 512^3) a tile of 8
+// columns (64-B rows) tops out at 3.3 TB/s there, 16 columns (128-B rows) at 5.3 TB/s,
+// while the y pass (2 KB stride) is already at 6.3 TB/s with 8.  x-pass tiles may straddle
+// y groups (the column index is the linear offset), so the pitch stays a multiple of 8.
+template <int L, int MODE>
+struct StridedCfg {
+  static constexpr int KZ = L >= 2048 ? 4 : ((MODE == PASS_XMID && L <= 512) ? 16 : 8);
+};
 
 // persistent, software-pipelined form (see StridedPipe in fft_pass_core.h)
 template <class Pipe>
@@ -117,7 +124,7 @@ static int launch_strided(int L, StridedParams p, cudaStream_t st) {
   finalize_strided(p, L);
 #define EVX_CASE(N)                                                                   \
   case N: {                                                                           \
-    constexpr int KZ = StridedCfg<N>::KZ;                                             \
+    constexpr int KZ = StridedCfg<N, MODE>::KZ;                                       \
     if (N >= 64 && use_pipeline()) return launch_pipe<StridedPipe<N, KZ, MODE>>(p, st); \
     return launch_pass<StridedPass<N, KZ, MODE>, StridedParams>(                      \
         p, (p.ncols_total + KZ - 1) / KZ, st);                                        \

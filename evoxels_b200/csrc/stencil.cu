@@ -94,7 +94,7 @@ int ch_rhs_impl(const T* c, const T* hom, T* rhs, int nx, int ny, int nz, const 
 // Allen-Cahn stage
 // ------------------------------------------------------------------------------------
 template <typename T, int V, int TY, int G>
-__global__ void __launch_bounds__(TY* G) ac_stage_kernel(const AcParams<T> p) {
+__global__ void __launch_bounds__(TY* G, 2) ac_stage_kernel(const AcParams<T> p) {
   AcProgram<T, V, TY, G>::run(p, threadIdx.x, blockIdx.x, blockIdx.y);
 }
 

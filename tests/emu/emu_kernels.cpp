@@ -190,6 +190,7 @@ static void run_pipe(const StridedParams& p, int nblocks) {
   }
 }
 
+static int g_emu_xkz = 8;           // columns per tile of the x pass (8 or 16; 16 may straddle y groups)
 static int g_emu_pipe_blocks = 0;   // 0: one block per tile (StridedPass), >0: pipelined with that many blocks
 
 template <int KZ, int MODE>
@@ -252,6 +253,7 @@ static int dispatch_z(int M, const ZParams& p) {
 extern "C" {
 
 void emu_set_pipe_blocks(int n) { g_emu_pipe_blocks = n; }
+void emu_set_xpass_columns(int kz) { g_emu_xkz = kz; }
 
 // out = u + irfftn(P * rfftn(r)) through the five native passes; spec is scratch
 // [nx*ny*P] complex with P = roundup(nz/2+1, 8).  mode: 0 full, 1 forward only (spec out),
@@ -285,7 +287,7 @@ int emu_native_apply(const float* u, const float* r, float* out, float* spec_out
   sp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
   sp.tw = twx.data(); sp.src = sp.dst = xio;
   sp.ncols_total = (long long)ny * P;
-  if (dispatch_strided<KZ, PASS_XMID>(nx, sp)) return -3;
+  if (g_emu_xkz == 16 ? dispatch_strided<16, PASS_XMID>(nx, sp) : dispatch_strided<KZ, PASS_XMID>(nx, sp)) return -3;
   sp.tw = twy.data(); sp.src = sp.dst = yio;
   sp.ncols_total = (long long)nx * P;
   if (dispatch_strided<KZ, PASS_INV>(ny, sp)) return -4;

@@ -69,7 +69,7 @@ def emu_ac(lib, u, sp, kw, bc, xchunk, vec, alpha=0.0, beta=0.0, acc=None, hlo=N
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_ch_rhs_program(emu, dtype):
-    tol = 1e-12 if dtype == np.float64 else 2e-5
+    tol = 5e-12 if dtype == np.float64 else 2e-5
     for shape, sp in SHAPES:
         u = (-0.2 + 1.4 * np.random.default_rng(3).random(shape)).astype(dtype)
         for bc in BCS:
@@ -99,12 +99,12 @@ def test_ch_rhs_program_custom_potential_and_halos(emu):
             lo = np.ascontiguousarray(np.take(u, [a - 2, a - 1], axis=0, mode="wrap")) if (per or a > 0) else None
             hi = np.ascontiguousarray(np.take(u, [b, b + 1], axis=0, mode="wrap")) if (per or b < 12) else None
             parts.append(emu_ch(emu, np.ascontiguousarray(u[a:b]), (1, 1, 1), 3.0, 1.0, bc, 3, 1, hlo=lo, hhi=hi))
-        assert rel_l2(np.concatenate(parts), ref) <= 1e-12, bc
+        assert rel_l2(np.concatenate(parts), ref) <= 5e-12, bc
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_ac_stage_program(emu, dtype):
-    tol = 1e-12 if dtype == np.float64 else 3e-5
+    tol = 5e-12 if dtype == np.float64 else 3e-5
     kw = dict(eps=3.0, gab=0.8, M=1.5, force=1.0, curvature=0.5)
     for shape, sp in SHAPES:
         u = (-0.2 + 1.4 * np.random.default_rng(3).random(shape)).astype(dtype)
@@ -131,7 +131,7 @@ def test_ac_stage_program_halos(emu):
             lo = np.ascontiguousarray(np.take(u, [a - 1], axis=0, mode="wrap")) if (per or a > 0) else None
             hi = np.ascontiguousarray(np.take(u, [b], axis=0, mode="wrap")) if (per or b < 12) else None
             parts.append(emu_ac(emu, np.ascontiguousarray(u[a:b]), (1, 1, 1), kw, bc, 3, 1, hlo=lo, hhi=hi)[0])
-        assert rel_l2(np.concatenate(parts), ref) <= 1e-12, bc
+        assert rel_l2(np.concatenate(parts), ref) <= 5e-12, bc
 
 
 def test_pad_and_padded_stencils(emu):
@@ -153,13 +153,15 @@ def test_pad_and_padded_stencils(emu):
                     assert rel_l2(o2, r2) <= (1e-12 if dtype == np.float64 else 2e-4)
 
 
-@pytest.mark.parametrize("pipe_blocks", [0, 1, 3])
+@pytest.mark.parametrize("pipe_blocks,xkz", [(0, 8), (1, 8), (3, 16), (0, 16)])
 @pytest.mark.parametrize("shape", [(8, 8, 16), (16, 32, 64), (32, 16, 128), (8, 8, 256), (64, 8, 32)])
-def test_native_fft_pipeline(emu, shape, pipe_blocks):
+def test_native_fft_pipeline(emu, shape, pipe_blocks, xkz):
     """Five-pass native FFT pipeline (ZFwd, Y, X fwd*filter*inv, Y inv, ZInv+u) replayed on
     the CPU: forward spectrum against numpy's rfftn, full update against the oracle."""
     # pipe_blocks > 0: persistent software-pipelined strided passes with that many blocks
+    # xkz: columns per x-pass tile; 16-column tiles straddle y groups when the pitch is 8 mod 16
     emu.emu_set_pipe_blocks(pipe_blocks)
+    emu.emu_set_xpass_columns(xkz)
     nx, ny, nz = shape
     rng = np.random.default_rng(0)
     r = rng.standard_normal(shape).astype(np.float32)
@@ -179,6 +181,7 @@ def test_native_fft_pipeline(emu, shape, pipe_blocks):
     pref = O.imex_prefactor(O.ch_symbol(shape, sp, 3.0, 1.0, 0.25), 0.1)
     want = O.imex_step(torch.from_numpy(u)[None], torch.from_numpy(r)[None], pref)[0].numpy()
     emu.emu_set_pipe_blocks(0)
+    emu.emu_set_xpass_columns(8)
     assert rel_l2(out - u, want - u) < 2e-6
     assert rel_l2(out, want) < 1e-6
 
