@@ -288,25 +288,32 @@ struct AcProgram {
       }
     }
 
-    // rolling window of three planes; the loop is unrolled by three so that the planes
-    // rotate by renaming instead of by register moves
-    Plane f0, f1, f2;
+    // rolling window of three planes plus one incoming plane: the loads of plane x+2 are
+    // issued before plane x is evaluated (software prefetch, the kernel has no other way to
+    // hide L2 latency at two blocks per SM); unrolled by four so that the planes rotate by
+    // renaming instead of by register moves
+    Plane f0, f1, f2, f3;
     load_plane(p, plane(p, xa - 1), ps, plain, f0);
     load_plane(p, plane(p, xa), ps, plain, f1);
+    load_plane(p, plane(p, xa + 1), ps, plain, f2);
     const long long plane_sz = (long long)p.ny * p.nz;
     long long o = (long long)xa * plane_sz + (long long)y * p.nz + z;
-    for (int x = xa; x < xb; x += 3) {
-      load_plane(p, plane(p, x + 1), ps, plain, f2);
+    for (int x = xa; x < xb; x += 4) {
+      if (x + 1 < xb) load_plane(p, plane(p, x + 2), ps, plain, f3);
       emit(p, f0, f1, f2, o);
       if (x + 1 < xb) {
-        load_plane(p, plane(p, x + 2), ps, plain, f0);
-        emit(p, f1, f2, f0, o + plane_sz);
+        if (x + 2 < xb) load_plane(p, plane(p, x + 3), ps, plain, f0);
+        emit(p, f1, f2, f3, o + plane_sz);
       }
       if (x + 2 < xb) {
-        load_plane(p, plane(p, x + 3), ps, plain, f1);
-        emit(p, f2, f0, f1, o + 2 * plane_sz);
+        if (x + 3 < xb) load_plane(p, plane(p, x + 4), ps, plain, f1);
+        emit(p, f2, f3, f0, o + 2 * plane_sz);
       }
-      o += 3 * plane_sz;
+      if (x + 3 < xb) {
+        if (x + 4 < xb) load_plane(p, plane(p, x + 5), ps, plain, f2);
+        emit(p, f3, f0, f1, o + 3 * plane_sz);
+      }
+      o += 4 * plane_sz;
     }
   }
 };

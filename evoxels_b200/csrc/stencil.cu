@@ -93,8 +93,8 @@ int ch_rhs_impl(const T* c, const T* hom, T* rhs, int nx, int ny, int nz, const 
 // ------------------------------------------------------------------------------------
 // Allen-Cahn stage
 // ------------------------------------------------------------------------------------
-template <typename T, int V, int TY, int G>
-__global__ void __launch_bounds__(TY* G, 2) ac_stage_kernel(const AcParams<T> p) {
+template <typename T, int V, int TY, int G, int MINB>
+__global__ void __launch_bounds__(TY* G, MINB) ac_stage_kernel(const AcParams<T> p) {
   AcProgram<T, V, TY, G>::run(p, threadIdx.x, blockIdx.x, blockIdx.y);
 }
 
@@ -106,7 +106,11 @@ static int launch_ac(AcParams<T> p, cudaStream_t st) {
   const int chunks = (p.nx + p.xchunk - 1) / p.xchunk;
   if (tiles > 2147483647LL || chunks > 65535) return EVX_ERR_UNSUPPORTED;
   dim3 grid((unsigned)tiles, (unsigned)chunks);
-  ac_stage_kernel<T, V, TY, G><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  static const int occ = [] { const char* e = getenv("EVX_AC_OCC"); return e ? atoi(e) : 2; }();
+  if (occ == 1)
+    ac_stage_kernel<T, V, TY, G, 1><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  else
+    ac_stage_kernel<T, V, TY, G, 2><<<grid, Prog::NTHREADS, 0, st>>>(p);
   count_launch();
   return (int)cudaGetLastError();
 }
