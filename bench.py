@@ -324,7 +324,7 @@ def run_ours_distributed(args, world, rank, local, dev):
     shape = weak_scaling_shape(args.size, world)
     nvox = shape[0] * shape[1] * shape[2]
     stepper = DistributedCahnHilliardIMEX(shape, (1.0, 1.0, 1.0), CH["dt"], CH["eps"], CH["D"],
-                                          CH["A"], device=dev)
+                                          CH["A"], device=dev, transport=args.transport)
     gen = torch.Generator(device=dev).manual_seed(rank)
     u0 = 0.5 + 0.1 * torch.rand(stepper.slab.local_shape, device=dev, generator=gen)
 
@@ -382,8 +382,9 @@ def run_ours_distributed(args, world, rank, local, dev):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"CH IMEX {shape[0]}x{shape[1]}x{shape[2]} fp32 periodic dt=0.1 "
                                    f"({args.size}^3 voxels per GPU)", **CH, "fft_backend": "native",
-                       "parallelism": f"x-slab over {world} GPUs: 2-plane halos (NCCL P2P) + "
-                                      "slab<->pencil all-to-all (NCCL) in the transposed FFT",
+                       "parallelism": f"x-slab over {world} GPUs: 2-plane halos (NCCL send/recv) + slab<->pencil "
+                                      + ("transposes fused into the FFT passes as NVLink peer stores (symmetric memory)"
+                                         if args.transport == "p2p" else "NCCL all-to-all"),
                        "l2": "slab (%.0f MB) larger than L2 (126 MB), no flush needed" % (slab_bytes / 1e6)},
             "clocks": clocks,
             "e2e": {"value": nvox * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
@@ -409,6 +410,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fft", default="auto", choices=["auto", "cufft", "native"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU transposes: fused peer stores over NVLink, or NCCL all-to-all")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

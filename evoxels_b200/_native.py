@@ -64,6 +64,9 @@ SIGNATURES = {
     "evx_dist_plan_sizes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t), _iptr],
     "evx_dist_forward_f32": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
     "evx_dist_middle_f32": [_c_void_p, _c_void_p, _dptr, _c_double, _c_double, _c_int, _c_void_p],
+    "evx_dist_forward_p2p_f32": [_c_void_p, _c_void_p, _c_void_p, ctypes.POINTER(_c_void_p), _c_void_p],
+    "evx_dist_middle_p2p_f32": [_c_void_p, _c_void_p, ctypes.POINTER(_c_void_p), _dptr, _c_double,
+                                _c_double, _c_int, _c_void_p],
     "evx_dist_backward_f32": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
 }
 _RESTYPES = {"evx_strerror": ctypes.c_char_p, "evx_launch_count": ctypes.c_ulonglong}
@@ -345,6 +348,25 @@ class DistPlan:
             check(load_library().evx_dist_middle_f32(self._handle, _ptr(recv), _h3(spacing), float(dt),
                                                      float(coef), int(power), _stream(recv)),
                   "evx_dist_middle")
+
+    @staticmethod
+    def _ptr_array(ptrs):
+        return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+    def forward_p2p(self, r_local, spec, peer_ptrs):
+        """ZFwd + y pass whose stores go straight into the peers' block buffers."""
+        require_cuda(r_local, spec)
+        with torch.cuda.device(self.device):
+            check(load_library().evx_dist_forward_p2p_f32(self._handle, _ptr(_field3(r_local)), _ptr(spec),
+                                                          self._ptr_array(peer_ptrs), _stream(r_local)),
+                  "evx_dist_forward_p2p")
+
+    def middle_p2p(self, recv, peer_ptrs, spacing, dt, coef, power):
+        require_cuda(recv)
+        with torch.cuda.device(self.device):
+            check(load_library().evx_dist_middle_p2p_f32(self._handle, _ptr(recv), self._ptr_array(peer_ptrs),
+                                                         _h3(spacing), float(dt), float(coef), int(power),
+                                                         _stream(recv)), "evx_dist_middle_p2p")
 
     def backward(self, recv, spec, u_local, out_local):
         require_cuda(recv, spec, u_local, out_local)

@@ -17,7 +17,7 @@
 // through L1 (no shared memory, no barrier).
 #pragma once
 #include "evx_hd.h"
-#include "packed_f32.h"
+#include "lanes.h"
 
 namespace evx {
 
@@ -43,71 +43,6 @@ struct AcParams {
   T ghost_off[3][2];
   T ghost_sgn[3];
 };
-
-// ------------------------------------------------------------------------------------
-// Lane types of the Allen-Cahn arithmetic: one value, or a pair of neighbouring z values
-// (float pairs use the packed FADD2/FMUL2/FFMA2 path on the device).
-// ------------------------------------------------------------------------------------
-template <typename T, int LW>
-struct AcLane;
-
-template <typename T>
-struct AcLane<T, 1> {
-  T a;
-  EVX_HD static AcLane load(const T* w, int k) { return AcLane{w[k]}; }
-  EVX_HD void store(T* w, int k) const { w[k] = a; }
-  EVX_HD static AcLane add(AcLane x, AcLane y) { return AcLane{x.a + y.a}; }
-  EVX_HD static AcLane sub(AcLane x, AcLane y) { return AcLane{x.a - y.a}; }
-  EVX_HD static AcLane mul(AcLane x, AcLane y) { return AcLane{x.a * y.a}; }
-  EVX_HD static AcLane fma(AcLane x, AcLane y, AcLane z) { return AcLane{x.a * y.a + z.a}; }
-  EVX_HD static AcLane muls(AcLane x, T s) { return AcLane{x.a * s}; }
-  EVX_HD static AcLane fmas(AcLane x, T s, AcLane z) { return AcLane{x.a * s + z.a}; }
-  EVX_HD static AcLane rsubs(T s, AcLane x) { return AcLane{s - x.a}; }
-  EVX_HD static AcLane guarded_div(AcLane n, AcLane d) {
-    return AcLane{n.a / (d.a <= T(1e-7) ? T(1) : d.a)};
-  }
-};
-
-template <typename T>
-struct AcLane<T, 2> {
-  T a, b;
-  EVX_HD static AcLane load(const T* w, int k) { return AcLane{w[k], w[k + 1]}; }
-  EVX_HD void store(T* w, int k) const { w[k] = a; w[k + 1] = b; }
-  EVX_HD static AcLane add(AcLane x, AcLane y) { return AcLane{x.a + y.a, x.b + y.b}; }
-  EVX_HD static AcLane sub(AcLane x, AcLane y) { return AcLane{x.a - y.a, x.b - y.b}; }
-  EVX_HD static AcLane mul(AcLane x, AcLane y) { return AcLane{x.a * y.a, x.b * y.b}; }
-  EVX_HD static AcLane fma(AcLane x, AcLane y, AcLane z) {
-    return AcLane{x.a * y.a + z.a, x.b * y.b + z.b};
-  }
-  EVX_HD static AcLane muls(AcLane x, T s) { return AcLane{x.a * s, x.b * s}; }
-  EVX_HD static AcLane fmas(AcLane x, T s, AcLane z) { return AcLane{x.a * s + z.a, x.b * s + z.b}; }
-  EVX_HD static AcLane rsubs(T s, AcLane x) { return AcLane{s - x.a, s - x.b}; }
-  EVX_HD static AcLane guarded_div(AcLane n, AcLane d) {
-    return AcLane{n.a / (d.a <= T(1e-7) ? T(1) : d.a), n.b / (d.b <= T(1e-7) ? T(1) : d.b)};
-  }
-};
-
-#if defined(__CUDA_ARCH__)
-template <>
-struct AcLane<float, 2> {
-  f2 v;
-  EVX_D static AcLane load(const float* w, int k) { return AcLane{f2{w[k], w[k + 1]}}; }
-  EVX_D void store(float* w, int k) const { w[k] = v.a; w[k + 1] = v.b; }
-  EVX_D static AcLane add(AcLane x, AcLane y) { return AcLane{f2_add(x.v, y.v)}; }
-  EVX_D static AcLane sub(AcLane x, AcLane y) { return AcLane{f2_sub(x.v, y.v)}; }
-  EVX_D static AcLane mul(AcLane x, AcLane y) { return AcLane{f2_mul(x.v, y.v)}; }
-  EVX_D static AcLane fma(AcLane x, AcLane y, AcLane z) { return AcLane{f2_fma(x.v, y.v, z.v)}; }
-  EVX_D static AcLane muls(AcLane x, float s) { return AcLane{f2_mul(x.v, f2_splat(s))}; }
-  EVX_D static AcLane fmas(AcLane x, float s, AcLane z) { return AcLane{f2_fma(x.v, f2_splat(s), z.v)}; }
-  EVX_D static AcLane rsubs(float s, AcLane x) { return AcLane{f2_sub(f2_splat(s), x.v)}; }
-  EVX_D static AcLane guarded_div(AcLane n, AcLane d) {
-    // hardware reciprocal (<= 2 ulp); the reference divides exactly, the difference is far
-    // below the test tolerances
-    const float da = d.v.a <= 1e-7f ? 1.0f : d.v.a, db = d.v.b <= 1e-7f ? 1.0f : d.v.b;
-    return AcLane{f2{__fdividef(n.v.a, da), __fdividef(n.v.b, db)}};
-  }
-};
-#endif
 
 template <typename T, int V, int TY, int G>
 struct AcProgram {
@@ -288,32 +223,25 @@ struct AcProgram {
       }
     }
 
-    // rolling window of three planes plus one incoming plane: the loads of plane x+2 are
-    // issued before plane x is evaluated (software prefetch, the kernel has no other way to
-    // hide L2 latency at two blocks per SM); unrolled by four so that the planes rotate by
-    // renaming instead of by register moves
-    Plane f0, f1, f2, f3;
+    // rolling window of three planes; the loop is unrolled by three so that the planes
+    // rotate by renaming instead of by register moves
+    Plane f0, f1, f2;
     load_plane(p, plane(p, xa - 1), ps, plain, f0);
     load_plane(p, plane(p, xa), ps, plain, f1);
-    load_plane(p, plane(p, xa + 1), ps, plain, f2);
     const long long plane_sz = (long long)p.ny * p.nz;
     long long o = (long long)xa * plane_sz + (long long)y * p.nz + z;
-    for (int x = xa; x < xb; x += 4) {
-      if (x + 1 < xb) load_plane(p, plane(p, x + 2), ps, plain, f3);
+    for (int x = xa; x < xb; x += 3) {
+      load_plane(p, plane(p, x + 1), ps, plain, f2);
       emit(p, f0, f1, f2, o);
       if (x + 1 < xb) {
-        if (x + 2 < xb) load_plane(p, plane(p, x + 3), ps, plain, f0);
-        emit(p, f1, f2, f3, o + plane_sz);
+        load_plane(p, plane(p, x + 2), ps, plain, f0);
+        emit(p, f1, f2, f0, o + plane_sz);
       }
       if (x + 2 < xb) {
-        if (x + 3 < xb) load_plane(p, plane(p, x + 4), ps, plain, f1);
-        emit(p, f2, f3, f0, o + 2 * plane_sz);
+        load_plane(p, plane(p, x + 3), ps, plain, f1);
+        emit(p, f2, f0, f1, o + 2 * plane_sz);
       }
-      if (x + 3 < xb) {
-        if (x + 4 < xb) load_plane(p, plane(p, x + 5), ps, plain, f2);
-        emit(p, f3, f0, f1, o + 3 * plane_sz);
-      }
-      o += 4 * plane_sz;
+      o += 3 * plane_sz;
     }
   }
 };

@@ -33,6 +33,7 @@
 // the rings are never consumed (they hold don't-care values).
 #pragma once
 #include "evx_hd.h"
+#include "lanes.h"
 
 namespace evx {
 
@@ -138,6 +139,13 @@ struct ChRhsProgram {
     const T* pl = plane(p, base, q, use_halo);
     if (pl) return vec_load<T, V>(pl + off);
     return vec_splat<T, V>(T(0));
+  }
+
+  static constexpr int LW = (V % 2 == 0) ? 2 : 1;   // lanes: pairs of z values when possible
+  using Ln = AcLane<T, LW>;
+  EVX_HD static Ln face_l(Ln ca, Ln cb, Ln ma, Ln mb) {
+    const Ln s = Ln::add(ca, cb);
+    return Ln::mul(Ln::mul(s, Ln::rsubs(T(2), s)), Ln::sub(mb, ma));
   }
 
   // 4 cf (1 - cf) (mb - ma) with cf = (ca + cb)/2
@@ -287,14 +295,27 @@ struct ChRhsProgram {
         if (is_ghost_plane(t, p, pl - 1)) cXm = ghostv(t.cC, ox0, sx);
         if (is_ghost_plane(t, p, pl + 1)) cXp = ghostv(t.cC, ox1, sx);
       }
+      // window of c^(pl) along z: [cL, c0..c(V-1), cR]
+      T cw[V + 2];
+      cw[0] = cL;
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        const T c0 = t.cC.v[k];
-        const T zl = k == 0 ? cL : t.cC.v[k - 1];
-        const T zr = k == V - 1 ? cR : t.cC.v[k + 1];
-        const T hom = HOM ? t.hC.v[k] : p.pot_scale * (c0 * (T(1) - c0)) * (T(1) - T(2) * c0);
-        mC.v[k] = hom + p.lx * (cXp.v[k] + cXm.v[k]) + p.ly * (cN.v[k] + cS.v[k]) +
-                  p.lz * (zr + zl) + p.l0 * c0;
+      for (int k = 0; k < V; ++k) cw[k + 1] = t.cC.v[k];
+      cw[V + 1] = cR;
+#pragma unroll
+      for (int k = 0; k < V; k += LW) {
+        const Ln c0 = Ln::load(cw, k + 1);
+        const Ln sx = Ln::add(Ln::load(cXp.v, k), Ln::load(cXm.v, k));
+        const Ln sy = Ln::add(Ln::load(cN.v, k), Ln::load(cS.v, k));
+        const Ln sz = Ln::add(Ln::load(cw, k + 2), Ln::load(cw, k));
+        Ln hom;
+        if (HOM) {
+          hom = Ln::load(t.hC.v, k);
+        } else {
+          const Ln cc = Ln::mul(c0, Ln::rsubs(T(1), c0));
+          hom = Ln::muls(Ln::mul(cc, Ln::rsubs(T(1), Ln::add(c0, c0))), p.pot_scale);
+        }
+        Ln::fmas(sx, p.lx, Ln::fmas(sy, p.ly, Ln::fmas(sz, p.lz, Ln::fmas(c0, p.l0, hom))))
+            .store(mC.v, k);
       }
     }
     s.mu[PAR][row - 1][col] = mC;
@@ -302,7 +323,9 @@ struct ChRhsProgram {
     // x-face term between planes pl-1 and pl (carried to the next plane as "minus" face)
     Vt fxp;
 #pragma unroll
-    for (int k = 0; k < V; ++k) fxp.v[k] = face(t.cB.v[k], t.cC.v[k], t.mB.v[k], mC.v[k]);
+    for (int k = 0; k < V; k += LW)
+      face_l(Ln::load(t.cB.v, k), Ln::load(t.cC.v, k), Ln::load(t.mB.v, k), Ln::load(mC.v, k))
+          .store(fxp.v, k);
 
     // rhs at plane x = pl-1: c^(x) = cB, mu(x) = mB; the x-faces are fxm (carried) and fxp
     const int x = pl - 1;
@@ -330,19 +353,27 @@ struct ChRhsProgram {
             fxp.v[k] = face(t.cB.v[k], ox1 + sx * t.cB.v[k], t.mB.v[k], ox1 + sx * t.mB.v[k]);
         }
       }
-      // z-face terms: fz[k] is the face between elements k-1 and k of the group
-      T fz[V + 1];
-      fz[0] = face(t.sL, t.cB.v[0], mL, t.mB.v[0]);
+      // z windows of c^(x) and mu(x): [left, 0..V-1, right]
+      T cw[V + 2], mw[V + 2];
+      cw[0] = t.sL; mw[0] = mL;
 #pragma unroll
-      for (int k = 1; k < V; ++k) fz[k] = face(t.cB.v[k - 1], t.cB.v[k], t.mB.v[k - 1], t.mB.v[k]);
-      fz[V] = face(t.cB.v[V - 1], t.sR, t.mB.v[V - 1], mR);
+      for (int k = 0; k < V; ++k) { cw[k + 1] = t.cB.v[k]; mw[k + 1] = t.mB.v[k]; }
+      cw[V + 1] = t.sR; mw[V + 1] = mR;
+      // z-face terms: fz[k] is the face between window elements k and k+1
+      T fz[V + 2];
+#pragma unroll
+      for (int k = 0; k + LW <= V + 1; k += LW)
+        face_l(Ln::load(cw, k), Ln::load(cw, k + 1), Ln::load(mw, k), Ln::load(mw, k + 1)).store(fz, k);
+      if ((V + 1) % LW) fz[V] = face(cw[V], cw[V + 1], mw[V], mw[V + 1]);
       Vt o;
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        const T c0 = t.cB.v[k], m0 = t.mB.v[k];
-        const T fyp = face(c0, t.sN.v[k], m0, mN.v[k]);
-        const T fym = face(t.sS.v[k], c0, mS.v[k], m0);
-        o.v[k] = p.fx * (fxp.v[k] - fxm.v[k]) + p.fy * (fyp - fym) + p.fz * (fz[k + 1] - fz[k]);
+      for (int k = 0; k < V; k += LW) {
+        const Ln c0 = Ln::load(t.cB.v, k), m0 = Ln::load(t.mB.v, k);
+        const Ln fyp = face_l(c0, Ln::load(t.sN.v, k), m0, Ln::load(mN.v, k));
+        const Ln fym = face_l(Ln::load(t.sS.v, k), c0, Ln::load(mS.v, k), m0);
+        const Ln dx = Ln::sub(Ln::load(fxp.v, k), Ln::load(fxm.v, k));
+        const Ln dz = Ln::sub(Ln::load(fz, k + 1), Ln::load(fz, k));
+        Ln::fmas(dx, p.fx, Ln::fmas(Ln::sub(fyp, fym), p.fy, Ln::muls(dz, p.fz))).store(o.v, k);
       }
       vec_store<T, V>(t.po, o);
       t.po += t.ps;

@@ -203,7 +203,7 @@ int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, v
   yp.in = spec; yp.out = spec; yp.tw = twy;
   yp.src = yp.dst = plain_io(P, (long long)ny * P, ny);
   yp.P = P; yp.ncols_valid = M + 1; yp.ncols_total = (long long)nx * P;
-  yp.kother_offset = 0;
+  yp.kother_offset = 0; yp.use_peers = 0;
   yp.filt = FilterParams{};
   if ((rc = launch_strided<PASS_FWD>(ny, yp, st))) return rc;
 
@@ -271,7 +271,15 @@ static StridedIO block_io(const DistPlan* p) {
   return StridedIO{p->P, (long long)p->nyl * p->P, (long long)p->nxl * p->nyl * p->P, ilog2(p->nyl)};
 }
 
-int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, cudaStream_t st) {
+static void set_peers(StridedParams& sp, const DistPlan* p, void* const* peers) {
+  sp.use_peers = peers ? 1 : 0;
+  sp.dst_peer_base = (long long)p->rank * p->nxl * p->nyl * p->P;
+  for (int i = 0; i < 8; ++i) sp.out_peers[i] = (peers && i < p->world) ? (cf*)peers[i] : nullptr;
+}
+
+// peers != null: block `rank` of every peer's buffer is written directly (NVLink stores)
+int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* const* peers,
+                 cudaStream_t st) {
   ZParams zp;
   zp.real_in = r_local; zp.real_out = nullptr; zp.spec = spec; zp.tw = tw_z(p); zp.twr = tw_r(p);
   zp.rows = (long long)p->nxl * p->ny; zp.nz = p->nz; zp.P = p->P;
@@ -283,14 +291,18 @@ int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, cudaStre
   yp.dst = block_io(p);
   yp.P = p->P; yp.ncols_valid = p->M + 1; yp.ncols_total = (long long)p->nxl * p->P;
   yp.kother_offset = 0; yp.filt = FilterParams{};
+  set_peers(yp, p, peers);
   return launch_strided<PASS_FWD>(p->ny, yp, st);
 }
 
-int dist_middle(DistPlan* p, cf* recv, const double* h, double dt, double coef, int power,
-                cudaStream_t st) {
+int dist_middle(DistPlan* p, cf* recv, void* const* peers, const double* h, double dt, double coef,
+                int power, cudaStream_t st) {
   StridedParams xp;
   xp.in = recv; xp.out = recv; xp.tw = tw_x(p);
   xp.src = xp.dst = plain_io((long long)p->nyl * p->P, p->P, p->nx);
+  set_peers(xp, p, peers);
+  if (peers)   // chunk x / nxl of every x line goes to that rank: [rank j block][xl][yl][kz]
+    xp.dst = StridedIO{(long long)p->nyl * p->P, p->P, 0, ilog2(p->nxl)};
   xp.P = p->P; xp.ncols_valid = p->M + 1; xp.ncols_total = (long long)p->nyl * p->P;
   xp.kother_offset = p->rank * p->nyl;
   const int n[3] = {p->nx, p->ny, p->nz};
@@ -305,7 +317,7 @@ int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, f
   yp.src = block_io(p);
   yp.dst = plain_io(p->P, (long long)p->ny * p->P, p->ny);
   yp.P = p->P; yp.ncols_valid = p->M + 1; yp.ncols_total = (long long)p->nxl * p->P;
-  yp.kother_offset = 0; yp.filt = FilterParams{};
+  yp.kother_offset = 0; yp.filt = FilterParams{}; yp.use_peers = 0;
   int rc = launch_strided<PASS_INV>(p->ny, yp, st);
   if (rc) return rc;
   ZParams zp;
@@ -318,6 +330,7 @@ int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, f
 int debug_strided_copy(cf* data, int nx, int ny, int P, int along_x, int kz_cols, cudaStream_t st) {
   StridedParams p;
   p.in = data; p.out = data; p.tw = nullptr; p.P = P; p.ncols_valid = P; p.kother_offset = 0;
+  p.use_peers = 0;
   p.filt = FilterParams{};
   int L;
   if (along_x) { p.src = p.dst = plain_io((long long)ny * P, P, nx); p.ncols_total = (long long)ny * P; L = nx; }
@@ -360,12 +373,24 @@ int evx_dist_plan_sizes(const evx_dist_plan* plan, size_t* spec_bytes, int* pitc
 int evx_dist_forward_f32(evx_dist_plan* plan, const float* r_local, void* spec, void* send,
                          void* stream) {
   if (!plan || !r_local || !spec || !send || spec == send) return EVX_ERR_ARG;
-  return dist_forward((DistPlan*)plan, r_local, (cf*)spec, (cf*)send, (cudaStream_t)stream);
+  return dist_forward((DistPlan*)plan, r_local, (cf*)spec, (cf*)send, nullptr, (cudaStream_t)stream);
+}
+int evx_dist_forward_p2p_f32(evx_dist_plan* plan, const float* r_local, void* spec,
+                             void* const* peer_recv, void* stream) {
+  if (!plan || !r_local || !spec || !peer_recv) return EVX_ERR_ARG;
+  if (((DistPlan*)plan)->world > 8) return EVX_ERR_UNSUPPORTED;
+  return dist_forward((DistPlan*)plan, r_local, (cf*)spec, nullptr, peer_recv, (cudaStream_t)stream);
+}
+int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_out, const double* h,
+                            double dt, double coef, int power, void* stream) {
+  if (!plan || !recv || !peer_out || !h || (power != 1 && power != 2)) return EVX_ERR_ARG;
+  if (((DistPlan*)plan)->world > 8) return EVX_ERR_UNSUPPORTED;
+  return dist_middle((DistPlan*)plan, (cf*)recv, peer_out, h, dt, coef, power, (cudaStream_t)stream);
 }
 int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double dt, double coef,
                         int power, void* stream) {
   if (!plan || !recv || !h || (power != 1 && power != 2)) return EVX_ERR_ARG;
-  return dist_middle((DistPlan*)plan, (cf*)recv, h, dt, coef, power, (cudaStream_t)stream);
+  return dist_middle((DistPlan*)plan, (cf*)recv, nullptr, h, dt, coef, power, (cudaStream_t)stream);
 }
 int evx_dist_backward_f32(evx_dist_plan* plan, const void* recv, void* spec, const float* u_local,
                           float* out_local, void* stream) {

@@ -59,6 +59,12 @@ struct StridedParams {
   FilterParams filt;       // XMID only; n0 = L (this axis), n1 = the other strided axis, n2 = nz
   long long src_step[8];   // strided_step(src, e * L/8), filled by finalize_strided()
   long long dst_step[8];
+  // peer-store mode (x-slab transposes over NVLink): chunk hi = idx >> dst.split_shift of a
+  // line is written straight into rank hi's buffer out_peers[hi] at element offset
+  // dst_peer_base + grp * plane_stride + kz + lo * line_stride  (no all-to-all afterwards)
+  cf* out_peers[8];
+  long long dst_peer_base;
+  int use_peers;
 };
 
 inline StridedIO plain_io(long long line_stride, long long plane_stride, int L) {
@@ -140,6 +146,16 @@ struct StridedPass {
   }
   EVX_HD static void store_global(Regs& r, const StridedParams& p) {
     if (!r.valid) return;
+    if (p.use_peers) {
+      const long long within = p.dst_peer_base + r.grp * p.dst.plane_stride + r.kz;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int idx = r.t + e * T;
+        const int hi = idx >> p.dst.split_shift, lo = idx & ((1 << p.dst.split_shift) - 1);
+        p.out_peers[hi][within + lo * p.dst.line_stride] = r.v[e];
+      }
+      return;
+    }
     cf* base = p.out + r.dst_base;
 #pragma unroll
     for (int e = 0; e < 8; ++e) base[p.dst_step[e]] = r.v[e];

@@ -117,18 +117,53 @@ class Comm:
         return t
 
 
-class CudaOps:
-    """The kernels behind one rank of the distributed step."""
+class PeerBuffers:
+    """Two all-to-all block buffers per rank, allocated in torch symmetric memory so that
+    every rank holds device pointers to every peer's copy (NVLink P2P on one NVSwitch box).
+    The transform kernels store their output chunks straight into the owning rank's buffer;
+    `barrier()` is the device-side cross-rank barrier enqueued on the current stream."""
 
-    def __init__(self, slab: Slab, spacing, device, spectral=True):
+    def __init__(self, block_shape, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._symm = symm_mem
+        group = group if group is not None else dist.group.WORLD
+        shape = tuple(block_shape) + (2,)                     # complex64 as float32 pairs
+        self.raw, self.handles, self.bufs, self.peer_ptrs = [], [], [], []
+        for _ in range(2):
+            t = symm_mem.empty(*shape, dtype=torch.float32, device=device)
+            h = symm_mem.rendezvous(t, group=group)
+            self.raw.append(t)
+            self.handles.append(h)
+            self.bufs.append(torch.view_as_complex(t))
+            self.peer_ptrs.append([int(x) for x in h.buffer_ptrs])
+        self._channel = 0
+
+    def barrier(self, which):
+        self.handles[which].barrier(channel=0)
+
+
+class CudaOps:
+    """The kernels behind one rank of the distributed step.
+
+    transport = 'p2p': the y pass / x pass write their output straight into the peers'
+    buffers over NVLink (fused transform + transpose, no collective call, no pack/unpack);
+    transport = 'nccl': local block buffers + NCCL all-to-all."""
+
+    def __init__(self, slab: Slab, spacing, device, spectral=True, transport="nccl", group=None):
         self.slab, self.spacing, self.device = slab, tuple(spacing), torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("evoxels_b200 has no CPU path: CudaOps needs a CUDA device")
+        self.transport = transport if slab.world > 1 else "nccl"
+        self.peers = None
         if spectral:
             self.plan = _native.DistPlan(slab.global_shape, slab.world, slab.rank, device)
             self.spec = self.plan.new_buffer()
-            self.buf_a = self.plan.new_buffer()
-            self.buf_b = self.plan.new_buffer()
+            if self.transport == "p2p":
+                self.peers = PeerBuffers(self.plan.block_shape, self.device, group)
+                self.buf_a, self.buf_b = self.peers.bufs
+            else:
+                self.buf_a = self.plan.new_buffer()
+                self.buf_b = self.plan.new_buffer()
 
     def new_field(self):
         return torch.empty(self.slab.local_shape, dtype=torch.float32, device=self.device)
@@ -148,6 +183,19 @@ class CudaOps:
     def spectral_middle(self, buf, dt, coef, power):
         self.plan.middle(buf, self.spacing, dt, coef, power)
 
+    # fused transform + transpose over peer memory --------------------------------------------
+    def spectral_forward_p2p(self, r):
+        """ZFwd + y pass; chunks land in every peer's buffer B.  Returns the local B."""
+        self.plan.forward_p2p(r, self.spec, self.peers.peer_ptrs[1])
+        self.peers.barrier(1)
+        return self.buf_b
+
+    def spectral_middle_p2p(self, dt, coef, power):
+        """x pass on the local B; chunks land in every peer's buffer A.  Returns the local A."""
+        self.plan.middle_p2p(self.buf_b, self.peers.peer_ptrs[0], self.spacing, dt, coef, power)
+        self.peers.barrier(0)
+        return self.buf_a
+
     def spectral_backward(self, buf, u, out):
         self.plan.backward(buf, self.spec, u, out)
 
@@ -160,12 +208,13 @@ class DistributedCahnHilliardIMEX:
     `step(u_local) -> u_local_new`; same arithmetic as the single-GPU step."""
 
     def __init__(self, global_shape, spacing, dt, eps=3.0, D=1.0, A=0.25, group=None,
-                 device=None, ops=None):
+                 device=None, ops=None, transport="p2p"):
         self.comm = Comm(group)
         self.slab = Slab(tuple(global_shape), self.comm.world, self.comm.rank)
         self.spacing, self.dt, self.eps, self.D, self.A = tuple(spacing), dt, eps, D, A
         self.bc = normalize_bc(("periodic",) * 3)
-        self.ops = ops if ops is not None else CudaOps(self.slab, spacing, device or "cuda")
+        self.ops = ops if ops is not None else CudaOps(self.slab, spacing, device or "cuda",
+                                                       transport=transport, group=group)
         self.rhs = self.ops.new_field()
 
     def step(self, u_local):
@@ -173,6 +222,13 @@ class DistributedCahnHilliardIMEX:
         u_local = u_local.contiguous()
         halo_lo, halo_hi = comm.exchange_halos(u_local, 2, periodic=True)
         ops.ch_rhs(u_local, self.rhs, self.eps, self.D, self.bc, halo_lo, halo_hi)
+        coef = 2.0 * self.eps * self.D * self.A
+        if getattr(ops, "transport", "nccl") == "p2p":
+            ops.spectral_forward_p2p(self.rhs)
+            a = ops.spectral_middle_p2p(self.dt, coef, 2)
+            out = ops.new_field()
+            ops.spectral_backward(a, u_local, out)
+            return out
         a, b = ops.exchange_buffers()
         send = ops.spectral_forward(self.rhs)            # fills `a`
         comm.all_to_all_blocks(send, b)

@@ -188,6 +188,15 @@ int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double
                         int power, void* stream);
 int evx_dist_backward_f32(evx_dist_plan* plan, const void* recv, void* spec, const float* u_local,
                           float* out_local, void* stream);
+/* Fused transform + transpose over NVLink peer memory (W <= 8): instead of filling a local
+ * send buffer for an all-to-all, the y pass (forward) / the x pass (middle) store every chunk
+ * straight into the owning rank's buffer - peer_recv[j] / peer_out[j] is rank j's mapped
+ * block buffer ([W][nx/W][ny/W][P], e.g. from torch symmetric memory); this rank fills block
+ * `rank` of each.  The caller puts a cross-rank barrier on the stream afterwards. */
+int evx_dist_forward_p2p_f32(evx_dist_plan* plan, const float* r_local, void* spec,
+                             void* const* peer_recv, void* stream);
+int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_out, const double* h,
+                            double dt, double coef, int power, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Adjoint of the Cahn-Hilliard right-hand side (fully periodic grids)

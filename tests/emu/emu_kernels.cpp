@@ -270,6 +270,7 @@ int emu_native_apply(const float* u, const float* r, float* out, float* spec_out
   if (dispatch_z<false>(M, zp)) return -1;
   StridedParams sp;
   sp.in = spec.data(); sp.out = spec.data(); sp.P = P; sp.ncols_valid = M + 1; sp.kother_offset = 0;
+  sp.use_peers = 0;
   const StridedIO yio = plain_io(P, (long long)ny * P, ny), xio = plain_io((long long)ny * P, P, nx);
   // y pass: columns (x, kz), line stride P, group stride ny*P
   sp.tw = twy.data(); sp.src = sp.dst = yio;

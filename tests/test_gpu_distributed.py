@@ -44,3 +44,32 @@ def test_single_rank_distributed_plan_equals_single_gpu_path(cuda_device):
     ref = PseudoSpectralIMEX(CahnHilliard(vg), 0.1, fft_backend="native").step(0.0, u[None])[0]
     got = DistributedCahnHilliardIMEX(shape, spacing, 0.1, device="cuda").step(u)
     assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_p2p_block_addressing_with_virtual_ranks(cuda_device, world):
+    """Peer-store mode of the distributed passes on ONE GPU: W plans ("virtual ranks") write
+    into each other's buffers exactly as real ranks do over NVLink; the assembled result must
+    equal the single-GPU spectral stage bit for bit."""
+    from evoxels_b200 import _native
+    shape, sp = (64, 32, 64), (1.0, 0.5, 2.0)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    r = torch.randn(shape, device="cuda", generator=gen)
+    u = torch.rand(shape, device="cuda", generator=gen)
+    ref = torch.empty_like(u)
+    _native.ImexPlan(shape, torch.float32, "cuda", _native.FFT_NATIVE).apply(u, r, ref, sp, 0.1, 1.5, 2)
+    plans = [_native.DistPlan(shape, world, k, "cuda") for k in range(world)]
+    A = [p.new_buffer().zero_() for p in plans]
+    B = [p.new_buffer().zero_() for p in plans]
+    spec = [p.new_buffer() for p in plans]
+    nxl = shape[0] // world
+    for k, p in enumerate(plans):
+        p.forward_p2p(r[k * nxl:(k + 1) * nxl].contiguous(), spec[k], [b.data_ptr() for b in B])
+    for k, p in enumerate(plans):
+        p.middle_p2p(B[k], [a.data_ptr() for a in A], sp, 0.1, 1.5, 2)
+    out = torch.empty_like(u)
+    for k, p in enumerate(plans):
+        o = torch.empty((nxl,) + shape[1:], device="cuda")
+        p.backward(A[k], spec[k], u[k * nxl:(k + 1) * nxl].contiguous(), o)
+        out[k * nxl:(k + 1) * nxl] = o
+    assert torch.equal(out, ref)
