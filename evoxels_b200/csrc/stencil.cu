@@ -12,9 +12,9 @@ std::atomic<unsigned long long> g_launches{0};
 // ------------------------------------------------------------------------------------
 // Cahn-Hilliard rhs
 // ------------------------------------------------------------------------------------
-template <typename T, int V, int TY, int G, bool HOM, bool GHOSTS>
+template <typename T, int V, int TY, int G, bool HOM, bool GHOSTS, int MINB = 2>
 __global__ void __launch_bounds__(ChRhsProgram<T, V, TY, G, HOM, GHOSTS>::NTHREADS,
-                                  (sizeof(T) == 4 && TY <= 16) ? 2 : 1)
+                                  (sizeof(T) == 4 && TY <= 16) ? MINB : 1)
     ch_rhs_kernel(const ChParams<T> p) {
   using Prog = ChRhsProgram<T, V, TY, G, HOM, GHOSTS>;
   __shared__ typename Prog::Smem s;
@@ -58,7 +58,11 @@ static int launch_ch(ChParams<T> p, cudaStream_t st) {
   } else if (ghosts) {
     ch_rhs_kernel<T, V, TY, G, false, true><<<grid, Prog::NTHREADS, 0, st>>>(p);
   } else {
-    ch_rhs_kernel<T, V, TY, G, false, false><<<grid, Prog::NTHREADS, 0, st>>>(p);
+    static const int occ = [] { const char* e = getenv("EVX_CH_OCC"); return e ? atoi(e) : 2; }();
+    if (occ == 3 && sizeof(T) == 4 && TY <= 16)
+      ch_rhs_kernel<T, V, TY, G, false, false, 3><<<grid, Prog::NTHREADS, 0, st>>>(p);
+    else
+      ch_rhs_kernel<T, V, TY, G, false, false><<<grid, Prog::NTHREADS, 0, st>>>(p);
   }
   count_launch();
   return (int)cudaGetLastError();
