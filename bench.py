@@ -44,7 +44,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -60,7 +60,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200", "-i", str(self.gpu)],
+                 "-lms", "100", "-i", str(self.gpu)],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -234,6 +234,7 @@ def run_ours(args):
     # ---- per-kernel timing of the own kernels (roofline) -----------------------------------
     peak, peak_src = measured_peaks()
     rhs_buf = torch.empty_like(u0)
+    out_buf = torch.empty_like(u0)
     reps = max(5, min(args.steps, 20))
 
     def timed(fn):
@@ -249,19 +250,35 @@ def run_ours(args):
         return a.elapsed_time(b) / reps
 
     per = (("periodic", None),) * 3
-    ms_rhs = timed(lambda: _native.ch_rhs(u0[0], rhs_buf[0], vg.spacing, CH["eps"], CH["D"], per))
-    out_buf = torch.empty_like(u0)
-    ms_apply = timed(lambda: plan.apply(u0[0], rhs_buf[0], out_buf[0], vg.spacing, CH["dt"],
-                                        2 * CH["eps"] * CH["D"] * CH["A"], 2))
-    gbs_rhs = B_ALG_RHS * nvox / (ms_rhs * 1e-3) / 1e9
+    coef = 2 * CH["eps"] * CH["D"] * CH["A"]
+    half = (n // 2 + 1) / (n // 2)          # half spectrum: (nz/2+1)/(nz/2) x 4 B per voxel
+    kernels = {}                            # name -> (ms, algorithmic bytes per voxel)
+    kernels["ch_rhs_kernel"] = (
+        timed(lambda: _native.ch_rhs(u0[0], rhs_buf[0], vg.spacing, CH["eps"], CH["D"], per)), 8.0)
+    if plan.backend_name == "native":
+        names = ["fft_z_forward (ZPass fwd)", "fft_y_forward (StridedPipe FWD)",
+                 "fft_x_fwd*filter*inv (StridedPipe XMID)", "fft_y_inverse (StridedPipe INV)",
+                 "fft_z_inverse+u (ZPass inv)"]
+        bpv = [4 + 4 * half, 8 * half, 8 * half, 8 * half, 4 * half + 8]
+        for which, (nm, bb) in enumerate(zip(names, bpv)):
+            kernels[nm] = (timed(lambda w=which: plan.native_pass(
+                w, u0[0], rhs_buf[0], out_buf[0], vg.spacing, CH["dt"], coef, 2)), bb)
+    else:
+        kernels["spectral_apply (cuFFT + filter + add kernels)"] = (
+            timed(lambda: plan.apply(u0[0], rhs_buf[0], out_buf[0], vg.spacing, CH["dt"], coef, 2)), 52.0)
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    dom_ms, dom_bpv = kernels[dom]
+    dom_gbs = dom_bpv * nvox / (dom_ms * 1e-3) / 1e9
     gbs_step = B_ALG_STEP * nvox / (ms_step * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "ch_rhs_kernel (fused CH rhs, 8 B/voxel)",
-        "achieved": gbs_rhs, "peak": peak, "unit": "GB/s", "frac": gbs_rhs / peak,
-        "traffic": None, "peak_source": peak_src, "ms": ms_rhs,
+        "bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
+        "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src, "ms": dom_ms,
+        "bytes_per_voxel": dom_bpv,
         "step": {"bytes_per_voxel": B_ALG_STEP, "achieved": gbs_step, "frac": gbs_step / peak,
                  "frac_of_8TBs": gbs_step / 8000.0, "ms": ms_step},
-        "stages_ms": {"ch_rhs": ms_rhs, "spectral_apply(fft+filter+ifft+add)": ms_apply},
+        "kernels": {k: {"ms": v[0], "bytes_per_voxel": v[1],
+                        "achieved_GBs": v[1] * nvox / (v[0] * 1e-3) / 1e9,
+                        "frac": v[1] * nvox / (v[0] * 1e-3) / 1e9 / peak} for k, v in kernels.items()},
     }
 
     if rank != 0:
@@ -404,7 +421,7 @@ def run_ours_distributed(args, world, rank, local, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

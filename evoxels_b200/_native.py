@@ -51,6 +51,8 @@ SIGNATURES = {
     "evx_imex_plan_workspace_bytes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t)],
     "evx_imex_apply_f32": _APPLY_ARGS, "evx_imex_apply_f64": _APPLY_ARGS,
     "evx_ch_imex_step_f32": _STEP_ARGS, "evx_ch_imex_step_f64": _STEP_ARGS,
+    "evx_imex_native_pass_f32": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _dptr,
+                                 _c_double, _c_double, _c_int, _c_void_p],
     "evx_spectral_filter_c64": _FILTER_ARGS, "evx_spectral_filter_c128": _FILTER_ARGS,
     "evx_ch_mu_f32": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
     "evx_ch_mu_f64": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
@@ -262,6 +264,14 @@ class ImexPlan:
                 _ptr(self.workspace), _h3(spacing), float(dt), float(coef), int(power),
                 _stream(r)), "evx_imex_apply")
         return out
+
+    def native_pass(self, which, u, r, out, spacing, dt, coef, power):
+        """One pass of the native pipeline (0 z fwd, 1 y fwd, 2 x fwd*filter*inv, 3 y inv, 4 z inv)."""
+        require_cuda(u, r, out)
+        with torch.cuda.device(self.device):
+            check(load_library().evx_imex_native_pass_f32(
+                self._handle, int(which), _ptr(u), _ptr(r), _ptr(out), _ptr(self.workspace),
+                _h3(spacing), float(dt), float(coef), int(power), _stream(r)), "evx_imex_native_pass")
 
     def ch_step(self, u, out, spacing, dt, eps, D, A, hom=None):
         require_cuda(u, out, hom)

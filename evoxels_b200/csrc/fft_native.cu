@@ -220,6 +220,40 @@ int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, v
   return launch_z<true>(M, zp, st);
 }
 
+// one pass of the pipeline on the plan's scratch (measurement aid for bench.py's per-kernel
+// roofline): which = 0 ZFwd, 1 Y fwd, 2 X fwd*filter*inv, 3 Y inv, 4 ZInv
+int native_single_pass(evx_imex_plan* p, int which, const float* u, const float* r, float* out,
+                       void* workspace, const double* h, double dt, double coef, int power,
+                       cudaStream_t st) {
+  const int nx = p->nx, ny = p->ny, nz = p->nz, M = nz / 2, P = p->spec_pitch;
+  cf* spec = reinterpret_cast<cf*>((char*)workspace + p->real_bytes);
+  const cf* twx = (const cf*)p->twiddles;
+  const cf* twy = twx + nx;
+  const cf* twz = twy + ny;
+  const cf* twr = twz + M;
+  ZParams zp;
+  zp.real_in = r; zp.real_out = nullptr; zp.spec = spec; zp.tw = twz; zp.twr = twr;
+  zp.rows = (long long)nx * ny; zp.nz = nz; zp.P = P;
+  StridedParams yp;
+  yp.in = spec; yp.out = spec; yp.tw = twy;
+  yp.src = yp.dst = plain_io(P, (long long)ny * P, ny);
+  yp.P = P; yp.ncols_valid = M + 1; yp.ncols_total = (long long)nx * P;
+  yp.kother_offset = 0; yp.use_peers = 0; yp.filt = FilterParams{};
+  if (which == 0) return launch_z<false>(M, zp, st);
+  if (which == 1) return launch_strided<PASS_FWD>(ny, yp, st);
+  if (which == 3) return launch_strided<PASS_INV>(ny, yp, st);
+  if (which == 2) {
+    StridedParams xp = yp;
+    xp.tw = twx; xp.src = xp.dst = plain_io((long long)ny * P, P, nx);
+    xp.ncols_total = (long long)ny * P;
+    const int n[3] = {nx, ny, nz};
+    xp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
+    return launch_strided<PASS_XMID>(nx, xp, st);
+  }
+  if (which == 4) { zp.real_in = u; zp.real_out = out; return launch_z<true>(M, zp, st); }
+  return EVX_ERR_ARG;
+}
+
 int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* out,
                    void* workspace, const double* h, double dt, double eps, double D, double A,
                    cudaStream_t st) {

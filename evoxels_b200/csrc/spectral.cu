@@ -271,6 +271,14 @@ int evx_ch_imex_step_f64(evx_imex_plan* plan, const double* u, const double* hom
                          double A, void* stream) {
   return ch_step_impl<double>(plan, u, hom, out, workspace, h, dt, eps, D, A, (cudaStream_t)stream);
 }
+int evx_imex_native_pass_f32(evx_imex_plan* plan, int which, const float* u, const float* r,
+                             float* out, void* workspace, const double* h, double dt, double coef,
+                             int power, void* stream) {
+  if (!plan || !workspace || !h || !u || !r || !out) return EVX_ERR_ARG;
+  if (plan->backend != EVX_FFT_NATIVE) return EVX_ERR_UNSUPPORTED;
+  return native_single_pass(plan, which, u, r, out, workspace, h, dt, coef, power,
+                            (cudaStream_t)stream);
+}
 int evx_spectral_filter_c64(void* spec, int nx, int ny, int nz, const double* h, double dt,
                             double coef, int power, double scale, void* stream) {
   return filter_entry<float>(spec, nx, ny, nz, h, dt, coef, power, scale, (cudaStream_t)stream);

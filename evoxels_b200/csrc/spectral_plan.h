@@ -31,6 +31,9 @@ int native_plan_init(evx_imex_plan* p);
 void native_plan_free(evx_imex_plan* p);
 int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, void* workspace,
                  const double* h, double dt, double coef, int power, cudaStream_t st);
+int native_single_pass(evx_imex_plan* p, int which, const float* u, const float* r, float* out,
+                       void* workspace, const double* h, double dt, double coef, int power,
+                       cudaStream_t st);
 int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* out,
                    void* workspace, const double* h, double dt, double eps, double D, double A,
                    cudaStream_t st);

@@ -157,6 +157,13 @@ int evx_ch_imex_step_f64(evx_imex_plan* plan, const double* u, const double* hom
                          void* workspace, const double* h, double dt, double eps, double D,
                          double A, void* stream);
 
+/* Measurement aid (bench.py per-kernel roofline): run ONE pass of the native pipeline on the
+ * plan's scratch - which = 0 z forward (r -> spectrum), 1 y forward, 2 x forward*filter*inverse,
+ * 3 y inverse, 4 z inverse (+u -> out).  Native back end only. */
+int evx_imex_native_pass_f32(evx_imex_plan* plan, int which, const float* u, const float* r,
+                             float* out, void* workspace, const double* h, double dt, double coef,
+                             int power, void* stream);
+
 /* The filter alone on a cuFFT-layout half spectrum [nx,ny,nz/2+1] (complex interleaved):
  * spec *= scale * dt / (1 + dt*coef*|k|^(2*power)).  Exposed for tests and for callers
  * that run their own transforms. */
