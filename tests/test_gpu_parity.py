@@ -274,6 +274,29 @@ def test_solver_drivers(cuda_device):
     assert np.linalg.norm(vf.fields["phi2"].squeeze()[sel] - ana[sel]) < 0.05
 
 
+def test_cuda_graph_solver_loop_matches_eager(cuda_device):
+    """solve(jit=True) replays CUDA graphs of several steps; the result must equal the eager
+    loop bit for bit (same kernels, same order)."""
+    res = {}
+    for jit in (False, True):
+        vf = evo.VoxelFields((100, 100, 100), (100, 100, 100))
+        vf.add_field("c", 0.5 + 0.1 * np.random.default_rng(0).random((100, 100, 100)).astype(np.float32))
+        s = evo.run_cahn_hilliard_solver(vf, "c", backend="torch", device="cuda", jit=jit, frames=2,
+                                         max_iters=100, time_increment=0.1, verbose=False)
+        res[jit] = (vf.fields["c"].copy(), s.computation_time)
+    assert np.array_equal(res[False][0], res[True][0])
+    vf = evo.VoxelFields((64, 64, 64), (64, 64, 64))
+    vf.add_field("p", np.random.default_rng(1).random((64, 64, 64)).astype(np.float32))
+    ref = vf.fields["p"].copy()
+    evo.run_allen_cahn_solver(vf, "p", backend="torch", device="cuda", jit=True, frames=1, max_iters=20,
+                              time_increment=0.05, verbose=False)
+    a = vf.fields["p"].copy()
+    vf.set_field("p", ref)
+    evo.run_allen_cahn_solver(vf, "p", backend="torch", device="cuda", jit=False, frames=1, max_iters=20,
+                              time_increment=0.05, verbose=False)
+    assert np.array_equal(a, vf.fields["p"])
+
+
 def test_rhs_convergence_order(cuda_device):
     """Spatial order 2 of CahnHilliard.rhs / TwoPhaseAllenCahn.rhs in float64, the check of
     the reference's tests/test_rhs.py:10-37 (MMS on the unit cube)."""
