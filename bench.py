@@ -341,7 +341,8 @@ def run_ours_distributed(args, world, rank, local, dev):
     shape = weak_scaling_shape(args.size, world)
     nvox = shape[0] * shape[1] * shape[2]
     stepper = DistributedCahnHilliardIMEX(shape, (1.0, 1.0, 1.0), CH["dt"], CH["eps"], CH["D"],
-                                          CH["A"], device=dev, transport=args.transport)
+                                          CH["A"], device=dev, transport=args.transport,
+                                          overlap_chunks=args.overlap_chunks)
     gen = torch.Generator(device=dev).manual_seed(rank)
     u0 = 0.5 + 0.1 * torch.rand(stepper.slab.local_shape, device=dev, generator=gen)
 
@@ -427,6 +428,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fft", default="auto", choices=["auto", "cufft", "native"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--overlap-chunks", type=int, default=4,
+                    help="multi-GPU p2p: x chunks pipelined on two streams in the forward half")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU transposes: fused peer stores over NVLink, or NCCL all-to-all")
     args = ap.parse_args()

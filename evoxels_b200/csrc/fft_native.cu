@@ -311,21 +311,29 @@ static void set_peers(StridedParams& sp, const DistPlan* p, void* const* peers) 
   for (int i = 0; i < 8; ++i) sp.out_peers[i] = (peers && i < p->world) ? (cf*)peers[i] : nullptr;
 }
 
-// peers != null: block `rank` of every peer's buffer is written directly (NVLink stores)
+// peers != null: block `rank` of every peer's buffer is written directly (NVLink stores).
+// [x0, x0+nxc) selects a chunk of local x planes (r_local / spec / send still point at the
+// start of the full local arrays), so that several chunks can be pipelined on streams:
+// the NVLink-bound y pass of one chunk overlaps the HBM-bound z pass of the next.
 int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* const* peers,
-                 cudaStream_t st) {
+                 int x0, int nxc, cudaStream_t st) {
+  if (x0 < 0 || nxc < 1 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
+  const long long spec_off = (long long)x0 * p->ny * p->P;
   ZParams zp;
-  zp.real_in = r_local; zp.real_out = nullptr; zp.spec = spec; zp.tw = tw_z(p); zp.twr = tw_r(p);
-  zp.rows = (long long)p->nxl * p->ny; zp.nz = p->nz; zp.P = p->P;
+  zp.real_in = r_local + (long long)x0 * p->ny * p->nz; zp.real_out = nullptr;
+  zp.spec = spec + spec_off; zp.tw = tw_z(p); zp.twr = tw_r(p);
+  zp.rows = (long long)nxc * p->ny; zp.nz = p->nz; zp.P = p->P;
   int rc = launch_z<false>(p->M, zp, st);
   if (rc) return rc;
   StridedParams yp;
-  yp.in = spec; yp.out = send; yp.tw = tw_y(p);
+  yp.in = spec + spec_off; yp.tw = tw_y(p);
   yp.src = plain_io(p->P, (long long)p->ny * p->P, p->ny);
   yp.dst = block_io(p);
-  yp.P = p->P; yp.ncols_valid = p->M + 1; yp.ncols_total = (long long)p->nxl * p->P;
+  yp.out = send ? send + (long long)x0 * yp.dst.plane_stride : nullptr;
+  yp.P = p->P; yp.ncols_valid = p->M + 1; yp.ncols_total = (long long)nxc * p->P;
   yp.kother_offset = 0; yp.filt = FilterParams{};
   set_peers(yp, p, peers);
+  yp.dst_peer_base += (long long)x0 * yp.dst.plane_stride;
   return launch_strided<PASS_FWD>(p->ny, yp, st);
 }
 
@@ -407,13 +415,22 @@ int evx_dist_plan_sizes(const evx_dist_plan* plan, size_t* spec_bytes, int* pitc
 int evx_dist_forward_f32(evx_dist_plan* plan, const float* r_local, void* spec, void* send,
                          void* stream) {
   if (!plan || !r_local || !spec || !send || spec == send) return EVX_ERR_ARG;
-  return dist_forward((DistPlan*)plan, r_local, (cf*)spec, (cf*)send, nullptr, (cudaStream_t)stream);
+  DistPlan* dp = (DistPlan*)plan;
+  return dist_forward(dp, r_local, (cf*)spec, (cf*)send, nullptr, 0, dp->nxl, (cudaStream_t)stream);
 }
 int evx_dist_forward_p2p_f32(evx_dist_plan* plan, const float* r_local, void* spec,
                              void* const* peer_recv, void* stream) {
   if (!plan || !r_local || !spec || !peer_recv) return EVX_ERR_ARG;
   if (((DistPlan*)plan)->world > 8) return EVX_ERR_UNSUPPORTED;
-  return dist_forward((DistPlan*)plan, r_local, (cf*)spec, nullptr, peer_recv, (cudaStream_t)stream);
+  DistPlan* dp = (DistPlan*)plan;
+  return dist_forward(dp, r_local, (cf*)spec, nullptr, peer_recv, 0, dp->nxl, (cudaStream_t)stream);
+}
+int evx_dist_forward_chunk_p2p_f32(evx_dist_plan* plan, const float* r_local, void* spec,
+                                   void* const* peer_recv, int x0, int nxc, void* stream) {
+  if (!plan || !r_local || !spec || !peer_recv) return EVX_ERR_ARG;
+  if (((DistPlan*)plan)->world > 8) return EVX_ERR_UNSUPPORTED;
+  return dist_forward((DistPlan*)plan, r_local, (cf*)spec, nullptr, peer_recv, x0, nxc,
+                      (cudaStream_t)stream);
 }
 int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_out, const double* h,
                             double dt, double coef, int power, void* stream) {

@@ -190,6 +190,31 @@ class CudaOps:
         self.peers.barrier(1)
         return self.buf_b
 
+    def forward_pipelined(self, u, rhs, eps, D, bc, halo_lo, halo_hi, chunks):
+        """rhs -> z pass -> y pass (+ NVLink peer stores) over `chunks` slices of the local x
+        range, alternating between two side streams: while one slice's y pass is pushing its
+        output over NVLink, the next slice's rhs / z pass keep HBM and the SMs busy."""
+        nxl = self.slab.nxl
+        bounds = [round(i * nxl / chunks) for i in range(chunks + 1)]
+        main = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_side"):
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for i in range(chunks):
+            x0, x1 = bounds[i], bounds[i + 1]
+            st = self._side[i % 2]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                lo = halo_lo if x0 == 0 else u[x0 - 2:x0]
+                hi = halo_hi if x1 == nxl else u[x1:x1 + 2]
+                _native.ch_rhs(u[x0:x1], rhs[x0:x1], self.spacing, eps, D, bc, halo_lo=lo, halo_hi=hi)
+                self.plan.forward_chunk_p2p(rhs, self.spec, self.peers.peer_ptrs[1], x0, x1 - x0)
+        for st in self._side:
+            main.wait_stream(st)
+        self.peers.barrier(1)
+        return self.buf_b
+
     def spectral_middle_p2p(self, dt, coef, power):
         """x pass on the local B; chunks land in every peer's buffer A.  Returns the local A."""
         self.plan.middle_p2p(self.buf_b, self.peers.peer_ptrs[0], self.spacing, dt, coef, power)
@@ -208,7 +233,7 @@ class DistributedCahnHilliardIMEX:
     `step(u_local) -> u_local_new`; same arithmetic as the single-GPU step."""
 
     def __init__(self, global_shape, spacing, dt, eps=3.0, D=1.0, A=0.25, group=None,
-                 device=None, ops=None, transport="p2p"):
+                 device=None, ops=None, transport="p2p", overlap_chunks=4):
         self.comm = Comm(group)
         self.slab = Slab(tuple(global_shape), self.comm.world, self.comm.rank)
         self.spacing, self.dt, self.eps, self.D, self.A = tuple(spacing), dt, eps, D, A
@@ -216,15 +241,25 @@ class DistributedCahnHilliardIMEX:
         self.ops = ops if ops is not None else CudaOps(self.slab, spacing, device or "cuda",
                                                        transport=transport, group=group)
         self.rhs = self.ops.new_field()
+        # forward pipeline depth: x chunks of the local slab issued on two streams (p2p only)
+        self.overlap_chunks = overlap_chunks if self.slab.nxl >= 8 * max(overlap_chunks, 1) else 1
 
     def step(self, u_local):
         ops, comm = self.ops, self.comm
         u_local = u_local.contiguous()
         halo_lo, halo_hi = comm.exchange_halos(u_local, 2, periodic=True)
-        ops.ch_rhs(u_local, self.rhs, self.eps, self.D, self.bc, halo_lo, halo_hi)
+        pipelined = getattr(ops, "transport", "nccl") == "p2p" and self.overlap_chunks > 1
+        if not pipelined:
+            ops.ch_rhs(u_local, self.rhs, self.eps, self.D, self.bc, halo_lo, halo_hi)
         coef = 2.0 * self.eps * self.D * self.A
         if getattr(ops, "transport", "nccl") == "p2p":
-            ops.spectral_forward_p2p(self.rhs)
+            if self.overlap_chunks > 1:
+                # the rhs was NOT computed above in this mode (see below): pipeline
+                # rhs -> z pass -> y pass(+NVLink stores) over x chunks on two streams
+                ops.forward_pipelined(u_local, self.rhs, self.eps, self.D, self.bc, halo_lo,
+                                      halo_hi, self.overlap_chunks)
+            else:
+                ops.spectral_forward_p2p(self.rhs)
             a = ops.spectral_middle_p2p(self.dt, coef, 2)
             out = ops.new_field()
             ops.spectral_backward(a, u_local, out)
