@@ -244,6 +244,39 @@ class DistributedCahnHilliardIMEX:
         # forward pipeline depth: x chunks of the local slab issued on two streams (p2p only)
         self.overlap_chunks = overlap_chunks if self.slab.nxl >= 8 * max(overlap_chunks, 1) else 1
 
+    def step_profiled(self, u_local):
+        """One step with CUDA events around every stage (diagnostics; p2p transport,
+        un-pipelined).  Returns (u_new, {stage: ms})."""
+        ops, comm = self.ops, self.comm
+        ev = []
+
+        def mark(name):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append((name, e))
+
+        u_local = u_local.contiguous()
+        mark("start")
+        halo_lo, halo_hi = comm.exchange_halos(u_local, 2, periodic=True)
+        mark("halo_exchange")
+        ops.ch_rhs(u_local, self.rhs, self.eps, self.D, self.bc, halo_lo, halo_hi)
+        mark("ch_rhs")
+        coef = 2.0 * self.eps * self.D * self.A
+        ops.plan.forward_p2p(self.rhs, ops.spec, ops.peers.peer_ptrs[1])
+        mark("z_fwd+y_fwd(p2p stores)")
+        ops.peers.barrier(1)
+        mark("barrier")
+        ops.plan.middle_p2p(ops.buf_b, ops.peers.peer_ptrs[0], self.spacing, self.dt, coef, 2)
+        mark("x_mid(p2p stores)")
+        ops.peers.barrier(0)
+        mark("barrier2")
+        out = ops.new_field()
+        ops.spectral_backward(ops.buf_a, u_local, out)
+        mark("y_inv+z_inv")
+        torch.cuda.synchronize()
+        times = {ev[i][0]: ev[i - 1][1].elapsed_time(ev[i][1]) for i in range(1, len(ev))}
+        return out, times
+
     def step(self, u_local):
         ops, comm = self.ops, self.comm
         u_local = u_local.contiguous()
