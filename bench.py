@@ -342,7 +342,7 @@ def run_ours_distributed(args, world, rank, local, dev):
     nvox = shape[0] * shape[1] * shape[2]
     stepper = DistributedCahnHilliardIMEX(shape, (1.0, 1.0, 1.0), CH["dt"], CH["eps"], CH["D"],
                                           CH["A"], device=dev, transport=args.transport,
-                                          overlap_chunks=args.overlap_chunks)
+                                          overlap_chunks=args.overlap_chunks, p2p_ctas=args.p2p_ctas)
     gen = torch.Generator(device=dev).manual_seed(rank)
     u0 = 0.5 + 0.1 * torch.rand(stepper.slab.local_shape, device=dev, generator=gen)
 
@@ -428,6 +428,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fft", default="auto", choices=["auto", "cufft", "native"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--p2p-ctas", type=int, default=0,
+                    help="grid cap of the NVLink-bound peer-store launches (0 = fill the GPU)")
     ap.add_argument("--overlap-chunks", type=int, default=4,
                     help="multi-GPU p2p: x chunks pipelined on two streams in the forward half")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],

@@ -63,6 +63,7 @@ SIGNATURES = {
     "evx_debug_strided_copy": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "evx_dist_plan_create": [ctypes.POINTER(_c_void_p), _c_int, _c_int, _c_int, _c_int, _c_int],
     "evx_dist_plan_destroy": [_c_void_p],
+    "evx_dist_plan_set_p2p_ctas": [_c_void_p, _c_int],
     "evx_dist_plan_sizes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t), _iptr],
     "evx_dist_forward_f32": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
     "evx_dist_middle_f32": [_c_void_p, _c_void_p, _dptr, _c_double, _c_double, _c_int, _c_void_p],
@@ -347,6 +348,9 @@ class DistPlan:
 
     def new_buffer(self):
         return torch.empty(self.block_shape, dtype=torch.complex64, device=self.device)
+
+    def set_p2p_ctas(self, n):
+        check(load_library().evx_dist_plan_set_p2p_ctas(self._handle, int(n)), "evx_dist_plan_set_p2p_ctas")
 
     def forward(self, r_local, spec, send):
         require_cuda(r_local, spec, send)

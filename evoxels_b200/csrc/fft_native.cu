@@ -112,7 +112,8 @@ static int launch_pipe(const StridedParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const long long resident = (long long)sm_count() * (Pipe::NTHREADS <= 512 ? 2 : 1);
+  long long resident = (long long)sm_count() * (Pipe::NTHREADS <= 512 ? 2 : 1);
+  if (p.max_ctas > 0 && p.max_ctas < resident) resident = p.max_ctas;
   const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);
   kern<<<grid, Pipe::NTHREADS, Pipe::SMEM_BYTES, st>>>(p);
   count_launch();
@@ -203,7 +204,7 @@ int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, v
   yp.in = spec; yp.out = spec; yp.tw = twy;
   yp.src = yp.dst = plain_io(P, (long long)ny * P, ny);
   yp.P = P; yp.ncols_valid = M + 1; yp.ncols_total = (long long)nx * P;
-  yp.kother_offset = 0; yp.use_peers = 0;
+  yp.kother_offset = 0; yp.use_peers = 0; yp.max_ctas = 0;
   yp.filt = FilterParams{};
   if ((rc = launch_strided<PASS_FWD>(ny, yp, st))) return rc;
 
@@ -238,7 +239,7 @@ int native_single_pass(evx_imex_plan* p, int which, const float* u, const float*
   yp.in = spec; yp.out = spec; yp.tw = twy;
   yp.src = yp.dst = plain_io(P, (long long)ny * P, ny);
   yp.P = P; yp.ncols_valid = M + 1; yp.ncols_total = (long long)nx * P;
-  yp.kother_offset = 0; yp.use_peers = 0; yp.filt = FilterParams{};
+  yp.kother_offset = 0; yp.use_peers = 0; yp.max_ctas = 0; yp.filt = FilterParams{};
   if (which == 0) return launch_z<false>(M, zp, st);
   if (which == 1) return launch_strided<PASS_FWD>(ny, yp, st);
   if (which == 3) return launch_strided<PASS_INV>(ny, yp, st);
@@ -270,6 +271,7 @@ int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* ou
 // ------------------------------------------------------------------------------------
 struct DistPlan {
   int nx, ny, nz, world, rank, nxl, nyl, P, M;
+  int p2p_ctas = 0;   // grid cap of the peer-store launches (0: fill the GPU)
   void* twiddles;
 };
 
@@ -307,6 +309,7 @@ static StridedIO block_io(const DistPlan* p) {
 
 static void set_peers(StridedParams& sp, const DistPlan* p, void* const* peers) {
   sp.use_peers = peers ? 1 : 0;
+  sp.max_ctas = peers ? p->p2p_ctas : 0;
   sp.dst_peer_base = (long long)p->rank * p->nxl * p->nyl * p->P;
   for (int i = 0; i < 8; ++i) sp.out_peers[i] = (peers && i < p->world) ? (cf*)peers[i] : nullptr;
 }
@@ -359,7 +362,7 @@ int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, f
   yp.src = block_io(p);
   yp.dst = plain_io(p->P, (long long)p->ny * p->P, p->ny);
   yp.P = p->P; yp.ncols_valid = p->M + 1; yp.ncols_total = (long long)p->nxl * p->P;
-  yp.kother_offset = 0; yp.filt = FilterParams{}; yp.use_peers = 0;
+  yp.kother_offset = 0; yp.filt = FilterParams{}; yp.use_peers = 0; yp.max_ctas = 0;
   int rc = launch_strided<PASS_INV>(p->ny, yp, st);
   if (rc) return rc;
   ZParams zp;
@@ -403,6 +406,11 @@ int evx_dist_plan_create(evx_dist_plan** plan, int nx, int ny, int nz, int world
 int evx_dist_plan_destroy(evx_dist_plan* plan) {
   DistPlan* p = (DistPlan*)plan;
   if (p) { if (p->twiddles) cudaFree(p->twiddles); delete p; }
+  return EVX_OK;
+}
+int evx_dist_plan_set_p2p_ctas(evx_dist_plan* plan, int ctas) {
+  if (!plan || ctas < 0) return EVX_ERR_ARG;
+  ((DistPlan*)plan)->p2p_ctas = ctas;
   return EVX_OK;
 }
 int evx_dist_plan_sizes(const evx_dist_plan* plan, size_t* spec_bytes, int* pitch) {

@@ -65,6 +65,7 @@ struct StridedParams {
   cf* out_peers[8];
   long long dst_peer_base;
   int use_peers;
+  int max_ctas;            // > 0: cap of the persistent grid (NVLink-bound launches leave SMs free)
 };
 
 inline StridedIO plain_io(long long line_stride, long long plane_stride, int L) {

@@ -233,7 +233,7 @@ class DistributedCahnHilliardIMEX:
     `step(u_local) -> u_local_new`; same arithmetic as the single-GPU step."""
 
     def __init__(self, global_shape, spacing, dt, eps=3.0, D=1.0, A=0.25, group=None,
-                 device=None, ops=None, transport="p2p", overlap_chunks=4):
+                 device=None, ops=None, transport="p2p", overlap_chunks=4, p2p_ctas=0):
         self.comm = Comm(group)
         self.slab = Slab(tuple(global_shape), self.comm.world, self.comm.rank)
         self.spacing, self.dt, self.eps, self.D, self.A = tuple(spacing), dt, eps, D, A
@@ -243,6 +243,8 @@ class DistributedCahnHilliardIMEX:
         self.rhs = self.ops.new_field()
         # forward pipeline depth: x chunks of the local slab issued on two streams (p2p only)
         self.overlap_chunks = overlap_chunks if self.slab.nxl >= 8 * max(overlap_chunks, 1) else 1
+        if ops is None and self.ops.transport == "p2p" and self.overlap_chunks > 1 and p2p_ctas:
+            self.ops.plan.set_p2p_ctas(p2p_ctas)
 
     def step_profiled(self, u_local):
         """One step with CUDA events around every stage (diagnostics; p2p transport,

@@ -189,6 +189,9 @@ typedef struct evx_dist_plan evx_dist_plan;
 int evx_dist_plan_create(evx_dist_plan** plan, int nx, int ny, int nz, int world, int rank);
 int evx_dist_plan_destroy(evx_dist_plan* plan);
 int evx_dist_plan_sizes(const evx_dist_plan* plan, size_t* spec_bytes, int* pitch);
+/* cap the persistent grid of the peer-store launches (they are NVLink-bound; leaving SMs free
+ * lets the next chunk's rhs / z pass run concurrently on another stream); 0 = fill the GPU */
+int evx_dist_plan_set_p2p_ctas(evx_dist_plan* plan, int ctas);
 int evx_dist_forward_f32(evx_dist_plan* plan, const float* r_local, void* spec, void* send,
                          void* stream);
 int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double dt, double coef,
