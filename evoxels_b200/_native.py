@@ -69,7 +69,7 @@ SIGNATURES = {
     "evx_dist_middle_f32": [_c_void_p, _c_void_p, _dptr, _c_double, _c_double, _c_int, _c_void_p],
     "evx_dist_forward_p2p_f32": [_c_void_p, _c_void_p, _c_void_p, ctypes.POINTER(_c_void_p), _c_void_p],
     "evx_dist_forward_chunk_p2p_f32": [_c_void_p, _c_void_p, _c_void_p, ctypes.POINTER(_c_void_p), _c_int,
-                                       _c_int, _c_void_p],
+                                       _c_int, _c_int, _c_void_p],
     "evx_dist_middle_p2p_f32": [_c_void_p, _c_void_p, ctypes.POINTER(_c_void_p), _dptr, _c_double,
                                 _c_double, _c_int, _c_void_p],
     "evx_dist_backward_f32": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
@@ -377,13 +377,14 @@ class DistPlan:
                                                           self._ptr_array(peer_ptrs), _stream(r_local)),
                   "evx_dist_forward_p2p")
 
-    def forward_chunk_p2p(self, r_local, spec, peer_ptrs, x0, nxc):
-        """forward_p2p for the local x planes [x0, x0+nxc) on the current stream."""
+    def forward_chunk_p2p(self, r_local, spec, peer_ptrs, x0, nxc, parts=3):
+        """forward_p2p for the local x planes [x0, x0+nxc) on the current stream
+        (parts: 1 z pass, 2 y pass with peer stores, 3 both)."""
         require_cuda(r_local, spec)
         with torch.cuda.device(self.device):
             check(load_library().evx_dist_forward_chunk_p2p_f32(
                 self._handle, _ptr(_field3(r_local)), _ptr(spec), self._ptr_array(peer_ptrs),
-                int(x0), int(nxc), _stream(r_local)), "evx_dist_forward_chunk_p2p")
+                int(x0), int(nxc), int(parts), _stream(r_local)), "evx_dist_forward_chunk_p2p")
 
     def middle_p2p(self, recv, peer_ptrs, spacing, dt, coef, power):
         require_cuda(recv)

@@ -319,15 +319,18 @@ static void set_peers(StridedParams& sp, const DistPlan* p, void* const* peers) 
 // start of the full local arrays), so that several chunks can be pipelined on streams:
 // the NVLink-bound y pass of one chunk overlaps the HBM-bound z pass of the next.
 int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* const* peers,
-                 int x0, int nxc, cudaStream_t st) {
+                 int x0, int nxc, cudaStream_t st, int parts = 3) {
   if (x0 < 0 || nxc < 1 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
   const long long spec_off = (long long)x0 * p->ny * p->P;
-  ZParams zp;
-  zp.real_in = r_local + (long long)x0 * p->ny * p->nz; zp.real_out = nullptr;
-  zp.spec = spec + spec_off; zp.tw = tw_z(p); zp.twr = tw_r(p);
-  zp.rows = (long long)nxc * p->ny; zp.nz = p->nz; zp.P = p->P;
-  int rc = launch_z<false>(p->M, zp, st);
-  if (rc) return rc;
+  if (parts & 1) {   // z pass
+    ZParams zp;
+    zp.real_in = r_local + (long long)x0 * p->ny * p->nz; zp.real_out = nullptr;
+    zp.spec = spec + spec_off; zp.tw = tw_z(p); zp.twr = tw_r(p);
+    zp.rows = (long long)nxc * p->ny; zp.nz = p->nz; zp.P = p->P;
+    int rc = launch_z<false>(p->M, zp, st);
+    if (rc) return rc;
+  }
+  if (!(parts & 2)) return EVX_OK;
   StridedParams yp;
   yp.in = spec + spec_off; yp.tw = tw_y(p);
   yp.src = plain_io(p->P, (long long)p->ny * p->P, p->ny);
@@ -434,11 +437,11 @@ int evx_dist_forward_p2p_f32(evx_dist_plan* plan, const float* r_local, void* sp
   return dist_forward(dp, r_local, (cf*)spec, nullptr, peer_recv, 0, dp->nxl, (cudaStream_t)stream);
 }
 int evx_dist_forward_chunk_p2p_f32(evx_dist_plan* plan, const float* r_local, void* spec,
-                                   void* const* peer_recv, int x0, int nxc, void* stream) {
-  if (!plan || !r_local || !spec || !peer_recv) return EVX_ERR_ARG;
+                                   void* const* peer_recv, int x0, int nxc, int parts, void* stream) {
+  if (!plan || !r_local || !spec || !peer_recv || parts < 1 || parts > 3) return EVX_ERR_ARG;
   if (((DistPlan*)plan)->world > 8) return EVX_ERR_UNSUPPORTED;
   return dist_forward((DistPlan*)plan, r_local, (cf*)spec, nullptr, peer_recv, x0, nxc,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, parts);
 }
 int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_out, const double* h,
                             double dt, double coef, int power, void* stream) {

@@ -192,26 +192,30 @@ class CudaOps:
 
     def forward_pipelined(self, u, rhs, eps, D, bc, halo_lo, halo_hi, chunks):
         """rhs -> z pass -> y pass (+ NVLink peer stores) over `chunks` slices of the local x
-        range, alternating between two side streams: while one slice's y pass is pushing its
-        output over NVLink, the next slice's rhs / z pass keep HBM and the SMs busy."""
+        range.  A compute stream runs rhs and z pass of slice i+1 while a link stream runs the
+        NVLink-bound y pass of slice i (launched with a capped grid so that SMs stay free)."""
         nxl = self.slab.nxl
         bounds = [round(i * nxl / chunks) for i in range(chunks + 1)]
         main = torch.cuda.current_stream(self.device)
-        if not hasattr(self, "_side"):
-            self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
-        ready = torch.cuda.Event()
-        ready.record(main)
+        if not hasattr(self, "_comp"):
+            self._comp = torch.cuda.Stream(device=self.device)
+            self._link = torch.cuda.Stream(device=self.device)
+        self._comp.wait_stream(main)
+        self._link.wait_stream(main)
         for i in range(chunks):
             x0, x1 = bounds[i], bounds[i + 1]
-            st = self._side[i % 2]
-            st.wait_event(ready)
-            with torch.cuda.stream(st):
+            with torch.cuda.stream(self._comp):
                 lo = halo_lo if x0 == 0 else u[x0 - 2:x0]
                 hi = halo_hi if x1 == nxl else u[x1:x1 + 2]
                 _native.ch_rhs(u[x0:x1], rhs[x0:x1], self.spacing, eps, D, bc, halo_lo=lo, halo_hi=hi)
-                self.plan.forward_chunk_p2p(rhs, self.spec, self.peers.peer_ptrs[1], x0, x1 - x0)
-        for st in self._side:
-            main.wait_stream(st)
+                self.plan.forward_chunk_p2p(rhs, self.spec, self.peers.peer_ptrs[1], x0, x1 - x0, parts=1)
+                done = torch.cuda.Event()
+                done.record(self._comp)
+            self._link.wait_event(done)
+            with torch.cuda.stream(self._link):
+                self.plan.forward_chunk_p2p(rhs, self.spec, self.peers.peer_ptrs[1], x0, x1 - x0, parts=2)
+        main.wait_stream(self._comp)
+        main.wait_stream(self._link)
         self.peers.barrier(1)
         return self.buf_b
 

@@ -208,10 +208,11 @@ int evx_dist_forward_p2p_f32(evx_dist_plan* plan, const float* r_local, void* sp
 int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_out, const double* h,
                             double dt, double coef, int power, void* stream);
 /* forward_p2p restricted to the local x planes [x0, x0+nxc) (pointers still address the full
- * local arrays): chunks issued on alternating streams overlap the NVLink-bound y pass of one
- * chunk with the HBM-bound rhs / z pass of the next. */
+ * local arrays); parts: 1 = z pass only, 2 = y pass (+peer stores) only, 3 = both.  Issuing the
+ * z passes on a compute stream and the NVLink-bound y passes on a second stream overlaps the
+ * transfer of one chunk with the rhs / z pass of the next. */
 int evx_dist_forward_chunk_p2p_f32(evx_dist_plan* plan, const float* r_local, void* spec,
-                                   void* const* peer_recv, int x0, int nxc, void* stream);
+                                   void* const* peer_recv, int x0, int nxc, int parts, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Adjoint of the Cahn-Hilliard right-hand side (fully periodic grids)
