@@ -237,7 +237,7 @@ class DistributedCahnHilliardIMEX:
     `step(u_local) -> u_local_new`; same arithmetic as the single-GPU step."""
 
     def __init__(self, global_shape, spacing, dt, eps=3.0, D=1.0, A=0.25, group=None,
-                 device=None, ops=None, transport="p2p", overlap_chunks=4, p2p_ctas=0):
+                 device=None, ops=None, transport="p2p", overlap_chunks=4, p2p_ctas=148):
         self.comm = Comm(group)
         self.slab = Slab(tuple(global_shape), self.comm.world, self.comm.rank)
         self.spacing, self.dt, self.eps, self.D, self.A = tuple(spacing), dt, eps, D, A
