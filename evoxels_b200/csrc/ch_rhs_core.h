@@ -91,13 +91,16 @@ struct ChRhsProgram {
     int qn;                   // index of the plane pn/ph/pe point into
     T* po;                    // own output element of the next plane to write
     int er, ec;               // smem row / col of the extra element
-    Vt cB, cC, cD;            // c^ at planes p-1, p, p+1 (own position)
+    // Rolling windows are indexed with COMPILE-TIME rotation counters (ROT mod 3 for c^,
+    // PAR mod 2 for everything else) and the plane loop is unrolled six-fold, so the windows
+    // rotate by renaming instead of by ~60 register moves per plane.
+    Vt c[3];                  // c^ at planes p-1, p, p+1 live in c[ROT], c[ROT+1], c[ROT+2] (mod 3)
     Vt hC, hD;                // hom at planes p, p+1
-    Vt mB;                    // mu at plane p-1
-    Vt fxm;                   // x-face term between planes p-2 and p-1
+    Vt m[2];                  // mu(p-1) = m[PAR^1]; mu(p) is written to m[PAR]
+    Vt fx[2];                 // x-face term (p-2,p-1) = fx[PAR^1]; (p-1,p) is written to fx[PAR]
     Vt nxt, hnxt, enxt;       // raw prefetched plane p+2 (own / hom / extra rows)
-    Vt sN, sS;                // y-neighbours of c^(p-1)
-    T sL, sR;                 // z-neighbours of c^(p-1)
+    Vt sN[2], sS[2];          // y-neighbours of c^(p-1) = s*[PAR^1]; those of c^(p) go to s*[PAR]
+    T sL[2], sR[2];           // z-neighbours, same convention
     int xa, xb;               // chunk [xa, xb)
   };
 
@@ -208,25 +211,25 @@ struct ChRhsProgram {
       t.eoff = (long long)yi * p.nz + zi;
     }
     const Vt zero = vec_splat<T, V>(T(0));
-    t.cB = t.cC = t.cD = zero;
+    t.c[0] = t.c[1] = t.c[2] = zero;
     t.hC = t.hD = zero;
-    t.mB = zero;
-    t.fxm = zero;
-    t.sN = t.sS = zero;
-    t.sL = t.sR = T(0);
+    t.m[0] = t.m[1] = zero;
+    t.fx[0] = t.fx[1] = zero;
+    t.sN[0] = t.sN[1] = t.sS[0] = t.sS[1] = zero;
+    t.sL[0] = t.sL[1] = t.sR[0] = t.sR[1] = T(0);
     t.nxt = t.hnxt = t.enxt = zero;
     if (t.has_pos) {
-      t.cB = clipv(load_plane(p, p.c, t.xa - 2, t.off, true));
-      t.cC = clipv(load_plane(p, p.c, t.xa - 1, t.off, true));
-      t.cD = clipv(load_plane(p, p.c, t.xa, t.off, true));
+      t.c[0] = clipv(load_plane(p, p.c, t.xa - 2, t.off, true));     // first plane: ROT = 0
+      t.c[1] = clipv(load_plane(p, p.c, t.xa - 1, t.off, true));
+      t.c[2] = clipv(load_plane(p, p.c, t.xa, t.off, true));
       t.nxt = load_plane(p, p.c, t.xa + 1, t.off, true);
       if (HOM) {
         t.hC = load_plane(p, p.hom, t.xa - 1, t.off, false);
         t.hD = load_plane(p, p.hom, t.xa, t.off, false);
         t.hnxt = load_plane(p, p.hom, t.xa + 1, t.off, false);
       }
-      s.c[0][t.row][t.col] = t.cC;     // slot = (plane - (xa-1)) & 1
-      s.c[1][t.row][t.col] = t.cD;
+      s.c[0][t.row][t.col] = t.c[1];   // slot = (plane - (xa-1)) & 1
+      s.c[1][t.row][t.col] = t.c[2];
     }
     if (t.has_extra) {
       s.c[0][t.er][t.ec] = clipv(load_plane(p, p.c, t.xa - 1, t.eoff, true));
@@ -264,9 +267,18 @@ struct ChRhsProgram {
   // ---- phase A of plane p: mu(p) -> smem, then rhs(x = p-1) -> global ------------------
   // PAR = (pl - (xa-1)) & 1 is the shared-memory slot of plane pl (static so that all
   // shared-memory offsets are immediates)
-  template <int PAR>
+  // ROT = (pl - (xa-1)) mod 3 names the registers of the c^ window
+  template <int PAR, int ROT>
   EVX_HD static void phase_a(Regs& t, Smem& s, const P& p, int pl) {
     if (!t.has_pos) return;
+    const Vt& cB_ = t.c[ROT % 3];
+    const Vt& cC_ = t.c[(ROT + 1) % 3];
+    const Vt& cD_ = t.c[(ROT + 2) % 3];
+    const Vt& mB_ = t.m[PAR ^ 1];
+    const Vt& fxm_ = t.fx[PAR ^ 1];
+    const Vt& sN_ = t.sN[PAR ^ 1];
+    const Vt& sS_ = t.sS[PAR ^ 1];
+    const T sL_ = t.sL[PAR ^ 1], sR_ = t.sR[PAR ^ 1];
     const int row = t.row, col = t.col;
     const T oy0 = p.ghost_off[1][0], oy1 = p.ghost_off[1][1], sy = p.ghost_sgn[1];
     const T oz0 = p.ghost_off[2][0], oz1 = p.ghost_off[2][1], sz = p.ghost_sgn[2];
@@ -282,24 +294,24 @@ struct ChRhsProgram {
       cL = s.c[sl][row][col - 1].v[V - 1];
       cR = s.c[sl][row][col + 1].v[0];
       if (GHOSTS) {
-        if (t.gy_lo) cS = ghostv(t.cC, oy0, sy);
-        if (t.gy_hi) cN = ghostv(t.cC, oy1, sy);
-        if (t.gz_lo) cL = oz0 + sz * t.cC.v[0];
-        if (t.gz_hi) cR = oz1 + sz * t.cC.v[V - 1];
+        if (t.gy_lo) cS = ghostv(cC_, oy0, sy);
+        if (t.gy_hi) cN = ghostv(cC_, oy1, sy);
+        if (t.gz_lo) cL = oz0 + sz * cC_.v[0];
+        if (t.gz_hi) cR = oz1 + sz * cC_.v[V - 1];
       }
     }
     Vt mC = vec_splat<T, V>(T(0));
     if (t.want_mu && !is_ghost_plane(t, p, pl)) {
-      Vt cXm = t.cB, cXp = t.cD;
+      Vt cXm = cB_, cXp = cD_;
       if (GHOSTS) {
-        if (is_ghost_plane(t, p, pl - 1)) cXm = ghostv(t.cC, ox0, sx);
-        if (is_ghost_plane(t, p, pl + 1)) cXp = ghostv(t.cC, ox1, sx);
+        if (is_ghost_plane(t, p, pl - 1)) cXm = ghostv(cC_, ox0, sx);
+        if (is_ghost_plane(t, p, pl + 1)) cXp = ghostv(cC_, ox1, sx);
       }
       // window of c^(pl) along z: [cL, c0..c(V-1), cR]
       T cw[V + 2];
       cw[0] = cL;
 #pragma unroll
-      for (int k = 0; k < V; ++k) cw[k + 1] = t.cC.v[k];
+      for (int k = 0; k < V; ++k) cw[k + 1] = cC_.v[k];
       cw[V + 1] = cR;
 #pragma unroll
       for (int k = 0; k < V; k += LW) {
@@ -324,7 +336,7 @@ struct ChRhsProgram {
     Vt fxp;
 #pragma unroll
     for (int k = 0; k < V; k += LW)
-      face_l(Ln::load(t.cB.v, k), Ln::load(t.cC.v, k), Ln::load(t.mB.v, k), Ln::load(mC.v, k))
+      face_l(Ln::load(cB_.v, k), Ln::load(cC_.v, k), Ln::load(mB_.v, k), Ln::load(mC.v, k))
           .store(fxp.v, k);
 
     // rhs at plane x = pl-1: c^(x) = cB, mu(x) = mB; the x-faces are fxm (carried) and fxp
@@ -336,29 +348,29 @@ struct ChRhsProgram {
       Vt mN = s.mu[ms][mrow + 1][col];
       T mL = s.mu[ms][mrow][col - 1].v[V - 1];
       T mR = s.mu[ms][mrow][col + 1].v[0];
-      Vt fxm = t.fxm;
+      Vt fxm = fxm_;
       if (GHOSTS) {
-        if (t.gy_lo) mS = ghostv(t.mB, oy0, sy);
-        if (t.gy_hi) mN = ghostv(t.mB, oy1, sy);
-        if (t.gz_lo) mL = oz0 + sz * t.mB.v[0];
-        if (t.gz_hi) mR = oz1 + sz * t.mB.v[V - 1];
+        if (t.gy_lo) mS = ghostv(mB_, oy0, sy);
+        if (t.gy_hi) mN = ghostv(mB_, oy1, sy);
+        if (t.gz_lo) mL = oz0 + sz * mB_.v[0];
+        if (t.gz_hi) mR = oz1 + sz * mB_.v[V - 1];
         if (is_ghost_plane(t, p, x - 1)) {
 #pragma unroll
           for (int k = 0; k < V; ++k)
-            fxm.v[k] = face(ox0 + sx * t.cB.v[k], t.cB.v[k], ox0 + sx * t.mB.v[k], t.mB.v[k]);
+            fxm.v[k] = face(ox0 + sx * cB_.v[k], cB_.v[k], ox0 + sx * mB_.v[k], mB_.v[k]);
         }
         if (is_ghost_plane(t, p, x + 1)) {
 #pragma unroll
           for (int k = 0; k < V; ++k)
-            fxp.v[k] = face(t.cB.v[k], ox1 + sx * t.cB.v[k], t.mB.v[k], ox1 + sx * t.mB.v[k]);
+            fxp.v[k] = face(cB_.v[k], ox1 + sx * cB_.v[k], mB_.v[k], ox1 + sx * mB_.v[k]);
         }
       }
       // z windows of c^(x) and mu(x): [left, 0..V-1, right]
       T cw[V + 2], mw[V + 2];
-      cw[0] = t.sL; mw[0] = mL;
+      cw[0] = sL_; mw[0] = mL;
 #pragma unroll
-      for (int k = 0; k < V; ++k) { cw[k + 1] = t.cB.v[k]; mw[k + 1] = t.mB.v[k]; }
-      cw[V + 1] = t.sR; mw[V + 1] = mR;
+      for (int k = 0; k < V; ++k) { cw[k + 1] = cB_.v[k]; mw[k + 1] = mB_.v[k]; }
+      cw[V + 1] = sR_; mw[V + 1] = mR;
       // z-face terms: fz[k] is the face between window elements k and k+1
       T fz[V + 2];
 #pragma unroll
@@ -368,9 +380,9 @@ struct ChRhsProgram {
       Vt o;
 #pragma unroll
       for (int k = 0; k < V; k += LW) {
-        const Ln c0 = Ln::load(t.cB.v, k), m0 = Ln::load(t.mB.v, k);
-        const Ln fyp = face_l(c0, Ln::load(t.sN.v, k), m0, Ln::load(mN.v, k));
-        const Ln fym = face_l(Ln::load(t.sS.v, k), c0, Ln::load(mS.v, k), m0);
+        const Ln c0 = Ln::load(cB_.v, k), m0 = Ln::load(mB_.v, k);
+        const Ln fyp = face_l(c0, Ln::load(sN_.v, k), m0, Ln::load(mN.v, k));
+        const Ln fym = face_l(Ln::load(sS_.v, k), c0, Ln::load(mS.v, k), m0);
         const Ln dx = Ln::sub(Ln::load(fxp.v, k), Ln::load(fxm.v, k));
         const Ln dz = Ln::sub(Ln::load(fz, k + 1), Ln::load(fz, k));
         Ln::fmas(dx, p.fx, Ln::fmas(Ln::sub(fyp, fym), p.fy, Ln::muls(dz, p.fz))).store(o.v, k);
@@ -378,28 +390,27 @@ struct ChRhsProgram {
       vec_store<T, V>(t.po, o);
       t.po += t.ps;
     }
-    // roll the mu window and remember the y/z neighbours of c^(pl) for the next plane
-    t.fxm = fxp;
-    t.mB = mC;
-    t.sN = cN;
-    t.sS = cS;
-    t.sL = cL;
-    t.sR = cR;
+    // hand the mu window and the y/z neighbours of c^(pl) to the next plane (no moves:
+    // the next plane reads them under the flipped parity)
+    t.fx[PAR] = fxp;
+    t.m[PAR] = mC;
+    t.sN[PAR] = cN;
+    t.sS[PAR] = cS;
+    t.sL[PAR] = cL;
+    t.sR[PAR] = cR;
   }
 
   // ---- phase B of plane p (after the barrier): roll c^ window, publish plane p+2 -------
-  template <int PAR>
+  template <int PAR, int ROT>
   EVX_HD static void phase_b(Regs& t, Smem& s, const P& p, int pl) {
     const bool more = t.qn <= t.xb + 1;       // plane qn = pl+3 is still needed as a centre value
     if (t.has_pos) {
-      t.cB = t.cC;
-      t.cC = t.cD;
-      t.cD = clipv(t.nxt);
+      t.c[ROT % 3] = clipv(t.nxt);            // plane pl+2 replaces plane pl-1
       if (HOM) {
         t.hC = t.hD;
         t.hD = t.hnxt;
       }
-      s.c[PAR][t.row][t.col] = t.cD;
+      s.c[PAR][t.row][t.col] = t.c[ROT % 3];
       if (more) {
         if (t.pn) t.nxt = vec_load<T, V>(t.pn);
         if (HOM && t.ph) t.hnxt = vec_load<T, V>(t.ph);

@@ -14,23 +14,24 @@ std::atomic<unsigned long long> g_launches{0};
 // ------------------------------------------------------------------------------------
 template <typename T, int V, int TY, int G, bool HOM, bool GHOSTS, int MINB = 2>
 __global__ void __launch_bounds__(ChRhsProgram<T, V, TY, G, HOM, GHOSTS>::NTHREADS,
-                                  (sizeof(T) == 4 && TY <= 16) ? MINB : 1)
+                                  (sizeof(T) == 4 && TY <= 16 && !HOM) ? MINB : 1)
     ch_rhs_kernel(const ChParams<T> p) {
   using Prog = ChRhsProgram<T, V, TY, G, HOM, GHOSTS>;
   __shared__ typename Prog::Smem s;
   typename Prog::Regs t;
   Prog::init(t, s, p, threadIdx.x, blockIdx.x, blockIdx.y);
   __syncthreads();
-  for (int pl = t.xa - 1; pl <= t.xb; pl += 2) {
-    Prog::template phase_a<0>(t, s, p, pl);
-    __syncthreads();
-    Prog::template phase_b<0>(t, s, p, pl);
-    if (pl + 1 <= t.xb) {          // uniform across the block
-      Prog::template phase_a<1>(t, s, p, pl + 1);
-      __syncthreads();
-      Prog::template phase_b<1>(t, s, p, pl + 1);
-    }
+#define EVX_CH_PLANE(PAR, ROT, OFF)                          \
+  if (pl + (OFF) <= t.xb) { /* uniform across the block */   \
+    Prog::template phase_a<PAR, ROT>(t, s, p, pl + (OFF));    \
+    __syncthreads();                                          \
+    Prog::template phase_b<PAR, ROT>(t, s, p, pl + (OFF));    \
   }
+  for (int pl = t.xa - 1; pl <= t.xb; pl += 6) {
+    EVX_CH_PLANE(0, 0, 0) EVX_CH_PLANE(1, 1, 1) EVX_CH_PLANE(0, 2, 2)
+    EVX_CH_PLANE(1, 0, 3) EVX_CH_PLANE(0, 1, 4) EVX_CH_PLANE(1, 2, 5)
+  }
+#undef EVX_CH_PLANE
 }
 
 static int pick_xchunk(int nx, long long tiles, int min_chunk) {

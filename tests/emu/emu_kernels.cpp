@@ -22,14 +22,16 @@ static void run_ch_(const ChParams<T>& p) {
     for (int tile = 0; tile < tiles; ++tile) {
       std::memset(s, 0, sizeof(*s));
       for (int t = 0; t < Prog::NTHREADS; ++t) Prog::init(regs[t], *s, p, t, tile, chunk);
-      for (int pl = regs[0].xa - 1; pl <= regs[0].xb; pl += 2) {
-        for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_a<0>(regs[t], *s, p, pl);
-        for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_b<0>(regs[t], *s, p, pl);
-        if (pl + 1 <= regs[0].xb) {
-          for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_a<1>(regs[t], *s, p, pl + 1);
-          for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_b<1>(regs[t], *s, p, pl + 1);
-        }
+#define EMU_CH_PLANE(PAR, ROT, OFF)                                                              \
+  if (pl + (OFF) <= regs[0].xb) {                                                                 \
+    for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_a<PAR, ROT>(regs[t], *s, p, pl + (OFF)); \
+    for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_b<PAR, ROT>(regs[t], *s, p, pl + (OFF)); \
+  }
+      for (int pl = regs[0].xa - 1; pl <= regs[0].xb; pl += 6) {
+        EMU_CH_PLANE(0, 0, 0) EMU_CH_PLANE(1, 1, 1) EMU_CH_PLANE(0, 2, 2)
+        EMU_CH_PLANE(1, 0, 3) EMU_CH_PLANE(0, 1, 4) EMU_CH_PLANE(1, 2, 5)
       }
+#undef EMU_CH_PLANE
     }
   delete s;
 }
