@@ -141,7 +141,12 @@ int ac_stage_impl(const T* phi, const T* pot, T* k_out, const T* base, T* y_out,
   const bool vec = nz % VW == 0 && aligned16(phi) && aligned16(pot) && aligned16(k_out) &&
                    aligned16(base) && aligned16(y_out) && aligned16(acc_in) &&
                    aligned16(acc_out) && aligned16(halo_lo) && aligned16(halo_hi);
-  if (vec) return launch_ac<T, VW, 8, 32>(p, st);
+  if (vec) {
+    static const int v = [] { const char* e = getenv("EVX_AC_V"); return e ? atoi(e) : 0; }();
+    if (sizeof(T) == 4 && v == 2) return launch_ac<T, 2, 8, 32>(p, st);
+    if (sizeof(T) == 4 && v == 22) return launch_ac<T, 2, 4, 64>(p, st);
+    return launch_ac<T, VW, 8, 32>(p, st);
+  }
   return launch_ac<T, 1, 8, 32>(p, st);
 }
 
