@@ -247,6 +247,163 @@ struct AcProgram {
 };
 
 // ------------------------------------------------------------------------------------
+// Shared-memory tile variant of the same update (the fast path for V = 4 floats).
+//
+// A block owns a (TY x TZ) tile of the y-z plane and marches along x.  Four plane slots of
+// the ghost-padded, clipped field live in shared memory ([TY+2][G+2] groups each, ring of
+// one cell); ghost values - periodic images, Neumann/Dirichlet rules, x-slab halos, edge and
+// corner ghosts in the reference's x,y,z order - are resolved ONCE when a plane is stored,
+// so the 19-point evaluation reads plain neighbours.  Per plane: evaluate plane x from slots
+// (x-1, x, x+1), barrier, publish plane x+3 (prefetched into a register one plane earlier)
+// into the slot of plane x-1.  Ring positions sit in their own warps and only move data.
+// Replaces the register-window kernel above where it applies: that one re-reads rows through
+// L1 with a 54-register window and is latency-bound at two blocks per SM.
+// ------------------------------------------------------------------------------------
+template <typename T, int V, int TY, int G>
+struct AcTileProgram {
+  static constexpr int TZ = G * V;
+  static constexpr int COLS = G + 2, ROWS = TY + 2;
+  static constexpr int N_INT = TY * G, N_RROW = 2 * G, N_RCOL = 2 * (TY + 2);
+  static constexpr int NPOS = N_INT + N_RROW + N_RCOL;
+  static constexpr int NTHREADS = ((NPOS + 31) / 32) * 32;
+  static_assert(V >= 2, "tile variant needs vector groups");
+  using Base = AcProgram<T, V, TY, G>;
+  using P = AcParams<T>;
+  using Vt = Vec<T, V>;
+  using Plane = typename Base::Plane;
+
+  struct Smem {
+    Vt c[4][ROWS][COLS];
+  };
+
+  struct Regs {
+    int row, col;            // smem indices of the own position
+    bool has_pos, interior;
+    int yside, zside;        // -1 or lo/hi ghost side of this position (non-periodic only)
+    long long off;           // element offset of the (mapped) position inside a plane
+    long long o;             // output element index of plane x at the own position
+    long long ps;
+    Vt nxt;                  // raw plane xa+3+i, prefetched
+    int xa, xb;
+  };
+
+  // value stored for this position: clip, then the x / y / z ghost rules in reference order
+  EVX_HD static Vt padded(const Regs& t, const P& p, const Vt& raw, int xside) {
+    Vt v;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      T a = clip01(raw.v[k]);
+      a = Base::rule(p, 0, xside, a);
+      a = Base::rule(p, 1, t.yside, a);
+      v.v[k] = a;
+    }
+    if (t.zside == 0) {        // left ghost group: its last element is the ghost of z = 0
+      v.v[V - 1] = Base::rule(p, 2, 0, v.v[0]);
+    } else if (t.zside == 1) { // right ghost group: its first element is the ghost of z = nz-1
+      v.v[0] = Base::rule(p, 2, 1, v.v[V - 1]);
+    }
+    return v;
+  }
+
+  EVX_HD static Vt load_plane(const Regs& t, const P& p, int q, int& xside) {
+    const typename Base::PlaneRef pl = Base::plane(p, q);
+    xside = pl.side;
+    return vec_load<T, V>(pl.ptr + t.off);
+  }
+
+  EVX_HD static void init(Regs& t, Smem& s, const P& p, int tid, int tile, int chunk) {
+    const int tiles_z = (p.nz + TZ - 1) / TZ;
+    const int y0 = (tile / tiles_z) * TY, z0 = (tile % tiles_z) * TZ;
+    t.xa = chunk * p.xchunk;
+    t.xb = t.xa + p.xchunk < p.nx ? t.xa + p.xchunk : p.nx;
+    t.has_pos = tid < NPOS;
+    int r, g;
+    if (tid < N_INT) {
+      r = tid / G; g = tid % G;
+    } else if (tid < N_INT + N_RROW) {
+      const int j = tid - N_INT;
+      r = j < G ? -1 : TY; g = j % G;
+    } else {
+      const int j = tid - N_INT - N_RROW;
+      r = j % (TY + 2) - 1; g = j < TY + 2 ? -1 : G;
+    }
+    t.row = r + 1; t.col = g + 1;
+    const bool per_y = p.bc_kind[1] == BC_PERIODIC, per_z = p.bc_kind[2] == BC_PERIODIC;
+    const int y = y0 + r, z = z0 + g * V;
+    const int yi = per_y ? wrap_index(y, p.ny) : clamp_index(y, 0, p.ny - 1);
+    const int zi = per_z ? wrap_index(z, p.nz) : clamp_index(z, 0, p.nz - V);
+    t.off = (long long)yi * p.nz + zi;
+    t.yside = (!per_y && y < 0) ? 0 : ((!per_y && y >= p.ny) ? 1 : -1);
+    t.zside = (!per_z && z < 0) ? 0 : ((!per_z && z >= p.nz) ? 1 : -1);
+    t.interior = tid < N_INT && y < p.ny && z + V <= p.nz;
+    t.ps = (long long)p.ny * p.nz;
+    t.o = (long long)t.xa * t.ps + (long long)y * p.nz + z;
+    t.nxt = vec_splat<T, V>(T(0));
+    if (t.has_pos) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {     // planes xa-1 .. xa+2 -> slots 0..3
+        int xs;
+        const Vt raw = load_plane(t, p, t.xa - 1 + i, xs);
+        s.c[i][t.row][t.col] = padded(t, p, raw, xs);
+      }
+      if (t.xa + 3 <= t.xb) {
+        int xs;
+        t.nxt = load_plane(t, p, t.xa + 3, xs);
+      }
+    }
+  }
+
+  // group `col` of row `row` of slot `sl` as a (V+2)-wide window incl. the neighbouring z values
+  EVX_HD static void window(const Smem& s, int sl, int row, int col, T* w) {
+    const Vt c = s.c[sl][row][col];
+#pragma unroll
+    for (int k = 0; k < V; ++k) w[k + 1] = c.v[k];
+    w[0] = s.c[sl][row][col - 1].v[V - 1];
+    w[V + 1] = s.c[sl][row][col + 1].v[0];
+  }
+  EVX_HD static void centre_only(const Smem& s, int sl, int row, int col, T* w) {
+    const Vt c = s.c[sl][row][col];
+#pragma unroll
+    for (int k = 0; k < V; ++k) w[k + 1] = c.v[k];
+    w[0] = w[V + 1] = T(0);          // (y+-1, z+-1) of the x+-1 planes are not in the stencil
+  }
+
+  // ROT = (x - xa) mod 4: planes x-1, x, x+1 live in slots ROT, ROT+1, ROT+2 (mod 4)
+  template <int ROT>
+  EVX_HD static void phase_a(Regs& t, Smem& s, const P& p, int x) {
+    if (!t.interior) return;
+    constexpr int sm = ROT % 4, sc = (ROT + 1) % 4, sp = (ROT + 2) % 4;
+    Plane fm, fc, fp;
+    centre_only(s, sm, t.row - 1, t.col, fm.w[0]);
+    window(s, sm, t.row, t.col, fm.w[1]);
+    centre_only(s, sm, t.row + 1, t.col, fm.w[2]);
+    window(s, sc, t.row - 1, t.col, fc.w[0]);
+    window(s, sc, t.row, t.col, fc.w[1]);
+    window(s, sc, t.row + 1, t.col, fc.w[2]);
+    centre_only(s, sp, t.row - 1, t.col, fp.w[0]);
+    window(s, sp, t.row, t.col, fp.w[1]);
+    centre_only(s, sp, t.row + 1, t.col, fp.w[2]);
+    Base::emit(p, fm, fc, fp, t.o);
+    t.o += t.ps;
+  }
+
+  // after the barrier: plane x+3 (already in a register) replaces plane x-1; fetch plane x+4
+  template <int ROT>
+  EVX_HD static void phase_b(Regs& t, Smem& s, const P& p, int x) {
+    if (!t.has_pos) return;
+    // planes needed by later iterations: up to xb (as "x+1" of the last plane xb-1)
+    if (x + 3 <= t.xb) {
+      const int xs = Base::plane(p, x + 3).side;
+      s.c[ROT % 4][t.row][t.col] = padded(t, p, t.nxt, xs);
+    }
+    if (x + 4 <= t.xb) {
+      int xs;
+      t.nxt = load_plane(t, p, x + 4, xs);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------
 // Generic ghost-layer fetch used by the pad kernel: value of the padded field at padded
 // coordinates (i,j,k) in [0,n+2)^3 (reference boundary_conditions.py:33-59).
 // ------------------------------------------------------------------------------------

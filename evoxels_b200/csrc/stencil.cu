@@ -104,6 +104,39 @@ __global__ void __launch_bounds__(TY* G, MINB) ac_stage_kernel(const AcParams<T>
 }
 
 template <typename T, int V, int TY, int G>
+__global__ void __launch_bounds__(AcTileProgram<T, V, TY, G>::NTHREADS, sizeof(T) == 4 ? 2 : 1)
+    ac_tile_kernel(const AcParams<T> p) {
+  using Prog = AcTileProgram<T, V, TY, G>;
+  __shared__ typename Prog::Smem s;
+  typename Prog::Regs t;
+  Prog::init(t, s, p, threadIdx.x, blockIdx.x, blockIdx.y);
+  __syncthreads();
+#define EVX_AC_PLANE(ROT, OFF)                              \
+  if (x + (OFF) < t.xb) { /* uniform across the block */    \
+    Prog::template phase_a<ROT>(t, s, p, x + (OFF));        \
+    __syncthreads();                                        \
+    Prog::template phase_b<ROT>(t, s, p, x + (OFF));        \
+  }
+  for (int x = t.xa; x < t.xb; x += 4) {
+    EVX_AC_PLANE(0, 0) EVX_AC_PLANE(1, 1) EVX_AC_PLANE(2, 2) EVX_AC_PLANE(3, 3)
+  }
+#undef EVX_AC_PLANE
+}
+
+template <typename T, int V, int TY, int G>
+static int launch_ac_tile(AcParams<T> p, cudaStream_t st) {
+  using Prog = AcTileProgram<T, V, TY, G>;
+  const long long tiles = (long long)((p.ny + TY - 1) / TY) * ((p.nz + Prog::TZ - 1) / Prog::TZ);
+  p.xchunk = pick_xchunk(p.nx, tiles, 32);
+  const int chunks = (p.nx + p.xchunk - 1) / p.xchunk;
+  if (tiles > 2147483647LL || chunks > 65535) return EVX_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)tiles, (unsigned)chunks);
+  ac_tile_kernel<T, V, TY, G><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <typename T, int V, int TY, int G>
 static int launch_ac(AcParams<T> p, cudaStream_t st) {
   using Prog = AcProgram<T, V, TY, G>;
   const long long tiles = (long long)((p.ny + TY - 1) / TY) * ((p.nz + Prog::TZ - 1) / Prog::TZ);
@@ -143,9 +176,8 @@ int ac_stage_impl(const T* phi, const T* pot, T* k_out, const T* base, T* y_out,
                    aligned16(acc_out) && aligned16(halo_lo) && aligned16(halo_hi);
   if (vec) {
     static const int v = [] { const char* e = getenv("EVX_AC_V"); return e ? atoi(e) : 0; }();
-    if (sizeof(T) == 4 && v == 2) return launch_ac<T, 2, 8, 32>(p, st);
-    if (sizeof(T) == 4 && v == 22) return launch_ac<T, 2, 4, 64>(p, st);
-    return launch_ac<T, VW, 8, 32>(p, st);
+    if (v == 1) return launch_ac<T, VW, 8, 32>(p, st);      // register-window variant
+    return launch_ac_tile<T, VW, 14, 16>(p, st);
   }
   return launch_ac<T, 1, 8, 32>(p, st);
 }

@@ -72,6 +72,30 @@ static void run_ac(const AcParams<T>& p) {
       for (int t = 0; t < Prog::NTHREADS; ++t) Prog::run(p, t, tile, chunk);
 }
 
+template <typename T, int V, int TY, int G>
+static void run_ac_tile(const AcParams<T>& p) {
+  using Prog = AcTileProgram<T, V, TY, G>;
+  const int tiles = ((p.ny + TY - 1) / TY) * ((p.nz + Prog::TZ - 1) / Prog::TZ);
+  const int chunks = (p.nx + p.xchunk - 1) / p.xchunk;
+  std::vector<typename Prog::Regs> regs(Prog::NTHREADS);
+  typename Prog::Smem* s = new typename Prog::Smem;
+  for (int chunk = 0; chunk < chunks; ++chunk)
+    for (int tile = 0; tile < tiles; ++tile) {
+      std::memset(s, 0, sizeof(*s));
+      for (int t = 0; t < Prog::NTHREADS; ++t) Prog::init(regs[t], *s, p, t, tile, chunk);
+#define EMU_AC_PLANE(ROT, OFF)                                                                  \
+  if (x + (OFF) < regs[0].xb) {                                                                  \
+    for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_a<ROT>(regs[t], *s, p, x + (OFF)); \
+    for (int t = 0; t < Prog::NTHREADS; ++t) Prog::template phase_b<ROT>(regs[t], *s, p, x + (OFF)); \
+  }
+      for (int x = regs[0].xa; x < regs[0].xb; x += 4) {
+        EMU_AC_PLANE(0, 0) EMU_AC_PLANE(1, 1) EMU_AC_PLANE(2, 2) EMU_AC_PLANE(3, 3)
+      }
+#undef EMU_AC_PLANE
+    }
+  delete s;
+}
+
 template <typename T>
 static int emu_ac(const T* phi, const T* pot, T* k_out, const T* base, T* y_out, double alpha,
                   const T* acc_in, T* acc_out, double beta, int nx, int ny, int nz,
@@ -84,7 +108,8 @@ static int emu_ac(const T* phi, const T* pot, T* k_out, const T* base, T* y_out,
   constexpr int VW = 16 / sizeof(T);
   if (vec) {
     if (nz % VW) return -1;
-    run_ac<T, VW, 8, 32>(p);
+    if (vec == 2) run_ac_tile<T, VW, 14, 16>(p);     // shared-memory tile variant
+    else run_ac<T, VW, 8, 32>(p);
   } else {
     run_ac<T, 1, 8, 32>(p);
   }
