@@ -274,22 +274,31 @@ struct AcTileProgram {
 
   struct Smem {
     Vt c[4][ROWS][COLS];
+    Vt stage[2][NTHREADS];   // raw planes in flight (cp.async), one cell per thread
   };
+  static_assert(sizeof(Vt) == 16, "the staging copy moves 16 bytes per thread");
 
   struct Regs {
-    int row, col;            // smem indices of the own position
+    int row, col, tid;       // smem indices of the own position
     bool has_pos, interior;
+    bool plain;              // no y / z ghost rule touches this position
     int yside, zside;        // -1 or lo/hi ghost side of this position (non-periodic only)
     long long off;           // element offset of the (mapped) position inside a plane
     long long o;             // output element index of plane x at the own position
     long long ps;
-    Vt nxt;                  // raw plane xa+3+i, prefetched
+    const T* pn;             // own element of plane qn, the next one to fetch
+    int qn;
     int xa, xb;
   };
 
   // value stored for this position: clip, then the x / y / z ghost rules in reference order
   EVX_HD static Vt padded(const Regs& t, const P& p, const Vt& raw, int xside) {
     Vt v;
+    if (t.plain && xside < 0) {          // steady state: clip only
+#pragma unroll
+      for (int k = 0; k < V; ++k) v.v[k] = clip01(raw.v[k]);
+      return v;
+    }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       T a = clip01(raw.v[k]);
@@ -311,11 +320,27 @@ struct AcTileProgram {
     return vec_load<T, V>(pl.ptr + t.off);
   }
 
+  // x ghost side of plane q (-1 inside the slab, for halos and for periodic images)
+  EVX_HD static int xside_of(const P& p, int q) {
+    if (q >= 0 && q < p.nx) return -1;
+    return Base::plane(p, q).side;
+  }
+
+  // start the copy of plane t.qn into staging cell `cell`, then step to the next plane
+  EVX_HD static void fetch_next(Regs& t, Smem& s, const P& p, int cell) {
+    async_copy16(&s.stage[cell][t.tid], t.pn);
+    async_copy_commit();
+    ++t.qn;
+    if (t.qn >= 1 && t.qn < p.nx) t.pn += t.ps;             // both planes inside the slab
+    else t.pn = Base::plane(p, t.qn).ptr + t.off;
+  }
+
   EVX_HD static void init(Regs& t, Smem& s, const P& p, int tid, int tile, int chunk) {
     const int tiles_z = (p.nz + TZ - 1) / TZ;
     const int y0 = (tile / tiles_z) * TY, z0 = (tile % tiles_z) * TZ;
     t.xa = chunk * p.xchunk;
     t.xb = t.xa + p.xchunk < p.nx ? t.xa + p.xchunk : p.nx;
+    t.tid = tid;
     t.has_pos = tid < NPOS;
     int r, g;
     if (tid < N_INT) {
@@ -335,10 +360,12 @@ struct AcTileProgram {
     t.off = (long long)yi * p.nz + zi;
     t.yside = (!per_y && y < 0) ? 0 : ((!per_y && y >= p.ny) ? 1 : -1);
     t.zside = (!per_z && z < 0) ? 0 : ((!per_z && z >= p.nz) ? 1 : -1);
+    t.plain = t.yside < 0 && t.zside < 0;
     t.interior = tid < N_INT && y < p.ny && z + V <= p.nz;
     t.ps = (long long)p.ny * p.nz;
     t.o = (long long)t.xa * t.ps + (long long)y * p.nz + z;
-    t.nxt = vec_splat<T, V>(T(0));
+    t.qn = t.xa + 3;
+    t.pn = Base::plane(p, t.qn).ptr + t.off;
     if (t.has_pos) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {     // planes xa-1 .. xa+2 -> slots 0..3
@@ -346,10 +373,7 @@ struct AcTileProgram {
         const Vt raw = load_plane(t, p, t.xa - 1 + i, xs);
         s.c[i][t.row][t.col] = padded(t, p, raw, xs);
       }
-      if (t.xa + 3 <= t.xb) {
-        int xs;
-        t.nxt = load_plane(t, p, t.xa + 3, xs);
-      }
+      if (t.qn <= t.xb) fetch_next(t, s, p, 0);     // plane xa+3 -> cell 0
     }
   }
 
@@ -387,18 +411,17 @@ struct AcTileProgram {
     t.o += t.ps;
   }
 
-  // after the barrier: plane x+3 (already in a register) replaces plane x-1; fetch plane x+4
+  // after the barrier: plane x+3 (staged by the previous iteration) replaces plane x-1, and
+  // the copy of plane x+4 starts
   template <int ROT>
   EVX_HD static void phase_b(Regs& t, Smem& s, const P& p, int x) {
     if (!t.has_pos) return;
     // planes needed by later iterations: up to xb (as "x+1" of the last plane xb-1)
     if (x + 3 <= t.xb) {
-      const int xs = Base::plane(p, x + 3).side;
-      s.c[ROT % 4][t.row][t.col] = padded(t, p, t.nxt, xs);
-    }
-    if (x + 4 <= t.xb) {
-      int xs;
-      t.nxt = load_plane(t, p, x + 4, xs);
+      async_copy_wait_all();
+      const Vt raw = s.stage[ROT & 1][t.tid];
+      s.c[ROT % 4][t.row][t.col] = padded(t, p, raw, xside_of(p, x + 3));
+      if (x + 4 <= t.xb) fetch_next(t, s, p, (ROT + 1) & 1);
     }
   }
 };

@@ -67,4 +67,34 @@ EVX_HD int wrap_index(int i, int n) {
 }
 EVX_HD int clamp_index(int i, int lo, int hi) { return i < lo ? lo : (i > hi ? hi : i); }
 
+// Asynchronous 16-byte global -> shared copy (cp.async / LDGSTS): the data never passes
+// through a register, so no scoreboard of the issuing warp is tied up while it is in flight.
+EVX_HD void async_copy16(void* smem_dst, const void* gmem_src) {
+#if defined(__CUDA_ARCH__)
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
+  // host replay: the copy lands immediately (callers never touch the destination between
+  // issue and wait)
+  const unsigned char* s = reinterpret_cast<const unsigned char*>(gmem_src);
+  unsigned char* d = reinterpret_cast<unsigned char*>(smem_dst);
+  for (int i = 0; i < 16; ++i) d[i] = s[i];
+#endif
+}
+EVX_HD void async_copy_commit_and_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+EVX_HD void async_copy_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+EVX_HD void async_copy_wait_all() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 }  // namespace evx

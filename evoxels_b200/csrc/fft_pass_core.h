@@ -222,29 +222,6 @@ struct StridedPass {
 // B swap.  Memory latency is thereby hidden inside one block instead of relying on other
 // resident blocks, and two blocks (2 x 111 KB for L = 512) still fit an SM.
 // ------------------------------------------------------------------------------------
-EVX_HD void async_copy16(void* smem_dst, const void* gmem_src) {
-#if defined(__CUDA_ARCH__)
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-#else
-  // host replay: the copy lands immediately (the destination buffer is not touched by
-  // anyone between issue and wait, see the buffer rotation above)
-  const float* s = reinterpret_cast<const float*>(gmem_src);
-  float* d = reinterpret_cast<float*>(smem_dst);
-  d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
-#endif
-}
-EVX_HD void async_copy_commit_and_wait() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-#endif
-}
-EVX_HD void async_copy_commit() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-
 template <int L, int KZ, int MODE>
 struct StridedPipe {
   using Base = StridedPass<L, KZ, MODE>;
