@@ -76,10 +76,15 @@ struct ChRhsProgram {
   struct Smem {
     Vt c[2][ROWS_C][COLS];
     Vt mu[2][ROWS_MU][COLS];
+    // raw planes in flight (cp.async): the own element, the extra outermost-row element of
+    // the ring-row threads, and the hom field; cell = parity of the plane that consumes it
+    Vt stage[2][NTHREADS];
+    Vt stage_e[2][N_RROW];
+    Vt stage_h[2][HOM ? NTHREADS : 1];
   };
 
   struct Regs {
-    int row, col;             // smem indices of the own position (row in s.c numbering)
+    int row, col, tid;        // smem indices of the own position (row in s.c numbering)
     bool has_pos, want_mu, interior, has_extra;
     bool gy_lo, gy_hi, gz_lo, gz_hi;   // neighbour in that direction is a non-periodic ghost
     bool xlo_ghost, xhi_ghost;         // planes below 0 / above nx-1 are non-periodic ghosts
@@ -98,7 +103,6 @@ struct ChRhsProgram {
     Vt hC, hD;                // hom at planes p, p+1
     Vt m[2];                  // mu(p-1) = m[PAR^1]; mu(p) is written to m[PAR]
     Vt fx[2];                 // x-face term (p-2,p-1) = fx[PAR^1]; (p-1,p) is written to fx[PAR]
-    Vt nxt, hnxt, enxt;       // raw prefetched plane p+2 (own / hom / extra rows)
     Vt sN[2], sS[2];          // y-neighbours of c^(p-1) = s*[PAR^1]; those of c^(p) go to s*[PAR]
     T sL[2], sR[2];           // z-neighbours, same convention
     int xa, xb;               // chunk [xa, xb)
@@ -217,16 +221,14 @@ struct ChRhsProgram {
     t.fx[0] = t.fx[1] = zero;
     t.sN[0] = t.sN[1] = t.sS[0] = t.sS[1] = zero;
     t.sL[0] = t.sL[1] = t.sR[0] = t.sR[1] = T(0);
-    t.nxt = t.hnxt = t.enxt = zero;
+    t.tid = tid;
     if (t.has_pos) {
       t.c[0] = clipv(load_plane(p, p.c, t.xa - 2, t.off, true));     // first plane: ROT = 0
       t.c[1] = clipv(load_plane(p, p.c, t.xa - 1, t.off, true));
       t.c[2] = clipv(load_plane(p, p.c, t.xa, t.off, true));
-      t.nxt = load_plane(p, p.c, t.xa + 1, t.off, true);
       if (HOM) {
         t.hC = load_plane(p, p.hom, t.xa - 1, t.off, false);
         t.hD = load_plane(p, p.hom, t.xa, t.off, false);
-        t.hnxt = load_plane(p, p.hom, t.xa + 1, t.off, false);
       }
       s.c[0][t.row][t.col] = t.c[1];   // slot = (plane - (xa-1)) & 1
       s.c[1][t.row][t.col] = t.c[2];
@@ -234,11 +236,31 @@ struct ChRhsProgram {
     if (t.has_extra) {
       s.c[0][t.er][t.ec] = clipv(load_plane(p, p.c, t.xa - 1, t.eoff, true));
       s.c[1][t.er][t.ec] = clipv(load_plane(p, p.c, t.xa, t.eoff, true));
-      t.enxt = load_plane(p, p.c, t.xa + 1, t.eoff, true);
     }
     t.ps = (long long)p.ny * p.nz;
-    t.qn = t.xa + 2;
+    t.qn = t.xa + 1;
     resolve_next(t, p);
+    fetch_next(t, s, p, 0);            // plane xa+1 -> cell 0 (read by the first phase B)
+    advance_next(t, p);
+  }
+
+  // start the copies of plane t.qn into staging cell `cell` (ghost planes: nothing to copy,
+  // the cell keeps a finite don't-care value)
+  EVX_HD static void fetch_next(Regs& t, Smem& s, const P& p, int cell) {
+    constexpr int B = (int)sizeof(Vt);
+    if (t.has_pos) {
+      if (t.pn) async_copy_bytes<B>(&s.stage[cell][t.tid], t.pn);
+      else s.stage[cell][t.tid] = vec_splat<T, V>(T(0));
+      if (HOM) {
+        if (t.ph) async_copy_bytes<B>(&s.stage_h[cell][t.tid], t.ph);
+        else s.stage_h[cell][HOM ? t.tid : 0] = vec_splat<T, V>(T(0));
+      }
+    }
+    if (t.has_extra) {
+      if (t.pe) async_copy_bytes<B>(&s.stage_e[cell][t.tid - N_INT], t.pe);
+      else s.stage_e[cell][t.tid - N_INT] = vec_splat<T, V>(T(0));
+    }
+    async_copy_commit();
   }
 
   // pointers into plane t.qn (general path: slab ends, halos, periodic images, ghosts)
@@ -404,23 +426,20 @@ struct ChRhsProgram {
   template <int PAR, int ROT>
   EVX_HD static void phase_b(Regs& t, Smem& s, const P& p, int pl) {
     const bool more = t.qn <= t.xb + 1;       // plane qn = pl+3 is still needed as a centre value
+    async_copy_wait_all();                    // own copies of plane pl+2 have landed
     if (t.has_pos) {
-      t.c[ROT % 3] = clipv(t.nxt);            // plane pl+2 replaces plane pl-1
+      t.c[ROT % 3] = clipv(s.stage[PAR][t.tid]);     // plane pl+2 replaces plane pl-1
       if (HOM) {
         t.hC = t.hD;
-        t.hD = t.hnxt;
+        t.hD = s.stage_h[PAR][HOM ? t.tid : 0];
       }
       s.c[PAR][t.row][t.col] = t.c[ROT % 3];
-      if (more) {
-        if (t.pn) t.nxt = vec_load<T, V>(t.pn);
-        if (HOM && t.ph) t.hnxt = vec_load<T, V>(t.ph);
-      }
     }
-    if (t.has_extra) {
-      s.c[PAR][t.er][t.ec] = clipv(t.enxt);
-      if (more && t.pe) t.enxt = vec_load<T, V>(t.pe);
+    if (t.has_extra) s.c[PAR][t.er][t.ec] = clipv(s.stage_e[PAR][t.tid - N_INT]);
+    if (more) {
+      fetch_next(t, s, p, PAR ^ 1);
+      advance_next(t, p);
     }
-    if (more) advance_next(t, p);
   }
 };
 

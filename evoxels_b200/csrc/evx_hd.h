@@ -81,6 +81,24 @@ EVX_HD void async_copy16(void* smem_dst, const void* gmem_src) {
   for (int i = 0; i < 16; ++i) d[i] = s[i];
 #endif
 }
+// same for a whole Vec<T, V> (4, 8 or 16 bytes)
+template <int BYTES>
+EVX_HD void async_copy_bytes(void* smem_dst, const void* gmem_src) {
+  static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async moves 4, 8 or 16 bytes");
+#if defined(__CUDA_ARCH__)
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+  else if (BYTES == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
+  const unsigned char* s = reinterpret_cast<const unsigned char*>(gmem_src);
+  unsigned char* d = reinterpret_cast<unsigned char*>(smem_dst);
+  for (int i = 0; i < BYTES; ++i) d[i] = s[i];
+#endif
+}
 EVX_HD void async_copy_commit_and_wait() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");

@@ -59,11 +59,7 @@ static int launch_ch(ChParams<T> p, cudaStream_t st) {
   } else if (ghosts) {
     ch_rhs_kernel<T, V, TY, G, false, true><<<grid, Prog::NTHREADS, 0, st>>>(p);
   } else {
-    static const int occ = [] { const char* e = getenv("EVX_CH_OCC"); return e ? atoi(e) : 2; }();
-    if (occ == 3 && sizeof(T) == 4 && TY <= 16)
-      ch_rhs_kernel<T, V, TY, G, false, false, 3><<<grid, Prog::NTHREADS, 0, st>>>(p);
-    else
-      ch_rhs_kernel<T, V, TY, G, false, false><<<grid, Prog::NTHREADS, 0, st>>>(p);
+    ch_rhs_kernel<T, V, TY, G, false, false><<<grid, Prog::NTHREADS, 0, st>>>(p);
   }
   count_launch();
   return (int)cudaGetLastError();
@@ -87,9 +83,6 @@ int ch_rhs_impl(const T* c, const T* hom, T* rhs, int nx, int ny, int nz, const 
                    aligned16(halo_lo) && aligned16(halo_hi);
   if (vec) {
     // tile height: 14 rows x 16 groups = 7 interior warps + 2 ring warps = 288 threads
-    static const int tile = [] { const char* e = getenv("EVX_CH_TILE"); return e ? atoi(e) : 14; }();
-    if (tile == 16) return launch_ch<T, VW, 16, 16>(p, st);
-    if (tile == 30) return launch_ch<T, VW, 30, 16>(p, st);
     return launch_ch<T, VW, 14, 16>(p, st);
   }
   return launch_ch<T, 1, 8, 32>(p, st);
