@@ -34,8 +34,12 @@ _APPLY_ARGS = [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _dptr, _c_
                _c_double, _c_int, _c_void_p]
 _STEP_ARGS = [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _dptr, _c_double,
               _c_double, _c_double, _c_double, _c_void_p]
+_RD2_ARGS = [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _dptr, _c_double, _c_double,
+             _c_double, _c_double, _c_void_p]
 _FILTER_ARGS = [_c_void_p, _c_int, _c_int, _c_int, _dptr, _c_double, _c_double, _c_int,
                 _c_double, _c_void_p]
+
+FILTER_ETD1 = 0x100      # EVX_FILTER_ETD1: OR into `power` for the exponential-Euler weight
 
 SIGNATURES = {
     "evx_version": [],
@@ -45,6 +49,7 @@ SIGNATURES = {
     "evx_ac_stage_f32": _AC_ARGS, "evx_ac_stage_f64": _AC_ARGS,
     "evx_pad_ghost_f32": _PAD_ARGS, "evx_pad_ghost_f64": _PAD_ARGS,
     "evx_padded_stencil_f32": _PST_ARGS, "evx_padded_stencil_f64": _PST_ARGS,
+    "evx_rd2_rhs_f32": _RD2_ARGS, "evx_rd2_rhs_f64": _RD2_ARGS,
     "evx_imex_plan_create": [ctypes.POINTER(_c_void_p), _c_int, _c_int, _c_int, _c_int, _c_int],
     "evx_imex_plan_destroy": [_c_void_p],
     "evx_imex_plan_backend": [_c_void_p],
@@ -213,6 +218,20 @@ def padded_stencil(padded, spacing, op):
         check(getattr(lib, "evx_padded_stencil_" + _suffix(padded))(
             _ptr(padded), _ptr(out), nx, ny, nz, _h3(spacing), int(op), _stream(padded)),
             "evx_padded_stencil")
+    return out
+
+
+def rd2_rhs(u, spacing, D_A, D_B, feed, kill, interaction=None):
+    """Two-species reaction-diffusion rhs of u [2,nx,ny,nz] (fully periodic)."""
+    require_cuda(u, interaction)
+    lib = load_library()
+    assert u.dim() == 4 and u.shape[0] == 2 and u.is_contiguous()
+    out = torch.empty_like(u)
+    _, nx, ny, nz = u.shape
+    with torch.cuda.device(u.device):
+        check(getattr(lib, "evx_rd2_rhs_" + _suffix(u))(
+            _ptr(u), _ptr(interaction), _ptr(out), nx, ny, nz, _h3(spacing), float(D_A),
+            float(D_B), float(feed), float(kill), _stream(u)), "evx_rd2_rhs")
     return out
 
 

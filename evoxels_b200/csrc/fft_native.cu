@@ -51,7 +51,7 @@ static int launch_pass(const Params& p, long long blocks, cudaStream_t st) {
 // y groups (the column index is the linear offset), so the pitch stays a multiple of 8.
 template <int L, int MODE>
 struct StridedCfg {
-  static constexpr int KZ = L >= 2048 ? 4 : ((MODE == PASS_XMID && L <= 512) ? 16 : 8);
+  static constexpr int KZ = L >= 2048 ? 4 : ((pass_is_xmid(MODE) && L <= 512) ? 16 : 8);
 };
 
 // persistent, software-pipelined form (see StridedPipe in fft_pass_core.h)
@@ -118,6 +118,15 @@ static int launch_pipe(const StridedParams& p, cudaStream_t st) {
   kern<<<grid, Pipe::NTHREADS, Pipe::SMEM_BYTES, st>>>(p);
   count_launch();
   return (int)cudaGetLastError();
+}
+
+template <int MODE>
+static int launch_strided(int L, StridedParams p, cudaStream_t st);
+// x forward . weight . x inverse; the weight formula is a compile-time choice so that the
+// rarely used exponential-Euler branch costs the IMEX kernel no registers
+static int launch_xmid(int L, const StridedParams& p, cudaStream_t st) {
+  if (p.filt.kind == FILTER_ETD1) return launch_strided<PASS_XMID_ETD1>(L, p, st);
+  return launch_strided<PASS_XMID>(L, p, st);
 }
 
 template <int MODE>
@@ -213,7 +222,7 @@ int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, v
   xp.ncols_total = (long long)ny * P;
   const int n[3] = {nx, ny, nz};
   xp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
-  if ((rc = launch_strided<PASS_XMID>(nx, xp, st))) return rc;
+  if ((rc = launch_xmid(nx, xp, st))) return rc;
 
   if ((rc = launch_strided<PASS_INV>(ny, yp, st))) return rc;
 
@@ -249,7 +258,7 @@ int native_single_pass(evx_imex_plan* p, int which, const float* u, const float*
     xp.ncols_total = (long long)ny * P;
     const int n[3] = {nx, ny, nz};
     xp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
-    return launch_strided<PASS_XMID>(nx, xp, st);
+    return launch_xmid(nx, xp, st);
   }
   if (which == 4) { zp.real_in = u; zp.real_out = out; return launch_z<true>(M, zp, st); }
   return EVX_ERR_ARG;
@@ -355,7 +364,7 @@ int dist_middle(DistPlan* p, cf* recv, void* const* peers, const double* h, doub
   xp.kother_offset = p->rank * p->nyl;
   const int n[3] = {p->nx, p->ny, p->nz};
   xp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)p->nx * p->ny * p->nz));
-  return launch_strided<PASS_XMID>(p->nx, xp, st);
+  return launch_xmid(p->nx, xp, st);
 }
 
 int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, float* out_local,
@@ -445,13 +454,13 @@ int evx_dist_forward_chunk_p2p_f32(evx_dist_plan* plan, const float* r_local, vo
 }
 int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_out, const double* h,
                             double dt, double coef, int power, void* stream) {
-  if (!plan || !recv || !peer_out || !h || (power != 1 && power != 2)) return EVX_ERR_ARG;
+  if (!plan || !recv || !peer_out || !h || !valid_filter_spec(power)) return EVX_ERR_ARG;
   if (((DistPlan*)plan)->world > 8) return EVX_ERR_UNSUPPORTED;
   return dist_middle((DistPlan*)plan, (cf*)recv, peer_out, h, dt, coef, power, (cudaStream_t)stream);
 }
 int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double dt, double coef,
                         int power, void* stream) {
-  if (!plan || !recv || !h || (power != 1 && power != 2)) return EVX_ERR_ARG;
+  if (!plan || !recv || !h || !valid_filter_spec(power)) return EVX_ERR_ARG;
   return dist_middle((DistPlan*)plan, (cf*)recv, nullptr, h, dt, coef, power, (cudaStream_t)stream);
 }
 int evx_dist_backward_f32(evx_dist_plan* plan, const void* recv, void* spec, const float* u_local,

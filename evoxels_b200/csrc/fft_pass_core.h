@@ -28,7 +28,9 @@ EVX_HD int zline_idx(int i) {
 template <int M>
 constexpr int zline_len() { return M >= 128 ? M + 16 : smem_padded_len(M + 1); }
 
-enum : int { PASS_FWD = 0, PASS_INV = 1, PASS_XMID = 2, PASS_COPY = 3 };   // COPY: access-pattern probe
+// COPY: access-pattern probe; XMID_ETD1: XMID with the exponential-Euler weight
+enum : int { PASS_FWD = 0, PASS_INV = 1, PASS_XMID = 2, PASS_COPY = 3, PASS_XMID_ETD1 = 4 };
+constexpr bool pass_is_xmid(int mode) { return mode == PASS_XMID || mode == PASS_XMID_ETD1; }
 
 // ------------------------------------------------------------------------------------
 // strided passes (y and x)
@@ -99,7 +101,7 @@ struct StridedPass {
   static constexpr int T = L / 8;
   static constexpr int NTHREADS = T * KZ;
   static constexpr int S = num_stages(L);
-  static constexpr int NPHASES = MODE == PASS_XMID ? 2 * S - 1 : (MODE == PASS_COPY ? 1 : S);
+  static constexpr int NPHASES = pass_is_xmid(MODE) ? 2 * S - 1 : (MODE == PASS_COPY ? 1 : S);
   static constexpr int LP = smem_padded_len(L);
   static constexpr size_t SMEM_BYTES =
       (S > 1 && MODE != PASS_COPY ? 2 : 0) * (size_t)LP * KZ * sizeof(cf);
@@ -170,7 +172,8 @@ struct StridedPass {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float k0 = s0 * (float)signed_freq(r.t + e * T, f.n0);
-      const float w = imex_prefactor_fast(k0 * k0 + k12, f) * f.scale;
+      const float kk = k0 * k0 + k12;
+      const float w = (MODE == PASS_XMID_ETD1 ? etd1_weight(kk, f) : imex_prefactor_fast(kk, f)) * f.scale;
       r.v[e] = cscale(r.v[e], w);
     }
   }

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) spectral_filter_kernel(Cplx<R>* __restric
     const float k1 = wavenumber(signed_freq(i1, f.n1), f.inv_len1);
     const float k2v = wavenumber((int)i2, f.inv_len2);
     const float ksq = __fadd_rn(__fadd_rn(__fmul_rn(k0, k0), __fmul_rn(k1, k1)), __fmul_rn(k2v, k2v));
-    const R w = (R)imex_prefactor(ksq, f) * (sizeof(R) == 8 ? (R)f.scale_d : (R)f.scale);
+    const R w = (R)spectral_weight(ksq, f) * (sizeof(R) == 8 ? (R)f.scale_d : (R)f.scale);
     Cplx<R> v = base[e];
     v.x *= w;
     v.y *= w;
@@ -198,7 +198,7 @@ template <typename T>
 int imex_apply_impl(evx_imex_plan* p, const T* u, const T* r, T* out, void* workspace,
                     const double* h, double dt, double coef, int power, cudaStream_t st) {
   if (!p || !r || !out || !workspace || !h || r == out) return EVX_ERR_ARG;
-  if (power != 1 && power != 2) return EVX_ERR_ARG;
+  if (!valid_filter_spec(power)) return EVX_ERR_ARG;
   if ((sizeof(T) == 8) != (p->is_f64 != 0)) return EVX_ERR_ARG;
   if (!aligned16(workspace)) return EVX_ERR_ALIGN;
   if (p->backend == EVX_FFT_NATIVE)
@@ -228,7 +228,7 @@ int ch_step_impl(evx_imex_plan* p, const T* u, const T* hom, T* out, void* works
 template <typename R>
 static int filter_entry(void* spec, int nx, int ny, int nz, const double* h, double dt,
                         double coef, int power, double scale, cudaStream_t st) {
-  if (!spec || !h || nx < 1 || ny < 1 || nz < 1 || (power != 1 && power != 2)) return EVX_ERR_ARG;
+  if (!spec || !h || nx < 1 || ny < 1 || nz < 1 || !valid_filter_spec(power)) return EVX_ERR_ARG;
   const int n[3] = {nx, ny, nz};
   FilterParams f = make_filter(n, h, dt, coef, power, scale);
   return launch_filter<R>((R*)spec, f, st);

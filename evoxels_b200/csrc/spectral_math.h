@@ -18,8 +18,17 @@ struct FilterParams {
   float inv_len0, inv_len1, inv_len2;   // float(1/(n*h)) per axis
   float dt, coef, scale;
   int power;                            // 1: |k|^2, 2: |k|^4
+  int kind;                             // FILTER_IMEX or FILTER_ETD1
   double scale_d;
 };
+
+// The `power` argument of the C ABI carries the filter kind in bit 8 (EVX_FILTER_ETD1 in
+// include/evoxels_b200.h): weight = dt / (1 + dt c |k|^2p)  or  dt * phi1(-dt c |k|^2p).
+enum : int { FILTER_IMEX = 0, FILTER_ETD1 = 1, FILTER_KIND_BIT = 0x100 };
+inline bool valid_filter_spec(int power) {
+  const int pw = power & ~FILTER_KIND_BIT;
+  return pw == 1 || pw == 2;
+}
 
 #if defined(__CUDA_ARCH__)
 EVX_HD float fmul_rn(float a, float b) { return __fmul_rn(a, b); }
@@ -55,6 +64,39 @@ EVX_HD float imex_prefactor(float k2, const FilterParams& f) {
   return fmul_rn(frcp_rn(den), f.dt);
 }
 
+// dt * varphi_1(dt * symbol), symbol = -coef |k|^2p, varphi_1(z) = (exp(z) - 1) / z with the
+// reference's (6,6) Pade branch for |z| < 0.5 (ExponentialEuler.phi1 / phiPade,
+// evoxels/timesteppers.py:155-192; float32 like the reference's symbol array).
+EVX_HD float etd1_weight(float k2, const FilterParams& f) {
+  const float kp = f.power == 2 ? fmul_rn(k2, k2) : k2;
+  const float z = fmul_rn(f.dt, -fmul_rn(f.coef, kp));
+  float phi;
+  if (fabsf(z) < 0.5f) {
+    const float N[7] = {1.f, (float)(1. / 26), (float)(5. / 156), (float)(1. / 858),
+                        (float)(1. / 5720), (float)(1. / 205920), (float)(1. / 8648640)};
+    const float D[7] = {1.f, (float)(-6. / 13), (float)(5. / 52), (float)(-5. / 429),
+                        (float)(1. / 1144), (float)(-1. / 25740), (float)(1. / 1235520)};
+    float num = N[6], den = D[6];
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+      num = fadd_rn(fmul_rn(num, z), N[k]);
+      den = fadd_rn(fmul_rn(den, z), D[k]);
+    }
+    phi = num / den;
+  } else {
+    phi = (expf(z) - 1.0f) / z;
+  }
+  return fmul_rn(f.dt, phi);
+}
+
+// weight applied to one spectral coefficient (without the FFT normalisation)
+EVX_HD float spectral_weight(float k2, const FilterParams& f) {
+  return f.kind == FILTER_ETD1 ? etd1_weight(k2, f) : imex_prefactor(k2, f);
+}
+EVX_HD float spectral_weight_fast(float k2, const FilterParams& f) {
+  return f.kind == FILTER_ETD1 ? etd1_weight(k2, f) : imex_prefactor_fast(k2, f);
+}
+
 inline FilterParams make_filter(const int n[3], const double len_h[3], double dt, double coef,
                                 int power, double scale) {
   FilterParams f;
@@ -64,7 +106,8 @@ inline FilterParams make_filter(const int n[3], const double len_h[3], double dt
   f.inv_len2 = (float)(1.0 / (n[2] * len_h[2]));
   f.dt = (float)dt;
   f.coef = (float)coef;
-  f.power = power;
+  f.power = power & 0xff;
+  f.kind = (power & FILTER_KIND_BIT) ? FILTER_ETD1 : FILTER_IMEX;
   f.scale = (float)scale;
   f.scale_d = scale;
   return f;

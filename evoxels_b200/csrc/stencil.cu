@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include "evx_internal.h"
 #include "evx_params.h"
+#include "rd_core.h"
 
 namespace evx {
 
@@ -227,6 +228,40 @@ int padded_stencil_impl(const T* g, T* out, int nx, int ny, int nz, const double
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------
+// two-species reaction-diffusion rhs
+// ------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256) rd_rhs_kernel(const RdParams<T> p) {
+  const long long groups = (long long)p.nx * p.ny * (p.nz / V);
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < groups;
+       g += (long long)gridDim.x * blockDim.x)
+    RdProgram<T, V>::run(p, g);
+}
+
+template <typename T>
+static int rd_rhs_impl(const T* u, const T* inter, T* out, int nx, int ny, int nz, const double* h,
+                       double DA, double DB, double feed, double kill, cudaStream_t st) {
+  if (!u || !out || !h || nx < 1 || ny < 1 || nz < 1 || u == out) return EVX_ERR_ARG;
+  RdParams<T> p;
+  p.u = u; p.inter = inter; p.out = out; p.nx = nx; p.ny = ny; p.nz = nz;
+  fill_rd_metric(p, h);
+  p.DA = (T)DA; p.DB = (T)DB; p.feed = (T)feed; p.kill = (T)kill;
+  constexpr int VW = 16 / (int)sizeof(T);
+  const long long n = (long long)nx * ny * nz;
+  // both species must be 16-byte aligned for the vector path (n * sizeof(T) offset)
+  const bool vec = nz % VW == 0 && aligned16(u) && aligned16(out) && aligned16(inter) &&
+                   (n * (long long)sizeof(T)) % 16 == 0;
+  const long long groups = vec ? n / VW : n;
+  long long blocks = (groups + 255) / 256;
+  const long long cap = 148LL * 8 * 8;       // grid-stride beyond ~8 waves of 8 CTAs/SM
+  if (blocks > cap) blocks = cap;
+  if (vec) rd_rhs_kernel<T, VW><<<(unsigned)blocks, 256, 0, st>>>(p);
+  else rd_rhs_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 template int ch_rhs_impl<float>(const float*, const float*, float*, int, int, int, const double*,
                                 double, double, const int*, const double*, const float*,
                                 const float*, cudaStream_t);
@@ -309,6 +344,19 @@ int evx_padded_stencil_f32(const float* padded, float* out, int nx, int ny, int 
 int evx_padded_stencil_f64(const double* padded, double* out, int nx, int ny, int nz,
                            const double* h, int op, void* stream) {
   return padded_stencil_impl<double>(padded, out, nx, ny, nz, h, op, (cudaStream_t)stream);
+}
+
+int evx_rd2_rhs_f32(const float* u, const float* interaction, float* out, int nx, int ny, int nz,
+                    const double* h, double D_A, double D_B, double feed, double kill,
+                    void* stream) {
+  return rd_rhs_impl<float>(u, interaction, out, nx, ny, nz, h, D_A, D_B, feed, kill,
+                            (cudaStream_t)stream);
+}
+int evx_rd2_rhs_f64(const double* u, const double* interaction, double* out, int nx, int ny,
+                    int nz, const double* h, double D_A, double D_B, double feed, double kill,
+                    void* stream) {
+  return rd_rhs_impl<double>(u, interaction, out, nx, ny, nz, h, D_A, D_B, feed, kill,
+                             (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -10,9 +10,10 @@ What differs is *how* `rhs` is evaluated: one fused CUDA kernel per call
 (`evx_ch_rhs_*`, `evx_ac_stage_*`) instead of ~60 / ~125 tensor operations on ghost-padded
 copies.  There is no CPU path - `rhs` raises for non-CUDA tensors.
 
-Other problem classes of the reference (ReactionDiffusionSBM, MultiPhaseAllenCahn,
-CoupledReactionDiffusion) are different physics and out of scope; users can still write
-them against `VoxelGridTorch`'s operator API.
+`CoupledReactionDiffusion` (:576-633) is fused the same way
+(`evx_rd2_rhs_*`).  The remaining problem classes of the reference (ReactionDiffusionSBM,
+MultiPhaseAllenCahn) are different physics and out of scope; users can still write them
+against `VoxelGridTorch`'s operator API.
 """
 from __future__ import annotations
 
@@ -319,3 +320,59 @@ class ReactionDiffusion(SemiLinearODE):
 
     def rhs(self, t, u):
         return self.D * self.vg.laplace(self.pad_bc(u)) + self._eval_f(t, u, self.vg.lib)
+
+
+@dataclass
+class CoupledReactionDiffusion(SemiLinearODE):
+    """Two-species reaction-diffusion system of Gray-Scott type; the species are the two
+    batch channels of `u` (reference problem_definition.py:576-633).  Always fully periodic,
+    like the reference (the class has no `bc` field).  With the default interaction
+    u0*u1**2 the whole right-hand side is ONE fused kernel (`evx_rd2_rhs_*`); a user
+    `interaction` closure is evaluated with torch and handed to the same kernel as a field."""
+    vg: VoxelGrid
+    D_A: float = 1.0
+    D_B: float = 0.5
+    feed: float = 0.055
+    kill: float = 0.117
+    interaction: Callable | None = None
+    _fourier_symbol: Any = field(init=False, repr=False, default=None)
+
+    def __post_init__(self):
+        self.initialize_boundary_conditions()
+        self._default_interaction = self.interaction is None
+        if self.interaction is None:
+            self.interaction = lambda u, lib=None: u[0] * u[1] ** 2
+
+    @property
+    def order(self):
+        return 2
+
+    @property
+    def fourier_symbol(self):
+        if self._fourier_symbol is None:
+            self._fourier_symbol = -max(self.D_A, self.D_B) * self.k_squared()
+        return self._fourier_symbol
+
+    def spectral_form(self):
+        return float(max(self.D_A, self.D_B)), 1
+
+    def _eval_interaction(self, u, lib):
+        return _call_closure(self.interaction, u, lib)
+
+    def rhs_analytic(self, t, u):
+        import sympy as sp
+        import sympy.vector as spv
+        interaction = self._eval_interaction(u, sp)
+        dc_A = self.D_A * spv.laplacian(u[0]) - interaction + self.feed * (1 - u[0])
+        dc_B = self.D_B * spv.laplacian(u[1]) + interaction - self.kill * u[1]
+        return (dc_A, dc_B)
+
+    def rhs(self, t, u):
+        _native.require_cuda(u)
+        if u.dim() != 4 or u.shape[0] != 2:
+            raise ValueError("CoupledReactionDiffusion expects a state of shape [2, Nx, Ny, Nz]")
+        u = u.contiguous()
+        inter = None
+        if not self._default_interaction:
+            inter = self._eval_interaction(u, self.vg.lib).to(u.dtype).contiguous()
+        return _native.rd2_rhs(u, self.vg.spacing, self.D_A, self.D_B, self.feed, self.kill, inter)

@@ -115,6 +115,17 @@ int evx_padded_stencil_f32(const float* padded, float* out, int nx, int ny, int 
 int evx_padded_stencil_f64(const double* padded, double* out, int nx, int ny, int nz,
                            const double* h, int op, void* stream);
 
+/* Two-species reaction-diffusion rhs, u and out are [2,nx,ny,nz], fully periodic:
+ *   out[0] = D_A lap7(u0) - I + feed (1 - u0),  out[1] = D_B lap7(u1) + I - kill u1,
+ *   I = u0 u1^2, or the caller's `interaction` field [nx,ny,nz] when non-NULL.
+ * Replaces CoupledReactionDiffusion.rhs (evoxels/problem_definition.py:614-633). */
+int evx_rd2_rhs_f32(const float* u, const float* interaction, float* out, int nx, int ny, int nz,
+                    const double* h, double D_A, double D_B, double feed, double kill,
+                    void* stream);
+int evx_rd2_rhs_f64(const double* u, const double* interaction, double* out, int nx, int ny,
+                    int nz, const double* h, double D_A, double D_B, double feed, double kill,
+                    void* stream);
+
 /* ---------------------------------------------------------------------------------
  * Spectral (semi-implicit) stage
  * ------------------------------------------------------------------------------- */
@@ -138,7 +149,12 @@ int evx_imex_plan_workspace_bytes(const evx_imex_plan* plan, size_t* bytes);
 /* out = u + irfftn( P * rfftn(r) ).  `r` is preserved, `out` may alias `u` but not `r`;
  * u == NULL gives the update alone (out = irfftn(P * rfftn(r))).
  * CH: coef = 2*eps*D*A, power = 2 (problem_definition.py:303).  AC / reaction-diffusion:
- * coef = M*gab or D*A, power = 1 (:198, :389). */
+ * coef = M*gab or D*A, power = 1 (:198, :389).
+ * OR-ing EVX_FILTER_ETD1 into `power` selects the exponential-Euler weight instead,
+ *   P = dt * phi1(-dt*coef*|k|^(2*power)),  phi1(z) = (exp(z)-1)/z  (Pade branch |z|<0.5),
+ * i.e. ExponentialEuler.step / phi1 / phiPade (evoxels/timesteppers.py:137-202).  The flag
+ * is accepted wherever a `power` argument appears. */
+#define EVX_FILTER_ETD1 0x100
 int evx_imex_apply_f32(evx_imex_plan* plan, const float* u, const float* r, float* out,
                        void* workspace, const double* h, double dt, double coef, int power,
                        void* stream);

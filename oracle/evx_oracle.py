@@ -277,6 +277,59 @@ def ch_imex_step(u, spacing, dt, eps=3.0, D=1.0, A=0.25, bc=_FULLY_PERIODIC,
     return imex_step(u, ch_rhs(u, spacing, eps, D, bc, mu_hom), prefac, x_kind)
 
 
+# ----------------------------------------------------------------------------------
+# two-species reaction-diffusion (Gray-Scott) + exponential Euler
+# ----------------------------------------------------------------------------------
+def crd_rhs(u: torch.Tensor, spacing, D_A=1.0, D_B=0.5, feed=0.055, kill=0.117,
+            interaction: Optional[Callable] = None) -> torch.Tensor:
+    """CoupledReactionDiffusion.rhs (problem_definition.py:614-633): channels are the two
+    species, always fully periodic (the class has no `bc` field)."""
+    inter = u[0] * u[1] ** 2 if interaction is None else interaction(u)
+    lap = laplace7(ghost_pad(u), spacing)
+    dA = D_A * lap[0] - inter + feed * (1 - u[0])
+    dB = D_B * lap[1] + inter - kill * u[1]
+    return torch.stack((dA, dB), 0)
+
+
+def crd_symbol(shape, spacing, D_A=1.0, D_B=0.5):
+    """-max(D_A, D_B) |k|^2  (problem_definition.py:589)."""
+    return -max(D_A, D_B) * k_squared(shape, spacing)
+
+
+def rd_symbol(shape, spacing, D, A=0.25, mirrored_x=False):
+    """-D A |k|^2  (problem_definition.py:206)."""
+    return -D * A * k_squared(shape, spacing, mirrored_x)
+
+
+_PADE_N = [1, 1 / 26, 5 / 156, 1 / 858, 1 / 5720, 1 / 205920, 1 / 8648640]
+_PADE_D = [1, -6 / 13, 5 / 52, -5 / 429, 1 / 1144, -1 / 25740, 1 / 1235520]
+
+
+def phi1(z: torch.Tensor) -> torch.Tensor:
+    """varphi_1(z) = (exp(z) - 1) / z with the (6,6) Pade branch for |z| < 0.5
+    (timesteppers.py:155-192)."""
+    phi = (torch.exp(z) - 1) / z
+    small = torch.abs(z) < 0.5
+    zs = z[small]
+    num = torch.full_like(zs, _PADE_N[6])
+    den = torch.full_like(zs, _PADE_D[6])
+    for k in range(5, -1, -1):
+        num = num * zs + _PADE_N[k]
+        den = den * zs + _PADE_D[k]
+    phi = phi.clone()
+    phi[small] = num / den
+    return phi
+
+
+def etd1_step(u: torch.Tensor, rhs: torch.Tensor, symbol: torch.Tensor, dt: float,
+              x_kind: str = PERIODIC) -> torch.Tensor:
+    """ExponentialEuler.step (timesteppers.py:198-202):
+    u + irfftn(dt * phi1(dt * symbol) * rfftn(pad(rhs)))[:, :Nx]."""
+    r = fft_mirror_pad(rhs, x_kind)
+    spec = dt * phi1(dt * symbol) * torch.fft.rfftn(r, s=r.shape)
+    return u + torch.fft.irfftn(spec, s=r.shape)[:, :u.shape[1]]
+
+
 def euler_step(u, rhs_fn: Callable, dt: float):
     """u + dt * rhs(u)  (timesteppers.py:42-43)."""
     return u + dt * rhs_fn(u)

@@ -315,13 +315,47 @@ int emu_native_apply(const float* u, const float* r, float* out, float* spec_out
   sp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
   sp.tw = twx.data(); sp.src = sp.dst = xio;
   sp.ncols_total = (long long)ny * P;
-  if (g_emu_xkz == 16 ? dispatch_strided<16, PASS_XMID>(nx, sp) : dispatch_strided<KZ, PASS_XMID>(nx, sp)) return -3;
+  if (sp.filt.kind == FILTER_ETD1) {
+    if (dispatch_strided<KZ, PASS_XMID_ETD1>(nx, sp)) return -3;
+  } else if (g_emu_xkz == 16 ? dispatch_strided<16, PASS_XMID>(nx, sp) : dispatch_strided<KZ, PASS_XMID>(nx, sp)) return -3;
   sp.tw = twy.data(); sp.src = sp.dst = yio;
   sp.ncols_total = (long long)nx * P;
   if (dispatch_strided<KZ, PASS_INV>(ny, sp)) return -4;
   zp.real_in = u; zp.real_out = out;
   if (dispatch_z<true>(M, zp)) return -5;
   return 0;
+}
+}
+
+// =====================================================================================
+// two-species reaction-diffusion rhs
+// =====================================================================================
+#include "../../evoxels_b200/csrc/rd_core.h"
+template <typename T>
+static int emu_rd2(const T* u, const T* inter, T* out, int nx, int ny, int nz, const double* h,
+                   double DA, double DB, double feed, double kill, int vec) {
+  RdParams<T> p;
+  p.u = u; p.inter = inter; p.out = out; p.nx = nx; p.ny = ny; p.nz = nz;
+  fill_rd_metric(p, h);
+  p.DA = (T)DA; p.DB = (T)DB; p.feed = (T)feed; p.kill = (T)kill;
+  constexpr int VW = 16 / (int)sizeof(T);
+  const long long n = (long long)nx * ny * nz;
+  if (vec) {
+    if (nz % VW) return -1;
+    for (long long g = 0; g < n / VW; ++g) RdProgram<T, VW>::run(p, g);
+  } else {
+    for (long long g = 0; g < n; ++g) RdProgram<T, 1>::run(p, g);
+  }
+  return 0;
+}
+extern "C" {
+int emu_rd2_rhs_f32(const float* u, const float* inter, float* out, int nx, int ny, int nz,
+                    const double* h, double DA, double DB, double feed, double kill, int vec) {
+  return emu_rd2<float>(u, inter, out, nx, ny, nz, h, DA, DB, feed, kill, vec);
+}
+int emu_rd2_rhs_f64(const double* u, const double* inter, double* out, int nx, int ny, int nz,
+                    const double* h, double DA, double DB, double feed, double kill, int vec) {
+  return emu_rd2<double>(u, inter, out, nx, ny, nz, h, DA, DB, feed, kill, vec);
 }
 }
 

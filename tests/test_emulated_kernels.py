@@ -186,6 +186,52 @@ def test_native_fft_pipeline(emu, shape, pipe_blocks, xkz):
     assert rel_l2(out, want) < 1e-6
 
 
+@pytest.mark.parametrize("shape", [(8, 8, 16), (16, 32, 64), (8, 16, 256)])
+def test_native_fft_pipeline_etd1_weight(emu, shape):
+    """Same pipeline with the exponential-Euler weight (EVX_FILTER_ETD1) against the oracle's
+    etd1_step; dt*coef*k^2 spans both the Pade branch (|z| < 0.5) and the exp branch."""
+    nx, ny, nz = shape
+    rng = np.random.default_rng(1)
+    r = rng.standard_normal(shape).astype(np.float32)
+    u = rng.random(shape).astype(np.float32)
+    sp = (1.0, 0.5, 2.0)
+    h = (ctypes.c_double * 3)(*sp)
+    d = ctypes.c_double
+    out = np.zeros(shape, np.float32)
+    assert emu.emu_native_apply(_p(u), _p(r), _p(out), None, nx, ny, nz, h, d(0.3), d(0.7), 1 | 0x100) == 0
+    sym = -0.7 * O.k_squared(shape, sp)
+    z = 0.3 * sym
+    assert float(z.abs().min()) < 0.5 < float(z.abs().max())
+    want = O.etd1_step(torch.from_numpy(u)[None], torch.from_numpy(r)[None], sym, 0.3)[0].numpy()
+    assert rel_l2(out - u, want - u) < 2e-6
+    assert rel_l2(out, want) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_rd2_rhs_program(emu, dtype):
+    """Two-species reaction-diffusion rhs (rd_core.h) against the oracle, scalar and vector
+    paths, default and caller-supplied interaction."""
+    tol = 5e-13 if dtype == np.float64 else 2e-6
+    f = emu.emu_rd2_rhs_f32 if dtype == np.float32 else emu.emu_rd2_rhs_f64
+    d = ctypes.c_double
+    kw = dict(D_A=0.8, D_B=1.3, feed=0.03, kill=0.06)
+    for shape, sp in SHAPES:
+        rng = np.random.default_rng(6)
+        u = np.stack([rng.random(shape), 0.5 * rng.random(shape)]).astype(dtype)
+        for custom in (False, True):
+            fn = (lambda v: v[0] ** 2 * v[1] + 0.1) if custom else None
+            ref = O.crd_rhs(torch.from_numpy(u), sp, interaction=fn, **kw).numpy()
+            inter = fn(u).astype(dtype) if custom else None
+            for vec in (0, 1):
+                if vec and shape[2] % (16 // np.dtype(dtype).itemsize):
+                    continue
+                out = np.full_like(u, np.nan)
+                rc = f(_p(u), _p(inter), _p(out), *shape, (ctypes.c_double * 3)(*sp), d(kw["D_A"]),
+                       d(kw["D_B"]), d(kw["feed"]), d(kw["kill"]), vec)
+                assert rc == 0
+                assert rel_l2(out, ref) <= tol, (shape, custom, vec)
+
+
 def test_ch_rhs_adjoint_against_autograd(emu):
     """The hand-written VJP of the periodic CH rhs (adjoint_core.h) against torch autograd
     through the oracle, float64, values outside [0,1] included (clip mask)."""

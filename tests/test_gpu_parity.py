@@ -18,9 +18,11 @@ pytestmark = pytest.mark.gpu
 
 import evoxels_b200 as evo  # noqa: E402
 from evoxels_b200 import _native  # noqa: E402
-from evoxels_b200.problem_definition import CahnHilliard, ReactionDiffusion, TwoPhaseAllenCahn  # noqa: E402
+from evoxels_b200.problem_definition import (CahnHilliard, CoupledReactionDiffusion,  # noqa: E402
+                                             ReactionDiffusion, TwoPhaseAllenCahn)
 from evoxels_b200.solvers import TimeDependentSolver  # noqa: E402
-from evoxels_b200.timesteppers import ForwardEuler, PseudoSpectralIMEX, RungeKutta4  # noqa: E402
+from evoxels_b200.timesteppers import (ExponentialEuler, ForwardEuler, PseudoSpectralIMEX,  # noqa: E402
+                                       RungeKutta4)
 from evoxels_b200.voxelgrid import VoxelGridTorch  # noqa: E402
 
 RHS_TOL = {torch.float32: 5e-6, torch.float64: 1e-12}
@@ -352,3 +354,80 @@ def test_ch_step_512_vs_oracle(cuda_device):
     got = PseudoSpectralIMEX(CahnHilliard(vg), 0.1).step(0, u.cuda()).cpu()
     assert rel_l2((got - u).numpy(), (ref - u).numpy()) <= 2e-5
     assert rel_l2(got.numpy(), ref.numpy()) <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------
+# CoupledReactionDiffusion / ReactionDiffusion + ExponentialEuler
+# ---------------------------------------------------------------------------------------
+def _two_species(vg, u0):
+    return torch.cat([vg.init_scalar_field(u0[0]), vg.init_scalar_field(u0[1])], 0)
+
+
+@pytest.mark.parametrize("name", ["crd_default", "crd_pow2", "crd_f64"])
+def test_crd_golden(cuda_device, name):
+    """Fused two-species rhs, IMEX and exponential-Euler steps against the reference's
+    outputs; crd_pow2 runs the native FFT (EVX_FILTER_ETD1 inside the x pass), the others
+    the cuFFT back end with the stand-alone weight kernel."""
+    g = load_golden(name)
+    prec = "float64" if g["u0"].dtype == np.float64 else "float32"
+    vf, vg = make_grid(g["u0"].shape[1:], g["spacing"], prec)
+    u = _two_species(vg, g["u0"])
+    prob = CoupledReactionDiffusion(vg, D_A=g["D_A"], D_B=g["D_B"], feed=g["feed"], kill=g["kill"])
+    assert rel_l2(prob.rhs(0.0, u).cpu().numpy(), g["rhs"]) <= RHS_TOL[u.dtype]
+    for cls, key in ((ExponentialEuler, "etd1"), (PseudoSpectralIMEX, "imex")):
+        ts = cls(prob, g["dt"])
+        v = u
+        for i in range(1, g["nsteps"] + 1):
+            v = ts.step(0.0, v)
+            if i == 1:
+                assert rel_l2(v.cpu().numpy(), g[key + "_step1"]) <= STEP_TOL[u.dtype], key
+        assert rel_l2(v.cpu().numpy(), g[key + "_stepn"]) <= 3 * STEP_TOL[u.dtype], key
+    ts = ExponentialEuler(prob, g["dt"])
+    assert rel_l2(ts.phi_1_k_squared.cpu().numpy(), g["phi1"]) <= 1e-6
+    if name == "crd_pow2":
+        assert ts._plan(u.shape[1:], u.dtype, u.device).backend_name == "native"
+
+
+def test_crd_custom_interaction_and_live_oracle(cuda_device):
+    shape, sp = (32, 24, 40), (0.5, 1.0, 0.8)
+    vf, vg = make_grid(shape, sp)
+    rng = np.random.default_rng(3)
+    u0 = np.stack([rng.random(shape), 0.5 * rng.random(shape)]).astype(np.float32)
+    u = _two_species(vg, u0)
+    fn = lambda v, lib=None: v[0] ** 2 * v[1] + 0.1          # noqa: E731
+    for inter in (None, fn):
+        prob = CoupledReactionDiffusion(vg, D_A=0.7, D_B=1.1, feed=0.04, kill=0.1, interaction=inter)
+        with torch.device("cpu"):
+            want = O.crd_rhs(torch.from_numpy(u0), sp, 0.7, 1.1, 0.04, 0.1, interaction=inter)
+        assert rel_l2(prob.rhs(0.0, u).cpu().numpy(), want.numpy()) <= RHS_TOL[torch.float32]
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 64), (128, 32, 256)])
+def test_crd_etd1_native_vs_live_oracle(cuda_device, shape):
+    sp = (1.0, 0.5, 2.0)
+    vf, vg = make_grid(shape, sp)
+    rng = np.random.default_rng(4)
+    u0 = np.stack([rng.random(shape), 0.5 * rng.random(shape)]).astype(np.float32)
+    u = _two_species(vg, u0)
+    prob = CoupledReactionDiffusion(vg, D_A=1.0, D_B=0.5)
+    out = ExponentialEuler(prob, 0.5, fft_backend="native").step(0.0, u)
+    with torch.device("cpu"):
+        t = torch.from_numpy(u0)
+        sym = O.crd_symbol(shape, sp, 1.0, 0.5)
+        want = O.etd1_step(t, O.crd_rhs(t, sp, 1.0, 0.5), sym, 0.5)
+    assert rel_l2(out.cpu().numpy(), want.numpy()) <= STEP_TOL[torch.float32]
+    assert rel_l2((out - u).cpu().numpy(), (want - t).numpy()) <= 2e-5
+
+
+@pytest.mark.parametrize("name", ["rd_etd1_periodic", "rd_etd1_neumann_x"])
+def test_rd_etd1_golden(cuda_device, name):
+    g = load_golden(name)
+    vf, vg = make_grid(g["u0"].shape, g["spacing"])
+    u = vg.init_scalar_field(g["u0"])
+    prob = quiet(ReactionDiffusion, vg, D=g["D"], f=lambda t, c, lib=None: c * (1 - c), bc=g["bc"])
+    assert rel_l2(prob.rhs(0.0, u)[0].cpu().numpy(), g["rhs"]) <= RHS_TOL[u.dtype]
+    ts = ExponentialEuler(prob, g["dt"])
+    v = ts.step(0.0, u)
+    assert rel_l2(v[0].cpu().numpy(), g["etd1_step1"]) <= STEP_TOL[u.dtype]
+    v = ts.step(0.0, v)
+    assert rel_l2(v[0].cpu().numpy(), g["etd1_stepn"]) <= 2 * STEP_TOL[u.dtype]
