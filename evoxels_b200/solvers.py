@@ -99,18 +99,66 @@ class BaseSolver(ABC):
             self.vf.set_field(name, self.vg.export_scalar_field_to_numpy(u_out[i:i + 1]))
 
     def _handle_outputs(self, u, frame, time, vtk_out, verbose, plot_bounds, colormap):
-        # the reference pads and trims here (solvers.py:154-157), which is the identity
-        # on a cell-centred grid; export the state directly
-        u_out = u
-        nan_flag = torch.isnan(u_out).any()          # device-side reduction
-        self._export_fields(u_out)                   # D2H copy
-        if bool(nan_flag):
-            print(f"NaN detected in frame {frame} at time {time}. Aborting simulation.")
-            sys.exit(1)
+        """Frame export (reference solvers.py:152-187).  The reference pads and trims here
+        (:154-157), which is the identity on a cell-centred grid, copies the state to the
+        host synchronously and checks for NaN on the host side.  Here the copy and a
+        device-side NaN reduction run on a side stream into pinned memory while the solver
+        keeps stepping; the frame is committed to `vf.fields` - and a
+        NaN aborts the run - when the next frame is submitted, at the end of the run, or
+        immediately if files are written."""
+        if u.device.type != "cuda":
+            raise RuntimeError("evoxels_b200 has no CPU path: the state must be a CUDA tensor")
+        if getattr(self, "_exporter", None) is None:
+            self._exporter = _FrameExporter(u.device)
+        self._exporter.submit(u, frame, time, self._commit_frame)
         if vtk_out:
+            self._exporter.finish()
             prefix = self.problem_cls.__name__ if self.problem_cls else "custom"
             self.vf.export_to_vtk(filename=f"{prefix}_{self.fieldnames[0]}_{frame:03d}.vtk",
                                   field_names=self.fieldnames)
+
+    def _commit_frame(self, host, has_nan, frame, time):
+        arr = host.numpy()
+        for i, name in enumerate(self.fieldnames):
+            self.vf.set_field(name, arr[i].copy())     # the pinned buffer is reused
+        if has_nan:
+            print(f"NaN detected in frame {frame} at time {time}. Aborting simulation.")
+            sys.exit(1)
+
+    def _finish_outputs(self):
+        if getattr(self, "_exporter", None) is not None:
+            self._exporter.finish()
+
+
+class _FrameExporter:
+    """One frame in flight: device -> pinned host copy plus isnan().any() on a side stream."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.host = None
+        self.flag = torch.zeros(1, dtype=torch.bool, device="cpu", pin_memory=True)
+        self.pending = None
+
+    def submit(self, u, frame, time, commit):
+        self.finish()                                   # the pinned buffer is free again
+        if self.host is None or self.host.shape != u.shape or self.host.dtype != u.dtype:
+            self.host = torch.empty(tuple(u.shape), dtype=u.dtype, device="cpu", pin_memory=True)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.host.copy_(u, non_blocking=True)
+            self.flag.copy_(torch.isnan(u).any().reshape(1), non_blocking=True)
+            done = self.stream.record_event()
+        u.record_stream(self.stream)                    # keep u's memory until the copy is done
+        self.pending = (done, frame, time, commit)
+
+    def finish(self):
+        if self.pending is None:
+            return
+        done, frame, time, commit = self.pending
+        self.pending = None
+        done.synchronize()
+        commit(self.host, bool(self.flag[0]), frame, time)
 
 
 class _GraphedSteps:
@@ -175,4 +223,5 @@ class TimeDependentSolver(BaseSolver):
                 i += 1
         self._handle_outputs(u, frame, max_iters * time_increment, vtk_out, verbose,
                              plot_bounds, colormap)
+        self._finish_outputs()
         return u

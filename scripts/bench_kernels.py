@@ -49,6 +49,21 @@ if n == 512:
             ms = timed(lambda: lib.evx_debug_strided_copy(ctypes.c_void_p(spec.data_ptr()), n, n, P, along_x, kz, st))
             res[f"probe_copy_{'x' if along_x else 'y'}_kz{kz}_ms"] = round(ms, 4)
     del spec
+# two-species reaction-diffusion (16 B/voxel rhs) and the ETD1 step
+u2 = torch.stack([torch.rand((n, n, n), device=dev), 0.5 * torch.rand((n, n, n), device=dev)])
+ms = timed(lambda: _native.rd2_rhs(u2, (1, 1, 1), 1.0, 0.5, 0.055, 0.117), reps=10)
+res["rd2_rhs_ms"] = ms; res["rd2_rhs_GBs"] = 16 * n**3 / ms / 1e6
+try:
+    plan = _native.ImexPlan((n, n, n), torch.float32, "cuda", _native.FFT_NATIVE)
+    r = torch.randn_like(u)
+    ms = timed(lambda: plan.apply(u, r, out, (1, 1, 1), 0.5, 1.0, 1 | _native.FILTER_ETD1), reps=10)
+    res["etd1_apply_native_ms"] = ms
+    ms = timed(lambda: plan.apply(u, r, out, (1, 1, 1), 0.5, 1.0, 1), reps=10)
+    res["imex_apply_native_p1_ms"] = ms
+    del plan, r
+except Exception as exc:
+    res["etd1_apply_native_ms"] = str(exc)
+del u2
 ms = timed(lambda: out.copy_(u))
 res["copy_ms"] = ms; res["copy_GBs"] = 8 * n**3 / ms / 1e6
 print(json.dumps(res))

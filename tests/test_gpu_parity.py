@@ -431,3 +431,30 @@ def test_rd_etd1_golden(cuda_device, name):
     assert rel_l2(v[0].cpu().numpy(), g["etd1_step1"]) <= STEP_TOL[u.dtype]
     v = ts.step(0.0, v)
     assert rel_l2(v[0].cpu().numpy(), g["etd1_stepn"]) <= 2 * STEP_TOL[u.dtype]
+
+
+# ---------------------------------------------------------------------------------------
+# asynchronous frame export
+# ---------------------------------------------------------------------------------------
+def test_async_frame_export_commits_every_frame_and_aborts_on_nan(cuda_device):
+    frames_seen = []
+
+    class Spy(TimeDependentSolver):
+        def _commit_frame(self, host, has_nan, frame, time):
+            frames_seen.append((frame, round(float(time), 6), float(host.numpy()[0, 0, 0, 0])))
+            super()._commit_frame(host, has_nan, frame, time)
+
+    vf = evo.VoxelFields((8, 8, 8))
+    vf.add_field("a", np.zeros(vf.shape, dtype=np.float32))
+    Spy(vf, "a", backend="torch", step_fn=lambda t, u: u + 1, device="cuda").solve(
+        time_increment=0.5, frames=4, max_iters=8, verbose=False, jit=False)
+    # frames at iterations 0, 2, 4, 6 and the final state, each with the value of its own time
+    assert frames_seen == [(0, 0.0, 0.0), (1, 1.0, 2.0), (2, 2.0, 4.0), (3, 3.0, 6.0), (4, 4.0, 8.0)]
+    assert np.all(vf.fields["a"] == 8)
+
+    vf = evo.VoxelFields((8, 8, 8))
+    vf.add_field("a", np.zeros(vf.shape, dtype=np.float32))
+    bad = TimeDependentSolver(vf, "a", backend="torch", device="cuda",
+                              step_fn=lambda t, u: u + float("nan"))
+    with pytest.raises(SystemExit):
+        bad.solve(time_increment=0.5, frames=2, max_iters=4, verbose=False, jit=False)
