@@ -198,6 +198,42 @@ EVX_HD void line_stage_compute(int s, cf* v, int t, const cf* tw) {
   }
 }
 
+// Twiddle prefetch.  Every twiddled stage is radix 8 with one butterfly per thread, whose
+// roots W^m, W^2m, W^4m depend only on (stage, thread).  The pass programs fetch them right
+// after the previous stage's shared-memory writes - i.e. BEFORE the barrier - so the table
+// lookups (L1/L2 latency) overlap the barrier wait instead of stalling the first multiply.
+template <int N>
+EVX_HD void stage_twiddles(int s, int t, const cf* tw, cf* w) {
+  using LP = LinePlan<N>;
+  if (s <= 0 || s >= LP::S) return;
+  const int Ns = LP::ns(s);
+  const int m = (t % Ns) * (N / (Ns * 8));
+  w[0] = tw[m];
+  w[1] = tw[2 * m];
+  w[2] = tw[4 * m];
+}
+
+// stage `s` with the roots already in registers (w from stage_twiddles; unused for s == 0)
+template <int N, int DIR>
+EVX_HD void line_stage_compute_pre(int s, cf* v, int t, const cf* w) {
+  using LP = LinePlan<N>;
+  if (s == 0) {
+    Stage<N, LP::R0, DIR>::compute(v, t, 1, nullptr);
+    return;
+  }
+  cf w1 = w[0], w2 = w[1], w4 = w[2];
+  if (DIR > 0) { w1 = cconj(w1); w2 = cconj(w2); w4 = cconj(w4); }
+  const cf w3 = cmul(w1, w2);
+  v[1] = cmul(v[1], w1);
+  v[2] = cmul(v[2], w2);
+  v[3] = cmul(v[3], w3);
+  v[4] = cmul(v[4], w4);
+  v[5] = cmul(v[5], cmul(w4, w1));
+  v[6] = cmul(v[6], cmul(w4, w2));
+  v[7] = cmul(v[7], cmul(w4, w3));
+  dft8<DIR>(v);
+}
+
 template <int N>
 EVX_HD int line_stage_out_index(int s, int t, int e) {
   using LP = LinePlan<N>;

@@ -108,6 +108,7 @@ struct StridedPass {
 
   struct Regs {
     cf v[8];
+    cf w[3];               // roots of the next twiddled stage (fetched before the barrier)
     int t, cl;
     bool valid;
     long long grp;
@@ -181,7 +182,11 @@ struct StridedPass {
   // transform step q of the pass: FWD/INV: stage q; XMID: q < S forward stage q, else inverse q-S
   template <int DIRSEL>
   EVX_HD static void compute(Regs& r, const StridedParams& p, int stage) {
-    line_stage_compute<L, DIRSEL>(stage, r.v, r.t, p.tw);
+    line_stage_compute_pre<L, DIRSEL>(stage, r.v, r.t, r.w);
+  }
+  // roots for `stage` (no-op for stage 0 and past the last stage)
+  EVX_HD static void fetch_tw(Regs& r, const StridedParams& p, int stage) {
+    stage_twiddles<L>(stage, r.t, p.tw, r.w);
   }
 
   EVX_HD static void phase(int k, Regs& r, cf* smem, const StridedParams& p) {
@@ -194,6 +199,7 @@ struct StridedPass {
       if (k == S - 1) store_global(r, p);
       else if (MODE == PASS_FWD) write_stage<-1>(r, buf(smem, k & 1), k);
       else write_stage<+1>(r, buf(smem, k & 1), k);
+      fetch_tw(r, p, k + 1);
     } else {
       // XMID: phases 0..S-2 forward stages, phase S-1: last forward + filter + first inverse,
       // phases S..2S-2 remaining inverse stages
@@ -201,15 +207,18 @@ struct StridedPass {
       if (k < S - 1) {
         compute<-1>(r, p, k);
         write_stage<-1>(r, buf(smem, k & 1), k);
+        fetch_tw(r, p, k + 1);
       } else if (k == S - 1) {
         compute<-1>(r, p, S - 1);
         apply_filter(r, p);
         compute<+1>(r, p, 0);
         if (S == 1) store_global(r, p); else write_stage<+1>(r, buf(smem, k & 1), 0);
+        fetch_tw(r, p, 1);
       } else {
         const int s = k - (S - 1);
         compute<+1>(r, p, s);
         if (s == S - 1) store_global(r, p); else write_stage<+1>(r, buf(smem, k & 1), s);
+        fetch_tw(r, p, s + 1);
       }
     }
   }
@@ -267,19 +276,23 @@ struct StridedPipe {
       if (k == S - 1) Base::store_global(r, p);
       else if (MODE == PASS_FWD) Base::template write_stage<-1>(r, wr, k);
       else Base::template write_stage<+1>(r, wr, k);
+      Base::fetch_tw(r, p, k + 1);
     } else {
       if (k < S - 1) {
         Base::template compute<-1>(r, p, k);
         Base::template write_stage<-1>(r, wr, k);
+        Base::fetch_tw(r, p, k + 1);
       } else if (k == S - 1) {
         Base::template compute<-1>(r, p, S - 1);
         Base::apply_filter(r, p);
         Base::template compute<+1>(r, p, 0);
         if (S == 1) Base::store_global(r, p); else Base::template write_stage<+1>(r, wr, 0);
+        Base::fetch_tw(r, p, 1);
       } else {
         const int s = k - (S - 1);
         Base::template compute<+1>(r, p, s);
         if (s == S - 1) Base::store_global(r, p); else Base::template write_stage<+1>(r, wr, s);
+        Base::fetch_tw(r, p, s + 1);
       }
     }
   }
@@ -309,6 +322,7 @@ struct ZPass {
 
   struct Regs {
     cf v[8];
+    cf w[3];                 // roots of the next twiddled stage
     cf u[INVERSE ? 8 : 1];   // ZInv: the u values added at the end, fetched up front
     int t, l;
     bool valid;
@@ -358,8 +372,9 @@ struct ZPass {
         } else {
           read_natural(r, buf(smem, (k - 1) & 1, r.l));
         }
-        line_stage_compute<M, -1>(k, r.v, r.t, p.tw);
+        line_stage_compute_pre<M, -1>(k, r.v, r.t, r.w);
         write_stage(r, buf(smem, k & 1, r.l), k);     // last stage lands in natural order
+        stage_twiddles<M>(k + 1, r.t, p.tw, r.w);
       } else {
         const cf* z = buf(smem, (S - 1) & 1, r.l);
         if (!r.valid) return;
@@ -406,9 +421,10 @@ struct ZPass {
         } else {
           read_natural(r, buf(smem, (s - 1) & 1, r.l));
         }
-        line_stage_compute<M, +1>(s, r.v, r.t, p.tw);
+        line_stage_compute_pre<M, +1>(s, r.v, r.t, r.w);
         if (s < S - 1) {
           write_stage(r, buf(smem, s & 1, r.l), s);
+          stage_twiddles<M>(s + 1, r.t, p.tw, r.w);
         } else if (r.valid) {
           cf* out = reinterpret_cast<cf*>(p.real_out + r.row * p.nz);
 #pragma unroll
