@@ -382,8 +382,8 @@ def weak_scaling_shape(n, world):
 
 def run_ours_distributed(args, world, rank, local, dev):
     """N > 1: ONE global Cahn-Hilliard problem, x-slab decomposed over the ranks (weak
-    scaling: args.size^3 voxels per GPU), halo planes over NCCL P2P, slab<->pencil NCCL
-    all-to-all inside the transposed FFT."""
+    scaling: args.size^3 voxels per GPU): halo planes and slab<->pencil transposes over
+    NVLink (see --transport)."""
     import torch
     import torch.distributed as dist
     from evoxels_b200 import _native
@@ -392,7 +392,8 @@ def run_ours_distributed(args, world, rank, local, dev):
     shape = weak_scaling_shape(args.size, world)
     nvox = shape[0] * shape[1] * shape[2]
     stepper = DistributedCahnHilliardIMEX(shape, (1.0, 1.0, 1.0), CH["dt"], CH["eps"], CH["D"],
-                                          CH["A"], device=dev, transport=args.transport,
+                                          CH["A"], device=dev, transport=args.transport, copier=args.copier,
+                                          scatter_ctas=args.scatter_ctas, mid_chunks=args.mid_chunks,
                                           overlap_chunks=args.overlap_chunks, p2p_ctas=args.p2p_ctas)
     gen = torch.Generator(device=dev).manual_seed(rank)
     u0 = 0.5 + 0.1 * torch.rand(stepper.slab.local_shape, device=dev, generator=gen)
@@ -447,9 +448,13 @@ def run_ours_distributed(args, world, rank, local, dev):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"CH IMEX {shape[0]}x{shape[1]}x{shape[2]} fp32 periodic dt=0.1 "
                                    f"({args.size}^3 voxels per GPU)", **CH, "fft_backend": "native",
-                       "parallelism": f"x-slab over {world} GPUs: 2-plane halos (NCCL send/recv) + slab<->pencil "
-                                      + ("transposes fused into the FFT passes as NVLink peer stores (symmetric memory)"
-                                         if args.transport == "p2p" else "NCCL all-to-all"),
+                       "parallelism": f"x-slab over {world} GPUs: 2-plane halos ("
+                                      + ("DMA writes into the neighbours' symmetric-memory slots" if args.transport == "ce"
+                                         else "NCCL send/recv") + ") + slab<->pencil "
+                                      + {"p2p": "transposes fused into the FFT passes as NVLink peer stores (symmetric memory)",
+                                         "ce": "transposes as DMA-engine copies between symmetric-memory block buffers, "
+                                               "pipelined against the kernels of the next chunk",
+                                         "nccl": "NCCL all-to-all"}[args.transport],
                        "l2": "slab (%.0f MB) larger than L2 (126 MB), no flush needed" % (slab_bytes / 1e6)},
             "clocks": clocks,
             "e2e": {"value": nvox * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
@@ -480,7 +485,12 @@ def main():
                     help="grid cap of the NVLink-bound peer-store launches (0 = fill the GPU)")
     ap.add_argument("--overlap-chunks", type=int, default=4,
                     help="multi-GPU p2p: x chunks pipelined on two streams in the forward half")
-    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+    ap.add_argument("--copier", default=None, choices=["kernel", "dma"],
+                    help="multi-GPU 'ce' transport: blocks moved by one scatter kernel per chunk or by DMA copies")
+    ap.add_argument("--mid-chunks", type=int, default=0,
+                    help="multi-GPU 'ce' transport: chunks of the x pass (0 = same as --overlap-chunks)")
+    ap.add_argument("--scatter-ctas", type=int, default=0, help="CTAs per peer of the scatter kernel (default 8)")
+    ap.add_argument("--transport", default="ce", choices=["p2p", "nccl", "ce"],
                     help="multi-GPU transposes: fused peer stores over NVLink, or NCCL all-to-all")
     args = ap.parse_args()
     if args.impl == "reference":

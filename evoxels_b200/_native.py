@@ -72,6 +72,15 @@ SIGNATURES = {
     "evx_dist_plan_sizes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t), _iptr],
     "evx_dist_forward_f32": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
     "evx_dist_middle_f32": [_c_void_p, _c_void_p, _dptr, _c_double, _c_double, _c_int, _c_void_p],
+    "evx_dist_forward_chunk_f32": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                                   _c_void_p],
+    "evx_dist_middle_chunk_f32": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _dptr, _c_double,
+                                  _c_double, _c_int, _c_void_p],
+    "evx_peer_scatter": [ctypes.POINTER(_c_void_p), ctypes.POINTER(_c_void_p), _c_int, ctypes.c_size_t,
+                         ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _c_int, _c_void_p],
+    "evx_copy_async": [_c_void_p, _c_void_p, ctypes.c_size_t, _c_void_p],
+    "evx_copy2d_async": [_c_void_p, ctypes.c_size_t, _c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                         ctypes.c_size_t, _c_void_p],
     "evx_dist_forward_p2p_f32": [_c_void_p, _c_void_p, _c_void_p, ctypes.POINTER(_c_void_p), _c_void_p],
     "evx_dist_forward_chunk_p2p_f32": [_c_void_p, _c_void_p, _c_void_p, ctypes.POINTER(_c_void_p), _c_int,
                                        _c_int, _c_int, _c_void_p],
@@ -235,6 +244,29 @@ def rd2_rhs(u, spacing, D_A, D_B, feed, kill, interaction=None):
     return out
 
 
+def peer_scatter(src_ptrs, dst_ptrs, row_bytes, rows, src_pitch, dst_pitch, ctas_per_region, stream):
+    """One kernel copying len(src_ptrs) pitched regions src[i] -> dst[i] (raw device pointers,
+    local or mapped peer memory) on `stream`."""
+    n = len(src_ptrs)
+    arr = ctypes.c_void_p * n
+    check(load_library().evx_peer_scatter(arr(*[int(p) for p in src_ptrs]), arr(*[int(p) for p in dst_ptrs]),
+                                          n, int(row_bytes), int(rows), int(src_pitch), int(dst_pitch),
+                                          int(ctas_per_region), _c_void_p(stream.cuda_stream)),
+          "evx_peer_scatter")
+
+
+def copy_async(dst_ptr, src_ptr, nbytes, stream):
+    """cudaMemcpyAsync between raw device pointers (local or mapped peer memory) on `stream`."""
+    check(load_library().evx_copy_async(_c_void_p(int(dst_ptr)), _c_void_p(int(src_ptr)), int(nbytes),
+                                        _c_void_p(stream.cuda_stream)), "evx_copy_async")
+
+
+def copy2d_async(dst_ptr, dpitch, src_ptr, spitch, width_bytes, height, stream):
+    check(load_library().evx_copy2d_async(_c_void_p(int(dst_ptr)), int(dpitch), _c_void_p(int(src_ptr)),
+                                          int(spitch), int(width_bytes), int(height),
+                                          _c_void_p(stream.cuda_stream)), "evx_copy2d_async")
+
+
 def spectral_filter(spec, shape, spacing, dt, coef, power, scale=1.0):
     """In-place P(k) multiply of a cuFFT-layout half spectrum (complex64/128 tensor)."""
     require_cuda(spec)
@@ -383,6 +415,24 @@ class DistPlan:
             check(load_library().evx_dist_middle_f32(self._handle, _ptr(recv), _h3(spacing), float(dt),
                                                      float(coef), int(power), _stream(recv)),
                   "evx_dist_middle")
+
+    def forward_chunk(self, r_local, spec, send, x0, nxc, self_block=None):
+        """z + y pass of the local x planes [x0, x0+nxc) into the block layout `send`; block
+        `rank` goes to `self_block` instead when given."""
+        require_cuda(r_local, spec, send, self_block)
+        with torch.cuda.device(self.device):
+            check(load_library().evx_dist_forward_chunk_f32(
+                self._handle, _ptr(_field3(r_local)), _ptr(spec), _ptr(send), _ptr(self_block),
+                int(x0), int(nxc), _stream(r_local)), "evx_dist_forward_chunk")
+
+    def middle_chunk(self, recv, yl0, nylc, spacing, dt, coef, power, self_block=None):
+        """x pass (forward * weight * inverse) of the local y-pencil rows [yl0, yl0+nylc), in
+        place except for the rows of block `rank`, which go to `self_block` when given."""
+        require_cuda(recv, self_block)
+        with torch.cuda.device(self.device):
+            check(load_library().evx_dist_middle_chunk_f32(
+                self._handle, _ptr(recv), _ptr(self_block), int(yl0), int(nylc), _h3(spacing),
+                float(dt), float(coef), int(power), _stream(recv)), "evx_dist_middle_chunk")
 
     @staticmethod
     def _ptr_array(ptrs):

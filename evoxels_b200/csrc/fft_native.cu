@@ -327,6 +327,15 @@ static void set_peers(StridedParams& sp, const DistPlan* p, void* const* peers) 
 // [x0, x0+nxc) selects a chunk of local x planes (r_local / spec / send still point at the
 // start of the full local arrays), so that several chunks can be pipelined on streams:
 // the NVLink-bound y pass of one chunk overlaps the HBM-bound z pass of the next.
+// Pointer table for "every block into `other`, except block `rank` into `self_buf`" in terms
+// of the peer-store addressing (which adds rank * block to the table entry).
+static void local_block_table(const DistPlan* p, cf* other, cf* self_buf, void** table) {
+  const long long blk = (long long)p->nxl * p->nyl * p->P;
+  for (int j = 0; j < 8; ++j)
+    table[j] = j >= p->world ? nullptr
+                             : (j == p->rank ? (void*)self_buf : (void*)(other + (j - p->rank) * blk));
+}
+
 int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* const* peers,
                  int x0, int nxc, cudaStream_t st, int parts = 3) {
   if (x0 < 0 || nxc < 1 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
@@ -352,16 +361,22 @@ int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* co
   return launch_strided<PASS_FWD>(p->ny, yp, st);
 }
 
+// [yl0, yl0+nylc): chunk of the local y-pencil rows (all x, all kz of those rows)
 int dist_middle(DistPlan* p, cf* recv, void* const* peers, const double* h, double dt, double coef,
-                int power, cudaStream_t st) {
+                int power, cudaStream_t st, int yl0 = 0, int nylc = -1) {
+  if (nylc < 0) nylc = p->nyl - yl0;
+  if (yl0 < 0 || nylc < 1 || yl0 + nylc > p->nyl) return EVX_ERR_ARG;
+  recv += (long long)yl0 * p->P;
   StridedParams xp;
   xp.in = recv; xp.out = recv; xp.tw = tw_x(p);
   xp.src = xp.dst = plain_io((long long)p->nyl * p->P, p->P, p->nx);
   set_peers(xp, p, peers);
-  if (peers)   // chunk x / nxl of every x line goes to that rank: [rank j block][xl][yl][kz]
+  if (peers) { // chunk x / nxl of every x line goes to that rank: [rank j block][xl][yl][kz]
     xp.dst = StridedIO{(long long)p->nyl * p->P, p->P, 0, ilog2(p->nxl)};
-  xp.P = p->P; xp.ncols_valid = p->M + 1; xp.ncols_total = (long long)p->nyl * p->P;
-  xp.kother_offset = p->rank * p->nyl;
+    xp.dst_peer_base += (long long)yl0 * p->P;
+  }
+  xp.P = p->P; xp.ncols_valid = p->M + 1; xp.ncols_total = (long long)nylc * p->P;
+  xp.kother_offset = p->rank * p->nyl + yl0;
   const int n[3] = {p->nx, p->ny, p->nz};
   xp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)p->nx * p->ny * p->nz));
   return launch_xmid(p->nx, xp, st);
@@ -381,6 +396,64 @@ int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, f
   zp.real_in = u_local; zp.real_out = out_local; zp.spec = spec; zp.tw = tw_z(p); zp.twr = tw_r(p);
   zp.rows = (long long)p->nxl * p->ny; zp.nz = p->nz; zp.P = p->P;
   return launch_z<true>(p->M, zp, st);
+}
+
+// ------------------------------------------------------------------------------------
+// Block scatter over peer memory: region i (rows x row_bytes, pitched) is copied from src[i]
+// to dst[i] - typically dst[i] lives on another GPU (mapped peer buffer), so the stores are
+// NVLink writes of whole 128-byte lines.  A handful of CTAs per peer saturates the links;
+// launched on a side stream it runs next to the kernels of the next chunk.  Used where the
+// DMA engines' per-copy latency would dominate (many small regions to many peers).
+// ------------------------------------------------------------------------------------
+struct ScatterParams {
+  const uint4* src[8];
+  uint4* dst[8];
+  long long row_vec, rows, src_pitch_vec, dst_pitch_vec;   // in 16-byte units
+};
+
+__global__ void __launch_bounds__(512) peer_scatter_kernel(const ScatterParams p) {
+  const uint4* __restrict__ src = p.src[blockIdx.y];
+  uint4* __restrict__ dst = p.dst[blockIdx.y];
+  const long long total = p.rows * p.row_vec;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // four independent 16-byte transfers per thread and iteration
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long j = i + k * stride, r = j / p.row_vec, c = j - r * p.row_vec;
+      v[k] = __ldcs(src + r * p.src_pitch_vec + c);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long j = i + k * stride, r = j / p.row_vec, c = j - r * p.row_vec;
+      dst[r * p.dst_pitch_vec + c] = v[k];
+    }
+  }
+  for (; i < total; i += stride) {
+    const long long r = i / p.row_vec, c = i - r * p.row_vec;
+    dst[r * p.dst_pitch_vec + c] = __ldcs(src + r * p.src_pitch_vec + c);
+  }
+}
+
+int peer_scatter(const void* const* src, void* const* dst, int n, size_t row_bytes, size_t rows,
+                 size_t src_pitch, size_t dst_pitch, int ctas_per_region, cudaStream_t st) {
+  if (n < 1 || n > 8 || !row_bytes || !rows) return EVX_ERR_ARG;
+  if (row_bytes % 16 || src_pitch % 16 || dst_pitch % 16) return EVX_ERR_UNSUPPORTED;
+  ScatterParams p;
+  for (int i = 0; i < 8; ++i) {
+    p.src[i] = i < n ? (const uint4*)src[i] : nullptr;
+    p.dst[i] = i < n ? (uint4*)dst[i] : nullptr;
+    if (i < n && (!src[i] || !dst[i] || ((uintptr_t)src[i] | (uintptr_t)dst[i]) % 16)) return EVX_ERR_ARG;
+  }
+  p.row_vec = (long long)(row_bytes / 16); p.rows = (long long)rows;
+  p.src_pitch_vec = (long long)(src_pitch / 16); p.dst_pitch_vec = (long long)(dst_pitch / 16);
+  if (ctas_per_region < 1) ctas_per_region = 8;
+  dim3 grid((unsigned)ctas_per_region, (unsigned)n);
+  peer_scatter_kernel<<<grid, 512, 0, st>>>(p);
+  count_launch();
+  return (int)cudaGetLastError();
 }
 
 // access-pattern probe: the load/store pattern of a strided pass without the transform
@@ -451,6 +524,52 @@ int evx_dist_forward_chunk_p2p_f32(evx_dist_plan* plan, const float* r_local, vo
   if (((DistPlan*)plan)->world > 8) return EVX_ERR_UNSUPPORTED;
   return dist_forward((DistPlan*)plan, r_local, (cf*)spec, nullptr, peer_recv, x0, nxc,
                       (cudaStream_t)stream, parts);
+}
+int evx_dist_forward_chunk_f32(evx_dist_plan* plan, const float* r_local, void* spec, void* send,
+                               void* self_block, int x0, int nxc, void* stream) {
+  if (!plan || !r_local || !spec || !send || spec == send) return EVX_ERR_ARG;
+  DistPlan* dp = (DistPlan*)plan;
+  if (!self_block)
+    return dist_forward(dp, r_local, (cf*)spec, (cf*)send, nullptr, x0, nxc, (cudaStream_t)stream);
+  if (dp->world > 8) return EVX_ERR_UNSUPPORTED;
+  void* table[8];
+  local_block_table(dp, (cf*)send, (cf*)self_block, table);
+  const int ctas = dp->p2p_ctas;
+  dp->p2p_ctas = 0;                       // local stores: fill the GPU
+  const int rc = dist_forward(dp, r_local, (cf*)spec, nullptr, table, x0, nxc, (cudaStream_t)stream);
+  dp->p2p_ctas = ctas;
+  return rc;
+}
+int evx_dist_middle_chunk_f32(evx_dist_plan* plan, void* recv, void* self_block, int yl0, int nylc,
+                              const double* h, double dt, double coef, int power, void* stream) {
+  if (!plan || !recv || !h || !valid_filter_spec(power)) return EVX_ERR_ARG;
+  DistPlan* dp = (DistPlan*)plan;
+  if (!self_block)
+    return dist_middle(dp, (cf*)recv, nullptr, h, dt, coef, power, (cudaStream_t)stream, yl0, nylc);
+  if (dp->world > 8) return EVX_ERR_UNSUPPORTED;
+  void* table[8];
+  local_block_table(dp, (cf*)recv, (cf*)self_block, table);
+  const int ctas = dp->p2p_ctas;
+  dp->p2p_ctas = 0;
+  const int rc = dist_middle(dp, (cf*)recv, table, h, dt, coef, power, (cudaStream_t)stream, yl0, nylc);
+  dp->p2p_ctas = ctas;
+  return rc;
+}
+int evx_peer_scatter(const void* const* src, void* const* dst, int n, size_t row_bytes, size_t rows,
+                     size_t src_pitch, size_t dst_pitch, int ctas_per_region, void* stream) {
+  if (!src || !dst) return EVX_ERR_ARG;
+  return peer_scatter(src, dst, n, row_bytes, rows, src_pitch, dst_pitch, ctas_per_region,
+                      (cudaStream_t)stream);
+}
+int evx_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
+  if (!dst || !src) return EVX_ERR_ARG;
+  return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+}
+int evx_copy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes,
+                     size_t height, void* stream) {
+  if (!dst || !src) return EVX_ERR_ARG;
+  return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height, cudaMemcpyDefault,
+                                (cudaStream_t)stream);
 }
 int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_out, const double* h,
                             double dt, double coef, int power, void* stream) {

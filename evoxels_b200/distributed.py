@@ -142,11 +142,44 @@ class PeerBuffers:
         self.handles[which].barrier(channel=0)
 
 
+class PeerHalos:
+    """Stencil halos through symmetric memory: every rank owns a [2][width][ny][nz] buffer
+    (slot 0 = planes below the slab, slot 1 = planes above); `exchange` has the DMA engines
+    write this rank's boundary planes straight into the ring neighbours' slots and enqueues
+    one cross-rank barrier - no NCCL call, no staging copies.  Periodic ring only."""
+
+    def __init__(self, width, ny, nz, device, group, world, rank):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.width, self.world, self.rank = width, world, rank
+        self.buf = symm_mem.empty(2, width, ny, nz, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group=group)
+        self.ptrs = [int(x) for x in self.handle.buffer_ptrs]
+        self.slot_bytes = width * ny * nz * 4
+
+    def exchange(self, u_local):
+        W, r, w = self.world, self.rank, self.width
+        if u_local.shape[0] < w:
+            raise ValueError("slab thinner than the halo width")
+        st = torch.cuda.current_stream(u_local.device)
+        lo, hi = (r - 1) % W, (r + 1) % W
+        plane = u_local.stride(0) * 4
+        # my first planes are the lower neighbour's "above" halo, my last planes the upper
+        # neighbour's "below" halo
+        _native.copy_async(self.ptrs[lo] + self.slot_bytes, u_local.data_ptr(), self.slot_bytes, st)
+        _native.copy_async(self.ptrs[hi], u_local.data_ptr() + (u_local.shape[0] - w) * plane,
+                           self.slot_bytes, st)
+        self.handle.barrier(channel=0)
+        return self.buf[0], self.buf[1]
+
+
 class CudaOps:
     """The kernels behind one rank of the distributed step.
 
     transport = 'p2p': the y pass / x pass write their output straight into the peers'
     buffers over NVLink (fused transform + transpose, no collective call, no pack/unpack);
+    transport = 'ce': local block buffers, blocks moved into the peers' buffers by the DMA
+    engines (cudaMemcpyAsync on copy streams), pipelined against the next chunk's kernels;
     transport = 'nccl': local block buffers + NCCL all-to-all."""
 
     def __init__(self, slab: Slab, spacing, device, spectral=True, transport="nccl", group=None):
@@ -158,9 +191,12 @@ class CudaOps:
         if spectral:
             self.plan = _native.DistPlan(slab.global_shape, slab.world, slab.rank, device)
             self.spec = self.plan.new_buffer()
-            if self.transport == "p2p":
+            if self.transport in ("p2p", "ce"):
                 self.peers = PeerBuffers(self.plan.block_shape, self.device, group)
                 self.buf_a, self.buf_b = self.peers.bufs
+                if self.transport == "ce":
+                    _, ny, nz = slab.global_shape
+                    self.halos = PeerHalos(2, ny, nz, self.device, group, slab.world, slab.rank)
             else:
                 self.buf_a = self.plan.new_buffer()
                 self.buf_b = self.plan.new_buffer()
@@ -219,6 +255,125 @@ class CudaOps:
         self.peers.barrier(1)
         return self.buf_b
 
+    # optional timeline (diagnostics): set ops.trace = [] to collect (name, event) pairs
+    trace = None
+    # 'ce' transport: who moves the blocks - "kernel" (evx_peer_scatter, a few CTAs per peer on
+    # a side stream) or "dma" (one cudaMemcpyAsync per peer and chunk; fine for 2 GPUs, but the
+    # per-copy latency of the DMA engines adds up with 7 peers)
+    copier = "dma"
+    scatter_ctas = 8
+
+    def _mark(self, name, stream=None):
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream if stream is not None else torch.cuda.current_stream(self.device))
+            self.trace.append((name, e))
+
+    # copy-engine transport: kernels write local block buffers, DMA engines move the blocks ---
+    def _ce_streams(self):
+        if not hasattr(self, "_comp"):
+            self._comp = torch.cuda.Stream(device=self.device)
+            self._link = torch.cuda.Stream(device=self.device)
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.slab.world)]
+        return self._comp, self._copy_streams
+
+    def forward_ce(self, u, rhs, eps, D, bc, halo_lo, halo_hi, chunks):
+        """rhs -> z pass -> y pass into the local block buffer A over `chunks` slices of the
+        local x range (the block that stays on this GPU goes straight into the local B); as
+        soon as a slice is done its rows of every other block are copied by the DMA engines
+        into block `rank` of the owning rank's buffer B (one copy stream per peer) while the
+        kernels of the next slice run.  Returns the local B."""
+        W, me, nxl, nyl, P = self.slab.world, self.slab.rank, self.slab.nxl, self.slab.nyl, self.plan.pitch
+        blk = nxl * nyl * P * 8                      # bytes per block
+        row = nyl * P * 8                            # bytes per local x plane inside a block
+        bounds = [round(i * nxl / chunks) for i in range(chunks + 1)]
+        main = torch.cuda.current_stream(self.device)
+        comp, copies = self._ce_streams()
+        comp.wait_stream(main)
+        a_ptr, b_ptrs = self.buf_a.data_ptr(), self.peers.peer_ptrs[1]
+        for i in range(chunks):
+            x0, x1 = bounds[i], bounds[i + 1]
+            with torch.cuda.stream(comp):
+                lo = halo_lo if x0 == 0 else u[x0 - 2:x0]
+                hi = halo_hi if x1 == nxl else u[x1:x1 + 2]
+                _native.ch_rhs(u[x0:x1], rhs[x0:x1], self.spacing, eps, D, bc, halo_lo=lo, halo_hi=hi)
+                self._mark(f"fwd{i} rhs", comp)
+                self.plan.forward_chunk(rhs, self.spec, self.buf_a, x0, x1 - x0, self_block=self.buf_b)
+                self._mark(f"fwd{i} z+y", comp)
+                done = torch.cuda.Event()
+                done.record(comp)
+            peers_ = [(me + 1 + k) % W for k in range(W - 1)]     # staggered across ranks
+            if self.copier == "kernel":
+                cs = copies[0]
+                cs.wait_event(done)
+                _native.peer_scatter([a_ptr + j * blk + x0 * row for j in peers_],
+                                     [b_ptrs[j] + me * blk + x0 * row for j in peers_],
+                                     (x1 - x0) * row, 1, (x1 - x0) * row, (x1 - x0) * row,
+                                     self.scatter_ctas, cs)
+                self._mark(f"fwd{i} scatter", cs)
+                continue
+            for j in peers_:
+                cs = copies[j]
+                cs.wait_event(done)
+                _native.copy_async(b_ptrs[j] + me * blk + x0 * row, a_ptr + j * blk + x0 * row,
+                                   (x1 - x0) * row, cs)
+                self._mark(f"fwd{i} copy->{j}", cs)
+        main.wait_stream(comp)
+        for cs in copies:
+            main.wait_stream(cs)
+        self._mark("fwd joined")
+        self.peers.barrier(1)
+        self._mark("fwd barrier")
+        return self.buf_b
+
+    def middle_ce(self, dt, coef, power, chunks):
+        """x pass in place on the local B over `chunks` slices of the local y-pencil rows; each
+        finished slice is copied (2-D region per block) into block `rank` of the owning
+        rank's buffer A.  Returns the local A."""
+        W, me, nxl, nyl, P = self.slab.world, self.slab.rank, self.slab.nxl, self.slab.nyl, self.plan.pitch
+        blk = nxl * nyl * P * 8
+        pitch = nyl * P * 8
+        chunks = max(1, min(chunks, nyl))
+        bounds = [round(i * nyl / chunks) for i in range(chunks + 1)]
+        main = torch.cuda.current_stream(self.device)
+        comp, copies = self._ce_streams()
+        comp.wait_stream(main)
+        b_ptr, a_ptrs = self.buf_b.data_ptr(), self.peers.peer_ptrs[0]
+        for i in range(chunks):
+            y0, y1 = bounds[i], bounds[i + 1]
+            with torch.cuda.stream(comp):
+                self.plan.middle_chunk(self.buf_b, y0, y1 - y0, self.spacing, dt, coef, power,
+                                       self_block=self.buf_a)
+                self._mark(f"mid{i} x", comp)
+                done = torch.cuda.Event()
+                done.record(comp)
+            peers_ = [(me + 1 + k) % W for k in range(W - 1)]
+            if self.copier == "kernel":
+                cs = copies[0]
+                cs.wait_event(done)
+                _native.peer_scatter([b_ptr + j * blk + y0 * P * 8 for j in peers_],
+                                     [a_ptrs[j] + me * blk + y0 * P * 8 for j in peers_],
+                                     (y1 - y0) * P * 8, nxl, pitch, pitch, self.scatter_ctas, cs)
+                self._mark(f"mid{i} scatter", cs)
+                continue
+            for j in peers_:
+                cs = copies[j]
+                cs.wait_event(done)
+                if y1 - y0 == nyl:       # whole block: one contiguous copy (fastest DMA path)
+                    _native.copy_async(a_ptrs[j] + me * blk, b_ptr + j * blk, blk, cs)
+                else:
+                    _native.copy2d_async(a_ptrs[j] + me * blk + y0 * P * 8, pitch,
+                                         b_ptr + j * blk + y0 * P * 8, pitch, (y1 - y0) * P * 8, nxl, cs)
+                self._mark(f"mid{i} copy->{j}", cs)
+        main.wait_stream(comp)
+        for cs in copies:
+            main.wait_stream(cs)
+        self._mark("mid joined")
+        self.peers.barrier(0)
+        self._mark("mid barrier")
+        return self.buf_a
+
     def spectral_middle_p2p(self, dt, coef, power):
         """x pass on the local B; chunks land in every peer's buffer A.  Returns the local A."""
         self.plan.middle_p2p(self.buf_b, self.peers.peer_ptrs[0], self.spacing, dt, coef, power)
@@ -237,13 +392,21 @@ class DistributedCahnHilliardIMEX:
     `step(u_local) -> u_local_new`; same arithmetic as the single-GPU step."""
 
     def __init__(self, global_shape, spacing, dt, eps=3.0, D=1.0, A=0.25, group=None,
-                 device=None, ops=None, transport="p2p", overlap_chunks=4, p2p_ctas=148):
+                 device=None, ops=None, transport="ce", overlap_chunks=4, p2p_ctas=148,
+                 copier=None, scatter_ctas=None, mid_chunks=None):
         self.comm = Comm(group)
         self.slab = Slab(tuple(global_shape), self.comm.world, self.comm.rank)
         self.spacing, self.dt, self.eps, self.D, self.A = tuple(spacing), dt, eps, D, A
         self.bc = normalize_bc(("periodic",) * 3)
         self.ops = ops if ops is not None else CudaOps(self.slab, spacing, device or "cuda",
                                                        transport=transport, group=group)
+        # x-pass pipeline depth of the 'ce' transport (measured on 8 GPUs, 512^3 per GPU:
+        # 4 chunks 3.39 ms/step, 2 chunks 3.40, unchunked 3.94)
+        self.mid_chunks = mid_chunks if mid_chunks else overlap_chunks
+        if copier is not None:
+            self.ops.copier = copier
+        if scatter_ctas:
+            self.ops.scatter_ctas = int(scatter_ctas)
         self.rhs = self.ops.new_field()
         # forward pipeline depth: x chunks of the local slab issued on two streams (p2p only)
         self.overlap_chunks = overlap_chunks if self.slab.nxl >= 8 * max(overlap_chunks, 1) else 1
@@ -286,8 +449,21 @@ class DistributedCahnHilliardIMEX:
     def step(self, u_local):
         ops, comm = self.ops, self.comm
         u_local = u_local.contiguous()
-        halo_lo, halo_hi = comm.exchange_halos(u_local, 2, periodic=True)
-        pipelined = getattr(ops, "transport", "nccl") == "p2p" and self.overlap_chunks > 1
+        transport = getattr(ops, "transport", "nccl")
+        if transport == "ce":
+            halo_lo, halo_hi = ops.halos.exchange(u_local)
+        else:
+            halo_lo, halo_hi = comm.exchange_halos(u_local, 2, periodic=True)
+        if transport == "ce":
+            ops._mark("halo done")
+            ops.forward_ce(u_local, self.rhs, self.eps, self.D, self.bc, halo_lo, halo_hi,
+                           max(self.overlap_chunks, 1))
+            a = ops.middle_ce(self.dt, 2.0 * self.eps * self.D * self.A, 2, max(self.mid_chunks, 1))
+            out = ops.new_field()
+            ops.spectral_backward(a, u_local, out)
+            ops._mark("bwd y+z")
+            return out
+        pipelined = transport == "p2p" and self.overlap_chunks > 1
         if not pipelined:
             ops.ch_rhs(u_local, self.rhs, self.eps, self.D, self.bc, halo_lo, halo_hi)
         coef = 2.0 * self.eps * self.D * self.A

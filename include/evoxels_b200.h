@@ -230,6 +230,31 @@ int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_o
 int evx_dist_forward_chunk_p2p_f32(evx_dist_plan* plan, const float* r_local, void* spec,
                                    void* const* peer_recv, int x0, int nxc, int parts, void* stream);
 
+/* Copy-engine transport: the same block buffers, but the transposes are plain device-to-device
+ * copies between mapped peer buffers issued on copy streams (DMA engines, no SM involved), so
+ * that they overlap the kernels of the next chunk.  forward_chunk = z + y pass of the local x
+ * planes [x0, x0+nxc) into block layout `send` (rows x0.. of every block are then contiguous:
+ * nxc*(ny/W)*P elements per peer); middle_chunk = the x pass restricted to the local y-pencil
+ * rows [yl0, yl0+nylc) of `recv` (a 2-D region per peer block: nx/W rows of nylc*P elements,
+ * pitch (ny/W)*P).  A non-NULL `self_block` names the buffer that receives block `rank` (the
+ * part that stays on this GPU) directly, so that no local copy is needed: the forward pass
+ * then fills block `rank` of `self_block` (the local recv buffer) and the other blocks of
+ * `send`; the middle pass writes rows x of block `rank` into `self_block` and the rest in place.
+ * evx_copy_async / evx_copy2d_async enqueue cudaMemcpyAsync / cudaMemcpy2DAsync
+ * (cudaMemcpyDefault) on `stream`. */
+int evx_dist_forward_chunk_f32(evx_dist_plan* plan, const float* r_local, void* spec, void* send,
+                               void* self_block, int x0, int nxc, void* stream);
+int evx_dist_middle_chunk_f32(evx_dist_plan* plan, void* recv, void* self_block, int yl0, int nylc,
+                              const double* h, double dt, double coef, int power, void* stream);
+/* One launch that copies n <= 8 pitched regions (rows x row_bytes; 16-byte aligned) src[i] ->
+ * dst[i] with `ctas_per_region` CTAs each: the SM-driven alternative to n DMA copies when the
+ * regions are small and go to many peers (dst[i] = mapped peer memory -> NVLink stores). */
+int evx_peer_scatter(const void* const* src, void* const* dst, int n, size_t row_bytes, size_t rows,
+                     size_t src_pitch, size_t dst_pitch, int ctas_per_region, void* stream);
+int evx_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+int evx_copy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes,
+                     size_t height, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * Adjoint of the Cahn-Hilliard right-hand side (fully periodic grids)
  *

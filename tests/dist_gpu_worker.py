@@ -37,7 +37,7 @@ def main():
         single = PseudoSpectralIMEX(CahnHilliard(vg), 0.1)
         slab = Slab(shape, world, rank)
         results = {}
-        for transport in ("nccl", "p2p"):
+        for transport in ("nccl", "p2p", "ce"):
             stepper = DistributedCahnHilliardIMEX(shape, spacing, 0.1, device=dev, transport=transport)
             v, w = u[None], slab.take(u).contiguous()
             m0 = stepper.total_mass(w)
@@ -51,6 +51,7 @@ def main():
             worst = max(worst, upd)
             results[transport] = w
         assert torch.equal(results["nccl"], results["p2p"]), (shape, rank)   # same arithmetic
+        assert torch.equal(results["nccl"], results["ce"]), (shape, rank)
         for bc in (("neumann",) * 3, ("periodic",) * 3, (("dirichlet", (0.0, 1.0)), "neumann", "periodic")):
             phi = torch.rand(shape, device=dev, generator=gen)
             import warnings
