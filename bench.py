@@ -33,14 +33,14 @@ CH = dict(eps=3.0, D=1.0, A=0.25, dt=0.1)
 B_ALG_STEP = 60.0       # algorithmic bytes / voxel / step
 B_ALG_RHS = 8.0         # fused rhs kernel: read c, write rhs
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 512^3 from the committed
-# `ncu --set full` capture (profiles/r01_ncu_full_summary_pch.txt); bytes
+# `ncu --set full` capture (profiles/r01_ncu_full_summary_final.txt); bytes
 NCU_TRAFFIC_512 = {
-    "ch_rhs_kernel": 0.5411e9 + 0.5002e9,
-    "fft_z_forward (ZPass fwd)": 0.5446e9 + 0.5031e9,
-    "fft_y_forward (StridedPipe FWD)": 0.5541e9 + 0.4931e9,
-    "fft_x_fwd*filter*inv (StridedPipe XMID)": 0.5538e9 + 0.4880e9,
-    "fft_y_inverse (StridedPipe INV)": 0.5544e9 + 0.4933e9,
-    "fft_z_inverse+u (ZPass inv)": 1.091e9 + 0.5083e9,
+    "ch_rhs_kernel": 0.5411e9 + 0.5019e9,
+    "fft_z_forward (ZPass fwd)": 0.5446e9 + 0.5025e9,
+    "fft_y_forward (StridedPipe FWD)": 0.5540e9 + 0.4933e9,
+    "fft_x_fwd*filter*inv (StridedPipe XMID)": 0.5537e9 + 0.4871e9,
+    "fft_y_inverse (StridedPipe INV)": 0.5540e9 + 0.4933e9,
+    "fft_z_inverse+u (ZPass inv)": 1.091e9 + 0.5084e9,
 }
 
 
@@ -320,7 +320,7 @@ def run_ours(args):
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
         "frac": dom_gbs / peak, "traffic": NCU_TRAFFIC_512.get(dom) if n == 512 else None,
-        "traffic_source": "profiles/r01_ncu_full_summary_pch.txt (ncu --set full, per launch)",
+        "traffic_source": "profiles/r01_ncu_full_summary_final.txt (ncu --set full, per launch)",
         "peak_source": peak_src, "ms": dom_ms,
         "bytes_per_voxel": dom_bpv,
         "step": {"bytes_per_voxel": B_ALG_STEP, "achieved": gbs_step, "frac": gbs_step / peak,

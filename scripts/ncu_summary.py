@@ -2,9 +2,10 @@
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[0]
+units = rows[1]          # ncu picks the unit per column (us/ms, Mbyte/Gbyte): print it
 def col(name): return hdr.index(name) if name in hdr else None
-want = [("gpu__time_duration.sum", "time_us"), ("dram__bytes_read.sum", "dram_rd_MB"),
-        ("dram__bytes_write.sum", "dram_wr_MB"),
+want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
+        ("dram__bytes_write.sum", "dram_wr"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_pct"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ_pct"),
@@ -36,5 +37,6 @@ for r in rows[2:]:
             v = r[i]
             try: v = f"{float(v.replace(',', '')):.4g}"
             except ValueError: pass
-            out.append(f"{short}={v}")
+            unit = units[i] if short in ("time", "dram_rd", "dram_wr") else ""
+            out.append(f"{short}={v}{unit}")
     print("   " + " ".join(out))
