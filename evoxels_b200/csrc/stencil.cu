@@ -58,9 +58,19 @@ static int launch_ch(ChParams<T> p, cudaStream_t st) {
   if (p.hom) {   // user potential: rare, keep one (general) instantiation
     ch_rhs_kernel<T, V, TY, G, true, true><<<grid, Prog::NTHREADS, 0, st>>>(p);
   } else if (ghosts) {
-    ch_rhs_kernel<T, V, TY, G, false, true><<<grid, Prog::NTHREADS, 0, st>>>(p);
+    static const int gocc = [] { const char* e = getenv("EVX_CH_GOCC"); return e ? atoi(e) : 3; }();
+    if (gocc == 3 && sizeof(T) == 4 && TY <= 16)
+      ch_rhs_kernel<T, V, TY, G, false, true, 3><<<grid, Prog::NTHREADS, 0, st>>>(p);
+    else
+      ch_rhs_kernel<T, V, TY, G, false, true><<<grid, Prog::NTHREADS, 0, st>>>(p);
   } else {
-    ch_rhs_kernel<T, V, TY, G, false, false><<<grid, Prog::NTHREADS, 0, st>>>(p);
+    // three resident CTAs per SM (72 registers, a few spilled words) beat two (94 registers):
+    // 0.365 vs 0.408 ms at 512^3 - the kernel is latency-bound, the extra warps pay
+    static const int occ = [] { const char* e = getenv("EVX_CH_OCC"); return e ? atoi(e) : 3; }();
+    if (occ == 3 && sizeof(T) == 4 && TY <= 16)
+      ch_rhs_kernel<T, V, TY, G, false, false, 3><<<grid, Prog::NTHREADS, 0, st>>>(p);
+    else
+      ch_rhs_kernel<T, V, TY, G, false, false><<<grid, Prog::NTHREADS, 0, st>>>(p);
   }
   count_launch();
   return (int)cudaGetLastError();
@@ -97,8 +107,8 @@ __global__ void __launch_bounds__(TY* G, MINB) ac_stage_kernel(const AcParams<T>
   AcProgram<T, V, TY, G>::run(p, threadIdx.x, blockIdx.x, blockIdx.y);
 }
 
-template <typename T, int V, int TY, int G>
-__global__ void __launch_bounds__(AcTileProgram<T, V, TY, G>::NTHREADS, sizeof(T) == 4 ? 2 : 1)
+template <typename T, int V, int TY, int G, int MINB = 2>
+__global__ void __launch_bounds__(AcTileProgram<T, V, TY, G>::NTHREADS, sizeof(T) == 4 ? MINB : 1)
     ac_tile_kernel(const AcParams<T> p) {
   using Prog = AcTileProgram<T, V, TY, G>;
   __shared__ typename Prog::Smem s;
@@ -125,7 +135,10 @@ static int launch_ac_tile(AcParams<T> p, cudaStream_t st) {
   const int chunks = (p.nx + p.xchunk - 1) / p.xchunk;
   if (tiles > 2147483647LL || chunks > 65535) return EVX_ERR_UNSUPPORTED;
   dim3 grid((unsigned)tiles, (unsigned)chunks);
-  ac_tile_kernel<T, V, TY, G><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  // 72 registers without spills at three CTAs per SM: 0.510 vs 0.540 ms at 512^3
+  static const int occ = [] { const char* e = getenv("EVX_AC_OCC"); return e ? atoi(e) : 3; }();
+  if (occ == 3) ac_tile_kernel<T, V, TY, G, 3><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  else ac_tile_kernel<T, V, TY, G, 2><<<grid, Prog::NTHREADS, 0, st>>>(p);
   count_launch();
   return (int)cudaGetLastError();
 }
