@@ -1,7 +1,6 @@
 #!/bin/bash
-# quick kernel timing session: general-BC CH kernel at 2 vs 3 CTAs per SM + stencil parity tests
-pick() { python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:round(v,4) for k,v in d.items() if k in ('ch_rhs_periodic_ms','ch_rhs_neumann_ms','ac_euler_ms','ch_step_native_ms')})"; }
-for v in "EVX_CH_GOCC=2" "EVX_CH_GOCC=3"; do
-  echo "$v"; env $v timeout 300 python scripts/bench_kernels.py 512 | tail -1 | pick
+# quick kernel timing session: z-pass residency variants, per-kernel times from bench.py
+for v in 0 5 6; do
+  echo "EVX_Z_OCC=$v"; EVX_Z_OCC=$v timeout 300 python bench.py --steps 50 --no-cpu 2>/dev/null | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],4), {k.split(' ')[0]:round(v['ms']*1000,1) for k,v in d['roofline']['kernels'].items()})"
 done
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -3
