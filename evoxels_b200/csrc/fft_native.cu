@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(Pipe::NTHREADS, Pipe::NTHREADS <= 512 ? 2 : 1)
   cf* c = t1 + Pipe::BUF;
   const long long ntiles = Pipe::num_tiles(p);
   long long tile = blockIdx.x;
-  if (tile < ntiles) Pipe::prefetch(threadIdx.x, p, tile, t0);
+  typename Pipe::Cursor q;
+  Pipe::cursor_init(q, p, threadIdx.x, tile, gridDim.x);
+  if (tile < ntiles) Pipe::prefetch_at(threadIdx.x, p, q.bgrp, q.bkz, t0);
   async_copy_commit();
   typename Pipe::Regs r;
   for (int par = 0; tile < ntiles; tile += gridDim.x, par ^= 1) {
@@ -73,10 +75,11 @@ __global__ void __launch_bounds__(Pipe::NTHREADS, Pipe::NTHREADS <= 512 ? 2 : 1)
     cf* b = par ? t0 : t1;
     async_copy_commit_and_wait();
     __syncthreads();
-    Pipe::Base::init(r, p, threadIdx.x, tile);
+    Pipe::Base::init_at(r, p, threadIdx.x, Pipe::cursor_column(q, p), q.grp, q.kz);
     Pipe::read_tile(r, a);
-    const long long next = tile + gridDim.x;
-    if (next < ntiles) Pipe::prefetch(threadIdx.x, p, next, b);
+    Pipe::cursor_step_own(q, p);
+    Pipe::cursor_step_base(q, p);
+    if (tile + gridDim.x < ntiles) Pipe::prefetch_at(threadIdx.x, p, q.bgrp, q.bkz, b);
     async_copy_commit();
 #pragma unroll
     for (int k = 0; k < Pipe::NPHASES; ++k) {

@@ -119,11 +119,16 @@ struct StridedPass {
   EVX_HD static cf* buf(cf* smem, int which) { return smem + (size_t)which * LP * KZ; }
 
   EVX_HD static void init(Regs& r, const StridedParams& p, int tid, long long block) {
+    const long long c = block * KZ + tid % KZ;
+    const long long grp = c / p.P;
+    init_at(r, p, tid, c, grp, (int)(c - grp * p.P));
+  }
+  // same with the (group, kz) decomposition of the thread's column c supplied by the caller
+  // (the persistent kernels step it from tile to tile without dividing)
+  EVX_HD static void init_at(Regs& r, const StridedParams& p, int tid, long long c, long long grp, int kz) {
     r.cl = tid % KZ;
     r.t = tid / KZ;
-    const long long c = block * KZ + r.cl;
-    const long long grp = c / p.P;
-    r.kz = (int)(c - grp * p.P);
+    r.kz = kz;
     r.kother = (int)grp + p.kother_offset;
     r.grp = grp;
     r.valid = c < p.ncols_total && r.kz < p.ncols_valid;
@@ -248,11 +253,43 @@ struct StridedPipe {
 
   EVX_HD static long long num_tiles(const StridedParams& p) { return (p.ncols_total + KZ - 1) / KZ; }
 
+  // Column position of a block's current tile, stepped by gridDim.x tiles per iteration with
+  // an add-and-carry instead of the two 64-bit divisions per tile a direct decode costs
+  // (they sat right behind the tile barrier, where every warp waits for them).
+  struct Cursor {
+    int grp, kz;             // own column of the current tile: c = grp*P + kz
+    int bgrp, bkz;           // first column of the NEXT tile to prefetch, same decomposition
+    int step_grp, step_kz;   // gridDim.x * KZ columns, decomposed
+  };
+  EVX_HD static void cursor_init(Cursor& q, const StridedParams& p, int tid, long long tile,
+                                 long long nblocks) {
+    const long long step = nblocks * KZ, c = tile * KZ + tid % KZ, bc = tile * KZ;
+    q.step_grp = (int)(step / p.P);
+    q.step_kz = (int)(step - (long long)q.step_grp * p.P);
+    q.grp = (int)(c / p.P);
+    q.kz = (int)(c - (long long)q.grp * p.P);
+    q.bgrp = (int)(bc / p.P);
+    q.bkz = (int)(bc - (long long)q.bgrp * p.P);
+  }
+  EVX_HD static long long cursor_column(const Cursor& q, const StridedParams& p) {
+    return (long long)q.grp * p.P + q.kz;
+  }
+  EVX_HD static void cursor_step_own(Cursor& q, const StridedParams& p) {
+    q.grp += q.step_grp; q.kz += q.step_kz;
+    if (q.kz >= p.P) { q.kz -= p.P; ++q.grp; }
+  }
+  EVX_HD static void cursor_step_base(Cursor& q, const StridedParams& p) {
+    q.bgrp += q.step_grp; q.bkz += q.step_kz;
+    if (q.bkz >= p.P) { q.bkz -= p.P; ++q.bgrp; }
+  }
+
   // all threads: enqueue the copy of tile `tile` (dense [L][KZ] rows of KZ*8 bytes) into dst
   EVX_HD static void prefetch(int tid, const StridedParams& p, long long tile, cf* dst) {
     const long long c0 = tile * KZ;
     const long long grp = c0 / p.P;
-    const int kz0 = (int)(c0 - grp * p.P);
+    prefetch_at(tid, p, grp, (int)(c0 - grp * p.P), dst);
+  }
+  EVX_HD static void prefetch_at(int tid, const StridedParams& p, long long grp, int kz0, cf* dst) {
     for (int q = tid; q < CHUNKS; q += NTHREADS) {
       const int row = q / CHUNKS_PER_ROW, part = q - row * CHUNKS_PER_ROW;
       const cf* src = p.in + strided_offset(p.src, grp, kz0, row) + part * (16 / (int)sizeof(cf));

@@ -137,7 +137,8 @@ static int launch_ac_tile(AcParams<T> p, cudaStream_t st) {
   dim3 grid((unsigned)tiles, (unsigned)chunks);
   // 72 registers without spills at three CTAs per SM: 0.510 vs 0.540 ms at 512^3
   static const int occ = [] { const char* e = getenv("EVX_AC_OCC"); return e ? atoi(e) : 3; }();
-  if (occ == 3) ac_tile_kernel<T, V, TY, G, 3><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  if (occ == 4) ac_tile_kernel<T, V, TY, G, 4><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  else if (occ == 3) ac_tile_kernel<T, V, TY, G, 3><<<grid, Prog::NTHREADS, 0, st>>>(p);
   else ac_tile_kernel<T, V, TY, G, 2><<<grid, Prog::NTHREADS, 0, st>>>(p);
   count_launch();
   return (int)cudaGetLastError();

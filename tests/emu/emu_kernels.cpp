@@ -201,16 +201,25 @@ static void run_pipe(const StridedParams& p, int nblocks) {
   using Pipe = StridedPipe<L, KZ, MODE>;
   const long long ntiles = Pipe::num_tiles(p);
   std::vector<typename Pipe::Regs> regs(Pipe::NTHREADS);
+  std::vector<typename Pipe::Cursor> cur(Pipe::NTHREADS);
   std::vector<cf> smem(3 * (size_t)Pipe::BUF);
   for (int blk = 0; blk < nblocks; ++blk) {
     cf* t0 = smem.data(); cf* t1 = t0 + Pipe::BUF; cf* c = t1 + Pipe::BUF;
     long long tile = blk;
-    if (tile < ntiles) for (int t = 0; t < Pipe::NTHREADS; ++t) Pipe::prefetch(t, p, tile, t0);
+    for (int t = 0; t < Pipe::NTHREADS; ++t) {
+      Pipe::cursor_init(cur[t], p, t, tile, nblocks);
+      if (tile < ntiles) Pipe::prefetch_at(t, p, cur[t].bgrp, cur[t].bkz, t0);
+    }
     for (int par = 0; tile < ntiles; tile += nblocks, par ^= 1) {
       cf* a = par ? t1 : t0; cf* b = par ? t0 : t1;
-      for (int t = 0; t < Pipe::NTHREADS; ++t) { Pipe::Base::init(regs[t], p, t, tile); Pipe::read_tile(regs[t], a); }
+      for (int t = 0; t < Pipe::NTHREADS; ++t) {
+        Pipe::Base::init_at(regs[t], p, t, Pipe::cursor_column(cur[t], p), cur[t].grp, cur[t].kz);
+        Pipe::read_tile(regs[t], a);
+        Pipe::cursor_step_own(cur[t], p);
+        Pipe::cursor_step_base(cur[t], p);
+      }
       const long long next = tile + nblocks;
-      if (next < ntiles) for (int t = 0; t < Pipe::NTHREADS; ++t) Pipe::prefetch(t, p, next, b);
+      if (next < ntiles) for (int t = 0; t < Pipe::NTHREADS; ++t) Pipe::prefetch_at(t, p, cur[t].bgrp, cur[t].bkz, b);
       for (int k = 0; k < Pipe::NPHASES; ++k)
         for (int t = 0; t < Pipe::NTHREADS; ++t) Pipe::phase(k, regs[t], a, c, p);
     }
