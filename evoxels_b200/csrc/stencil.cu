@@ -135,10 +135,10 @@ static int launch_ac_tile(AcParams<T> p, cudaStream_t st) {
   const int chunks = (p.nx + p.xchunk - 1) / p.xchunk;
   if (tiles > 2147483647LL || chunks > 65535) return EVX_ERR_UNSUPPORTED;
   dim3 grid((unsigned)tiles, (unsigned)chunks);
-  // 72 registers without spills at three CTAs per SM: 0.510 vs 0.540 ms at 512^3
+  // 72 registers without spills at three CTAs per SM: 0.510 vs 0.540 ms at 512^3 (four CTAs
+  // at 56 registers spill and fall back to 0.534 ms)
   static const int occ = [] { const char* e = getenv("EVX_AC_OCC"); return e ? atoi(e) : 3; }();
-  if (occ == 4) ac_tile_kernel<T, V, TY, G, 4><<<grid, Prog::NTHREADS, 0, st>>>(p);
-  else if (occ == 3) ac_tile_kernel<T, V, TY, G, 3><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  if (occ == 3) ac_tile_kernel<T, V, TY, G, 3><<<grid, Prog::NTHREADS, 0, st>>>(p);
   else ac_tile_kernel<T, V, TY, G, 2><<<grid, Prog::NTHREADS, 0, st>>>(p);
   count_launch();
   return (int)cudaGetLastError();
@@ -152,11 +152,7 @@ static int launch_ac(AcParams<T> p, cudaStream_t st) {
   const int chunks = (p.nx + p.xchunk - 1) / p.xchunk;
   if (tiles > 2147483647LL || chunks > 65535) return EVX_ERR_UNSUPPORTED;
   dim3 grid((unsigned)tiles, (unsigned)chunks);
-  static const int occ = [] { const char* e = getenv("EVX_AC_OCC"); return e ? atoi(e) : 2; }();
-  if (occ == 1)
-    ac_stage_kernel<T, V, TY, G, 1><<<grid, Prog::NTHREADS, 0, st>>>(p);
-  else
-    ac_stage_kernel<T, V, TY, G, 2><<<grid, Prog::NTHREADS, 0, st>>>(p);
+  ac_stage_kernel<T, V, TY, G, 2><<<grid, Prog::NTHREADS, 0, st>>>(p);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -183,11 +179,9 @@ int ac_stage_impl(const T* phi, const T* pot, T* k_out, const T* base, T* y_out,
                    aligned16(base) && aligned16(y_out) && aligned16(acc_in) &&
                    aligned16(acc_out) && aligned16(halo_lo) && aligned16(halo_hi);
   if (vec) {
-    static const int v = [] { const char* e = getenv("EVX_AC_V"); return e ? atoi(e) : 0; }();
-    if (v == 1) return launch_ac<T, VW, 8, 32>(p, st);      // register-window variant
     return launch_ac_tile<T, VW, 14, 16>(p, st);
   }
-  return launch_ac<T, 1, 8, 32>(p, st);
+  return launch_ac<T, 1, 8, 32>(p, st);     // register-window variant: unaligned / odd nz
 }
 
 // ------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ def timed(fn, reps=20):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
 
-res = {"n": n, "tile": os.environ.get("EVX_CH_TILE", "default")}
+res = {"n": n}
 ms = timed(lambda: _native.ch_rhs(u, out, (1, 1, 1), 3.0, 1.0, per))
 res["ch_rhs_periodic_ms"] = ms; res["ch_rhs_periodic_GBs"] = 8 * n**3 / ms / 1e6
 ms = timed(lambda: _native.ch_rhs(u, out, (1, 1, 1), 3.0, 1.0, neu))
