@@ -100,6 +100,10 @@ def test_ch_rhs_program_custom_potential_and_halos(emu):
             hi = np.ascontiguousarray(np.take(u, [b, b + 1], axis=0, mode="wrap")) if (per or b < 12) else None
             parts.append(emu_ch(emu, np.ascontiguousarray(u[a:b]), (1, 1, 1), 3.0, 1.0, bc, 3, 1, hlo=lo, hhi=hi))
         assert rel_l2(np.concatenate(parts), ref) <= 5e-12, bc
+        # every phase of the 6-fold unrolled plane loop and of the cp.async staging cells
+        for xchunk in (1, 2, 4, 5, 6, 7, 12):
+            got = emu_ch(emu, u, (1, 1, 1), 3.0, 1.0, bc, xchunk, 1)
+            assert rel_l2(got, ref) <= 5e-12, (bc, xchunk)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -111,7 +115,10 @@ def test_ac_stage_program(emu, dtype):
         acc = np.random.default_rng(4).random(shape).astype(dtype)
         for bc in BCS:
             ref = O.ac_rhs(torch.from_numpy(u)[None], sp, bc=bc, **kw)[0].numpy()
-            for vec in (0, 1):
+            # vec: 0 scalar register-window program, 1 vector register-window program,
+            #      2 shared-memory tile program (AcTileProgram - the one the library launches
+            #      for aligned shapes)
+            for vec in (0, 1, 2):
                 if vec and shape[2] % (16 // np.dtype(dtype).itemsize):
                     continue
                 k, y, a = emu_ac(emu, u, sp, kw, bc, 3, vec, alpha=0.05, beta=2.0, acc=acc)
@@ -132,6 +139,14 @@ def test_ac_stage_program_halos(emu):
             hi = np.ascontiguousarray(np.take(u, [b], axis=0, mode="wrap")) if (per or b < 12) else None
             parts.append(emu_ac(emu, np.ascontiguousarray(u[a:b]), (1, 1, 1), kw, bc, 3, 1, hlo=lo, hhi=hi)[0])
         assert rel_l2(np.concatenate(parts), ref) <= 5e-12, bc
+        for xchunk in (1, 2, 3, 5, 7):      # tile program: every prefetch / slot-rotation phase
+            parts = []
+            for a, b in [(0, 5), (5, 12)]:
+                lo = np.ascontiguousarray(np.take(u, [a - 1], axis=0, mode="wrap")) if (per or a > 0) else None
+                hi = np.ascontiguousarray(np.take(u, [b], axis=0, mode="wrap")) if (per or b < 12) else None
+                parts.append(emu_ac(emu, np.ascontiguousarray(u[a:b]), (1, 1, 1), kw, bc, xchunk, 2,
+                                    hlo=lo, hhi=hi)[0])
+            assert rel_l2(np.concatenate(parts), ref) <= 5e-12, (bc, xchunk)
 
 
 def test_pad_and_padded_stencils(emu):
