@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libevx_b200.so")
 
 BC_CODES = {"periodic": 0, "neumann": 1, "dirichlet": 2}
-FFT_AUTO, FFT_CUFFT, FFT_NATIVE = 0, 1, 2
+FFT_AUTO, FFT_CUFFT, FFT_NATIVE, FFT_NATIVE_MIXED = 0, 1, 2, 3
 
 _c_void_p, _c_int, _c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
 _dptr = ctypes.POINTER(ctypes.c_double)
@@ -305,7 +305,7 @@ class ImexPlan:
 
     @property
     def backend_name(self):
-        return {FFT_CUFFT: "cufft", FFT_NATIVE: "native"}[self.backend]
+        return {FFT_CUFFT: "cufft", FFT_NATIVE: "native", FFT_NATIVE_MIXED: "native-mixed"}[self.backend]
 
     def apply(self, u, r, out, spacing, dt, coef, power):
         """out = u + irfftn(P * rfftn(r)); u may be None (out = update only)."""

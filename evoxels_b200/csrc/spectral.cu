@@ -96,7 +96,7 @@ static int cufft_err(cufftResult r) { return r == CUFFT_SUCCESS ? 0 : EVX_ERR_CU
 
 int plan_create(evx_imex_plan** out, int nx, int ny, int nz, int is_f64, int backend) {
   if (!out || nx < 1 || ny < 1 || nz < 1) return EVX_ERR_ARG;
-  if (backend < EVX_FFT_AUTO || backend > EVX_FFT_NATIVE) return EVX_ERR_ARG;
+  if (backend < EVX_FFT_AUTO || backend > EVX_FFT_NATIVE_MIXED) return EVX_ERR_ARG;
   evx_imex_plan* p = new (std::nothrow) evx_imex_plan();
   if (!p) return EVX_ERR_ARG;
   p->nx = nx; p->ny = ny; p->nz = nz; p->is_f64 = is_f64;
@@ -112,15 +112,24 @@ int plan_create(evx_imex_plan** out, int nx, int ny, int nz, int is_f64, int bac
   p->real_elems = (size_t)nx * ny * nz;
   p->spec_elems = (size_t)p->n[0] * p->n[1] * (p->n[2] / 2 + 1);
 
+  // auto: radix-8 passes for power-of-two float32 grids, mixed-radix passes for every other
+  // grid whose extents are 7-smooth, cuFFT for the rest (a prime factor > 7 somewhere)
   const bool native_ok = !is_f64 && native_fft_supported(nx, ny, nz);
+  const bool mixed_ok = generic_fft_supported(nx, ny, nz);
   if (backend == EVX_FFT_NATIVE && !native_ok) { delete p; return EVX_ERR_UNSUPPORTED; }
-  p->backend = (backend == EVX_FFT_NATIVE || (backend == EVX_FFT_AUTO && native_ok))
-                   ? EVX_FFT_NATIVE : EVX_FFT_CUFFT;
+  if (backend == EVX_FFT_NATIVE_MIXED && !mixed_ok) { delete p; return EVX_ERR_UNSUPPORTED; }
+  if (backend == EVX_FFT_AUTO)
+    p->backend = native_ok ? EVX_FFT_NATIVE : (mixed_ok ? EVX_FFT_NATIVE_MIXED : EVX_FFT_CUFFT);
+  else
+    p->backend = backend;
 
   const size_t esz = is_f64 ? 8 : 4;
   p->real_bytes = align256(p->real_elems * esz);
   if (p->backend == EVX_FFT_NATIVE) {
     int rc = native_plan_init(p);
+    if (rc) { delete p; return rc; }
+  } else if (p->backend == EVX_FFT_NATIVE_MIXED) {
+    int rc = generic_plan_init(p);
     if (rc) { delete p; return rc; }
   } else {
     p->spec_bytes = align256(p->spec_elems * 2 * esz);
@@ -204,6 +213,8 @@ int imex_apply_impl(evx_imex_plan* p, const T* u, const T* r, T* out, void* work
   if (p->backend == EVX_FFT_NATIVE)
     return native_apply(p, (const float*)u, (const float*)r, (float*)out, workspace, h, dt, coef,
                         power, st);
+  if (p->backend == EVX_FFT_NATIVE_MIXED)
+    return generic_apply<T>(p, u, r, out, workspace, h, dt, coef, power, st);
   return apply_cufft<T>(p, u, r, out, workspace, h, dt, coef, power, st);
 }
 
@@ -222,6 +233,8 @@ int ch_step_impl(evx_imex_plan* p, const T* u, const T* hom, T* out, void* works
   int rc = ch_rhs_impl<T>(u, hom, rhs, p->nx, p->ny, p->nz, h, eps, D, per, nullptr, nullptr,
                           nullptr, st);
   if (rc) return rc;
+  if (p->backend == EVX_FFT_NATIVE_MIXED)
+    return generic_apply<T>(p, u, rhs, out, workspace, h, dt, 2.0 * eps * D * A, 2, st);
   return apply_cufft<T>(p, u, rhs, out, workspace, h, dt, 2.0 * eps * D * A, 2, st);
 }
 

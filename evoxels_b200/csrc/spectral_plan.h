@@ -25,6 +25,13 @@ namespace evx {
 int plan_create(evx_imex_plan** out, int nx, int ny, int nz, int is_f64, int backend);
 int plan_destroy(evx_imex_plan* p);
 
+// fft_generic.cu (mixed-radix passes: extents with prime factors <= 7, float32 / float64)
+bool generic_fft_supported(int nx, int ny, int nz);
+int generic_plan_init(evx_imex_plan* p);
+template <typename R>
+int generic_apply(evx_imex_plan* p, const R* u, const R* r, R* out, void* workspace,
+                  const double* h, double dt, double coef, int power, cudaStream_t st);
+
 // fft_native.cu
 bool native_fft_supported(int nx, int ny, int nz);
 int native_plan_init(evx_imex_plan* p);

@@ -96,7 +96,7 @@ class PseudoSpectralIMEX(TimeStepper):
     u+ = u + F^-1[ dt / (1 - dt * symbol) * F[ rhs(u) ] ]."""
     problem: SemiLinearODE
     dt: float
-    fft_backend: str = "auto"      # 'auto' | 'cufft' | 'native'
+    fft_backend: str = "auto"      # 'auto' | 'cufft' | 'native' | 'native-mixed'
 
     def __post_init__(self):
         self.problem.verify_fft_bc_config()
@@ -120,7 +120,8 @@ class PseudoSpectralIMEX(TimeStepper):
         key = (tuple(shape), dtype, str(device))
         if key not in self._plans:
             code = {"auto": _native.FFT_AUTO, "cufft": _native.FFT_CUFFT,
-                    "native": _native.FFT_NATIVE}[self.fft_backend]
+                    "native": _native.FFT_NATIVE,
+                    "native-mixed": _native.FFT_NATIVE_MIXED}[self.fft_backend]
             self._plans[key] = _native.ImexPlan(shape, dtype, device, code)
         return self._plans[key]
 

@@ -42,6 +42,8 @@ extern "C" {
 #define EVX_FFT_AUTO 0
 #define EVX_FFT_CUFFT 1   /* cuFFT R2C/C2R + fused filter / add kernels (any extents)   */
 #define EVX_FFT_NATIVE 2  /* hand-written sm_100a pass kernels (power-of-two extents)   */
+#define EVX_FFT_NATIVE_MIXED 3 /* hand-written mixed-radix passes: any extents whose prime
+                                  factors are <= 7 (e.g. the README's 100^3), fp32 and fp64 */
 
 int evx_version(void);
 const char* evx_strerror(int code);
@@ -137,12 +139,13 @@ typedef struct evx_imex_plan evx_imex_plan;
  * 203-207) and the stored prefactor array built from VoxelGrid.rfft_k_squared
  * (evoxels/voxelgrid.py:84-90,110-114): wavenumbers are recomputed on the fly in float32
  * with the reference's rounding sequence, nothing of size O(N^3) is stored.
- *   is_f64   0: float32 fields, 1: float64 fields (always cuFFT back end)
- *   backend  EVX_FFT_AUTO / EVX_FFT_CUFFT / EVX_FFT_NATIVE (ERR_UNSUPPORTED if the extents
- *            are not all powers of two in the supported range)                        */
+ *   is_f64   0: float32 fields, 1: float64 fields (mixed-radix or cuFFT back end)
+ *   backend  EVX_FFT_AUTO picks EVX_FFT_NATIVE for power-of-two float32 grids, else
+ *            EVX_FFT_NATIVE_MIXED when every extent is 7-smooth, else EVX_FFT_CUFFT; asking
+ *            for a back end that cannot do the grid returns EVX_ERR_UNSUPPORTED         */
 int evx_imex_plan_create(evx_imex_plan** plan, int nx, int ny, int nz, int is_f64, int backend);
 int evx_imex_plan_destroy(evx_imex_plan* plan);
-int evx_imex_plan_backend(const evx_imex_plan* plan);            /* EVX_FFT_CUFFT|NATIVE */
+int evx_imex_plan_backend(const evx_imex_plan* plan);   /* EVX_FFT_CUFFT|NATIVE|NATIVE_MIXED */
 /* bytes of caller-provided scratch every apply/step call needs (256-byte aligned) */
 int evx_imex_plan_workspace_bytes(const evx_imex_plan* plan, size_t* bytes);
 

@@ -399,3 +399,65 @@ int emu_ch_rhs_vjp_f64(const double* u, const double* w, double* lam, double* de
   return 0;
 }
 }
+
+// =====================================================================================
+// mixed-radix passes (non-power-of-two extents)
+// =====================================================================================
+#include "../../evoxels_b200/csrc/fft_generic_core.h"
+template <typename R>
+static int emu_generic_pass(const GenericParams<R>& p, long long nblocks, int nthreads) {
+  std::vector<gcplx<R>> smem(GenericProgram<R>::smem_elems(p));
+  const int nph = GenericProgram<R>::nphases(p);
+  for (long long b = 0; b < nblocks; ++b)
+    for (int k = 0; k < nph; ++k)
+      for (int t = 0; t < nthreads; ++t) GenericProgram<R>::phase(k, p, smem.data(), b, t, nthreads);
+  return 0;
+}
+
+template <typename R>
+static int emu_generic_apply(const R* u, const R* r, R* out, int nx, int ny, int nz, const double* h,
+                             double dt, double coef, int power, int W, int nthreads) {
+  LineDesc lx, ly, lz;
+  if (!factor_line(nx, lx) || !factor_line(ny, ly) || !factor_line(nz, lz)) return -1;
+  const int P = ((nz / 2 + 1 + 7) / 8) * 8;
+  std::vector<gcplx<R>> spec((size_t)nx * ny * P, gcplx<R>{R(0), R(0)});
+  auto roots = [](int n) {
+    std::vector<gcplx<R>> w(n);
+    for (int m = 0; m < n; ++m) {
+      const double a = -2.0 * M_PI * (double)m / (double)n;
+      w[m] = gcplx<R>{(R)std::cos(a), (R)std::sin(a)};
+    }
+    return w;
+  };
+  auto twx = roots(nx), twy = roots(ny), twz = roots(nz);
+  GenericParams<R> p{};
+  p.spec = spec.data(); p.nz = nz; p.P = P; p.rows = (long long)nx * ny; p.ncols_valid = nz / 2 + 1;
+  p.W = W;
+  p.mode = GEN_Z_FWD; p.line = lz; p.tw = twz.data(); p.real_in = r; p.real_out = nullptr;
+  emu_generic_pass(p, (p.rows + W - 1) / W, nthreads);
+  GenericParams<R> y = p;
+  y.mode = GEN_FWD; y.line = ly; y.tw = twy.data();
+  y.line_stride = P; y.group_stride = (long long)ny * P; y.ncols_total = (long long)nx * P;
+  emu_generic_pass(y, (y.ncols_total + W - 1) / W, nthreads);
+  GenericParams<R> x = p;
+  x.mode = GEN_XMID; x.line = lx; x.tw = twx.data();
+  x.line_stride = (long long)ny * P; x.group_stride = P; x.ncols_total = (long long)ny * P;
+  const int n[3] = {nx, ny, nz};
+  x.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
+  emu_generic_pass(x, (x.ncols_total + W - 1) / W, nthreads);
+  y.mode = GEN_INV;
+  emu_generic_pass(y, (y.ncols_total + W - 1) / W, nthreads);
+  p.mode = GEN_Z_INV; p.real_in = u; p.real_out = out;
+  emu_generic_pass(p, (p.rows + W - 1) / W, nthreads);
+  return 0;
+}
+extern "C" {
+int emu_generic_apply_f32(const float* u, const float* r, float* out, int nx, int ny, int nz,
+                          const double* h, double dt, double coef, int power, int W, int nthreads) {
+  return emu_generic_apply<float>(u, r, out, nx, ny, nz, h, dt, coef, power, W, nthreads);
+}
+int emu_generic_apply_f64(const double* u, const double* r, double* out, int nx, int ny, int nz,
+                          const double* h, double dt, double coef, int power, int W, int nthreads) {
+  return emu_generic_apply<double>(u, r, out, nx, ny, nz, h, dt, coef, power, W, nthreads);
+}
+}

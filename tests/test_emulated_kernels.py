@@ -247,6 +247,34 @@ def test_rd2_rhs_program(emu, dtype):
                 assert rel_l2(out, ref) <= tol, (shape, custom, vec)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,W,nthreads", [((10, 12, 14), 8, 32), ((9, 7, 5), 4, 7), ((16, 1, 1), 8, 16),
+                                              ((1, 6, 1), 2, 5), ((20, 25, 18), 8, 64), ((3, 4, 35), 1, 3),
+                                              ((8, 8, 16), 8, 32), ((21, 2, 49), 8, 33)])
+def test_mixed_radix_fft_pipeline(emu, shape, W, nthreads, dtype):
+    """The mixed-radix passes (fft_generic_core.h: extents with prime factors <= 7, odd and
+    degenerate axes included) replayed on the CPU against the oracle's IMEX and ETD1 steps."""
+    nx, ny, nz = shape
+    rng = np.random.default_rng(2)
+    r = rng.standard_normal(shape).astype(dtype)
+    u = rng.random(shape).astype(dtype)
+    sp = (1.0, 0.5, 2.0)
+    h = (ctypes.c_double * 3)(*sp)
+    d = ctypes.c_double
+    f = emu.emu_generic_apply_f32 if dtype == np.float32 else emu.emu_generic_apply_f64
+    tol = 2e-6 if dtype == np.float32 else 2e-7      # fp64: the weight is float32 upstream
+    out = np.zeros(shape, dtype)
+    assert f(_p(u), _p(r), _p(out), nx, ny, nz, h, d(0.1), d(1.5), 2, W, nthreads) == 0
+    pref = O.imex_prefactor(O.ch_symbol(shape, sp, 3.0, 1.0, 0.25), 0.1)
+    want = O.imex_step(torch.from_numpy(u)[None], torch.from_numpy(r)[None], pref)[0].numpy()
+    assert rel_l2(out - u, want - u) < tol, rel_l2(out - u, want - u)
+    out = np.zeros(shape, dtype)
+    assert f(_p(u), _p(r), _p(out), nx, ny, nz, h, d(0.3), d(0.7), 1 | 0x100, W, nthreads) == 0
+    sym = -0.7 * O.k_squared(shape, sp)
+    want = O.etd1_step(torch.from_numpy(u)[None], torch.from_numpy(r)[None], sym, 0.3)[0].numpy()
+    assert rel_l2(out - u, want - u) < tol
+
+
 def test_ch_rhs_adjoint_against_autograd(emu):
     """The hand-written VJP of the periodic CH rhs (adjoint_core.h) against torch autograd
     through the oracle, float64, values outside [0,1] included (clip mask)."""

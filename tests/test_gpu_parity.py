@@ -161,7 +161,8 @@ def test_ac_vs_live_oracle(cuda_device, shape, bc):
 @pytest.mark.parametrize("shape,backend", [((64, 64, 64), "cufft"), ((100, 100, 100), "cufft"),
                                            ((33, 20, 18), "cufft"), ((128, 64, 256), "cufft"),
                                            ((64, 64, 64), "native"), ((128, 64, 256), "native"),
-                                           ((256, 256, 256), "native")])
+                                           ((256, 256, 256), "native"), ((100, 100, 100), "native-mixed"),
+                                           ((35, 20, 18), "native-mixed"), ((64, 64, 64), "native-mixed")])
 def test_ch_imex_step_vs_live_oracle(cuda_device, shape, backend):
     u = O.noise_field(shape, seed=0)
     orc = O.CHOracle(shape, (1.0, 1.0, 1.0), 0.1)
@@ -214,12 +215,51 @@ def test_on_the_fly_prefactor_is_the_reference_array(cuda_device):
         assert (got == g["prefac"]).mean() >= 0.9, name      # bit-identical almost everywhere
 
 
-def test_native_fft_unsupported_sizes_fall_back(cuda_device):
-    assert _native.ImexPlan((100, 100, 100), torch.float32, "cuda").backend_name == "cufft"
-    assert _native.ImexPlan((64, 64, 64), torch.float32, "cuda").backend_name == "native"
-    assert _native.ImexPlan((64, 64, 64), torch.float64, "cuda").backend_name == "cufft"
+def test_fft_backend_selection(cuda_device):
+    P = _native.ImexPlan
+    assert P((64, 64, 64), torch.float32, "cuda").backend_name == "native"          # radix-8 passes
+    assert P((100, 100, 100), torch.float32, "cuda").backend_name == "native-mixed"  # 2^2 5^2
+    assert P((64, 64, 64), torch.float64, "cuda").backend_name == "native-mixed"     # fp64
+    assert P((12, 9, 7), torch.float32, "cuda").backend_name == "native-mixed"
+    assert P((16, 1, 1), torch.float32, "cuda").backend_name == "native-mixed"       # degenerate axes
+    assert P((22, 8, 8), torch.float32, "cuda").backend_name == "cufft"              # prime factor 11
+    assert P((100, 100, 100), torch.float32, "cuda", _native.FFT_CUFFT).backend_name == "cufft"
     with pytest.raises(_native.NativeLibraryError):
-        _native.ImexPlan((100, 64, 64), torch.float32, "cuda", _native.FFT_NATIVE)
+        P((100, 64, 64), torch.float32, "cuda", _native.FFT_NATIVE)
+    with pytest.raises(_native.NativeLibraryError):
+        P((22, 8, 8), torch.float32, "cuda", _native.FFT_NATIVE_MIXED)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("shape", [(100, 100, 100), (12, 9, 7), (16, 1, 1), (1, 6, 1), (48, 40, 126),
+                                   (35, 27, 50), (64, 64, 64), (3, 2048, 5)])
+def test_mixed_radix_fft_backend_matches_cufft_backend_and_oracle(cuda_device, shape, dtype):
+    """The hand-written mixed-radix passes against the cuFFT back end (same filter arithmetic)
+    and against the oracle's IMEX / ETD1 updates."""
+    sp = (1.0, 0.5, 2.0)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    u = torch.rand(shape, device="cuda", generator=gen).to(dtype)
+    r = torch.randn(shape, device="cuda", generator=gen).to(dtype)
+    mixed = _native.ImexPlan(shape, dtype, "cuda", _native.FFT_NATIVE_MIXED)
+    lib = _native.ImexPlan(shape, dtype, "cuda", _native.FFT_CUFFT)
+    tol = 3e-6 if dtype == torch.float32 else 1e-10
+    for dt, coef, power in ((0.1, 1.5, 2), (0.3, 0.7, 1), (0.3, 0.7, 1 | _native.FILTER_ETD1)):
+        a, b = torch.empty_like(u), torch.empty_like(u)
+        mixed.apply(u, r, a, sp, dt, coef, power)
+        lib.apply(u, r, b, sp, dt, coef, power)
+        assert rel_l2((a - u).cpu().numpy(), (b - u).cpu().numpy()) <= tol, (dt, coef, power)
+    if max(shape) <= 132:
+        with torch.device("cpu"):
+            pref = O.imex_prefactor(O.ch_symbol(shape, sp, 3.0, 1.0, 0.25), 0.1)
+            want = O.imex_step(u.cpu()[None], r.cpu()[None], pref)[0]
+        a = torch.empty_like(u)
+        mixed.apply(u, r, a, sp, 0.1, 1.5, 2)
+        assert rel_l2((a - u).cpu().numpy(), (want - u.cpu()).numpy()) <= (3e-6 if dtype == torch.float32 else 2e-7)
+    # update-only form (u = NULL) used by the mirrored-x path
+    a, b = torch.empty_like(u), torch.empty_like(u)
+    mixed.apply(None, r, a, sp, 0.1, 1.5, 2)
+    lib.apply(None, r, b, sp, 0.1, 1.5, 2)
+    assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) <= tol
 
 
 def test_ch_nonperiodic_x_imex(cuda_device):
