@@ -192,12 +192,18 @@ class CudaOps:
             self.plan = _native.DistPlan(slab.global_shape, slab.world, slab.rank, device)
             self.spec = self.plan.new_buffer()
             if self.transport in ("p2p", "ce"):
-                self.peers = PeerBuffers(self.plan.block_shape, self.device, group)
-                self.buf_a, self.buf_b = self.peers.bufs
-                if self.transport == "ce":
-                    _, ny, nz = slab.global_shape
-                    self.halos = PeerHalos(2, ny, nz, self.device, group, slab.world, slab.rank)
-            else:
+                try:
+                    self.peers = PeerBuffers(self.plan.block_shape, self.device, group)
+                    if self.transport == "ce":
+                        _, ny, nz = slab.global_shape
+                        self.halos = PeerHalos(2, ny, nz, self.device, group, slab.world, slab.rank)
+                    self.buf_a, self.buf_b = self.peers.bufs
+                except Exception as exc:      # no symmetric memory on this platform / topology
+                    import warnings
+                    warnings.warn(f"torch symmetric memory is not available ({exc}); the slab<->pencil "
+                                  "transposes use NCCL all-to-all instead of peer memory")
+                    self.peers, self.transport = None, "nccl"
+            if self.transport == "nccl":
                 self.buf_a = self.plan.new_buffer()
                 self.buf_b = self.plan.new_buffer()
 
