@@ -40,6 +40,7 @@ _FILTER_ARGS = [_c_void_p, _c_int, _c_int, _c_int, _dptr, _c_double, _c_double, 
                 _c_double, _c_void_p]
 
 FILTER_ETD1 = 0x100      # EVX_FILTER_ETD1: OR into `power` for the exponential-Euler weight
+SCHED_RING_INV, SCHED_CHUNK_RHS = 1, 2     # EVX_SCHED_*: options of the L2-blocked schedule
 
 SIGNATURES = {
     "evx_version": [],
@@ -54,6 +55,8 @@ SIGNATURES = {
     "evx_imex_plan_destroy": [_c_void_p],
     "evx_imex_plan_backend": [_c_void_p],
     "evx_imex_plan_workspace_bytes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t)],
+    "evx_imex_plan_set_schedule": [_c_void_p, _c_int, _c_int, _c_int],
+    "evx_imex_plan_get_schedule": [_c_void_p, _iptr, _iptr, _iptr],
     "evx_imex_apply_f32": _APPLY_ARGS, "evx_imex_apply_f64": _APPLY_ARGS,
     "evx_ch_imex_step_f32": _STEP_ARGS, "evx_ch_imex_step_f64": _STEP_ARGS,
     "evx_imex_native_pass_f32": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _dptr,
@@ -302,6 +305,8 @@ class ImexPlan:
             self.workspace = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8,
                                          device=self.device)
         self.backend = int(lib.evx_imex_plan_backend(handle))
+        self.tuned = False         # tune_ch_step has run (or a schedule was forced)
+        self.tune_report = None
 
     @property
     def backend_name(self):
@@ -337,6 +342,89 @@ class ImexPlan:
                 _ptr(self.workspace), _h3(spacing), float(dt), float(eps), float(D), float(A),
                 _stream(u)), "evx_ch_imex_step")
         return out
+
+    # ---- L2-blocked launch schedule (native back end) --------------------------------------
+    def set_schedule(self, chunk_planes=0, streams=1, flags=0):
+        """chunk_planes x-planes per chunk of the z/y pass pairs (0: one launch per pass), on
+        1 or 2 streams, flags = SCHED_RING_INV | SCHED_CHUNK_RHS (include/evoxels_b200.h)."""
+        with torch.cuda.device(self.device):
+            check(load_library().evx_imex_plan_set_schedule(
+                self._handle, int(chunk_planes), int(streams), int(flags)),
+                "evx_imex_plan_set_schedule")
+
+    def schedule(self):
+        c, s, f = _c_int(), _c_int(), _c_int()
+        check(load_library().evx_imex_plan_get_schedule(
+            self._handle, ctypes.byref(c), ctypes.byref(s), ctypes.byref(f)),
+            "evx_imex_plan_get_schedule")
+        return int(c.value), int(s.value), int(f.value)
+
+    def schedule_candidates(self):
+        """Chunk sizes worth timing: powers of two and the plane counts whose y-pass tiles
+        fill k waves of the persistent grid (2 CTAs on each of the SMs), each with one or two
+        streams and the ring options."""
+        nx, ny, nz = self.shape
+        cap = min(32, nx // 4)
+        if cap < 2:
+            return []
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        tiles_per_plane = max(1, (((nz // 2 + 1 + 7) // 8) * 8) // 8)
+        sizes = {x for x in (8, 16, 32) if x <= cap}
+        sizes |= {k * 2 * sms // tiles_per_plane for k in (1, 2, 3)}
+        sizes = sorted(x for x in sizes if 2 <= x <= cap)
+        return [(x, st, fl) for x in sizes for st in (2, 1)
+                for fl in (SCHED_RING_INV, SCHED_RING_INV | SCHED_CHUNK_RHS, 0)]
+
+    def tune_ch_step(self, u, spacing, dt, eps, D, A, budget_s=1.5, min_gain=0.03, log=None):
+        """Time the fused CH step under every candidate schedule (CUDA events on the current
+        stream) and keep the fastest one that reproduces the one-launch-per-pass result bit for
+        bit.  The measurement runs the real step on the caller's field `u` ([nx,ny,nz]) into
+        scratch outputs; nothing the caller owns is modified.  Returns (schedule, report)."""
+        self.tuned = True
+        report = {"candidates": []}
+        if self.backend != FFT_NATIVE:
+            return self.schedule(), report
+        cands = self.schedule_candidates()
+        free, _total = torch.cuda.mem_get_info(self.device)
+        if not cands or free < 3 * u.numel() * u.element_size():
+            report["skipped"] = "no candidates" if not cands else "not enough free memory"
+            return self.schedule(), report
+        ref = torch.empty_like(u)
+        got = torch.empty_like(u)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def timed(sched, out, reps):
+            self.set_schedule(*sched)
+            self.ch_step(u, out, spacing, dt, eps, D, A)          # warm-up + the result to compare
+            a.record()
+            for _ in range(reps):
+                self.ch_step(u, out, spacing, dt, eps, D, A)
+            b.record()
+            b.synchronize()
+            return a.elapsed_time(b) / reps
+
+        base = (0, 1, 0)
+        t_base = timed(base, ref, 3)
+        reps = 4
+        if t_base * 1e-3 * (reps + 1) * len(cands) > budget_s:       # large grids: fewer candidates
+            cands = [c for c in cands if c[1] == 2 and c[2] != 0][:6]
+            reps = 2
+        best, t_best = base, t_base
+        report.update(baseline_ms=t_base)
+        for sched in cands:
+            t = timed(sched, got, reps)
+            same = bool(torch.equal(got, ref))
+            report["candidates"].append({"schedule": sched, "ms": t, "bit_identical": same})
+            if log:
+                log(f"evoxels_b200 tune {self.shape}: {sched} {t:.3f} ms "
+                    f"(baseline {t_base:.3f}){'' if same else '  MISMATCH - rejected'}")
+            if same and t < t_best:
+                best, t_best = sched, t
+        if t_best > (1.0 - min_gain) * t_base:
+            best, t_best = base, t_base
+        self.set_schedule(*best)
+        report.update(chosen=best, chosen_ms=t_best)
+        return best, report
 
     def close(self):
         if self._handle is not None and _lib is not None:

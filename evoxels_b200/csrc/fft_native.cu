@@ -8,6 +8,7 @@
 #include "evx_internal.h"
 #include "spectral_plan.h"
 #include "fft_pass_core.h"
+#include "native_schedule.h"
 
 namespace evx {
 
@@ -182,7 +183,9 @@ int native_plan_init(evx_imex_plan* p) {
   const int M = p->nz / 2;
   p->spec_pitch = ((M + 1 + kPitchAlign - 1) / kPitchAlign) * kPitchAlign;
   p->spec_bytes = ((size_t)p->nx * p->ny * p->spec_pitch * sizeof(cf) + 255) & ~(size_t)255;
-  p->work_bytes = 0;
+  // two chunk-sized slots behind the spectrum for the ring option of the L2-blocked schedule
+  p->ring_planes = p->nx >= 16 ? (p->nx / 4 < kMaxChunkPlanes ? p->nx / 4 : kMaxChunkPlanes) : 0;
+  p->work_bytes = (2 * (size_t)p->ring_planes * p->ny * p->spec_pitch * sizeof(cf) + 255) & ~(size_t)255;
   // tables: W_nx | W_ny | W_M | W_nz[0..M]
   const size_t total = (size_t)p->nx + p->ny + M + (M + 1);
   std::vector<cf> host(total);
@@ -198,43 +201,85 @@ int native_plan_init(evx_imex_plan* p) {
 }
 
 void native_plan_free(evx_imex_plan* p) {
-  if (p && p->twiddles) { cudaFree(p->twiddles); p->twiddles = nullptr; }
+  if (!p) return;
+  if (p->twiddles) { cudaFree(p->twiddles); p->twiddles = nullptr; }
+  for (int i = 0; i < 6; ++i)
+    if (p->ev[i]) { cudaEventDestroy(p->ev[i]); p->ev[i] = nullptr; }
+  if (p->side) { cudaStreamDestroy(p->side); p->side = nullptr; }
+}
+
+// ---- schedule execution (native_schedule.h builds the operation list) ----------------
+static NativeDims dims_of(const evx_imex_plan* p) {
+  return NativeDims{p->nx, p->ny, p->nz, p->nz / 2, p->spec_pitch};
+}
+
+static NativeBufs bufs_of(const evx_imex_plan* p, const float* u, const float* r, float* out,
+                          void* workspace) {
+  NativeBufs b;
+  b.u = u; b.r = r; b.out = out;
+  b.spec = reinterpret_cast<cf*>((char*)workspace + p->real_bytes);
+  b.ring_slot_elems = (long long)p->ring_planes * p->ny * p->spec_pitch;
+  b.ring = p->ring_planes ? reinterpret_cast<cf*>((char*)workspace + p->real_bytes + p->spec_bytes)
+                          : nullptr;
+  b.twx = (const cf*)p->twiddles;
+  b.twy = b.twx + p->nx;
+  b.twz = b.twy + p->ny;
+  b.twr = b.twz + p->nz / 2;
+  return b;
+}
+
+// rhs_u != null: fused CH step, OP_RHS evaluates the rhs of rhs_u into the real scratch
+static int run_schedule(evx_imex_plan* p, const NativeBufs& b, const float* rhs_u, const double* h,
+                        double dt, double coef, int power, double eps, double D, cudaStream_t st) {
+  const NativeDims d = dims_of(p);
+  std::vector<SchedOp> ops;
+  build_schedule(d.nx, p->chunk_planes, p->side ? p->chunk_streams : 1, p->chunk_flags,
+                 p->ring_planes, rhs_u != nullptr, ops);
+  const int per[3] = {BC_PERIODIC, BC_PERIODIC, BC_PERIODIC};
+  for (const SchedOp& o : ops) {
+    cudaStream_t s = o.stream ? p->side : st;
+    int rc = EVX_OK;
+    switch (o.kind) {
+      case OP_RHS: {
+        const RhsChunk k = rhs_chunk(d, rhs_u, const_cast<float*>(b.r), o);
+        rc = ch_rhs_impl<float>(k.c, nullptr, k.out, o.nxc, d.ny, d.nz, h, eps, D, per, nullptr,
+                                k.halo_lo, k.halo_hi, s);
+        break;
+      }
+      case OP_ZFWD: rc = launch_z<false>(d.M, z_chunk_params(d, b, o), s); break;
+      case OP_ZINV: rc = launch_z<true>(d.M, z_chunk_params(d, b, o), s); break;
+      case OP_YFWD: rc = launch_strided<PASS_FWD>(d.ny, y_chunk_params(d, b, o), s); break;
+      case OP_YINV: rc = launch_strided<PASS_INV>(d.ny, y_chunk_params(d, b, o), s); break;
+      case OP_XMID: rc = launch_xmid(d.nx, x_params(d, b, h, dt, coef, power), s); break;
+      case OP_RECORD: rc = (int)cudaEventRecord(p->ev[o.event], s); break;
+      case OP_WAIT: rc = (int)cudaStreamWaitEvent(s, p->ev[o.event], 0); break;
+      default: rc = EVX_ERR_ARG;
+    }
+    if (rc) return rc;
+  }
+  return EVX_OK;
 }
 
 int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, void* workspace,
                  const double* h, double dt, double coef, int power, cudaStream_t st) {
-  const int nx = p->nx, ny = p->ny, nz = p->nz, M = nz / 2, P = p->spec_pitch;
-  cf* spec = reinterpret_cast<cf*>((char*)workspace + p->real_bytes);
-  const cf* twx = (const cf*)p->twiddles;
-  const cf* twy = twx + nx;
-  const cf* twz = twy + ny;
-  const cf* twr = twz + M;
+  return run_schedule(p, bufs_of(p, u, r, out, workspace), nullptr, h, dt, coef, power, 0.0, 0.0, st);
+}
 
-  ZParams zp;
-  zp.real_in = r; zp.real_out = nullptr; zp.spec = spec; zp.tw = twz; zp.twr = twr;
-  zp.rows = (long long)nx * ny; zp.nz = nz; zp.P = P;
-  int rc = launch_z<false>(M, zp, st);
-  if (rc) return rc;
-
-  StridedParams yp;
-  yp.in = spec; yp.out = spec; yp.tw = twy;
-  yp.src = yp.dst = plain_io(P, (long long)ny * P, ny);
-  yp.P = P; yp.ncols_valid = M + 1; yp.ncols_total = (long long)nx * P;
-  yp.kother_offset = 0; yp.use_peers = 0; yp.max_ctas = 0;
-  yp.filt = FilterParams{};
-  if ((rc = launch_strided<PASS_FWD>(ny, yp, st))) return rc;
-
-  StridedParams xp = yp;
-  xp.tw = twx; xp.src = xp.dst = plain_io((long long)ny * P, P, nx);
-  xp.ncols_total = (long long)ny * P;
-  const int n[3] = {nx, ny, nz};
-  xp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
-  if ((rc = launch_xmid(nx, xp, st))) return rc;
-
-  if ((rc = launch_strided<PASS_INV>(ny, yp, st))) return rc;
-
-  zp.real_in = u; zp.real_out = out;
-  return launch_z<true>(M, zp, st);
+int native_set_schedule(evx_imex_plan* p, int chunk_planes, int streams, int flags) {
+  if (chunk_planes < 0 || streams < 1 || streams > 2 || (flags & ~(SCHED_RING_INV | SCHED_CHUNK_RHS)))
+    return EVX_ERR_ARG;
+  if (streams == 2 && !p->side) {
+    cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { p->side = nullptr; return (int)e; }
+    for (int i = 0; i < 6; ++i) {
+      e = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) return (int)e;
+    }
+  }
+  p->chunk_planes = chunk_planes;
+  p->chunk_streams = streams;
+  p->chunk_flags = flags;
+  return EVX_OK;
 }
 
 // one pass of the pipeline on the plan's scratch (measurement aid for bench.py's per-kernel
@@ -274,12 +319,16 @@ int native_single_pass(evx_imex_plan* p, int which, const float* u, const float*
 int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* out,
                    void* workspace, const double* h, double dt, double eps, double D, double A,
                    cudaStream_t st) {
-  const int per[3] = {BC_PERIODIC, BC_PERIODIC, BC_PERIODIC};
   float* rhs = (float*)workspace;
-  int rc = ch_rhs_impl<float>(u, hom, rhs, p->nx, p->ny, p->nz, h, eps, D, per, nullptr, nullptr,
-                              nullptr, st);
-  if (rc) return rc;
-  return native_apply(p, u, rhs, out, workspace, h, dt, 2.0 * eps * D * A, 2, st);
+  const double coef = 2.0 * eps * D * A;
+  if (hom) {   // user potential field: the rhs kernel takes no halos with it -> one launch
+    const int per[3] = {BC_PERIODIC, BC_PERIODIC, BC_PERIODIC};
+    int rc = ch_rhs_impl<float>(u, hom, rhs, p->nx, p->ny, p->nz, h, eps, D, per, nullptr, nullptr,
+                                nullptr, st);
+    if (rc) return rc;
+    return native_apply(p, u, rhs, out, workspace, h, dt, coef, 2, st);
+  }
+  return run_schedule(p, bufs_of(p, u, rhs, out, workspace), u, h, dt, coef, 2, eps, D, st);
 }
 
 // ------------------------------------------------------------------------------------

@@ -18,6 +18,15 @@ struct evx_imex_plan {
   // native back end
   void* twiddles = nullptr;    // device table(s), owned
   int spec_pitch = 0;          // complex elements per (x,y) row of the native spectrum
+  // native back end: L2-blocked schedule (evx_imex_plan_set_schedule; 0 planes = one launch
+  // per pass).  The z/y pass pairs walk the grid in chunks of `chunk_planes` x planes so that
+  // the spectrum written by the first pass of a pair is still in L2 when the second reads it.
+  int chunk_planes = 0;
+  int chunk_streams = 1;       // 2: second pass of chunk i on `side`, next to the first of chunk i+1
+  int chunk_flags = 0;         // EVX_SCHED_* bits
+  int ring_planes = 0;         // capacity of one inverse-ring slot in x planes (0: no ring)
+  cudaStream_t side = nullptr; // owned; created on demand
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace evx {
@@ -41,6 +50,7 @@ int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, v
 int native_single_pass(evx_imex_plan* p, int which, const float* u, const float* r, float* out,
                        void* workspace, const double* h, double dt, double coef, int power,
                        cudaStream_t st);
+int native_set_schedule(evx_imex_plan* p, int chunk_planes, int streams, int flags);
 int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* out,
                    void* workspace, const double* h, double dt, double eps, double D, double A,
                    cudaStream_t st);

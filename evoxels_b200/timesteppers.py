@@ -20,6 +20,8 @@ and not provided.
 """
 from __future__ import annotations
 
+import os
+import warnings
 from abc import ABC, abstractmethod
 from dataclasses import dataclass
 from typing import Any
@@ -125,6 +127,38 @@ class PseudoSpectralIMEX(TimeStepper):
             self._plans[key] = _native.ImexPlan(shape, dtype, device, code)
         return self._plans[key]
 
+    # Launch schedule of the native pipeline (see include/evoxels_b200.h,
+    # evx_imex_plan_set_schedule): like an FFT library's "measure" planning, the first large
+    # periodic CH step times the L2-blocked schedules against the one-launch-per-pass baseline
+    # and keeps the fastest one whose result is bit-identical.  EVX_TUNE=0 keeps the baseline,
+    # EVX_SCHEDULE="planes,streams,flags" forces a schedule.
+    TUNE_MIN_VOXELS = 1 << 24
+
+    def _choose_schedule(self, plan, u3, spacing):
+        prob = self.problem
+        forced = os.environ.get("EVX_SCHEDULE")
+        if plan.backend != _native.FFT_NATIVE:
+            plan.tuned = True
+            return
+        if forced:
+            plan.set_schedule(*[int(v) for v in forced.split(",")])
+            plan.tuned = True
+            return
+        if os.environ.get("EVX_TUNE", "1") == "0" or u3.numel() < self.TUNE_MIN_VOXELS:
+            plan.tuned = True
+            return
+        if torch.cuda.is_current_stream_capturing():
+            return                       # no timing inside a graph capture; try again later
+        try:
+            log = print if os.environ.get("EVX_TUNE_VERBOSE") else None
+            _, plan.tune_report = plan.tune_ch_step(u3, spacing, self.dt, prob.eps, prob.D, prob.A,
+                                                    log=log)
+        except Exception as exc:          # keep stepping with the baseline schedule
+            plan.tuned = True
+            warnings.warn(f"evoxels_b200: schedule tuning failed ({exc!r}); "
+                          "keeping one launch per pass")
+            plan.set_schedule(0, 1, 0)
+
     def step(self, t, u):
         _native.require_cuda(u)
         prob = self.problem
@@ -142,6 +176,8 @@ class PseudoSpectralIMEX(TimeStepper):
         if isinstance(prob, CahnHilliard) and periodic:
             plan = self._plan(u.shape[1:], u.dtype, u.device)
             hom = prob.hom_field(u)
+            if not plan.tuned and hom is None:
+                self._choose_schedule(plan, u[0], spacing)
             for ch in range(u.shape[0]):
                 plan.ch_step(u[ch], out[ch], spacing, self.dt, prob.eps, prob.D, prob.A,
                              hom=None if hom is None else hom[ch])

@@ -149,6 +149,25 @@ int evx_imex_plan_backend(const evx_imex_plan* plan);   /* EVX_FFT_CUFFT|NATIVE|
 /* bytes of caller-provided scratch every apply/step call needs (256-byte aligned) */
 int evx_imex_plan_workspace_bytes(const evx_imex_plan* plan, size_t* bytes);
 
+/* L2-blocked launch schedule of the EVX_FFT_NATIVE back end (others: EVX_ERR_UNSUPPORTED).
+ * chunk_planes = 0 (default): every pass is one launch over the whole grid and the spectrum
+ * crosses HBM between any two passes.  chunk_planes = X > 0: the z and y passes of each
+ * direction run pairwise on chunks of X x-planes, so that the second pass of a pair reads the
+ * chunk the first one wrote from L2 (X * ny * nz * 8 B should stay well below the 126 MB L2).
+ *   streams  1, or 2: the second pass of chunk i is enqueued on a stream owned by the plan,
+ *            next to the first pass of chunk i+1 (forked from / joined to `stream` with events;
+ *            legal inside CUDA-graph capture)
+ *   flags    EVX_SCHED_RING_INV: the inverse y pass writes a two-slot ring in the workspace
+ *            instead of the spectrum (no write-back of data that is read exactly once);
+ *            EVX_SCHED_CHUNK_RHS: evx_ch_imex_step_f32 also evaluates the rhs per chunk.
+ * Results are bit-identical for every schedule (same kernels on sub-ranges).  The setting is
+ * part of the plan; do not change it while work of this plan is being enqueued elsewhere. */
+#define EVX_SCHED_RING_INV 1
+#define EVX_SCHED_CHUNK_RHS 2
+int evx_imex_plan_set_schedule(evx_imex_plan* plan, int chunk_planes, int streams, int flags);
+int evx_imex_plan_get_schedule(const evx_imex_plan* plan, int* chunk_planes, int* streams,
+                               int* flags);
+
 /* out = u + irfftn( P * rfftn(r) ).  `r` is preserved, `out` may alias `u` but not `r`;
  * u == NULL gives the update alone (out = irfftn(P * rfftn(r))).
  * CH: coef = 2*eps*D*A, power = 2 (problem_definition.py:303).  AC / reaction-diffusion:

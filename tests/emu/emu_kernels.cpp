@@ -336,6 +336,68 @@ int emu_native_apply(const float* u, const float* r, float* out, float* spec_out
 }
 }
 
+// -------------------------------------------------------------------------------------
+// L2-blocked schedule: the operation list of native_schedule.h executed serially (issue order)
+// -------------------------------------------------------------------------------------
+#include "../../evoxels_b200/csrc/native_schedule.h"
+extern "C" {
+
+// kind, stream, x0, nxc, slot, event per op (6 ints each); returns the number of ops
+int emu_schedule_ops(int nx, int chunk_planes, int streams, int flags, int ring_planes, int with_rhs,
+                     int* out, int capacity) {
+  std::vector<SchedOp> ops;
+  build_schedule(nx, chunk_planes, streams, flags, ring_planes, with_rhs != 0, ops);
+  if ((int)ops.size() > capacity) return -(int)ops.size();
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const SchedOp& o = ops[i];
+    int* q = out + 6 * i;
+    q[0] = o.kind; q[1] = o.stream; q[2] = o.x0; q[3] = o.nxc; q[4] = o.slot; q[5] = o.event;
+  }
+  return (int)ops.size();
+}
+
+// out = u + irfftn(P * rfftn(r)) with r = CahnHilliard.rhs(u) when with_rhs (eps, D), else the
+// given r, through the scheduled pipeline.  Scratch is poisoned with NaN so that any read of a
+// chunk or ring slot that was not produced first shows up in the result.
+int emu_native_sched(const float* u, const float* r_in, float* out, int nx, int ny, int nz,
+                     const double* h, double dt, double coef, int power, double eps, double D,
+                     int with_rhs, int chunk_planes, int streams, int flags, int ring_planes) {
+  const int M = nz / 2, P = ((M + 1 + 7) / 8) * 8;
+  const NativeDims d{nx, ny, nz, M, P};
+  const float nanv = std::nanf("");
+  std::vector<cf> spec((size_t)nx * ny * P, cf{nanv, nanv});
+  std::vector<cf> ring(2 * (size_t)(ring_planes > 0 ? ring_planes : 1) * ny * P, cf{nanv, nanv});
+  std::vector<float> rhs((size_t)nx * ny * nz, nanv);
+  auto twx = make_roots(nx, nx), twy = make_roots(ny, ny), twz = make_roots(M, M),
+       twr = make_roots(nz, M + 1);
+  NativeBufs b;
+  b.u = u; b.r = with_rhs ? rhs.data() : r_in; b.out = out; b.spec = spec.data();
+  b.ring = ring_planes > 0 ? ring.data() : nullptr;
+  b.ring_slot_elems = (long long)ring_planes * ny * P;
+  b.twx = twx.data(); b.twy = twy.data(); b.twz = twz.data(); b.twr = twr.data();
+  std::vector<SchedOp> ops;
+  build_schedule(nx, chunk_planes, streams, flags, ring_planes, with_rhs != 0, ops);
+  const int per[3] = {BC_PERIODIC, BC_PERIODIC, BC_PERIODIC};
+  for (const SchedOp& o : ops) {
+    switch (o.kind) {
+      case OP_RHS: {
+        const RhsChunk k = rhs_chunk(d, u, rhs.data(), o);
+        if (emu_ch<float>(k.c, nullptr, k.out, o.nxc, ny, nz, h, eps, D, per, nullptr, k.halo_lo,
+                          k.halo_hi, o.nxc, nz % 4 == 0 ? 1 : 0)) return -10;
+        break;
+      }
+      case OP_ZFWD: if (dispatch_z<false>(M, z_chunk_params(d, b, o))) return -1; break;
+      case OP_ZINV: if (dispatch_z<true>(M, z_chunk_params(d, b, o))) return -5; break;
+      case OP_YFWD: if (dispatch_strided<8, PASS_FWD>(ny, y_chunk_params(d, b, o))) return -2; break;
+      case OP_YINV: if (dispatch_strided<8, PASS_INV>(ny, y_chunk_params(d, b, o))) return -4; break;
+      case OP_XMID: if (dispatch_strided<8, PASS_XMID>(nx, x_params(d, b, h, dt, coef, power))) return -3; break;
+      default: break;   // RECORD / WAIT: the serial replay is one legal order
+    }
+  }
+  return 0;
+}
+}
+
 // =====================================================================================
 // two-species reaction-diffusion rhs
 // =====================================================================================

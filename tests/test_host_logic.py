@@ -152,3 +152,113 @@ def test_solver_rejects_other_backends():
     vf.add_field("a")
     with pytest.raises(ValueError, match="Unsupported backend"):
         TimeDependentSolver(vf, "a", backend="jax", step_fn=lambda t, u: u, device="cpu")
+
+
+class _FakeClock:
+    now = 0.0
+
+
+class _FakeEvent:
+    def __init__(self, enable_timing=False):
+        self.t = None
+
+    def record(self):
+        self.t = _FakeClock.now
+
+    def synchronize(self):
+        pass
+
+    def elapsed_time(self, other):
+        return other.t - self.t
+
+
+def _fake_plan(monkeypatch, cost, wrong=()):
+    """An ImexPlan whose ch_step is a stand-in: it costs cost(schedule) fake milliseconds and
+    writes a schedule-independent field, except for the schedules in `wrong`."""
+    plan = object.__new__(_native.ImexPlan)
+    plan._handle = None
+    plan.shape = (512, 512, 512)
+    plan.backend = _native.FFT_NATIVE
+    plan.device = torch.device("cpu")
+    plan.tuned = False
+    plan.tune_report = None
+    plan.current = (0, 1, 0)
+    plan.log = []
+
+    def set_schedule(chunk_planes=0, streams=1, flags=0):
+        plan.current = (chunk_planes, streams, flags)
+        plan.log.append(plan.current)
+
+    def ch_step(u, out, spacing, dt, eps, D, A, hom=None):
+        _FakeClock.now += cost(plan.current)
+        out.copy_(u * 2 + (1 if plan.current in wrong else 0))
+        return out
+
+    plan.set_schedule, plan.ch_step, plan.schedule = set_schedule, ch_step, lambda: plan.current
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda dev=None: (1 << 40, 1 << 40))
+
+    class Props:
+        multi_processor_count = 148
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda dev=None: Props)
+    return plan
+
+
+def test_schedule_tuner_picks_the_fastest_bit_identical_candidate(monkeypatch):
+    u = torch.rand(4, 4, 4)
+    fast, faster_but_wrong = (17, 2, 1), (26, 2, 3)
+    cost = lambda s: {fast: 1.2, faster_but_wrong: 0.9, (0, 1, 0): 1.8}.get(s, 1.5 + 0.01 * s[0])
+    plan = _fake_plan(monkeypatch, cost, wrong={faster_but_wrong})
+    cands = plan.schedule_candidates()
+    assert {c[0] for c in cands} == {8, 16, 17, 26, 32} and all(c[0] <= 32 for c in cands)
+    best, report = plan.tune_ch_step(u, (1, 1, 1), 0.1, 3.0, 1.0, 0.25)
+    assert best == fast and plan.current == fast and plan.tuned
+    assert report["chosen"] == fast and abs(report["baseline_ms"] - 1.8) < 1e-9
+    rejected = [c for c in report["candidates"] if not c["bit_identical"]]
+    assert [c["schedule"] for c in rejected] == [faster_but_wrong]
+    # a gain below the threshold keeps the one-launch-per-pass schedule
+    plan = _fake_plan(monkeypatch, lambda s: 1.0 if s == (0, 1, 0) else 0.99)
+    best, _ = plan.tune_ch_step(u, (1, 1, 1), 0.1, 3.0, 1.0, 0.25)
+    assert best == (0, 1, 0) and plan.current == (0, 1, 0)
+    # large grids: the candidate list is cut to fit the time budget
+    plan = _fake_plan(monkeypatch, lambda s: 120.0 if s == (0, 1, 0) else 100.0)
+    best, report = plan.tune_ch_step(u, (1, 1, 1), 0.1, 3.0, 1.0, 0.25)
+    assert len(report["candidates"]) <= 6 and best[1] == 2 and best[2] != 0
+
+
+def test_stepper_schedule_policy(monkeypatch):
+    """Small grids and EVX_TUNE=0 keep the baseline without measuring, EVX_SCHEDULE forces a
+    schedule, and a failing tuner falls back to the baseline with a warning."""
+    ts = PseudoSpectralIMEX(CahnHilliard(host_grid()), 0.1)
+    calls = []
+
+    def tune(*a, **k):
+        calls.append(a)
+        return (8, 2, 1), {"chosen": (8, 2, 1)}
+    plan = _fake_plan(monkeypatch, lambda s: 1.0)
+    plan.tune_ch_step = tune
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    small, large = torch.rand(8, 8, 8), torch.empty(0).new_empty((1 << 24,))
+    ts._choose_schedule(plan, small, (1, 1, 1))
+    assert plan.tuned and not calls and not plan.log
+    plan.tuned = False
+    monkeypatch.setenv("EVX_TUNE", "0")
+    ts._choose_schedule(plan, large, (1, 1, 1))
+    assert plan.tuned and not calls
+    monkeypatch.delenv("EVX_TUNE")
+    plan.tuned = False
+    monkeypatch.setenv("EVX_SCHEDULE", "16,2,3")
+    ts._choose_schedule(plan, small, (1, 1, 1))
+    assert plan.current == (16, 2, 3) and plan.tuned and not calls
+    monkeypatch.delenv("EVX_SCHEDULE")
+    plan.tuned = False
+    ts._choose_schedule(plan, large, (1, 1, 1))
+    assert len(calls) == 1 and plan.tune_report == {"chosen": (8, 2, 1)}
+
+    def broken(*a, **k):
+        raise RuntimeError("boom")
+    plan.tune_ch_step = broken
+    plan.tuned = False
+    with pytest.warns(UserWarning, match="schedule tuning failed"):
+        ts._choose_schedule(plan, large, (1, 1, 1))
+    assert plan.tuned and plan.current == (0, 1, 0)
