@@ -72,6 +72,7 @@ SIGNATURES = {
     "evx_dist_plan_create": [ctypes.POINTER(_c_void_p), _c_int, _c_int, _c_int, _c_int, _c_int],
     "evx_dist_plan_destroy": [_c_void_p],
     "evx_dist_plan_set_p2p_ctas": [_c_void_p, _c_int],
+    "evx_dist_plan_set_l2_planes": [_c_void_p, _c_int],
     "evx_dist_plan_sizes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t), _iptr],
     "evx_dist_forward_f32": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
     "evx_dist_middle_f32": [_c_void_p, _c_void_p, _dptr, _c_double, _c_double, _c_int, _c_void_p],
@@ -491,6 +492,10 @@ class DistPlan:
 
     def new_buffer(self):
         return torch.empty(self.block_shape, dtype=torch.complex64, device=self.device)
+
+    def set_l2_planes(self, n):
+        """L2 blocking of the local z/y pass pairs (0 = off), see evx_dist_plan_set_l2_planes."""
+        check(load_library().evx_dist_plan_set_l2_planes(self._handle, int(n)), "evx_dist_plan_set_l2_planes")
 
     def set_p2p_ctas(self, n):
         check(load_library().evx_dist_plan_set_p2p_ctas(self._handle, int(n)), "evx_dist_plan_set_p2p_ctas")

@@ -337,6 +337,7 @@ int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* ou
 struct DistPlan {
   int nx, ny, nz, world, rank, nxl, nyl, P, M;
   int p2p_ctas = 0;   // grid cap of the peer-store launches (0: fill the GPU)
+  int l2_planes = 0;  // > 0: z/y pass pairs run on sub-chunks of this many x planes (L2 blocking)
   void* twiddles;
 };
 
@@ -395,6 +396,15 @@ static void local_block_table(const DistPlan* p, cf* other, cf* self_buf, void**
 int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* const* peers,
                  int x0, int nxc, cudaStream_t st, int parts = 3) {
   if (x0 < 0 || nxc < 1 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
+  if (p->l2_planes > 0 && parts == 3 && nxc > p->l2_planes) {
+    // L2 blocking: z then y on sub-chunks small enough for the spectrum to stay in L2 in between
+    for (int xs = x0; xs < x0 + nxc; xs += p->l2_planes) {
+      const int n = x0 + nxc - xs < p->l2_planes ? x0 + nxc - xs : p->l2_planes;
+      const int rc = dist_forward(p, r_local, spec, send, peers, xs, n, st, 3);
+      if (rc) return rc;
+    }
+    return EVX_OK;
+  }
   const long long spec_off = (long long)x0 * p->ny * p->P;
   if (parts & 1) {   // z pass
     ZParams zp;
@@ -438,20 +448,40 @@ int dist_middle(DistPlan* p, cf* recv, void* const* peers, const double* h, doub
   return launch_xmid(p->nx, xp, st);
 }
 
-int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, float* out_local,
-                  cudaStream_t st) {
+// y inverse (block layout -> plain spectrum) and z inverse (+u) of the local x planes
+// [x0, x0+nxc); the intermediate spectrum of the chunk is written at `spec_chunk`
+static int dist_backward_chunk(DistPlan* p, const cf* recv, cf* spec_chunk, const float* u_local,
+                               float* out_local, int x0, int nxc, cudaStream_t st) {
   StridedParams yp;
-  yp.in = recv; yp.out = spec; yp.tw = tw_y(p);
   yp.src = block_io(p);
   yp.dst = plain_io(p->P, (long long)p->ny * p->P, p->ny);
-  yp.P = p->P; yp.ncols_valid = p->M + 1; yp.ncols_total = (long long)p->nxl * p->P;
+  yp.in = recv + (long long)x0 * yp.src.plane_stride; yp.out = spec_chunk; yp.tw = tw_y(p);
+  yp.P = p->P; yp.ncols_valid = p->M + 1; yp.ncols_total = (long long)nxc * p->P;
   yp.kother_offset = 0; yp.filt = FilterParams{}; yp.use_peers = 0; yp.max_ctas = 0;
   int rc = launch_strided<PASS_INV>(p->ny, yp, st);
   if (rc) return rc;
+  const long long real_off = (long long)x0 * p->ny * p->nz;
   ZParams zp;
-  zp.real_in = u_local; zp.real_out = out_local; zp.spec = spec; zp.tw = tw_z(p); zp.twr = tw_r(p);
-  zp.rows = (long long)p->nxl * p->ny; zp.nz = p->nz; zp.P = p->P;
+  zp.real_in = u_local ? u_local + real_off : nullptr; zp.real_out = out_local + real_off;
+  zp.spec = spec_chunk; zp.tw = tw_z(p); zp.twr = tw_r(p);
+  zp.rows = (long long)nxc * p->ny; zp.nz = p->nz; zp.P = p->P;
   return launch_z<true>(p->M, zp, st);
+}
+
+int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, float* out_local,
+                  cudaStream_t st) {
+  const int X = p->l2_planes;
+  if (X <= 0 || 2 * X > p->nxl) return dist_backward_chunk(p, recv, spec, u_local, out_local, 0, p->nxl, st);
+  // L2 blocking: the chunk's spectrum goes through two alternating slots at the start of
+  // `spec` (read exactly once, overwritten two chunks later - it never has to reach HBM)
+  const long long slot = (long long)X * p->ny * p->P;
+  int i = 0;
+  for (int x0 = 0; x0 < p->nxl; x0 += X, ++i) {
+    const int n = p->nxl - x0 < X ? p->nxl - x0 : X;
+    const int rc = dist_backward_chunk(p, recv, spec + (i & 1) * slot, u_local, out_local, x0, n, st);
+    if (rc) return rc;
+  }
+  return EVX_OK;
 }
 
 // ------------------------------------------------------------------------------------
@@ -552,6 +582,11 @@ int evx_dist_plan_destroy(evx_dist_plan* plan) {
 int evx_dist_plan_set_p2p_ctas(evx_dist_plan* plan, int ctas) {
   if (!plan || ctas < 0) return EVX_ERR_ARG;
   ((DistPlan*)plan)->p2p_ctas = ctas;
+  return EVX_OK;
+}
+int evx_dist_plan_set_l2_planes(evx_dist_plan* plan, int planes) {
+  if (!plan || planes < 0) return EVX_ERR_ARG;
+  ((DistPlan*)plan)->l2_planes = planes;
   return EVX_OK;
 }
 int evx_dist_plan_sizes(const evx_dist_plan* plan, size_t* spec_bytes, int* pitch) {

@@ -18,6 +18,7 @@ shipped `CudaOps` has no CPU path.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -190,6 +191,9 @@ class CudaOps:
         self.peers = None
         if spectral:
             self.plan = _native.DistPlan(slab.global_shape, slab.world, slab.rank, device)
+            l2 = int(os.environ.get("EVX_DIST_L2_PLANES", "0"))      # experimental, default off
+            if l2 > 0:
+                self.plan.set_l2_planes(l2)
             self.spec = self.plan.new_buffer()
             if self.transport in ("p2p", "ce"):
                 try:

@@ -230,6 +230,11 @@ int evx_dist_plan_sizes(const evx_dist_plan* plan, size_t* spec_bytes, int* pitc
 /* cap the persistent grid of the peer-store launches (they are NVLink-bound; leaving SMs free
  * lets the next chunk's rhs / z pass run concurrently on another stream); 0 = fill the GPU */
 int evx_dist_plan_set_p2p_ctas(evx_dist_plan* plan, int ctas);
+/* L2 blocking of the local transform pairs (default 0 = off): forward calls run z then y, and
+ * evx_dist_backward_f32 runs y then z (+u), on sub-chunks of `planes` local x planes, so that the
+ * chunk's spectrum is still in L2 when the second pass of the pair reads it (cf.
+ * evx_imex_plan_set_schedule).  Same kernels on sub-ranges: results are bit-identical. */
+int evx_dist_plan_set_l2_planes(evx_dist_plan* plan, int planes);
 int evx_dist_forward_f32(evx_dist_plan* plan, const float* r_local, void* spec, void* send,
                          void* stream);
 int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double dt, double coef,
