@@ -206,24 +206,36 @@ def _fake_plan(monkeypatch, cost, wrong=()):
 
 def test_schedule_tuner_picks_the_fastest_bit_identical_candidate(monkeypatch):
     u = torch.rand(4, 4, 4)
-    fast, faster_but_wrong = (17, 2, 1), (26, 2, 3)
-    cost = lambda s: {fast: 1.2, faster_but_wrong: 0.9, (0, 1, 0): 1.8}.get(s, 1.5 + 0.01 * s[0])
+    R, C = _native.SCHED_RING_INV, _native.SCHED_CHUNK_RHS
+    fast, faster_but_wrong = (17, 2, 0), (26, 2, R)
+    cost = lambda s: {fast: 1.2, (17, 2, R): 1.3, faster_but_wrong: 0.9, (0, 1, 0): 1.8}.get(s, 1.5 + 0.01 * s[0])
     plan = _fake_plan(monkeypatch, cost, wrong={faster_but_wrong})
-    cands = plan.schedule_candidates()
-    assert {c[0] for c in cands} == {8, 16, 17, 26, 32} and all(c[0] <= 32 for c in cands)
+    assert plan.schedule_sizes() == [2, 3, 4, 6, 8, 9, 11, 12, 16, 17, 18, 23, 24, 26, 27, 32]
     best, report = plan.tune_ch_step(u, (1, 1, 1), 0.1, 3.0, 1.0, 0.25)
+    # phase 1 finds size 17 through its ring variant, phase 2 then finds the faster no-ring form
     assert best == fast and plan.current == fast and plan.tuned
     assert report["chosen"] == fast and abs(report["baseline_ms"] - 1.8) < 1e-9
     rejected = [c for c in report["candidates"] if not c["bit_identical"]]
     assert [c["schedule"] for c in rejected] == [faster_but_wrong]
+    tried = {c["schedule"] for c in report["candidates"]}
+    assert (17, 1, R | C) in tried and (26, 2, 0) not in tried      # phase 2 skips rejected sizes
     # a gain below the threshold keeps the one-launch-per-pass schedule
     plan = _fake_plan(monkeypatch, lambda s: 1.0 if s == (0, 1, 0) else 0.99)
     best, _ = plan.tune_ch_step(u, (1, 1, 1), 0.1, 3.0, 1.0, 0.25)
     assert best == (0, 1, 0) and plan.current == (0, 1, 0)
-    # large grids: the candidate list is cut to fit the time budget
+    # large grids: only chunks whose spectrum fits L2 are candidates; too small grids: none
     plan = _fake_plan(monkeypatch, lambda s: 120.0 if s == (0, 1, 0) else 100.0)
+    plan.shape = (2048, 2048, 2048)
+    assert plan.schedule_sizes() == [2, 3]
     best, report = plan.tune_ch_step(u, (1, 1, 1), 0.1, 3.0, 1.0, 0.25)
-    assert len(report["candidates"]) <= 6 and best[1] == 2 and best[2] != 0
+    assert best[0] in (2, 3) and len(report["candidates"]) <= 12
+    plan.shape = (1024, 1024, 1024)
+    assert plan.schedule_sizes() == [2, 3, 4, 6, 8, 9, 11, 12]
+    plan.shape = (4, 64, 64)
+    plan.current = (0, 1, 0)
+    assert plan.schedule_sizes() == []
+    best, report = plan.tune_ch_step(u, (1, 1, 1), 0.1, 3.0, 1.0, 0.25)
+    assert best == (0, 1, 0) and report["skipped"] == "grid too small"
 
 
 def test_stepper_schedule_policy(monkeypatch):
