@@ -10,6 +10,24 @@ namespace evx {
 extern std::atomic<unsigned long long> g_launches;
 inline void count_launch(unsigned long long n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Opt-in to > 48 KB of dynamic shared memory.  cudaFuncSetAttribute is a per-device setting,
+// so it is remembered per (kernel instantiation, device): one `static SmemOptIn` per launcher.
+struct SmemOptIn {
+  std::atomic<unsigned long long> done{0};   // bit d: made on device d (d < 64)
+  template <class K>
+  int ensure(K kern, size_t bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return 0;
+    const cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    done.fetch_or(bit, std::memory_order_release);
+    return 0;
+  }
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // defined in stencil.cu, used by the fused step in spectral.cu

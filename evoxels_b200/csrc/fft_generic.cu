@@ -47,13 +47,8 @@ static int launch_generic(GenericParams<R> p, long long nblocks, cudaStream_t st
   const size_t smem = GenericProgram<R>::smem_elems(p) * sizeof(gcplx<R>);
   if (smem > kGenSmemCap) return EVX_ERR_UNSUPPORTED;
   auto kern = fft_generic_kernel<R>;
-  static bool configured = false;      // per instantiation (float / double)
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kGenSmemCap);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static SmemOptIn optin;              // per instantiation (float / double)
+  if (int rc = optin.ensure(kern, kGenSmemCap)) return rc;
   const long long cap = 148LL * 16;
   const unsigned grid = (unsigned)(nblocks < cap ? nblocks : cap);
   kern<<<grid, kGenThreads, smem, st>>>(p, nblocks);

@@ -33,13 +33,8 @@ static int launch_pass(const Params& p, long long blocks, cudaStream_t st) {
   if (blocks < 1 || blocks > 2147483647LL) return EVX_ERR_UNSUPPORTED;
   auto kern = fft_pass_kernel<Prog, Params, MINB>;
   if (Prog::SMEM_BYTES > 48 * 1024) {
-    static bool configured = false;   // per instantiation
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)Prog::SMEM_BYTES);
-      if (e != cudaSuccess) return (int)e;
-      configured = true;
-    }
+    static SmemOptIn optin;           // per instantiation
+    if (int rc = optin.ensure(kern, Prog::SMEM_BYTES)) return rc;
   }
   kern<<<(unsigned)blocks, Prog::NTHREADS, Prog::SMEM_BYTES, st>>>(p);
   count_launch();
@@ -110,13 +105,8 @@ static int launch_pipe(const StridedParams& p, cudaStream_t st) {
   const long long ntiles = Pipe::num_tiles(p);
   if (ntiles < 1) return EVX_ERR_UNSUPPORTED;
   auto kern = fft_pipe_kernel<Pipe>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Pipe::SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = optin.ensure(kern, Pipe::SMEM_BYTES)) return rc;
   long long resident = (long long)sm_count() * (Pipe::NTHREADS <= 512 ? 2 : 1);
   if (p.max_ctas > 0 && p.max_ctas < resident) resident = p.max_ctas;
   const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);
