@@ -347,7 +347,7 @@ class ImexPlan:
     # ---- L2-blocked launch schedule (native back end) --------------------------------------
     def set_schedule(self, chunk_planes=0, streams=1, flags=0):
         """chunk_planes x-planes per chunk of the z/y pass pairs (0: one launch per pass), on
-        1 or 2 streams, flags = SCHED_RING_INV | SCHED_CHUNK_RHS (include/evoxels_b200.h)."""
+        1, 2 or 3 streams, flags = SCHED_RING_INV | SCHED_CHUNK_RHS (include/evoxels_b200.h)."""
         with torch.cuda.device(self.device):
             check(load_library().evx_imex_plan_set_schedule(
                 self._handle, int(chunk_planes), int(streams), int(flags)),
@@ -427,9 +427,9 @@ class ImexPlan:
             if s[0] not in best_sizes:
                 best_sizes.append(s[0])
         for x in best_sizes[:2]:                                    # phase 2
-            for streams in (2, 1):
-                for flags in (0, SCHED_RING_INV | SCHED_CHUNK_RHS):
-                    trial((x, streams, flags))
+            for streams, flags in ((3, SCHED_RING_INV | SCHED_CHUNK_RHS), (2, SCHED_RING_INV | SCHED_CHUNK_RHS),
+                                   (1, SCHED_RING_INV | SCHED_CHUNK_RHS), (3, SCHED_CHUNK_RHS), (2, 0), (1, 0)):
+                trial((x, streams, flags))
         best, t_best = base, t_base
         for s, (t, same) in results.items():
             if same and t < t_best:

@@ -193,9 +193,10 @@ int native_plan_init(evx_imex_plan* p) {
 void native_plan_free(evx_imex_plan* p) {
   if (!p) return;
   if (p->twiddles) { cudaFree(p->twiddles); p->twiddles = nullptr; }
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 12; ++i)
     if (p->ev[i]) { cudaEventDestroy(p->ev[i]); p->ev[i] = nullptr; }
-  if (p->side) { cudaStreamDestroy(p->side); p->side = nullptr; }
+  for (int i = 0; i < 2; ++i)
+    if (p->side[i]) { cudaStreamDestroy(p->side[i]); p->side[i] = nullptr; }
 }
 
 // ---- schedule execution (native_schedule.h builds the operation list) ----------------
@@ -211,6 +212,8 @@ static NativeBufs bufs_of(const evx_imex_plan* p, const float* u, const float* r
   b.ring_slot_elems = (long long)p->ring_planes * p->ny * p->spec_pitch;
   b.ring = p->ring_planes ? reinterpret_cast<cf*>((char*)workspace + p->real_bytes + p->spec_bytes)
                           : nullptr;
+  const int X = (p->chunk_planes > 0 && p->chunk_planes < p->nx) ? p->chunk_planes : p->nx;
+  b.rhs_slot_elems = (long long)X * p->ny * p->nz;
   b.twx = (const cf*)p->twiddles;
   b.twy = b.twx + p->nx;
   b.twz = b.twy + p->ny;
@@ -223,15 +226,15 @@ static int run_schedule(evx_imex_plan* p, const NativeBufs& b, const float* rhs_
                         double dt, double coef, int power, double eps, double D, cudaStream_t st) {
   const NativeDims d = dims_of(p);
   std::vector<SchedOp> ops;
-  build_schedule(d.nx, p->chunk_planes, p->side ? p->chunk_streams : 1, p->chunk_flags,
+  build_schedule(d.nx, p->chunk_planes, p->side[0] ? p->chunk_streams : 1, p->chunk_flags,
                  p->ring_planes, rhs_u != nullptr, ops);
   const int per[3] = {BC_PERIODIC, BC_PERIODIC, BC_PERIODIC};
   for (const SchedOp& o : ops) {
-    cudaStream_t s = o.stream ? p->side : st;
+    cudaStream_t s = o.stream ? p->side[o.stream - 1] : st;
     int rc = EVX_OK;
     switch (o.kind) {
       case OP_RHS: {
-        const RhsChunk k = rhs_chunk(d, rhs_u, const_cast<float*>(b.r), o);
+        const RhsChunk k = rhs_chunk(d, rhs_u, const_cast<float*>(b.r), b.rhs_slot_elems, o);
         rc = ch_rhs_impl<float>(k.c, nullptr, k.out, o.nxc, d.ny, d.nz, h, eps, D, per, nullptr,
                                 k.halo_lo, k.halo_hi, s);
         break;
@@ -256,14 +259,17 @@ int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, v
 }
 
 int native_set_schedule(evx_imex_plan* p, int chunk_planes, int streams, int flags) {
-  if (chunk_planes < 0 || streams < 1 || streams > 2 || (flags & ~(SCHED_RING_INV | SCHED_CHUNK_RHS)))
+  if (chunk_planes < 0 || streams < 1 || streams > kSchedStreams ||
+      (flags & ~(SCHED_RING_INV | SCHED_CHUNK_RHS)))
     return EVX_ERR_ARG;
-  if (streams == 2 && !p->side) {
-    cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { p->side = nullptr; return (int)e; }
-    for (int i = 0; i < 6; ++i) {
-      e = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming);
-      if (e != cudaSuccess) return (int)e;
+  if (streams >= 2 && !p->side[0]) {
+    for (int i = 0; i < kSchedStreams - 1; ++i) {
+      cudaError_t e = cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking);
+      if (e != cudaSuccess) { p->side[i] = nullptr; p->side[0] = nullptr; return (int)e; }
+    }
+    for (int i = 0; i < kSchedEvents; ++i) {
+      cudaError_t e = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) { p->side[0] = nullptr; return (int)e; }
     }
   }
   p->chunk_planes = chunk_planes;

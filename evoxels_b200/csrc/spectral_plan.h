@@ -22,11 +22,11 @@ struct evx_imex_plan {
   // per pass).  The z/y pass pairs walk the grid in chunks of `chunk_planes` x planes so that
   // the spectrum written by the first pass of a pair is still in L2 when the second reads it.
   int chunk_planes = 0;
-  int chunk_streams = 1;       // 2: second pass of chunk i on `side`, next to the first of chunk i+1
+  int chunk_streams = 1;       // 2 / 3: passes of consecutive chunks overlap on the side streams
   int chunk_flags = 0;         // EVX_SCHED_* bits
   int ring_planes = 0;         // capacity of one inverse-ring slot in x planes (0: no ring)
-  cudaStream_t side = nullptr; // owned; created on demand
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t side[2] = {nullptr, nullptr};   // owned; created on demand
+  cudaEvent_t ev[12] = {};
 };
 
 namespace evx {

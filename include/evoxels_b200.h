@@ -154,9 +154,10 @@ int evx_imex_plan_workspace_bytes(const evx_imex_plan* plan, size_t* bytes);
  * crosses HBM between any two passes.  chunk_planes = X > 0: the z and y passes of each
  * direction run pairwise on chunks of X x-planes, so that the second pass of a pair reads the
  * chunk the first one wrote from L2 (X * ny * nz * 8 B should stay well below the 126 MB L2).
- *   streams  1, or 2: the second pass of chunk i is enqueued on a stream owned by the plan,
+ *   streams  1; or 2: the second pass of chunk i is enqueued on a stream owned by the plan,
  *            next to the first pass of chunk i+1 (forked from / joined to `stream` with events;
- *            legal inside CUDA-graph capture)
+ *            legal inside CUDA-graph capture); or 3 (with EVX_SCHED_CHUNK_RHS, else like 2):
+ *            rhs, z forward and y forward of three consecutive chunks run next to each other
  *   flags    EVX_SCHED_RING_INV: the inverse y pass writes a two-slot ring in the workspace
  *            instead of the spectrum (no write-back of data that is read exactly once);
  *            EVX_SCHED_CHUNK_RHS: evx_ch_imex_step_f32 also evaluates the rhs per chunk.

@@ -374,6 +374,8 @@ int emu_native_sched(const float* u, const float* r_in, float* out, int nx, int 
   b.u = u; b.r = with_rhs ? rhs.data() : r_in; b.out = out; b.spec = spec.data();
   b.ring = ring_planes > 0 ? ring.data() : nullptr;
   b.ring_slot_elems = (long long)ring_planes * ny * P;
+  const int X = (chunk_planes > 0 && chunk_planes < nx) ? chunk_planes : nx;
+  b.rhs_slot_elems = (long long)X * ny * nz;
   b.twx = twx.data(); b.twy = twy.data(); b.twz = twz.data(); b.twr = twr.data();
   std::vector<SchedOp> ops;
   build_schedule(nx, chunk_planes, streams, flags, ring_planes, with_rhs != 0, ops);
@@ -381,7 +383,7 @@ int emu_native_sched(const float* u, const float* r_in, float* out, int nx, int 
   for (const SchedOp& o : ops) {
     switch (o.kind) {
       case OP_RHS: {
-        const RhsChunk k = rhs_chunk(d, u, rhs.data(), o);
+        const RhsChunk k = rhs_chunk(d, u, rhs.data(), b.rhs_slot_elems, o);
         if (emu_ch<float>(k.c, nullptr, k.out, o.nxc, ny, nz, h, eps, D, per, nullptr, k.halo_lo,
                           k.halo_hi, o.nxc, nz % 4 == 0 ? 1 : 0)) return -10;
         break;

@@ -301,7 +301,8 @@ def test_ch_rhs_adjoint_against_autograd(emu):
 # ------------------------------------------------------------------------------------------
 OP = {"rhs": 0, "zfwd": 1, "yfwd": 2, "xmid": 3, "yinv": 4, "zinv": 5, "record": 6, "wait": 7}
 SCHEDULES = [(0, 1, 0), (4, 1, 0), (4, 1, 1), (4, 2, 0), (4, 2, 1), (4, 2, 3), (4, 1, 3), (6, 2, 3),
-             (5, 2, 3), (2, 2, 3), (8, 2, 1), (16, 2, 3), (3, 1, 2), (31, 2, 3), (7, 1, 3)]
+             (5, 2, 3), (2, 2, 3), (8, 2, 1), (16, 2, 3), (3, 1, 2), (31, 2, 3), (7, 1, 3),
+             (4, 3, 3), (4, 3, 2), (5, 3, 3), (8, 3, 1), (16, 3, 3), (2, 3, 3), (31, 3, 3)]
 
 
 def _ops(emu, nx, chunk, streams, flags, ring, with_rhs):
@@ -318,10 +319,10 @@ def _footprint(op, nx, ring_used, rhs_slot_used):
     S = {("spec", x) for x in planes}
     if kind == OP["rhs"]:
         rd = {("u", (x0 + k) % nx) for k in range(-2, nxc + 2)}
-        wr = {("rhs_slot", 0)} if slot >= 0 else {("rhs", x) for x in planes}
+        wr = {("rhs_slot", slot)} if slot >= 0 else {("rhs", x) for x in planes}
         return rd, wr
     if kind == OP["zfwd"]:
-        return ({("rhs_slot", 0)} if slot >= 0 else {("rhs", x) for x in planes}), S
+        return ({("rhs_slot", slot)} if slot >= 0 else {("rhs", x) for x in planes}), S
     if kind == OP["yfwd"]:
         return S, S
     if kind == OP["xmid"]:
@@ -366,10 +367,18 @@ def _check_ordering(ops, nx):
             rb, wb = fp[b]
             if (wa & (rb | wb)) or (ra & wb):
                 assert a in before[b], f"ops {seq[a]} and {seq[b]} conflict but are unordered"
-    # everything enqueued on the side stream is joined to the caller's stream at the end
+    # everything enqueued on the side streams is joined to the caller's stream at the end
     tail = max(i for i, op in enumerate(seq) if op[1] == 0)
     for i in comp:
         assert i == tail or i in before[tail], f"op {seq[i]} is not joined to the caller's stream"
+    # ... and explicitly so (stream capture wants the LAST operation of every forked stream to be
+    # an event record that the origin stream waits for)
+    for side in {op[1] for op in ops} - {0}:
+        last = max(i for i, op in enumerate(ops) if op[1] == side)
+        assert ops[last][0] == OP["record"], f"stream {side} ends with {ops[last]}"
+        waits = [i for i, op in enumerate(ops)
+                 if i > last and op[0] == OP["wait"] and op[1] == 0 and op[5] == ops[last][5]]
+        assert waits, f"stream {side} is not joined explicitly"
 
 
 @pytest.mark.parametrize("with_rhs", [False, True])
@@ -432,6 +441,15 @@ def test_schedule_checker_detects_a_missing_wait(emu):
     ops = _ops(emu, 64, 8, 2, 3, 32, True)
     _check_ordering(ops, 64)
     for ev in (1, 3, 4):
+        broken = [o for o in ops if not (o[0] == OP["wait"] and o[5] == ev)]
+        assert len(broken) < len(ops)
+        with pytest.raises(AssertionError):
+            _check_ordering(broken, 64)
+    # three streams: rhs / z forward / y forward of consecutive chunks overlap
+    ops = _ops(emu, 64, 8, 3, 3, 32, True)
+    assert {o[1] for o in ops if o[0] == OP["zfwd"]} == {2} and {o[4] for o in ops if o[0] == OP["rhs"]} == {0, 1}
+    _check_ordering(ops, 64)
+    for ev in (6, 8, 9, 10, 2):
         broken = [o for o in ops if not (o[0] == OP["wait"] and o[5] == ev)]
         assert len(broken) < len(ops)
         with pytest.raises(AssertionError):

@@ -20,7 +20,8 @@ from evoxels_b200.voxelgrid import VoxelGridTorch  # noqa: E402
 
 R, C = _native.SCHED_RING_INV, _native.SCHED_CHUNK_RHS
 SCHEDULES = [(8, 1, 0), (8, 1, R), (8, 2, 0), (8, 2, R), (8, 2, R | C), (8, 1, R | C), (16, 2, R | C),
-             (5, 2, R | C), (6, 1, C), (2, 2, R | C), (31, 2, R | C), (13, 2, R)]
+             (5, 2, R | C), (6, 1, C), (2, 2, R | C), (31, 2, R | C), (13, 2, R),
+             (8, 3, R | C), (16, 3, C), (5, 3, R | C), (2, 3, R | C), (8, 3, R)]
 SP = (1.0, 0.5, 2.0)
 
 
@@ -59,7 +60,7 @@ def test_every_schedule_is_bit_identical(cuda_device, shape):
 
 def test_schedule_argument_errors(cuda_device):
     plan = _native.ImexPlan((32, 32, 32), torch.float32, "cuda", _native.FFT_NATIVE)
-    for bad in [(-1, 1, 0), (8, 0, 0), (8, 3, 0), (8, 1, 4)]:
+    for bad in [(-1, 1, 0), (8, 0, 0), (8, 4, 0), (8, 1, 4)]:
         with pytest.raises(_native.NativeLibraryError):
             plan.set_schedule(*bad)
     other = _native.ImexPlan((20, 20, 20), torch.float32, "cuda")       # mixed-radix back end
@@ -81,7 +82,7 @@ def test_two_stream_schedule_on_side_stream_and_in_a_graph(cuda_device):
     a0, b0 = torch.empty_like(u), torch.empty_like(u)
     three_steps(a0, b0)
     want = a0.clone()
-    plan.set_schedule(8, 2, R | C)
+    plan.set_schedule(8, 3, R | C)
     # caller's stream is not the default stream
     s = torch.cuda.Stream()
     a1, b1 = torch.empty_like(u), torch.empty_like(u)
