@@ -61,6 +61,7 @@ struct StridedParams {
   FilterParams filt;       // XMID only; n0 = L (this axis), n1 = the other strided axis, n2 = nz
   long long src_step[8];   // strided_step(src, e * L/8), filled by finalize_strided()
   long long dst_step[8];
+  long long src_pf_step[4];  // strided_step(src, it * L/4): row steps of the tile prefetch
   // peer-store mode (x-slab transposes over NVLink): chunk hi = idx >> dst.split_shift of a
   // line is written straight into rank hi's buffer out_peers[hi] at element offset
   // dst_peer_base + grp * plane_stride + kz + lo * line_stride  (no all-to-all afterwards)
@@ -94,6 +95,7 @@ inline void finalize_strided(StridedParams& p, int L) {
     p.src_step[e] = strided_step(p.src, e * (L / 8));
     p.dst_step[e] = strided_step(p.dst, e * (L / 8));
   }
+  for (int it = 0; it < 4; ++it) p.src_pf_step[it] = strided_step(p.src, it * (L / 4));
 }
 
 template <int L, int KZ, int MODE>
@@ -289,7 +291,29 @@ struct StridedPipe {
     const long long grp = c0 / p.P;
     prefetch_at(tid, p, grp, (int)(c0 - grp * p.P), dst);
   }
+  // Every thread moves PF_ITERS = 4 16-byte chunks of the tile: chunk q = tid + it * NTHREADS is
+  // (row0 + it * L/4, part) with row0 = tid / CHUNKS_PER_ROW < L/4.  Because L/4 and the split
+  // of the addressing are powers of two, the row part of the offset is additive,
+  //   offset(row0 + it * L/4) = offset(row0) + strided_step(src, it * L/4)
+  // (same argument as strided_base / strided_step), so one 64-bit address is computed per tile
+  // and the four copies use host-tabulated steps - the per-chunk division and the two 64-bit
+  // multiplies of the direct form cost 19 instructions per copy in an issue-bound loop.
+  static constexpr int PF_ITERS = CHUNKS / NTHREADS;
+  static constexpr int PF_ROWS = NTHREADS / CHUNKS_PER_ROW;
+  static_assert(PF_ITERS == 4 && CHUNKS % NTHREADS == 0 && NTHREADS % CHUNKS_PER_ROW == 0 &&
+                PF_ROWS * 4 == L, "tile prefetch: four chunks per thread, L/4 rows apart");
   EVX_HD static void prefetch_at(int tid, const StridedParams& p, long long grp, int kz0, cf* dst) {
+    constexpr int CF16 = 16 / (int)sizeof(cf);
+    const int row0 = tid / CHUNKS_PER_ROW, part = tid - row0 * CHUNKS_PER_ROW;
+    const cf* src = p.in + strided_offset(p.src, grp, kz0, row0) + part * CF16;
+    cf* d = dst + (size_t)row0 * KZ + part * CF16;
+#pragma unroll
+    for (int it = 0; it < PF_ITERS; ++it)
+      async_copy16(d + (size_t)it * PF_ROWS * KZ, src + p.src_pf_step[it]);
+  }
+  // direct form of the same copies (one address computation per chunk): kept for the CPU
+  // replay, which checks that both forms touch the same (destination, source) pairs
+  EVX_HD static void prefetch_at_direct(int tid, const StridedParams& p, long long grp, int kz0, cf* dst) {
     for (int q = tid; q < CHUNKS; q += NTHREADS) {
       const int row = q / CHUNKS_PER_ROW, part = q - row * CHUNKS_PER_ROW;
       const cf* src = p.in + strided_offset(p.src, grp, kz0, row) + part * (16 / (int)sizeof(cf));

@@ -336,6 +336,49 @@ int emu_native_apply(const float* u, const float* r, float* out, float* spec_out
 }
 }
 
+// tile prefetch: tabulated-step form against the direct form, same (destination, source) pairs.
+// layout 0: plain y pass [nx][L][P]; 1: plain x pass [L][ny][P]; 2: all-to-all block layout
+// [W][nxl][L/W][P] read along y (the source of the distributed inverse y pass)
+template <int L, int KZ>
+static long long prefetch_mismatches(int layout, int groups, int P, int W) {
+  using Pipe = StridedPipe<L, KZ, PASS_FWD>;
+  StridedParams p{};
+  long long elems;
+  if (layout == 0) { p.src = plain_io(P, (long long)L * P, L); elems = (long long)groups * L * P; }
+  else if (layout == 1) { p.src = plain_io((long long)groups * P, P, L); elems = (long long)L * groups * P; }
+  else {
+    const int nyl = L / W;
+    p.src = StridedIO{P, (long long)nyl * P, (long long)groups * nyl * P, ilog2(nyl)};
+    elems = (long long)W * groups * nyl * P;
+  }
+  p.dst = p.src;
+  std::vector<cf> in((size_t)elems);
+  for (size_t i = 0; i < in.size(); ++i) in[i] = cf{(float)(i & 0xffff), (float)(i >> 16)};
+  p.in = in.data(); p.out = nullptr; p.P = P; p.ncols_valid = P; p.ncols_total = (long long)groups * P;
+  finalize_strided(p, L);
+  std::vector<cf> a((size_t)Pipe::BUF), b((size_t)Pipe::BUF);
+  long long bad = 0;
+  for (long long tile = 0; tile < Pipe::num_tiles(p); ++tile) {
+    const long long c0 = tile * KZ, grp = c0 / P;
+    const int kz0 = (int)(c0 - grp * P);
+    std::fill(a.begin(), a.end(), cf{-1.f, -1.f});
+    std::fill(b.begin(), b.end(), cf{-2.f, -2.f});
+    for (int t = 0; t < Pipe::NTHREADS; ++t) {
+      Pipe::prefetch_at(t, p, grp, kz0, a.data());
+      Pipe::prefetch_at_direct(t, p, grp, kz0, b.data());
+    }
+    for (int i = 0; i < L * KZ; ++i) bad += (a[i].x != b[i].x || a[i].y != b[i].y);
+  }
+  return bad;
+}
+extern "C" long long emu_prefetch_mismatches(int L, int KZ, int layout, int groups, int P, int W) {
+#define EMU_PF(LL, KK) if (L == LL && KZ == KK) return prefetch_mismatches<LL, KK>(layout, groups, P, W);
+  EMU_PF(64, 8) EMU_PF(128, 8) EMU_PF(256, 8) EMU_PF(512, 8) EMU_PF(512, 16) EMU_PF(1024, 8)
+  EMU_PF(2048, 4) EMU_PF(64, 16) EMU_PF(256, 16)
+#undef EMU_PF
+  return -1;
+}
+
 // -------------------------------------------------------------------------------------
 // L2-blocked schedule: the operation list of native_schedule.h executed serially (issue order)
 // -------------------------------------------------------------------------------------

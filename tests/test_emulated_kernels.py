@@ -456,3 +456,21 @@ def test_schedule_checker_detects_a_missing_wait(emu):
         assert len(broken) < len(ops)
         with pytest.raises(AssertionError):
             _check_ordering(broken, 64)
+
+
+@pytest.mark.parametrize("L,KZ", [(64, 8), (128, 8), (256, 8), (512, 8), (512, 16), (1024, 8), (2048, 4),
+                                  (64, 16), (256, 16)])
+def test_tile_prefetch_forms_agree(emu, L, KZ):
+    """The tabulated-step tile prefetch of the persistent strided passes copies exactly what the
+    direct per-chunk address computation copies - for the plain y and x layouts and for the
+    all-to-all block layout of the distributed inverse y pass (W = 2, 4, 8 splits)."""
+    emu.emu_prefetch_mismatches.restype = ctypes.c_longlong
+    for P in (KZ, 3 * KZ, 40 if KZ <= 8 else 48):
+        if P % KZ and (3 * P) % KZ:
+            continue
+        groups = 3 if L <= 512 else 2
+        if (groups * P) % KZ == 0:
+            assert emu.emu_prefetch_mismatches(L, KZ, 0, groups, P, 1) == 0
+            assert emu.emu_prefetch_mismatches(L, KZ, 1, groups, P, 1) == 0
+            for W in (2, 4, 8):
+                assert emu.emu_prefetch_mismatches(L, KZ, 2, groups, P, W) == 0
