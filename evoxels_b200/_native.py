@@ -370,7 +370,9 @@ class ImexPlan:
         plane_bytes = ny * (((nz // 2 + 1 + 7) // 8) * 8) * 8
         cap = min(cap, (64 << 20) // plane_bytes)
         ladder = (2, 3, 4, 6, 8, 9, 11, 12, 16, 17, 18, 23, 24, 26, 27, 32)
-        return [x for x in ladder if x <= cap]
+        sizes = [x for x in ladder if x <= cap]
+        # tiny chunks are launch-bound; they are only candidates where L2 leaves nothing else
+        return [x for x in sizes if x >= 8] or sizes
 
     def tune_ch_step(self, u, spacing, dt, eps, D, A, min_gain=0.03, log=None):
         """Time the fused CH step under candidate schedules (CUDA events on the current stream)
