@@ -9,6 +9,7 @@
 #include "spectral_plan.h"
 #include "fft_pass_core.h"
 #include "native_schedule.h"
+#include "dist_params.h"
 
 namespace evx {
 
@@ -330,26 +331,27 @@ int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* ou
 // ------------------------------------------------------------------------------------
 // x-slab distributed variant: the y passes write / read the all-to-all block layout
 // ------------------------------------------------------------------------------------
-struct DistPlan {
-  int nx, ny, nz, world, rank, nxl, nyl, P, M;
+struct DistPlan : DistDims {
   int p2p_ctas = 0;   // grid cap of the peer-store launches (0: fill the GPU)
   int l2_planes = 0;  // > 0: z/y pass pairs run on sub-chunks of this many x planes (L2 blocking)
-  void* twiddles;
+  void* twiddles = nullptr;
 };
 
-static const cf* tw_x(const DistPlan* p) { return (const cf*)p->twiddles; }
-static const cf* tw_y(const DistPlan* p) { return tw_x(p) + p->nx; }
-static const cf* tw_z(const DistPlan* p) { return tw_y(p) + p->ny; }
-static const cf* tw_r(const DistPlan* p) { return tw_z(p) + p->M; }
+static DistTables tables_of(const DistPlan* p) {
+  DistTables t;
+  t.twx = (const cf*)p->twiddles;
+  t.twy = t.twx + p->nx;
+  t.twz = t.twy + p->ny;
+  t.twr = t.twz + p->M;
+  return t;
+}
 
 int dist_plan_create(DistPlan** out, int nx, int ny, int nz, int world, int rank) {
   if (!out || world < 1 || rank < 0 || rank >= world) return EVX_ERR_ARG;
   if (!native_fft_supported(nx, ny, nz) || !is_pow2(world) || nx % world || ny % world)
     return EVX_ERR_UNSUPPORTED;
   DistPlan* p = new DistPlan();
-  p->nx = nx; p->ny = ny; p->nz = nz; p->world = world; p->rank = rank;
-  p->nxl = nx / world; p->nyl = ny / world; p->M = nz / 2;
-  p->P = ((p->M + 1 + kPitchAlign - 1) / kPitchAlign) * kPitchAlign;
+  static_cast<DistDims&>(*p) = make_dist_dims(nx, ny, nz, world, rank, kPitchAlign);
   const size_t total = (size_t)nx + ny + p->M + (p->M + 1);
   std::vector<cf> host(total);
   fill_roots(host, 0, nx, nx);
@@ -364,63 +366,28 @@ int dist_plan_create(DistPlan** out, int nx, int ny, int nz, int world, int rank
   return EVX_OK;
 }
 
-// block layout [world][nxl][nyl][P] seen from local group xl: chunks nxl*nyl*P apart
-static StridedIO block_io(const DistPlan* p) {
-  return StridedIO{p->P, (long long)p->nyl * p->P, (long long)p->nxl * p->nyl * p->P, ilog2(p->nyl)};
-}
-
-static void set_peers(StridedParams& sp, const DistPlan* p, void* const* peers) {
-  sp.use_peers = peers ? 1 : 0;
-  sp.max_ctas = peers ? p->p2p_ctas : 0;
-  sp.dst_peer_base = (long long)p->rank * p->nxl * p->nyl * p->P;
-  for (int i = 0; i < 8; ++i) sp.out_peers[i] = (peers && i < p->world) ? (cf*)peers[i] : nullptr;
-}
-
-// peers != null: block `rank` of every peer's buffer is written directly (NVLink stores).
-// [x0, x0+nxc) selects a chunk of local x planes (r_local / spec / send still point at the
-// start of the full local arrays), so that several chunks can be pipelined on streams:
-// the NVLink-bound y pass of one chunk overlaps the HBM-bound z pass of the next.
-// Pointer table for "every block into `other`, except block `rank` into `self_buf`" in terms
-// of the peer-store addressing (which adds rank * block to the table entry).
-static void local_block_table(const DistPlan* p, cf* other, cf* self_buf, void** table) {
-  const long long blk = (long long)p->nxl * p->nyl * p->P;
-  for (int j = 0; j < 8; ++j)
-    table[j] = j >= p->world ? nullptr
-                             : (j == p->rank ? (void*)self_buf : (void*)(other + (j - p->rank) * blk));
-}
-
+// Parameters: dist_params.h.  [x0, x0+nxc) selects a chunk of local x planes (r_local / spec /
+// send still point at the start of the full local arrays), so that several chunks can be
+// pipelined on streams: the NVLink-bound y pass of one chunk overlaps the HBM-bound z pass of
+// the next.  parts: 1 = z pass, 2 = y pass, 3 = both (then with L2 blocking if set).
 int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* const* peers,
                  int x0, int nxc, cudaStream_t st, int parts = 3) {
   if (x0 < 0 || nxc < 1 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
-  if (p->l2_planes > 0 && parts == 3 && nxc > p->l2_planes) {
-    // L2 blocking: z then y on sub-chunks small enough for the spectrum to stay in L2 in between
-    for (int xs = x0; xs < x0 + nxc; xs += p->l2_planes) {
-      const int n = x0 + nxc - xs < p->l2_planes ? x0 + nxc - xs : p->l2_planes;
-      const int rc = dist_forward(p, r_local, spec, send, peers, xs, n, st, 3);
+  const DistTables t = tables_of(p);
+  std::vector<DistChunk> chunks;
+  dist_forward_chunks(x0, nxc, parts == 3 ? p->l2_planes : 0, chunks);
+  for (const DistChunk& c : chunks) {
+    if (parts & 1) {
+      const int rc = launch_z<false>(p->M, dist_zfwd_params(*p, t, r_local, spec, c.x0, c.nxc), st);
       if (rc) return rc;
     }
-    return EVX_OK;
+    if (parts & 2) {
+      const int rc = launch_strided<PASS_FWD>(
+          p->ny, dist_yfwd_params(*p, t, spec, send, peers, p->p2p_ctas, c.x0, c.nxc), st);
+      if (rc) return rc;
+    }
   }
-  const long long spec_off = (long long)x0 * p->ny * p->P;
-  if (parts & 1) {   // z pass
-    ZParams zp;
-    zp.real_in = r_local + (long long)x0 * p->ny * p->nz; zp.real_out = nullptr;
-    zp.spec = spec + spec_off; zp.tw = tw_z(p); zp.twr = tw_r(p);
-    zp.rows = (long long)nxc * p->ny; zp.nz = p->nz; zp.P = p->P;
-    int rc = launch_z<false>(p->M, zp, st);
-    if (rc) return rc;
-  }
-  if (!(parts & 2)) return EVX_OK;
-  StridedParams yp;
-  yp.in = spec + spec_off; yp.tw = tw_y(p);
-  yp.src = plain_io(p->P, (long long)p->ny * p->P, p->ny);
-  yp.dst = block_io(p);
-  yp.out = send ? send + (long long)x0 * yp.dst.plane_stride : nullptr;
-  yp.P = p->P; yp.ncols_valid = p->M + 1; yp.ncols_total = (long long)nxc * p->P;
-  yp.kother_offset = 0; yp.filt = FilterParams{};
-  set_peers(yp, p, peers);
-  yp.dst_peer_base += (long long)x0 * yp.dst.plane_stride;
-  return launch_strided<PASS_FWD>(p->ny, yp, st);
+  return EVX_OK;
 }
 
 // [yl0, yl0+nylc): chunk of the local y-pencil rows (all x, all kz of those rows)
@@ -428,53 +395,20 @@ int dist_middle(DistPlan* p, cf* recv, void* const* peers, const double* h, doub
                 int power, cudaStream_t st, int yl0 = 0, int nylc = -1) {
   if (nylc < 0) nylc = p->nyl - yl0;
   if (yl0 < 0 || nylc < 1 || yl0 + nylc > p->nyl) return EVX_ERR_ARG;
-  recv += (long long)yl0 * p->P;
-  StridedParams xp;
-  xp.in = recv; xp.out = recv; xp.tw = tw_x(p);
-  xp.src = xp.dst = plain_io((long long)p->nyl * p->P, p->P, p->nx);
-  set_peers(xp, p, peers);
-  if (peers) { // chunk x / nxl of every x line goes to that rank: [rank j block][xl][yl][kz]
-    xp.dst = StridedIO{(long long)p->nyl * p->P, p->P, 0, ilog2(p->nxl)};
-    xp.dst_peer_base += (long long)yl0 * p->P;
-  }
-  xp.P = p->P; xp.ncols_valid = p->M + 1; xp.ncols_total = (long long)nylc * p->P;
-  xp.kother_offset = p->rank * p->nyl + yl0;
-  const int n[3] = {p->nx, p->ny, p->nz};
-  xp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)p->nx * p->ny * p->nz));
-  return launch_xmid(p->nx, xp, st);
-}
-
-// y inverse (block layout -> plain spectrum) and z inverse (+u) of the local x planes
-// [x0, x0+nxc); the intermediate spectrum of the chunk is written at `spec_chunk`
-static int dist_backward_chunk(DistPlan* p, const cf* recv, cf* spec_chunk, const float* u_local,
-                               float* out_local, int x0, int nxc, cudaStream_t st) {
-  StridedParams yp;
-  yp.src = block_io(p);
-  yp.dst = plain_io(p->P, (long long)p->ny * p->P, p->ny);
-  yp.in = recv + (long long)x0 * yp.src.plane_stride; yp.out = spec_chunk; yp.tw = tw_y(p);
-  yp.P = p->P; yp.ncols_valid = p->M + 1; yp.ncols_total = (long long)nxc * p->P;
-  yp.kother_offset = 0; yp.filt = FilterParams{}; yp.use_peers = 0; yp.max_ctas = 0;
-  int rc = launch_strided<PASS_INV>(p->ny, yp, st);
-  if (rc) return rc;
-  const long long real_off = (long long)x0 * p->ny * p->nz;
-  ZParams zp;
-  zp.real_in = u_local ? u_local + real_off : nullptr; zp.real_out = out_local + real_off;
-  zp.spec = spec_chunk; zp.tw = tw_z(p); zp.twr = tw_r(p);
-  zp.rows = (long long)nxc * p->ny; zp.nz = p->nz; zp.P = p->P;
-  return launch_z<true>(p->M, zp, st);
+  return launch_xmid(p->nx, dist_xmid_params(*p, tables_of(p), recv, peers, p->p2p_ctas, h, dt, coef,
+                                             power, yl0, nylc), st);
 }
 
 int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, float* out_local,
                   cudaStream_t st) {
-  const int X = p->l2_planes;
-  if (X <= 0 || 2 * X > p->nxl) return dist_backward_chunk(p, recv, spec, u_local, out_local, 0, p->nxl, st);
-  // L2 blocking: the chunk's spectrum goes through two alternating slots at the start of
-  // `spec` (read exactly once, overwritten two chunks later - it never has to reach HBM)
-  const long long slot = (long long)X * p->ny * p->P;
-  int i = 0;
-  for (int x0 = 0; x0 < p->nxl; x0 += X, ++i) {
-    const int n = p->nxl - x0 < X ? p->nxl - x0 : X;
-    const int rc = dist_backward_chunk(p, recv, spec + (i & 1) * slot, u_local, out_local, x0, n, st);
+  const DistTables t = tables_of(p);
+  std::vector<DistChunk> chunks;
+  dist_backward_chunks(p->nxl, p->l2_planes, chunks);
+  for (const DistChunk& c : chunks) {
+    cf* sc = dist_backward_spec(*p, spec, p->l2_planes, c);
+    int rc = launch_strided<PASS_INV>(p->ny, dist_yinv_params(*p, t, recv, sc, c.x0, c.nxc), st);
+    if (rc) return rc;
+    rc = launch_z<true>(p->M, dist_zinv_params(*p, t, sc, u_local, out_local, c.x0, c.nxc), st);
     if (rc) return rc;
   }
   return EVX_OK;
@@ -620,7 +554,7 @@ int evx_dist_forward_chunk_f32(evx_dist_plan* plan, const float* r_local, void* 
     return dist_forward(dp, r_local, (cf*)spec, (cf*)send, nullptr, x0, nxc, (cudaStream_t)stream);
   if (dp->world > 8) return EVX_ERR_UNSUPPORTED;
   void* table[8];
-  local_block_table(dp, (cf*)send, (cf*)self_block, table);
+  local_block_table(*dp, (cf*)send, (cf*)self_block, table);
   const int ctas = dp->p2p_ctas;
   dp->p2p_ctas = 0;                       // local stores: fill the GPU
   const int rc = dist_forward(dp, r_local, (cf*)spec, nullptr, table, x0, nxc, (cudaStream_t)stream);
@@ -635,7 +569,7 @@ int evx_dist_middle_chunk_f32(evx_dist_plan* plan, void* recv, void* self_block,
     return dist_middle(dp, (cf*)recv, nullptr, h, dt, coef, power, (cudaStream_t)stream, yl0, nylc);
   if (dp->world > 8) return EVX_ERR_UNSUPPORTED;
   void* table[8];
-  local_block_table(dp, (cf*)recv, (cf*)self_block, table);
+  local_block_table(*dp, (cf*)recv, (cf*)self_block, table);
   const int ctas = dp->p2p_ctas;
   dp->p2p_ctas = 0;
   const int rc = dist_middle(dp, (cf*)recv, table, h, dt, coef, power, (cudaStream_t)stream, yl0, nylc);

@@ -443,6 +443,103 @@ int emu_native_sched(const float* u, const float* r_in, float* out, int nx, int 
 }
 }
 
+// -------------------------------------------------------------------------------------
+// x-slab distributed pipeline: W virtual ranks through the parameters of dist_params.h
+// -------------------------------------------------------------------------------------
+#include "../../evoxels_b200/csrc/dist_params.h"
+extern "C" {
+
+// out = u + irfftn(P * rfftn(r)) on the global [nx,ny,nz] grid, computed by `world` virtual
+// ranks (x slabs).  transport 0: local send buffer + all-to-all (NCCL path), 1: local block
+// buffers with the self block written in place + block copies (copy-engine path), 2: stores
+// straight into the peers' buffers (peer-store path).  fwd_chunks / mid_chunks: pipeline chunks
+// of the host orchestration; l2_planes: evx_dist_plan_set_l2_planes.
+int emu_dist_apply(const float* u, const float* r, float* out, int nx, int ny, int nz, int world,
+                   int transport, int fwd_chunks, int mid_chunks, int l2_planes, const double* h,
+                   double dt, double coef, int power) {
+  if (nx % world || ny % world || world > 8) return -1;
+  std::vector<DistDims> dims;
+  for (int k = 0; k < world; ++k) dims.push_back(make_dist_dims(nx, ny, nz, world, k, 8));
+  const DistDims& d0 = dims[0];
+  const int M = d0.M, P = d0.P, nxl = d0.nxl, nyl = d0.nyl;
+  const long long blk = (long long)nxl * nyl * P, slab_spec = (long long)nxl * ny * P;
+  const long long slab_real = (long long)nxl * ny * nz;
+  auto twx = make_roots(nx, nx), twy = make_roots(ny, ny), twz = make_roots(M, M),
+       twr = make_roots(nz, M + 1);
+  const DistTables t{twx.data(), twy.data(), twz.data(), twr.data()};
+  const float nanv = std::nanf("");
+  std::vector<std::vector<cf>> spec(world), A(world), B(world);
+  for (int k = 0; k < world; ++k) {
+    spec[k].assign((size_t)slab_spec, cf{nanv, nanv});
+    A[k].assign((size_t)world * blk, cf{nanv, nanv});
+    B[k].assign((size_t)world * blk, cf{nanv, nanv});
+  }
+  auto bounds = [](int n, int chunks, int i) { return (int)std::lround((double)i * n / chunks); };
+  std::vector<DistChunk> chunks;
+  // ---- forward: z + y passes, blocks into the peers' B -------------------------------------
+  for (int k = 0; k < world; ++k) {
+    const DistDims& d = dims[k];
+    const float* r_local = r + k * slab_real;
+    void* table[8];
+    void* const* peers = nullptr;
+    cf* send = A[k].data();
+    if (transport == 1) { local_block_table(d, A[k].data(), B[k].data(), table); peers = table; send = nullptr; }
+    if (transport == 2) { for (int j = 0; j < 8; ++j) table[j] = j < world ? B[j].data() : nullptr; peers = table; send = nullptr; }
+    for (int i = 0; i < fwd_chunks; ++i) {
+      const int x0 = bounds(nxl, fwd_chunks, i), x1 = bounds(nxl, fwd_chunks, i + 1);
+      if (x1 <= x0) continue;
+      dist_forward_chunks(x0, x1 - x0, l2_planes, chunks);
+      for (const DistChunk& c : chunks) {
+        if (dispatch_z<false>(M, dist_zfwd_params(d, t, r_local, spec[k].data(), c.x0, c.nxc))) return -2;
+        if (dispatch_strided<8, PASS_FWD>(ny, dist_yfwd_params(d, t, spec[k].data(), send, peers, 0, c.x0, c.nxc))) return -3;
+      }
+    }
+  }
+  if (transport != 2)   // all-to-all / block copies: block j of rank k's A -> block k of rank j's B
+    for (int k = 0; k < world; ++k)
+      for (int j = 0; j < world; ++j) {
+        if (transport == 1 && j == k) continue;          // written in place by the pass
+        std::memcpy(B[j].data() + k * blk, A[k].data() + j * blk, (size_t)blk * sizeof(cf));
+      }
+  // ---- middle: x pass on the y-pencils, blocks into the peers' A ---------------------------
+  for (int k = 0; k < world; ++k) std::fill(A[k].begin(), A[k].end(), cf{nanv, nanv});
+  for (int k = 0; k < world; ++k) {
+    const DistDims& d = dims[k];
+    void* table[8];
+    void* const* peers = nullptr;
+    if (transport == 1) { local_block_table(d, B[k].data(), A[k].data(), table); peers = table; }
+    if (transport == 2) { for (int j = 0; j < 8; ++j) table[j] = j < world ? A[j].data() : nullptr; peers = table; }
+    const int mc = mid_chunks < 1 ? 1 : (mid_chunks > nyl ? nyl : mid_chunks);
+    for (int i = 0; i < mc; ++i) {
+      const int y0 = bounds(nyl, mc, i), y1 = bounds(nyl, mc, i + 1);
+      if (y1 <= y0) continue;
+      const StridedParams xp = dist_xmid_params(d, t, B[k].data(), peers, 0, h, dt, coef, power, y0, y1 - y0);
+      if (xp.filt.kind == FILTER_ETD1 ? dispatch_strided<8, PASS_XMID_ETD1>(nx, xp)
+                                      : dispatch_strided<8, PASS_XMID>(nx, xp)) return -4;
+    }
+  }
+  if (transport != 2)
+    for (int k = 0; k < world; ++k)
+      for (int j = 0; j < world; ++j) {
+        if (transport == 1 && j == k) continue;
+        std::memcpy(A[j].data() + k * blk, B[k].data() + j * blk, (size_t)blk * sizeof(cf));
+      }
+  // ---- backward: y inverse + z inverse (+u) ------------------------------------------------
+  for (int k = 0; k < world; ++k) {
+    const DistDims& d = dims[k];
+    std::fill(spec[k].begin(), spec[k].end(), cf{nanv, nanv});
+    dist_backward_chunks(nxl, l2_planes, chunks);
+    for (const DistChunk& c : chunks) {
+      cf* sc = dist_backward_spec(d, spec[k].data(), l2_planes, c);
+      if (dispatch_strided<8, PASS_INV>(ny, dist_yinv_params(d, t, A[k].data(), sc, c.x0, c.nxc))) return -5;
+      if (dispatch_z<true>(M, dist_zinv_params(d, t, sc, u ? u + k * slab_real : nullptr,
+                                               out + k * slab_real, c.x0, c.nxc))) return -6;
+    }
+  }
+  return 0;
+}
+}
+
 // =====================================================================================
 // two-species reaction-diffusion rhs
 // =====================================================================================

@@ -474,3 +474,38 @@ def test_tile_prefetch_forms_agree(emu, L, KZ):
             assert emu.emu_prefetch_mismatches(L, KZ, 1, groups, P, 1) == 0
             for W in (2, 4, 8):
                 assert emu.emu_prefetch_mismatches(L, KZ, 2, groups, P, W) == 0
+
+
+@pytest.mark.parametrize("shape,world", [((16, 16, 32), 2), ((32, 16, 64), 4), ((64, 32, 32), 8), ((32, 64, 16), 8)])
+@pytest.mark.parametrize("pipe_blocks", [0, 3])
+def test_distributed_pipeline_virtual_ranks(emu, shape, world, pipe_blocks):
+    """The x-slab pipeline replayed for W virtual ranks with the launch parameters of
+    dist_params.h (block-layout y passes, global ky offset in the x pass, peer tables) gives the
+    single-domain result bit for bit - for the all-to-all, block-copy and peer-store transports,
+    with and without pipeline chunks and with the L2 sub-chunking of the transform pairs."""
+    emu.emu_set_pipe_blocks(pipe_blocks)
+    emu.emu_set_xpass_columns(8)
+    nx, ny, nz = shape
+    rng = np.random.default_rng(11)
+    r = rng.standard_normal(shape).astype(np.float32)
+    u = rng.random(shape).astype(np.float32)
+    h = (ctypes.c_double * 3)(1.0, 0.5, 2.0)
+    d = ctypes.c_double
+    want = np.zeros(shape, np.float32)
+    assert emu.emu_native_apply(_p(u), _p(r), _p(want), None, nx, ny, nz, h, d(0.1), d(1.5), 2) == 0
+    nxl = nx // world
+    cases = [(tr, fc, mc, l2) for tr in (0, 1, 2) for fc, mc in ((1, 1), (4, 2)) for l2 in (0, 2, 4)
+             if fc <= nxl]
+    for transport, fwd_chunks, mid_chunks, l2 in cases:
+        got = np.full(shape, np.nan, np.float32)
+        rc = emu.emu_dist_apply(_p(u), _p(r), _p(got), nx, ny, nz, world, transport, fwd_chunks,
+                                mid_chunks, l2, h, d(0.1), d(1.5), 2)
+        assert rc == 0
+        assert np.array_equal(got, want), (transport, fwd_chunks, mid_chunks, l2)
+    # update only (u = NULL) with the exponential-Euler weight
+    want = np.zeros(shape, np.float32)
+    assert emu.emu_native_apply(None, _p(r), _p(want), None, nx, ny, nz, h, d(0.3), d(0.7), 1 | 0x100) == 0
+    got = np.full(shape, np.nan, np.float32)
+    assert emu.emu_dist_apply(None, _p(r), _p(got), nx, ny, nz, world, 1, 2, 2, 2, h, d(0.3), d(0.7), 1 | 0x100) == 0
+    assert np.array_equal(got, want)
+    emu.emu_set_pipe_blocks(0)
