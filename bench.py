@@ -479,6 +479,7 @@ def run_ours_distributed(args, world, rank, local, dev):
                                          "ce": "transposes as DMA-engine copies between symmetric-memory block buffers, "
                                                "pipelined against the kernels of the next chunk",
                                          "nccl": "NCCL all-to-all"}[args.transport],
+                       "l2_blocking": stepper.tune_report or "not searched",
                        "l2": "slab (%.0f MB) larger than L2 (126 MB), no flush needed" % (slab_bytes / 1e6)},
             "clocks": clocks,
             "e2e": {"value": nvox * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
