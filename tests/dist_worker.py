@@ -120,8 +120,8 @@ def run(rank, world, port, shape):
     # the schedule search ran on the first step: every candidate was tried, no mismatch, and all
     # ranks ended on the same setting (the decision is taken on all-reduced numbers)
     rep = stepper.tune_report
-    assert rep is not None and rep["settings"] == [0, 4] and rep["mismatch"] == [0.0, 0.0]
-    assert ops.l2_log[:2] == [0, 4] and ops.l2_log[-1] == rep["chosen"]
+    assert rep is not None and rep["settings"] == [0, 4, 0] and rep["mismatch"] == [0.0, 0.0, 0.0]
+    assert ops.l2_log[:4] == [0, 0, 4, 0] and ops.l2_log[-1] == rep["chosen"]
     chosen = torch.tensor([float(rep["chosen"])], dtype=torch.float64)
     lo, hi = chosen.clone(), chosen.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
