@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE, NOT PRODUCT.  Only `tests/`, `__graft_entry__.smoke()` and the
 `cpu_baseline` / `--impl reference` legs of `bench.py` may import this module; the
-package `evoxels_b200` never does (tests/test_no_oracle_in_product.py checks it).
+package `evoxels_b200` never does (tests/test_host_logic.py::test_product_never_imports_the_oracle
+checks it).
 
 This is a restatement, in plain torch-on-CPU tensor arithmetic, of what the reference
 computes (cites are into /root/reference/evoxels/):
