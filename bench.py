@@ -264,24 +264,6 @@ def run_ours(args):
     value = world * nvox * args.steps / (ms * 1e-3)
     mass_drift = abs(float(u.double().mean()) - float(u0.double().mean()))
 
-    # the same loop under the one-launch-per-pass schedule, for the record (the plan's tuner
-    # picked `schedule` during warm-up; see evx_imex_plan_set_schedule)
-    schedule = plan.schedule() if plan.backend_name == "native" else (0, 1, 0)
-    ms_serial = None
-    if schedule != (0, 1, 0):
-        plan.set_schedule(0, 1, 0)
-        ab_steps = max(5, min(args.steps, 50))
-        v = ts.step(0.0, u0)
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(ab_steps):
-            v = ts.step(0.0, v)
-        a1.record()
-        barrier()
-        ms_serial = a0.elapsed_time(a1) / ab_steps
-        plan.set_schedule(*schedule)
-
     # ---- end to end: pinned host -> device -> step -> pinned host, every step ------------
     e2e_steps = max(6, min(args.steps, 20))
     h_in = torch.empty((1,) + shape, dtype=torch.float32, device="cpu", pin_memory=True)
@@ -372,12 +354,6 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"CH IMEX {n}^3 fp32 periodic dt=0.1 per GPU", **CH,
                    "fft_backend": plan.backend_name,
-                   "schedule": {"chunk_planes": schedule[0], "streams": schedule[1], "flags": schedule[2],
-                                "chosen_by": "plan tuner (timed during warm-up, bit-identical results)"
-                                if plan.tune_report else "default",
-                                "ms_per_step_one_launch_per_pass": ms_serial,
-                                "tuner_baseline_ms": (plan.tune_report or {}).get("baseline_ms"),
-                                "tuner_chosen_ms": (plan.tune_report or {}).get("chosen_ms")},
                    "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
                    "l2": "field (%.0f MB) larger than L2 (126 MB), no flush needed" % (field_bytes / 1e6)},
         "clocks": clocks,
@@ -479,7 +455,6 @@ def run_ours_distributed(args, world, rank, local, dev):
                                          "ce": "transposes as DMA-engine copies between symmetric-memory block buffers, "
                                                "pipelined against the kernels of the next chunk",
                                          "nccl": "NCCL all-to-all"}[args.transport],
-                       "l2_blocking": stepper.tune_report or "not searched",
                        "l2": "slab (%.0f MB) larger than L2 (126 MB), no flush needed" % (slab_bytes / 1e6)},
             "clocks": clocks,
             "e2e": {"value": nvox * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
@@ -521,18 +496,7 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    try:
-        run_ours(args)
-    except Exception as exc:
-        # the measured schedule search is the one part of the path that changes what is launched
-        # from box to box: if a run with it fails, measure once more with one launch per pass
-        single = int(os.environ.get("WORLD_SIZE", "1")) == 1
-        if single and os.environ.get("EVX_TUNE") != "0" and not os.environ.get("EVX_BENCH_RETRIED"):
-            print(f"bench: run failed ({exc!r}); retrying with EVX_TUNE=0", file=sys.stderr, flush=True)
-            os.environ["EVX_TUNE"] = "0"
-            os.environ["EVX_BENCH_RETRIED"] = "1"
-            os.execv(sys.executable, [sys.executable] + sys.argv)
-        raise
+    run_ours(args)
 
 
 if __name__ == "__main__":

@@ -40,7 +40,6 @@ _FILTER_ARGS = [_c_void_p, _c_int, _c_int, _c_int, _dptr, _c_double, _c_double, 
                 _c_double, _c_void_p]
 
 FILTER_ETD1 = 0x100      # EVX_FILTER_ETD1: OR into `power` for the exponential-Euler weight
-SCHED_RING_INV, SCHED_CHUNK_RHS = 1, 2     # EVX_SCHED_*: options of the L2-blocked schedule
 
 SIGNATURES = {
     "evx_version": [],
@@ -55,8 +54,6 @@ SIGNATURES = {
     "evx_imex_plan_destroy": [_c_void_p],
     "evx_imex_plan_backend": [_c_void_p],
     "evx_imex_plan_workspace_bytes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t)],
-    "evx_imex_plan_set_schedule": [_c_void_p, _c_int, _c_int, _c_int],
-    "evx_imex_plan_get_schedule": [_c_void_p, _iptr, _iptr, _iptr],
     "evx_imex_apply_f32": _APPLY_ARGS, "evx_imex_apply_f64": _APPLY_ARGS,
     "evx_ch_imex_step_f32": _STEP_ARGS, "evx_ch_imex_step_f64": _STEP_ARGS,
     "evx_imex_native_pass_f32": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _dptr,
@@ -68,11 +65,9 @@ SIGNATURES = {
     "evx_ch_adjoint_flux_f64": [_c_void_p] * 5 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
     "evx_ch_adjoint_combine_f32": [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
     "evx_ch_adjoint_combine_f64": [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
-    "evx_debug_strided_copy": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "evx_dist_plan_create": [ctypes.POINTER(_c_void_p), _c_int, _c_int, _c_int, _c_int, _c_int],
     "evx_dist_plan_destroy": [_c_void_p],
     "evx_dist_plan_set_p2p_ctas": [_c_void_p, _c_int],
-    "evx_dist_plan_set_l2_planes": [_c_void_p, _c_int],
     "evx_dist_plan_sizes": [_c_void_p, ctypes.POINTER(ctypes.c_size_t), _iptr],
     "evx_dist_forward_f32": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
     "evx_dist_middle_f32": [_c_void_p, _c_void_p, _dptr, _c_double, _c_double, _c_int, _c_void_p],
@@ -152,6 +147,23 @@ def require_cuda(*tensors):
                 f"{getattr(t, 'device', 'host')}).")
 
 
+def refuse_grad(what: str, *tensors):
+    """The kernels behind these wrappers record no autograd node.  Called with grad mode on
+    and an input that requires grad, they would return a detached result and backprop would
+    silently treat it as a constant (the reference's torch ops are differentiable) - raise
+    instead.  Inside `torch.autograd.Function.forward/backward` (autograd.py) grad mode is
+    off, so the hand-written adjoint path is not affected."""
+    if not torch.is_grad_enabled():
+        return
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.requires_grad:
+            raise NotImplementedError(
+                f"{what} runs a CUDA kernel without a backward pass; an input requires grad. "
+                "Differentiable on this path: CahnHilliard (fully periodic, default mu_hom) "
+                "through PseudoSpectralIMEX.step / CahnHilliard.rhs. Wrap the call in "
+                "torch.no_grad() if no gradient is wanted.")
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -184,6 +196,7 @@ def _field3(t: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 def ch_rhs(c, out, spacing, eps, D, bc, hom=None, halo_lo=None, halo_hi=None):
     require_cuda(c, out, hom, halo_lo, halo_hi)
+    refuse_grad("evx_ch_rhs", c, hom, halo_lo, halo_hi)
     lib = load_library()
     nx, ny, nz = _field3(c).shape
     kinds, vals = bc_to_c(bc)
@@ -198,6 +211,7 @@ def ac_stage(phi, spacing, eps, gab, M, force, curvature, bc, *, pot=None, k_out
              base=None, y_out=None, alpha=0.0, acc_in=None, acc_out=None, beta=0.0,
              halo_lo=None, halo_hi=None):
     require_cuda(phi, pot, k_out, base, y_out, acc_in, acc_out, halo_lo, halo_hi)
+    refuse_grad("evx_ac_stage", phi, pot, base, acc_in, halo_lo, halo_hi)
     lib = load_library()
     nx, ny, nz = _field3(phi).shape
     kinds, vals = bc_to_c(bc)
@@ -211,6 +225,7 @@ def ac_stage(phi, spacing, eps, gab, M, force, curvature, bc, *, pot=None, k_out
 
 def pad_ghost(field, bc):
     require_cuda(field)
+    refuse_grad("evx_pad_ghost", field)
     lib = load_library()
     nx, ny, nz = _field3(field).shape
     out = torch.empty((nx + 2, ny + 2, nz + 2), dtype=field.dtype, device=field.device)
@@ -223,6 +238,7 @@ def pad_ghost(field, bc):
 
 def padded_stencil(padded, spacing, op):
     require_cuda(padded)
+    refuse_grad("evx_padded_stencil", padded)
     lib = load_library()
     px, py, pz = _field3(padded).shape
     nx, ny, nz = px - 2, py - 2, pz - 2
@@ -237,6 +253,7 @@ def padded_stencil(padded, spacing, op):
 def rd2_rhs(u, spacing, D_A, D_B, feed, kill, interaction=None):
     """Two-species reaction-diffusion rhs of u [2,nx,ny,nz] (fully periodic)."""
     require_cuda(u, interaction)
+    refuse_grad("evx_rd2_rhs", u, interaction)
     lib = load_library()
     assert u.dim() == 4 and u.shape[0] == 2 and u.is_contiguous()
     out = torch.empty_like(u)
@@ -274,6 +291,7 @@ def copy2d_async(dst_ptr, dpitch, src_ptr, spitch, width_bytes, height, stream):
 def spectral_filter(spec, shape, spacing, dt, coef, power, scale=1.0):
     """In-place P(k) multiply of a cuFFT-layout half spectrum (complex64/128 tensor)."""
     require_cuda(spec)
+    refuse_grad("evx_spectral_filter", spec)
     lib = load_library()
     fn = lib.evx_spectral_filter_c64 if spec.dtype == torch.complex64 else lib.evx_spectral_filter_c128
     nx, ny, nz = shape
@@ -306,8 +324,6 @@ class ImexPlan:
             self.workspace = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8,
                                          device=self.device)
         self.backend = int(lib.evx_imex_plan_backend(handle))
-        self.tuned = False         # tune_ch_step has run (or a schedule was forced)
-        self.tune_report = None
 
     @property
     def backend_name(self):
@@ -316,6 +332,7 @@ class ImexPlan:
     def apply(self, u, r, out, spacing, dt, coef, power):
         """out = u + irfftn(P * rfftn(r)); u may be None (out = update only)."""
         require_cuda(u, r, out)
+        refuse_grad("evx_imex_apply", u, r)
         lib = load_library()
         assert tuple(r.shape) == self.shape and r.dtype == self.dtype
         with torch.cuda.device(self.device):
@@ -335,6 +352,7 @@ class ImexPlan:
 
     def ch_step(self, u, out, spacing, dt, eps, D, A, hom=None):
         require_cuda(u, out, hom)
+        refuse_grad("evx_ch_imex_step", u, hom)
         lib = load_library()
         assert tuple(u.shape) == self.shape and u.dtype == self.dtype
         with torch.cuda.device(self.device):
@@ -343,109 +361,6 @@ class ImexPlan:
                 _ptr(self.workspace), _h3(spacing), float(dt), float(eps), float(D), float(A),
                 _stream(u)), "evx_ch_imex_step")
         return out
-
-    # ---- L2-blocked launch schedule (native back end) --------------------------------------
-    def set_schedule(self, chunk_planes=0, streams=1, flags=0):
-        """chunk_planes x-planes per chunk of the z/y pass pairs (0: one launch per pass), on
-        1, 2 or 3 streams, flags = SCHED_RING_INV | SCHED_CHUNK_RHS (include/evoxels_b200.h)."""
-        with torch.cuda.device(self.device):
-            check(load_library().evx_imex_plan_set_schedule(
-                self._handle, int(chunk_planes), int(streams), int(flags)),
-                "evx_imex_plan_set_schedule")
-
-    def schedule(self):
-        c, s, f = _c_int(), _c_int(), _c_int()
-        check(load_library().evx_imex_plan_get_schedule(
-            self._handle, ctypes.byref(c), ctypes.byref(s), ctypes.byref(f)),
-            "evx_imex_plan_get_schedule")
-        return int(c.value), int(s.value), int(f.value)
-
-    def schedule_sizes(self):
-        """Chunk sizes (x planes) worth timing: a dense ladder - wave quantisation of the short
-        z / y launches makes the optimum jump between neighbouring sizes - limited to chunks
-        whose spectrum (planes * ny * pitch * 8 B) stays well inside the 126 MB L2 and to the
-        ring capacity the plan reserved (min(32, nx / 4) planes)."""
-        nx, ny, nz = self.shape
-        cap = min(32, nx // 4)
-        plane_bytes = ny * (((nz // 2 + 1 + 7) // 8) * 8) * 8
-        cap = min(cap, (64 << 20) // plane_bytes)
-        ladder = (2, 3, 4, 6, 8, 9, 11, 12, 16, 17, 18, 23, 24, 26, 27, 32)
-        sizes = [x for x in ladder if x <= cap]
-        # tiny chunks are launch-bound; they are only candidates where L2 leaves nothing else
-        return [x for x in sizes if x >= 8] or sizes
-
-    def tune_ch_step(self, u, spacing, dt, eps, D, A, min_gain=0.03, log=None):
-        """Time the fused CH step under candidate schedules (CUDA events on the current stream)
-        and keep the fastest one that reproduces the one-launch-per-pass result bit for bit.
-        Phase 1 sweeps the chunk size with the inverse ring on one and two streams; phase 2
-        tries the remaining options (no ring, rhs per chunk) at the two best sizes.  The
-        measurement runs the real step on the caller's field `u` ([nx,ny,nz]) into scratch
-        outputs; nothing the caller owns is modified.  Returns (schedule, report)."""
-        self.tuned = True
-        report = {"candidates": []}
-        if self.backend != FFT_NATIVE:
-            return self.schedule(), report
-        sizes = self.schedule_sizes()
-        free, _total = torch.cuda.mem_get_info(self.device)
-        if not sizes or free < 3 * u.numel() * u.element_size():
-            report["skipped"] = "grid too small" if not sizes else "not enough free memory"
-            return self.schedule(), report
-        ref = torch.empty_like(u)
-        got = torch.empty_like(u)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-        def timed(sched, out, reps):
-            self.set_schedule(*sched)
-            self.ch_step(u, out, spacing, dt, eps, D, A)          # warm-up + the result to compare
-            a.record()
-            for _ in range(reps):
-                self.ch_step(u, out, spacing, dt, eps, D, A)
-            b.record()
-            b.synchronize()
-            return a.elapsed_time(b) / reps
-
-        base = (0, 1, 0)
-        timed(base, ref, 8)                       # untimed in effect: lets the clocks ramp up
-        t_base = timed(base, ref, 3)
-        reps = 4 if t_base < 5.0 else 2
-        results = {}
-
-        def trial(sched):
-            if sched in results:
-                return
-            t = timed(sched, got, reps)
-            same = bool(torch.equal(got, ref))
-            results[sched] = (t, same)
-            report["candidates"].append({"schedule": sched, "ms": t, "bit_identical": same})
-            if log:
-                log(f"evoxels_b200 tune {self.shape}: {sched} {t:.3f} ms "
-                    f"(baseline {t_base:.3f}){'' if same else '  MISMATCH - rejected'}")
-
-        for x in sizes:                                             # phase 1
-            for streams in (2, 1):
-                trial((x, streams, SCHED_RING_INV))
-        ok = sorted((t, s) for s, (t, same) in results.items() if same)
-        best_sizes = []
-        for _t, s in ok:
-            if s[0] not in best_sizes:
-                best_sizes.append(s[0])
-        for x in best_sizes[:2]:                                    # phase 2
-            for streams, flags in ((3, SCHED_RING_INV | SCHED_CHUNK_RHS), (2, SCHED_RING_INV | SCHED_CHUNK_RHS),
-                                   (1, SCHED_RING_INV | SCHED_CHUNK_RHS), (3, SCHED_CHUNK_RHS), (2, 0), (1, 0)):
-                trial((x, streams, flags))
-        best, t_best = base, t_base
-        for s, (t, same) in results.items():
-            if same and t < t_best:
-                best, t_best = s, t
-        # the baseline again at the end (clocks settle while the candidates run): a candidate
-        # must beat the better of the two baseline timings by min_gain
-        t_base2 = timed(base, got, reps)
-        report.update(baseline_ms=t_base, baseline_ms_after=t_base2)
-        if t_best > (1.0 - min_gain) * min(t_base, t_base2):
-            best, t_best = base, min(t_base, t_base2)
-        self.set_schedule(*best)
-        report.update(chosen=best, chosen_ms=t_best)
-        return best, report
 
     def close(self):
         if self._handle is not None and _lib is not None:
@@ -508,10 +423,6 @@ class DistPlan:
 
     def new_buffer(self):
         return torch.empty(self.block_shape, dtype=torch.complex64, device=self.device)
-
-    def set_l2_planes(self, n):
-        """L2 blocking of the local z/y pass pairs (0 = off), see evx_dist_plan_set_l2_planes."""
-        check(load_library().evx_dist_plan_set_l2_planes(self._handle, int(n)), "evx_dist_plan_set_l2_planes")
 
     def set_p2p_ctas(self, n):
         check(load_library().evx_dist_plan_set_p2p_ctas(self._handle, int(n)), "evx_dist_plan_set_p2p_ctas")

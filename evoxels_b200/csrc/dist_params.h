@@ -115,31 +115,4 @@ inline ZParams dist_zinv_params(const DistDims& d, const DistTables& t, cf* spec
   return zp;
 }
 
-// ---- L2 blocking (evx_dist_plan_set_l2_planes) ----------------------------------------------
-// The z/y pass pairs run on sub-chunks of l2_planes x planes, so that the chunk's spectrum is
-// still in L2 when the second pass of the pair reads it.
-struct DistChunk {
-  int x0, nxc;
-  int slot;     // backward: the chunk's spectrum lives in slot `slot` of `spec` (-1: at its own place)
-};
-inline void dist_forward_chunks(int x0, int nxc, int l2_planes, std::vector<DistChunk>& out) {
-  out.clear();
-  const int X = (l2_planes > 0 && l2_planes < nxc) ? l2_planes : nxc;
-  for (int xs = x0; xs < x0 + nxc; xs += X)
-    out.push_back(DistChunk{xs, x0 + nxc - xs < X ? x0 + nxc - xs : X, -1});
-}
-// backward: two alternating slots of l2_planes planes at the start of `spec` (read exactly once,
-// overwritten two chunks later - the intermediate never has to reach HBM)
-inline void dist_backward_chunks(int nxl, int l2_planes, std::vector<DistChunk>& out) {
-  out.clear();
-  if (l2_planes <= 0 || 2 * l2_planes > nxl) { out.push_back(DistChunk{0, nxl, -1}); return; }
-  int i = 0;
-  for (int x0 = 0; x0 < nxl; x0 += l2_planes, ++i)
-    out.push_back(DistChunk{x0, nxl - x0 < l2_planes ? nxl - x0 : l2_planes, i & 1});
-}
-inline cf* dist_backward_spec(const DistDims& d, cf* spec, int l2_planes, const DistChunk& c) {
-  return c.slot < 0 ? spec + (long long)c.x0 * d.ny * d.P
-                    : spec + (long long)c.slot * l2_planes * d.ny * d.P;
-}
-
 }  // namespace evx

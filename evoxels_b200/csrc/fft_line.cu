@@ -1,0 +1,235 @@
+// TMA-tiled strided FFT passes (y / x axis of the half spectrum) - kernel and launcher for the
+// program in fft_line_core.h.  One thread per block drives the tensor copies:
+//
+//   full[b]   mbarrier, completes when the TMA load of the tile in buffer b has landed
+//   done[b]   counter of groups that have finished the tile in buffer b; the thread that
+//             completes the count issues the TMA store of the tile (bulk async-group) and,
+//             once the store has read shared memory, the TMA load of the tile after next
+//
+// so HBM -> smem, the transform and smem -> HBM of consecutive tiles overlap inside one block
+// without a dedicated producer warp (a 17th warp would not fit the 64-register budget at two
+// blocks per SM).
+#include <cuda.h>
+#include <cstdlib>
+#include "evx_internal.h"
+#include "fft_line_core.h"
+#include "fft_line.h"
+
+namespace evx {
+
+// ---- PTX wrappers -------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a pipeline bug must end in a trap, not in a hung GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (unsigned spin = 0;; ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    if ((spin & 1023u) == 1023u && clock64() - t0 > 4000000000LL) __trap();   // ~2 s
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(src)),
+                 "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---- kernel -------------------------------------------------------------------------
+template <class Prog>
+__global__ void __launch_bounds__(Prog::NTHREADS, Prog::NTHREADS <= 512 ? 2 : 1)
+    fft_line_kernel(const __grid_constant__ CUtensorMap tmap, const LineParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  // swizzled TMA tiles want 1024-byte aligned shared memory
+  unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* tiles = sm;
+  cf* xall = reinterpret_cast<cf*>(sm + 2 * Prog::TILE_BYTES);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + 2 * Prog::TILE_BYTES + Prog::X_BYTES);
+  int* done = reinterpret_cast<int*>(full + 2);
+
+  const int tid = threadIdx.x;
+  typename Prog::Regs r;
+  Prog::init(r, tid);
+  cf* xg = xall + r.g * Prog::XG;
+  const bool leader = (tid % Prog::GT) == 0;           // one signalling thread per group
+  const int tpr = p.tiles_per_row;
+  const long long ntiles = p.ntiles;
+  const int nblk = gridDim.x;
+
+  // tile -> (row, kz0); rows of a tile are BOX_ROWS-high boxes along y (along_x = 0) or x
+  auto load_tile = [&](long long tile, int buf) {
+    const int row = (int)(tile / tpr), kz0 = (int)(tile - (long long)row * tpr) * Prog::COLS;
+    unsigned char* dst = tiles + buf * Prog::TILE_BYTES;
+    mbar_expect_tx(&full[buf], Prog::TILE_BYTES);
+#pragma unroll
+    for (int h = 0; h < 512 / Prog::BOX_ROWS; ++h) {
+      if (p.along_x) tma_load_3d(dst + h * Prog::BOX_ROWS * Prog::ROWB, &tmap, &full[buf], kz0, row, h * Prog::BOX_ROWS);
+      else tma_load_3d(dst + h * Prog::BOX_ROWS * Prog::ROWB, &tmap, &full[buf], kz0, h * Prog::BOX_ROWS, row);
+    }
+  };
+  auto store_tile = [&](long long tile, int buf) {
+    const int row = (int)(tile / tpr), kz0 = (int)(tile - (long long)row * tpr) * Prog::COLS;
+    const unsigned char* src = tiles + buf * Prog::TILE_BYTES;
+#pragma unroll
+    for (int h = 0; h < 512 / Prog::BOX_ROWS; ++h) {
+      if (p.along_x) tma_store_3d(&tmap, src + h * Prog::BOX_ROWS * Prog::ROWB, kz0, row, h * Prog::BOX_ROWS);
+      else tma_store_3d(&tmap, src + h * Prog::BOX_ROWS * Prog::ROWB, kz0, h * Prog::BOX_ROWS, row);
+    }
+    tma_store_commit();
+  };
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    done[0] = 0;
+    done[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if ((long long)blockIdx.x < ntiles) load_tile(blockIdx.x, 0);
+    if ((long long)blockIdx.x + nblk < ntiles) load_tile((long long)blockIdx.x + nblk, 1);
+  }
+
+  // tile cursor: (row, tcol) advanced by nblk tiles per iteration without dividing
+  int row = blockIdx.x / tpr, tcol = blockIdx.x - row * tpr;
+  const int step_row = nblk / tpr, step_col = nblk - step_row * tpr;
+  long long pending_tile = -1;      // leader only: tile to load into pending_buf once the store
+  int pending_buf = -1;             // issued by this thread has read shared memory
+
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += nblk, ++it) {
+    const int buf = it & 1;
+    unsigned char* tb = tiles + buf * Prog::TILE_BYTES;
+    Prog::set_tile(r, row, tcol * Prog::COLS);
+    mbar_wait(&full[buf], (unsigned)(it >> 1) & 1u);
+#pragma unroll
+    for (int k = 0; k < Prog::NPHASES; ++k) {
+      if (k) {
+        group_sync(1 + r.g, Prog::GT);
+        if (k == 1 && pending_buf >= 0) {       // deferred half of the previous tile's hand-over
+          tma_store_wait_read();
+          if (pending_tile >= 0) load_tile(pending_tile, pending_buf);
+          pending_buf = -1;
+        }
+      }
+      Prog::phase(k, r, tb, xg, p);
+    }
+    fence_proxy_async();                        // my tile writes -> visible to the TMA store
+    group_sync(1 + r.g, Prog::GT);
+    if (leader) {
+      __threadfence_block();
+      const int old = atomicAdd(&done[buf], 1);
+      if (old == Prog::NG - 1) {                // last group: the tile is complete
+        done[buf] = 0;
+        __threadfence_block();
+        fence_proxy_async();
+        store_tile(tile, buf);
+        pending_buf = buf;
+        pending_tile = tile + 2LL * nblk < ntiles ? tile + 2LL * nblk : -1;
+      }
+    }
+    row += step_row; tcol += step_col;
+    if (tcol >= tpr) { tcol -= tpr; ++row; }
+  }
+  tma_store_wait_read();            // shared memory must outlive the stores this thread issued
+}
+
+// ---- host ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      sym = nullptr;
+    return (EncodeTiledFn)sym;
+  }();
+  return fn;
+}
+
+bool line_pass_available() { return encode_fn() != nullptr; }
+
+int line_make_tmap(void* out, void* spec, int nx, int ny, int P, int ncols_valid, int along_x, int kz) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return EVX_ERR_UNSUPPORTED;
+  if (kz != 8 && kz != 16) return EVX_ERR_ARG;
+  // (kz, y, x) with 8-byte elements; only the valid columns are part of the tensor, so the
+  // pitch padding is neither read nor written
+  const cuuint64_t dims[3] = {(cuuint64_t)ncols_valid, (cuuint64_t)ny, (cuuint64_t)nx};
+  const cuuint64_t strides[2] = {(cuuint64_t)P * sizeof(cf), (cuuint64_t)ny * P * sizeof(cf)};
+  const cuuint32_t box_y[3] = {(cuuint32_t)kz, 256, 1}, box_x[3] = {(cuuint32_t)kz, 1, 256};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult rc = enc((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, spec, dims, strides,
+                          along_x ? box_x : box_y, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          kz == 8 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? EVX_OK : EVX_ERR_UNSUPPORTED;
+}
+
+static int line_sms() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+template <int KZ, int MODE>
+static int launch_line_t(LineParams p, const void* tmap, cudaStream_t st) {
+  using Prog = StridedLine<512, KZ, MODE>;
+  p.tiles_per_row = (p.ncols_valid + KZ - 1) / KZ;
+  p.ntiles = (long long)(p.along_x ? p.ny : p.nx) * p.tiles_per_row;
+  auto kern = fft_line_kernel<Prog>;
+  static SmemOptIn optin;
+  if (int rc = optin.ensure(kern, Prog::SMEM_BYTES)) return rc;
+  long long resident = (long long)line_sms() * (Prog::NTHREADS <= 512 ? 2 : 1);
+  const unsigned grid = (unsigned)(p.ntiles < resident ? p.ntiles : resident);
+  kern<<<grid, Prog::NTHREADS, Prog::SMEM_BYTES, st>>>(*(const CUtensorMap*)tmap, p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int line_pass_launch(int mode, int kz, const LineParams& p, const void* tmap, cudaStream_t st) {
+  if ((p.along_x ? p.nx : p.ny) != 512) return EVX_ERR_UNSUPPORTED;
+#define EVX_LINE(M)                                                  \
+  case M:                                                            \
+    return kz == 16 ? launch_line_t<16, M>(p, tmap, st) : launch_line_t<8, M>(p, tmap, st);
+  switch (mode) {
+    EVX_LINE(PASS_FWD) EVX_LINE(PASS_INV) EVX_LINE(PASS_XMID) EVX_LINE(PASS_XMID_ETD1)
+    default: return EVX_ERR_ARG;
+  }
+#undef EVX_LINE
+}
+
+}  // namespace evx

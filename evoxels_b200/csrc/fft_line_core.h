@@ -1,0 +1,201 @@
+// Strided FFT pass (y or x axis of the half spectrum), TMA-tiled form for 512-point lines.
+//
+// Same arithmetic as StridedPass / StridedPipe in fft_pass_core.h (same radix-8 Stockham
+// stages, same roots, same thread -> butterfly assignment, hence bit-identical results), but
+// re-organised around what measurement showed to bound those kernels on B200:
+//
+//  * Tiles of [512 rows][KZ columns] move between HBM and shared memory with TMA tensor copies
+//    (cp.async.bulk.tensor, 64/128-byte swizzle) issued by ONE thread, in both directions.
+//    The per-thread cp.async prefetch, the eight strided 64-bit global stores and their
+//    64-bit address arithmetic were ~45 % of the instructions of the pipelined y pass.
+//  * A line (column) is transformed by 64 threads; TWO neighbouring lines form a "group" of
+//    128 threads (4 warps) that synchronises with its own named barrier.  Lines of different
+//    groups never exchange data, so there is no block-wide barrier in the tile loop: groups
+//    drift apart and their shared-memory bursts and FP32 bursts overlap instead of all 16/32
+//    warps of a block running in lockstep.
+//  * Stage exchanges alternate between a per-group padded buffer X and the group's own two
+//    columns of the tile buffer (in place), so one barrier per exchange suffices and the last
+//    stage leaves its natural-order output exactly where the TMA store expects it.
+//
+// Shared-memory indexing (all accesses are 64-bit, conflict-free per half-warp; a half-warp
+// is 8 consecutive t x the 2 lines of a group):
+//   tile   element (row r, column c) at byte  r*ROWB + ((c*8) ^ swz(r)),  ROWB = 8*KZ,
+//          swz(r) = ((r>>1)&3)<<4 for 64-byte rows (CU_TENSOR_MAP_SWIZZLE_64B),
+//                   (r&7)<<4      for 128-byte rows (CU_TENSOR_MAP_SWIZZLE_128B)
+//   X      element i of line c2 of the group at cf index  (i + (i>>3)) * 2 + c2
+// With r = t + 64 e (natural order) or r = 64 (t/8) + t%8 + 8 e (output of stage 1) the swizzle
+// term depends on t only, so every access is one base register plus an immediate.
+#pragma once
+#include "fft_pass_core.h"
+
+namespace evx {
+
+struct LineParams {
+  cf* spec;                 // [nx][ny][P] half spectrum (host replay and address checks)
+  const cf* tw;             // W_512 table
+  int nx, ny, P;
+  int ncols_valid;          // nz/2 + 1
+  int tiles_per_row;        // ceil(ncols_valid / KZ)
+  long long ntiles;         // (along_x ? ny : nx) * tiles_per_row
+  int along_x;              // 0: lines run along y (tile row index = x), 1: along x (row index = y)
+  FilterParams filt;        // XMID only; n0 = nx
+};
+
+template <int L, int KZ, int MODE>
+struct StridedLine {
+  static_assert(L == 512, "TMA-tiled strided pass: 512-point lines (three radix-8 stages)");
+  static_assert(KZ == 8 || KZ == 16, "64- or 128-byte tile rows");
+  static constexpr int COLS = KZ;              // columns (lines) per tile
+  static constexpr int T = L / 8;              // threads per line
+  static constexpr int G = 2;                  // lines per synchronisation group
+  static constexpr int GT = T * G;             // threads per group
+  static constexpr int NG = KZ / G;            // groups per block
+  static constexpr int NTHREADS = T * KZ;
+  static constexpr int S = 3;
+  static constexpr bool XMID = pass_is_xmid(MODE);
+  static constexpr int NPHASES = XMID ? 2 * S - 1 : S;
+  static constexpr int ROWB = KZ * (int)sizeof(cf);
+  static constexpr int TILE_BYTES = L * ROWB;
+  static constexpr int BOX_ROWS = 256;         // TMA box height (boxDim <= 256)
+  static constexpr int LP = smem_padded_len(L);
+  static constexpr int XG = LP * G;            // cf elements of one group's exchange buffer
+  static constexpr int X_BYTES = NG * XG * (int)sizeof(cf);
+  // [tile 0 | tile 1 | X | 2 mbarriers | 2 completion counters] + slack to align to 1024 bytes
+  static constexpr int CTRL_BYTES = 64;
+  static constexpr size_t SMEM_BYTES = 1024 + 2 * (size_t)TILE_BYTES + X_BYTES + CTRL_BYTES;
+
+  struct Regs {
+    cf v[8];
+    cf w[3];
+    int t, c2, g, col;       // position in the line, line of the group, group, column in the tile
+    int tb;                  // byte offset of tile element (row t, col)
+    int sb;                  // byte offset of tile element (row 64*(t/8) + t%8, col): stage-1 output
+    int xn, xs;              // cf index in X: natural order base / stage-0 output base
+    int kz, kother;          // XMID: global column and index along the other strided axis
+  };
+
+  EVX_HD static int swz(int r) { return KZ == 8 ? ((r >> 1) & 3) << 4 : (r & 7) << 4; }
+  EVX_HD static int tile_off(int r, int c) { return r * ROWB + ((c * (int)sizeof(cf)) ^ swz(r)); }
+
+  EVX_HD static void init(Regs& r, int tid) {
+    r.g = tid / GT;
+    const int tg = tid - r.g * GT;
+    r.c2 = tg % G;
+    r.t = tg / G;
+    r.col = r.g * G + r.c2;
+    r.tb = tile_off(r.t, r.col);
+    r.sb = tile_off(stage_out_base<L>(1, r.t), r.col);
+    r.xn = smem_pad(r.t) * G + r.c2;
+    r.xs = smem_pad(stage_out_base<L>(0, r.t)) * G + r.c2;
+  }
+  // per tile: where the thread's line sits in the spectrum (only the filter needs it)
+  EVX_HD static void set_tile(Regs& r, int row, int kz0) {
+    r.kz = kz0 + r.col;
+    r.kother = row;
+  }
+
+  EVX_HD static cf* tile_at(unsigned char* tile, int byte_off) {
+    return reinterpret_cast<cf*>(tile + byte_off);
+  }
+  EVX_HD static void read_tile_natural(Regs& r, unsigned char* tile) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r.v[e] = *tile_at(tile, r.tb + e * T * ROWB);
+  }
+  EVX_HD static void write_tile_natural(Regs& r, unsigned char* tile) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) *tile_at(tile, r.tb + e * T * ROWB) = r.v[e];
+  }
+  // output of stage 1 (Ns = 8): element e belongs at row 64*(t/8) + t%8 + 8 e
+  EVX_HD static void write_tile_stage1(Regs& r, unsigned char* tile) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) *tile_at(tile, r.sb + stage_out_const<L>(1, e) * ROWB) = r.v[e];
+  }
+  EVX_HD static void read_x_natural(Regs& r, const cf* xg) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r.v[e] = xg[r.xn + smem_pad(e * T) * G];
+  }
+  // output of stage 0 (Ns = 1): element e belongs at index 8 t + e
+  EVX_HD static void write_x_stage0(Regs& r, cf* xg) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xg[r.xs + smem_pad(stage_out_const<L>(0, e)) * G] = r.v[e];
+  }
+
+  EVX_HD static void apply_filter(Regs& r, const LineParams& p) {
+    const FilterParams& f = p.filt;
+    const float k1 = wavenumber(signed_freq(r.kother, f.n1), f.inv_len1);
+    const float k2 = wavenumber(r.kz, f.inv_len2);
+    const float k12 = k1 * k1 + k2 * k2;
+    const float s0 = 6.283185307179586f * f.inv_len0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float k0 = s0 * (float)signed_freq(r.t + e * T, f.n0);
+      const float kk = k0 * k0 + k12;
+      const float w = (MODE == PASS_XMID_ETD1 ? etd1_weight(kk, f) : imex_prefactor_fast(kk, f)) * f.scale;
+      r.v[e] = cscale(r.v[e], w);
+    }
+  }
+
+  EVX_HD static void fetch_tw(Regs& r, const LineParams& p, int stage) {
+    stage_twiddles<L>(stage, r.t, p.tw, r.w);
+  }
+
+  // Phase k of a tile; the caller synchronises the GROUP between phases.  `tile` is the block's
+  // current tile buffer, `xg` the group's exchange buffer.
+  EVX_HD static void phase(int k, Regs& r, unsigned char* tile, cf* xg, const LineParams& p) {
+    constexpr int DIR = MODE == PASS_INV ? +1 : -1;      // direction of the first transform
+    if (k == 0) {
+      read_tile_natural(r, tile);
+      line_stage_compute_pre<L, DIR>(0, r.v, r.t, r.w);
+      write_x_stage0(r, xg);
+      fetch_tw(r, p, 1);
+    } else if (k == 1) {
+      read_x_natural(r, xg);
+      line_stage_compute_pre<L, DIR>(1, r.v, r.t, r.w);
+      write_tile_stage1(r, tile);
+      fetch_tw(r, p, 2);
+    } else if (k == 2) {
+      read_tile_natural(r, tile);
+      line_stage_compute_pre<L, DIR>(2, r.v, r.t, r.w);
+      if (!XMID) {
+        write_tile_natural(r, tile);
+      } else {
+        apply_filter(r, p);
+        line_stage_compute_pre<L, +1>(0, r.v, r.t, r.w);
+        write_x_stage0(r, xg);
+        fetch_tw(r, p, 1);
+      }
+    } else if (k == 3) {
+      read_x_natural(r, xg);
+      line_stage_compute_pre<L, +1>(1, r.v, r.t, r.w);
+      write_tile_stage1(r, tile);
+      fetch_tw(r, p, 2);
+    } else {
+      read_tile_natural(r, tile);
+      line_stage_compute_pre<L, +1>(2, r.v, r.t, r.w);
+      write_tile_natural(r, tile);
+    }
+  }
+
+  // ---- what the tensor copies do, restated for the host replay (tests/emu) ---------------
+  // element (kz, y, x) of the spectrum; tile (row, kz0): rows run along y (along_x = 0, x = row)
+  // or along x (along_x = 1, y = row).  Out-of-range columns read as zero and are not written.
+  EVX_HD static long long spec_index(const LineParams& p, int row, int kz, int i) {
+    return p.along_x ? ((long long)i * p.ny + row) * p.P + kz : ((long long)row * p.ny + i) * p.P + kz;
+  }
+  static void host_tile_load(const LineParams& p, int row, int kz0, unsigned char* tile) {
+    for (int i = 0; i < L; ++i)
+      for (int c = 0; c < KZ; ++c) {
+        const int kz = kz0 + c;
+        *tile_at(tile, tile_off(i, c)) = kz < p.ncols_valid ? p.spec[spec_index(p, row, kz, i)] : cf{0.f, 0.f};
+      }
+  }
+  static void host_tile_store(const LineParams& p, int row, int kz0, unsigned char* tile) {
+    for (int i = 0; i < L; ++i)
+      for (int c = 0; c < KZ; ++c) {
+        const int kz = kz0 + c;
+        if (kz < p.ncols_valid) p.spec[spec_index(p, row, kz, i)] = *tile_at(tile, tile_off(i, c));
+      }
+  }
+};
+
+}  // namespace evx

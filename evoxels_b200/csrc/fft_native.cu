@@ -8,7 +8,7 @@
 #include "evx_internal.h"
 #include "spectral_plan.h"
 #include "fft_pass_core.h"
-#include "native_schedule.h"
+#include "fft_line.h"
 #include "dist_params.h"
 
 namespace evx {
@@ -16,7 +16,11 @@ namespace evx {
 constexpr int kPitchAlign = 8;   // spectrum rows are padded to a multiple of 8 complex
 
 // MINB = 0: default residency for the block size
-template <class Prog, class Params, int MINB = 0>
+// WARP_LINES: every line of the program is owned by exactly one warp (z passes with M/8 == 32
+// threads per line) - the phases then only need warp-level synchronisation, the eight warps of
+// a block drift apart and their load, exchange and arithmetic phases overlap
+// (512^3: inverse z pass 279 -> 256 us, forward 228 -> 224 us; profiles/r02_exp_passes.json)
+template <class Prog, class Params, int MINB = 0, bool WARP_LINES = false>
 __global__ void __launch_bounds__(Prog::NTHREADS, MINB ? MINB : (Prog::NTHREADS <= 256 ? 4 : (Prog::NTHREADS <= 512 ? 2 : 1))) fft_pass_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf* smem = reinterpret_cast<cf*>(smem_raw);
@@ -24,15 +28,15 @@ __global__ void __launch_bounds__(Prog::NTHREADS, MINB ? MINB : (Prog::NTHREADS 
   Prog::init(r, p, threadIdx.x, (long long)blockIdx.x);
 #pragma unroll
   for (int k = 0; k < Prog::NPHASES; ++k) {
-    if (k) __syncthreads();
+    if (k) { if (WARP_LINES) __syncwarp(); else __syncthreads(); }
     Prog::phase(k, r, smem, p);
   }
 }
 
-template <class Prog, class Params, int MINB = 0>
+template <class Prog, class Params, int MINB = 0, bool WARP_LINES = false>
 static int launch_pass(const Params& p, long long blocks, cudaStream_t st) {
   if (blocks < 1 || blocks > 2147483647LL) return EVX_ERR_UNSUPPORTED;
-  auto kern = fft_pass_kernel<Prog, Params, MINB>;
+  auto kern = fft_pass_kernel<Prog, Params, MINB, WARP_LINES>;
   if (Prog::SMEM_BYTES > 48 * 1024) {
     static SmemOptIn optin;           // per instantiation
     if (int rc = optin.ensure(kern, Prog::SMEM_BYTES)) return rc;
@@ -43,7 +47,7 @@ static int launch_pass(const Params& p, long long blocks, cudaStream_t st) {
 }
 
 // Columns per tile.  The x pass walks lines whose points are ny*P elements (~1 MB) apart:
-// measured with the access-pattern probe (evx_debug_strided_copy, 512^3) a tile of 8
+// measured with an access-pattern probe (PASS_COPY, 512^3; scripts/exp) a tile of 8
 // columns (64-B rows) tops out at 3.3 TB/s there, 16 columns (128-B rows) at 5.3 TB/s,
 // while the y pass (2 KB stride) is already at 6.3 TB/s with 8.  x-pass tiles may straddle
 // y groups (the column index is the linear offset), so the pitch stays a multiple of 8.
@@ -147,7 +151,8 @@ template <bool INV>
 static int launch_z(int M, const ZParams& p, cudaStream_t st) {
   // forward z pass of 512-point lines: 48 registers (no spills) let five CTAs share an SM
   // (227 vs 233 us at 512^3); the inverse pass spills below 64 registers and stays at four
-  if (M == 256 && !INV) return launch_pass<ZPass<256, 8, INV>, ZParams, 5>(p, (p.rows + 7) / 8, st);
+  if (M == 256 && !INV) return launch_pass<ZPass<256, 8, INV>, ZParams, 5, true>(p, (p.rows + 7) / 8, st);
+  if (M == 256 && INV) return launch_pass<ZPass<256, 8, INV>, ZParams, 0, true>(p, (p.rows + 7) / 8, st);
 #define EVX_CASE(N, NL)                                                               \
   case N: return launch_pass<ZPass<N, NL, INV>, ZParams>(p, (p.rows + NL - 1) / NL, st);
   switch (M) {
@@ -174,9 +179,7 @@ int native_plan_init(evx_imex_plan* p) {
   const int M = p->nz / 2;
   p->spec_pitch = ((M + 1 + kPitchAlign - 1) / kPitchAlign) * kPitchAlign;
   p->spec_bytes = ((size_t)p->nx * p->ny * p->spec_pitch * sizeof(cf) + 255) & ~(size_t)255;
-  // two chunk-sized slots behind the spectrum for the ring option of the L2-blocked schedule
-  p->ring_planes = p->nx >= 16 ? (p->nx / 4 < kMaxChunkPlanes ? p->nx / 4 : kMaxChunkPlanes) : 0;
-  p->work_bytes = (2 * (size_t)p->ring_planes * p->ny * p->spec_pitch * sizeof(cf) + 255) & ~(size_t)255;
+  p->work_bytes = 0;
   // tables: W_nx | W_ny | W_M | W_nz[0..M]
   const size_t total = (size_t)p->nx + p->ny + M + (M + 1);
   std::vector<cf> host(total);
@@ -194,89 +197,108 @@ int native_plan_init(evx_imex_plan* p) {
 void native_plan_free(evx_imex_plan* p) {
   if (!p) return;
   if (p->twiddles) { cudaFree(p->twiddles); p->twiddles = nullptr; }
-  for (int i = 0; i < 12; ++i)
-    if (p->ev[i]) { cudaEventDestroy(p->ev[i]); p->ev[i] = nullptr; }
-  for (int i = 0; i < 2; ++i)
-    if (p->side[i]) { cudaStreamDestroy(p->side[i]); p->side[i] = nullptr; }
 }
 
-// ---- schedule execution (native_schedule.h builds the operation list) ----------------
-static NativeDims dims_of(const evx_imex_plan* p) {
-  return NativeDims{p->nx, p->ny, p->nz, p->nz / 2, p->spec_pitch};
+// ---- the five passes on the plan's buffers --------------------------------------------
+struct NativeView {
+  int nx, ny, nz, M, P;
+  cf* spec;
+  const cf *twx, *twy, *twz, *twr;
+};
+
+static NativeView view_of(const evx_imex_plan* p, void* workspace) {
+  NativeView v;
+  v.nx = p->nx; v.ny = p->ny; v.nz = p->nz; v.M = p->nz / 2; v.P = p->spec_pitch;
+  v.spec = reinterpret_cast<cf*>((char*)workspace + p->real_bytes);
+  v.twx = (const cf*)p->twiddles;
+  v.twy = v.twx + p->nx;
+  v.twz = v.twy + p->ny;
+  v.twr = v.twz + v.M;
+  return v;
 }
 
-static NativeBufs bufs_of(const evx_imex_plan* p, const float* u, const float* r, float* out,
-                          void* workspace) {
-  NativeBufs b;
-  b.u = u; b.r = r; b.out = out;
-  b.spec = reinterpret_cast<cf*>((char*)workspace + p->real_bytes);
-  b.ring_slot_elems = (long long)p->ring_planes * p->ny * p->spec_pitch;
-  b.ring = p->ring_planes ? reinterpret_cast<cf*>((char*)workspace + p->real_bytes + p->spec_bytes)
-                          : nullptr;
-  const int X = (p->chunk_planes > 0 && p->chunk_planes < p->nx) ? p->chunk_planes : p->nx;
-  b.rhs_slot_elems = (long long)X * p->ny * p->nz;
-  b.twx = (const cf*)p->twiddles;
-  b.twy = b.twx + p->nx;
-  b.twz = b.twy + p->ny;
-  b.twr = b.twz + p->nz / 2;
-  return b;
+// TMA-tiled form of a strided pass (fft_line.cu): 512-point lines on a driver that can encode
+// tensor maps.  EVX_FFT_TMA=0 keeps the cp.async passes (A/B measurements), EVX_FFT_TMA_KZ=16
+// selects 128-byte tile rows.
+// (read per call: a getenv costs nothing next to a launch, and tests switch paths in-process)
+static bool use_line_pass(int L) {
+  const char* e = getenv("EVX_FFT_TMA");
+  return (!e || atoi(e) != 0) && L == 512 && line_pass_available();
+}
+static int line_kz() {
+  const char* e = getenv("EVX_FFT_TMA_KZ");
+  return (e && atoi(e) == 16) ? 16 : 8;
 }
 
-// rhs_u != null: fused CH step, OP_RHS evaluates the rhs of rhs_u into the real scratch
-static int run_schedule(evx_imex_plan* p, const NativeBufs& b, const float* rhs_u, const double* h,
-                        double dt, double coef, int power, double eps, double D, cudaStream_t st) {
-  const NativeDims d = dims_of(p);
-  std::vector<SchedOp> ops;
-  build_schedule(d.nx, p->chunk_planes, p->side[0] ? p->chunk_streams : 1, p->chunk_flags,
-                 p->ring_planes, rhs_u != nullptr, ops);
-  const int per[3] = {BC_PERIODIC, BC_PERIODIC, BC_PERIODIC};
-  for (const SchedOp& o : ops) {
-    cudaStream_t s = o.stream ? p->side[o.stream - 1] : st;
-    int rc = EVX_OK;
-    switch (o.kind) {
-      case OP_RHS: {
-        const RhsChunk k = rhs_chunk(d, rhs_u, const_cast<float*>(b.r), b.rhs_slot_elems, o);
-        rc = ch_rhs_impl<float>(k.c, nullptr, k.out, o.nxc, d.ny, d.nz, h, eps, D, per, nullptr,
-                                k.halo_lo, k.halo_hi, s);
-        break;
-      }
-      case OP_ZFWD: rc = launch_z<false>(d.M, z_chunk_params(d, b, o), s); break;
-      case OP_ZINV: rc = launch_z<true>(d.M, z_chunk_params(d, b, o), s); break;
-      case OP_YFWD: rc = launch_strided<PASS_FWD>(d.ny, y_chunk_params(d, b, o), s); break;
-      case OP_YINV: rc = launch_strided<PASS_INV>(d.ny, y_chunk_params(d, b, o), s); break;
-      case OP_XMID: rc = launch_xmid(d.nx, x_params(d, b, h, dt, coef, power), s); break;
-      case OP_RECORD: rc = (int)cudaEventRecord(p->ev[o.event], s); break;
-      case OP_WAIT: rc = (int)cudaStreamWaitEvent(s, p->ev[o.event], 0); break;
-      default: rc = EVX_ERR_ARG;
-    }
-    if (rc) return rc;
-  }
+// tensor maps are keyed by the spectrum's address (the caller owns the workspace and may pass
+// a different one per call; encoding is a host-side table fill of about a microsecond)
+static int line_tmaps(evx_imex_plan* p, const NativeView& v) {
+  if (p->tmap_spec == (void*)v.spec && p->tmap_kz == line_kz()) return EVX_OK;
+  int rc = line_make_tmap(p->tmap_y, v.spec, v.nx, v.ny, v.P, v.M + 1, 0, line_kz());
+  if (!rc) rc = line_make_tmap(p->tmap_x, v.spec, v.nx, v.ny, v.P, v.M + 1, 1, line_kz());
+  if (rc) { p->tmap_spec = nullptr; return rc; }
+  p->tmap_spec = (void*)v.spec;
+  p->tmap_kz = line_kz();
   return EVX_OK;
+}
+
+static ZParams z_params(const NativeView& v, const float* real_in, float* real_out) {
+  ZParams zp;
+  zp.real_in = real_in; zp.real_out = real_out; zp.spec = v.spec; zp.tw = v.twz; zp.twr = v.twr;
+  zp.rows = (long long)v.nx * v.ny; zp.nz = v.nz; zp.P = v.P;
+  return zp;
+}
+
+static StridedParams y_params(const NativeView& v) {
+  StridedParams yp;
+  yp.in = v.spec; yp.out = v.spec; yp.tw = v.twy;
+  yp.src = yp.dst = plain_io(v.P, (long long)v.ny * v.P, v.ny);
+  yp.P = v.P; yp.ncols_valid = v.M + 1; yp.ncols_total = (long long)v.nx * v.P;
+  yp.kother_offset = 0; yp.use_peers = 0; yp.max_ctas = 0; yp.dst_peer_base = 0;
+  for (int i = 0; i < 8; ++i) yp.out_peers[i] = nullptr;
+  yp.filt = FilterParams{};
+  return yp;
+}
+
+static FilterParams filter_of(const NativeView& v, const double* h, double dt, double coef, int power) {
+  const int n[3] = {v.nx, v.ny, v.nz};
+  return make_filter(n, h, dt, coef, power, 1.0 / ((double)v.nx * v.ny * v.nz));
+}
+
+// which: 1 y forward, 2 x forward * weight * x inverse, 3 y inverse
+static int strided_pass(evx_imex_plan* p, const NativeView& v, int which, const double* h, double dt,
+                        double coef, int power, cudaStream_t st) {
+  const bool along_x = which == 2;
+  const int L = along_x ? v.nx : v.ny;
+  if (use_line_pass(L)) {
+    if (int rc = line_tmaps(p, v)) return rc;
+    LineParams lp;
+    lp.spec = v.spec; lp.tw = along_x ? v.twx : v.twy;
+    lp.nx = v.nx; lp.ny = v.ny; lp.P = v.P; lp.ncols_valid = v.M + 1;
+    lp.tiles_per_row = 0; lp.ntiles = 0; lp.along_x = along_x ? 1 : 0;
+    lp.filt = along_x ? filter_of(v, h, dt, coef, power) : FilterParams{};
+    const int mode = which == 1 ? PASS_FWD
+                                : (which == 3 ? PASS_INV
+                                              : (lp.filt.kind == FILTER_ETD1 ? PASS_XMID_ETD1 : PASS_XMID));
+    return line_pass_launch(mode, line_kz(), lp, along_x ? p->tmap_x : p->tmap_y, st);
+  }
+  StridedParams sp = y_params(v);
+  if (which == 1) return launch_strided<PASS_FWD>(v.ny, sp, st);
+  if (which == 3) return launch_strided<PASS_INV>(v.ny, sp, st);
+  sp.tw = v.twx;
+  sp.src = sp.dst = plain_io((long long)v.ny * v.P, v.P, v.nx);
+  sp.ncols_total = (long long)v.ny * v.P;
+  sp.filt = filter_of(v, h, dt, coef, power);
+  return launch_xmid(v.nx, sp, st);
 }
 
 int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, void* workspace,
                  const double* h, double dt, double coef, int power, cudaStream_t st) {
-  return run_schedule(p, bufs_of(p, u, r, out, workspace), nullptr, h, dt, coef, power, 0.0, 0.0, st);
-}
-
-int native_set_schedule(evx_imex_plan* p, int chunk_planes, int streams, int flags) {
-  if (chunk_planes < 0 || streams < 1 || streams > kSchedStreams ||
-      (flags & ~(SCHED_RING_INV | SCHED_CHUNK_RHS)))
-    return EVX_ERR_ARG;
-  if (streams >= 2 && !p->side[0]) {
-    for (int i = 0; i < kSchedStreams - 1; ++i) {
-      cudaError_t e = cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking);
-      if (e != cudaSuccess) { p->side[i] = nullptr; p->side[0] = nullptr; return (int)e; }
-    }
-    for (int i = 0; i < kSchedEvents; ++i) {
-      cudaError_t e = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming);
-      if (e != cudaSuccess) { p->side[0] = nullptr; return (int)e; }
-    }
-  }
-  p->chunk_planes = chunk_planes;
-  p->chunk_streams = streams;
-  p->chunk_flags = flags;
-  return EVX_OK;
+  const NativeView v = view_of(p, workspace);
+  if (int rc = launch_z<false>(v.M, z_params(v, r, nullptr), st)) return rc;
+  for (int which = 1; which <= 3; ++which)
+    if (int rc = strided_pass(p, v, which, h, dt, coef, power, st)) return rc;
+  return launch_z<true>(v.M, z_params(v, u, out), st);
 }
 
 // one pass of the pipeline on the plan's scratch (measurement aid for bench.py's per-kernel
@@ -284,32 +306,10 @@ int native_set_schedule(evx_imex_plan* p, int chunk_planes, int streams, int fla
 int native_single_pass(evx_imex_plan* p, int which, const float* u, const float* r, float* out,
                        void* workspace, const double* h, double dt, double coef, int power,
                        cudaStream_t st) {
-  const int nx = p->nx, ny = p->ny, nz = p->nz, M = nz / 2, P = p->spec_pitch;
-  cf* spec = reinterpret_cast<cf*>((char*)workspace + p->real_bytes);
-  const cf* twx = (const cf*)p->twiddles;
-  const cf* twy = twx + nx;
-  const cf* twz = twy + ny;
-  const cf* twr = twz + M;
-  ZParams zp;
-  zp.real_in = r; zp.real_out = nullptr; zp.spec = spec; zp.tw = twz; zp.twr = twr;
-  zp.rows = (long long)nx * ny; zp.nz = nz; zp.P = P;
-  StridedParams yp;
-  yp.in = spec; yp.out = spec; yp.tw = twy;
-  yp.src = yp.dst = plain_io(P, (long long)ny * P, ny);
-  yp.P = P; yp.ncols_valid = M + 1; yp.ncols_total = (long long)nx * P;
-  yp.kother_offset = 0; yp.use_peers = 0; yp.max_ctas = 0; yp.filt = FilterParams{};
-  if (which == 0) return launch_z<false>(M, zp, st);
-  if (which == 1) return launch_strided<PASS_FWD>(ny, yp, st);
-  if (which == 3) return launch_strided<PASS_INV>(ny, yp, st);
-  if (which == 2) {
-    StridedParams xp = yp;
-    xp.tw = twx; xp.src = xp.dst = plain_io((long long)ny * P, P, nx);
-    xp.ncols_total = (long long)ny * P;
-    const int n[3] = {nx, ny, nz};
-    xp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
-    return launch_xmid(nx, xp, st);
-  }
-  if (which == 4) { zp.real_in = u; zp.real_out = out; return launch_z<true>(M, zp, st); }
+  const NativeView v = view_of(p, workspace);
+  if (which == 0) return launch_z<false>(v.M, z_params(v, r, nullptr), st);
+  if (which >= 1 && which <= 3) return strided_pass(p, v, which, h, dt, coef, power, st);
+  if (which == 4) return launch_z<true>(v.M, z_params(v, u, out), st);
   return EVX_ERR_ARG;
 }
 
@@ -317,15 +317,11 @@ int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* ou
                    void* workspace, const double* h, double dt, double eps, double D, double A,
                    cudaStream_t st) {
   float* rhs = (float*)workspace;
-  const double coef = 2.0 * eps * D * A;
-  if (hom) {   // user potential field: the rhs kernel takes no halos with it -> one launch
-    const int per[3] = {BC_PERIODIC, BC_PERIODIC, BC_PERIODIC};
-    int rc = ch_rhs_impl<float>(u, hom, rhs, p->nx, p->ny, p->nz, h, eps, D, per, nullptr, nullptr,
-                                nullptr, st);
-    if (rc) return rc;
-    return native_apply(p, u, rhs, out, workspace, h, dt, coef, 2, st);
-  }
-  return run_schedule(p, bufs_of(p, u, rhs, out, workspace), u, h, dt, coef, 2, eps, D, st);
+  const int per[3] = {BC_PERIODIC, BC_PERIODIC, BC_PERIODIC};
+  if (int rc = ch_rhs_impl<float>(u, hom, rhs, p->nx, p->ny, p->nz, h, eps, D, per, nullptr, nullptr,
+                                  nullptr, st))
+    return rc;
+  return native_apply(p, u, rhs, out, workspace, h, dt, 2.0 * eps * D * A, 2, st);
 }
 
 // ------------------------------------------------------------------------------------
@@ -333,7 +329,6 @@ int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* ou
 // ------------------------------------------------------------------------------------
 struct DistPlan : DistDims {
   int p2p_ctas = 0;   // grid cap of the peer-store launches (0: fill the GPU)
-  int l2_planes = 0;  // > 0: z/y pass pairs run on sub-chunks of this many x planes (L2 blocking)
   void* twiddles = nullptr;
 };
 
@@ -374,18 +369,14 @@ int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* co
                  int x0, int nxc, cudaStream_t st, int parts = 3) {
   if (x0 < 0 || nxc < 1 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
   const DistTables t = tables_of(p);
-  std::vector<DistChunk> chunks;
-  dist_forward_chunks(x0, nxc, parts == 3 ? p->l2_planes : 0, chunks);
-  for (const DistChunk& c : chunks) {
-    if (parts & 1) {
-      const int rc = launch_z<false>(p->M, dist_zfwd_params(*p, t, r_local, spec, c.x0, c.nxc), st);
-      if (rc) return rc;
-    }
-    if (parts & 2) {
-      const int rc = launch_strided<PASS_FWD>(
-          p->ny, dist_yfwd_params(*p, t, spec, send, peers, p->p2p_ctas, c.x0, c.nxc), st);
-      if (rc) return rc;
-    }
+  if (parts & 1) {
+    const int rc = launch_z<false>(p->M, dist_zfwd_params(*p, t, r_local, spec, x0, nxc), st);
+    if (rc) return rc;
+  }
+  if (parts & 2) {
+    const int rc = launch_strided<PASS_FWD>(
+        p->ny, dist_yfwd_params(*p, t, spec, send, peers, p->p2p_ctas, x0, nxc), st);
+    if (rc) return rc;
   }
   return EVX_OK;
 }
@@ -402,16 +393,9 @@ int dist_middle(DistPlan* p, cf* recv, void* const* peers, const double* h, doub
 int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, float* out_local,
                   cudaStream_t st) {
   const DistTables t = tables_of(p);
-  std::vector<DistChunk> chunks;
-  dist_backward_chunks(p->nxl, p->l2_planes, chunks);
-  for (const DistChunk& c : chunks) {
-    cf* sc = dist_backward_spec(*p, spec, p->l2_planes, c);
-    int rc = launch_strided<PASS_INV>(p->ny, dist_yinv_params(*p, t, recv, sc, c.x0, c.nxc), st);
-    if (rc) return rc;
-    rc = launch_z<true>(p->M, dist_zinv_params(*p, t, sc, u_local, out_local, c.x0, c.nxc), st);
-    if (rc) return rc;
-  }
-  return EVX_OK;
+  int rc = launch_strided<PASS_INV>(p->ny, dist_yinv_params(*p, t, recv, spec, 0, p->nxl), st);
+  if (rc) return rc;
+  return launch_z<true>(p->M, dist_zinv_params(*p, t, spec, u_local, out_local, 0, p->nxl), st);
 }
 
 // ------------------------------------------------------------------------------------
@@ -472,34 +456,11 @@ int peer_scatter(const void* const* src, void* const* dst, int n, size_t row_byt
   return (int)cudaGetLastError();
 }
 
-// access-pattern probe: the load/store pattern of a strided pass without the transform
-int debug_strided_copy(cf* data, int nx, int ny, int P, int along_x, int kz_cols, cudaStream_t st) {
-  StridedParams p;
-  p.in = data; p.out = data; p.tw = nullptr; p.P = P; p.ncols_valid = P; p.kother_offset = 0;
-  p.use_peers = 0;
-  p.filt = FilterParams{};
-  int L;
-  if (along_x) { p.src = p.dst = plain_io((long long)ny * P, P, nx); p.ncols_total = (long long)ny * P; L = nx; }
-  else { p.src = p.dst = plain_io(P, (long long)ny * P, ny); p.ncols_total = (long long)nx * P; L = ny; }
-  if (L != 512) return EVX_ERR_UNSUPPORTED;
-  finalize_strided(p, L);
-  switch (kz_cols) {
-    case 4: return launch_pass<StridedPass<512, 4, PASS_COPY>, StridedParams>(p, (p.ncols_total + 3) / 4, st);
-    case 8: return launch_pass<StridedPass<512, 8, PASS_COPY>, StridedParams>(p, (p.ncols_total + 7) / 8, st);
-    case 16: return launch_pass<StridedPass<512, 16, PASS_COPY>, StridedParams>(p, (p.ncols_total + 15) / 16, st);
-    default: return EVX_ERR_ARG;
-  }
-}
-
 }  // namespace evx
 
 using namespace evx;
 
 extern "C" {
-
-int evx_debug_strided_copy(void* data, int nx, int ny, int P, int along_x, int kz_cols, void* stream) {
-  return debug_strided_copy((cf*)data, nx, ny, P, along_x, kz_cols, (cudaStream_t)stream);
-}
 
 int evx_dist_plan_create(evx_dist_plan** plan, int nx, int ny, int nz, int world, int rank) {
   return dist_plan_create((DistPlan**)plan, nx, ny, nz, world, rank);
@@ -512,11 +473,6 @@ int evx_dist_plan_destroy(evx_dist_plan* plan) {
 int evx_dist_plan_set_p2p_ctas(evx_dist_plan* plan, int ctas) {
   if (!plan || ctas < 0) return EVX_ERR_ARG;
   ((DistPlan*)plan)->p2p_ctas = ctas;
-  return EVX_OK;
-}
-int evx_dist_plan_set_l2_planes(evx_dist_plan* plan, int planes) {
-  if (!plan || planes < 0) return EVX_ERR_ARG;
-  ((DistPlan*)plan)->l2_planes = planes;
   return EVX_OK;
 }
 int evx_dist_plan_sizes(const evx_dist_plan* plan, size_t* spec_bytes, int* pitch) {

@@ -264,19 +264,6 @@ int evx_imex_plan_workspace_bytes(const evx_imex_plan* plan, size_t* bytes) {
   return EVX_OK;
 }
 
-int evx_imex_plan_set_schedule(evx_imex_plan* plan, int chunk_planes, int streams, int flags) {
-  if (!plan) return EVX_ERR_ARG;
-  if (plan->backend != EVX_FFT_NATIVE) return EVX_ERR_UNSUPPORTED;
-  return native_set_schedule(plan, chunk_planes, streams, flags);
-}
-int evx_imex_plan_get_schedule(const evx_imex_plan* plan, int* chunk_planes, int* streams, int* flags) {
-  if (!plan) return EVX_ERR_ARG;
-  if (chunk_planes) *chunk_planes = plan->chunk_planes;
-  if (streams) *streams = plan->chunk_streams;
-  if (flags) *flags = plan->chunk_flags;
-  return EVX_OK;
-}
-
 int evx_imex_apply_f32(evx_imex_plan* plan, const float* u, const float* r, float* out,
                        void* workspace, const double* h, double dt, double coef, int power,
                        void* stream) {

@@ -18,15 +18,12 @@ struct evx_imex_plan {
   // native back end
   void* twiddles = nullptr;    // device table(s), owned
   int spec_pitch = 0;          // complex elements per (x,y) row of the native spectrum
-  // native back end: L2-blocked schedule (evx_imex_plan_set_schedule; 0 planes = one launch
-  // per pass).  The z/y pass pairs walk the grid in chunks of `chunk_planes` x planes so that
-  // the spectrum written by the first pass of a pair is still in L2 when the second reads it.
-  int chunk_planes = 0;
-  int chunk_streams = 1;       // 2 / 3: passes of consecutive chunks overlap on the side streams
-  int chunk_flags = 0;         // EVX_SCHED_* bits
-  int ring_planes = 0;         // capacity of one inverse-ring slot in x planes (0: no ring)
-  cudaStream_t side[2] = {nullptr, nullptr};   // owned; created on demand
-  cudaEvent_t ev[12] = {};
+  // TMA tensor maps of the native spectrum (y-pass and x-pass boxes), encoded on first use
+  // for the workspace address `tmap_spec` (fft_line.cu)
+  alignas(64) unsigned char tmap_y[128];
+  alignas(64) unsigned char tmap_x[128];
+  void* tmap_spec = nullptr;
+  int tmap_kz = 0;
 };
 
 namespace evx {
@@ -50,7 +47,6 @@ int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, v
 int native_single_pass(evx_imex_plan* p, int which, const float* u, const float* r, float* out,
                        void* workspace, const double* h, double dt, double coef, int power,
                        cudaStream_t st);
-int native_set_schedule(evx_imex_plan* p, int chunk_planes, int streams, int flags);
 int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* out,
                    void* workspace, const double* h, double dt, double eps, double D, double A,
                    cudaStream_t st);

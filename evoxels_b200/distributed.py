@@ -196,9 +196,6 @@ class CudaOps:
         self.peers = None
         if spectral:
             self.plan = _native.DistPlan(slab.global_shape, slab.world, slab.rank, device)
-            self.l2_forced = os.environ.get("EVX_DIST_L2_PLANES")     # "n": no search, use n
-            if self.l2_forced:
-                self.plan.set_l2_planes(int(self.l2_forced))
             self.spec = self.plan.new_buffer()
             if self.transport in ("p2p", "ce"):
                 try:
@@ -218,30 +215,6 @@ class CudaOps:
 
     def new_field(self):
         return torch.empty(self.slab.local_shape, dtype=torch.float32, device=self.device)
-
-    # ---- hooks of the stepper's schedule search (DistributedCahnHilliardIMEX._tune) ---------
-    def l2_candidates(self):
-        """Sub-chunk sizes (local x planes) worth timing for the L2 blocking of the z/y pass
-        pairs: the largest power of two whose spectrum stays well inside the 126 MB L2."""
-        _, ny, _ = self.slab.global_shape
-        plane_bytes = ny * self.plan.pitch * 8
-        x = 32
-        while x >= 2 and (x * plane_bytes > (48 << 20) or 2 * x > self.slab.nxl):
-            x //= 2
-        return [x] if x >= 2 else []
-
-    def set_l2_planes(self, planes):
-        self.plan.set_l2_planes(planes)
-
-    def clock(self):
-        e = torch.cuda.Event(enable_timing=True)
-        e.record(torch.cuda.current_stream(self.device))
-        return e
-
-    def elapsed_ms(self, start):
-        e = self.clock()
-        e.synchronize()
-        return start.elapsed_time(e)
 
     def ch_rhs(self, u, out, eps, D, bc, halo_lo, halo_hi):
         _native.ch_rhs(u, out, self.spacing, eps, D, bc, halo_lo=halo_lo, halo_hi=halo_hi)
@@ -447,8 +420,6 @@ class DistributedCahnHilliardIMEX:
         if scatter_ctas:
             self.ops.scatter_ctas = int(scatter_ctas)
         self.rhs = self.ops.new_field()
-        self._tuned = False
-        self.tune_report = None
         # forward pipeline depth: x chunks of the local slab issued on two streams (p2p only)
         self.overlap_chunks = overlap_chunks if self.slab.nxl >= 8 * max(overlap_chunks, 1) else 1
         if ops is None and self.ops.transport == "p2p" and self.overlap_chunks > 1 and p2p_ctas:
@@ -488,54 +459,6 @@ class DistributedCahnHilliardIMEX:
         return out, times
 
     def step(self, u_local):
-        if not self._tuned:
-            self._tune(u_local)
-        return self._step_impl(u_local)
-
-    def _tune(self, u_local, reps=3, min_gain=0.03):
-        """First step: decide by measurement whether the local z/y pass pairs run L2-blocked
-        (ops.set_l2_planes).  Every rank times the same candidates on the same collective
-        sequence; the decision uses the MAX over ranks of every time and of every mismatch flag,
-        so all ranks end on the same setting.  A candidate must reproduce the un-blocked step
-        bit for bit and gain at least min_gain.  EVX_DIST_TUNE=0 or a forced
-        EVX_DIST_L2_PLANES skips the search."""
-        self._tuned = True
-        ops = self.ops
-        if os.environ.get("EVX_DIST_TUNE", "1") == "0" or getattr(ops, "l2_forced", None):
-            return
-        cands = ops.l2_candidates() if hasattr(ops, "l2_candidates") else []
-        if not cands:
-            return
-        # un-blocked first and last: the clocks ramp up / settle while the search runs, and a
-        # candidate has to beat the better of the two baseline timings
-        settings = [0] + list(cands) + [0]
-        times, bad, ref = [], [], None
-        ops.set_l2_planes(0)
-        for _ in range(reps):
-            self._step_impl(u_local)                        # ramp-up, untimed
-        for planes in settings:
-            ops.set_l2_planes(planes)
-            v = self._step_impl(u_local)                    # warm-up + the result to compare
-            if ref is None:
-                ref = v
-            bad.append(0.0 if torch.equal(v, ref) else 1.0)
-            start = ops.clock()
-            for _ in range(reps):
-                v = self._step_impl(u_local)
-            times.append(ops.elapsed_ms(start) / reps)
-        t = torch.tensor(times + bad, dtype=torch.float64, device=u_local.device)
-        t = self.comm.all_reduce_max(t).tolist()
-        times, bad = t[:len(settings)], t[len(settings):]
-        t_base = min(times[0], times[-1])
-        best, t_best = 0, t_base
-        for i in range(1, len(settings) - 1):
-            if not bad[i] and times[i] < (1.0 - min_gain) * t_base and times[i] < t_best:
-                best, t_best = i, times[i]
-        ops.set_l2_planes(settings[best])
-        self.tune_report = {"settings": settings, "ms": times, "mismatch": bad,
-                            "chosen": settings[best]}
-
-    def _step_impl(self, u_local):
         ops, comm = self.ops, self.comm
         u_local = u_local.contiguous()
         transport = getattr(ops, "transport", "nccl")

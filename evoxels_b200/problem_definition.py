@@ -82,6 +82,11 @@ def _call_closure(fn, *args):
 
 
 class ODE(ABC):
+    # True when rhs(t, u) does not depend on t.  Only then may the solver capture a few
+    # steps in a CUDA graph (jit=True) - a graph freezes the time argument.  User problem
+    # classes are non-autonomous unless they say otherwise.
+    autonomous = False
+
     @property
     @abstractmethod
     def order(self) -> int:
@@ -146,6 +151,16 @@ class SemiLinearODE(ODE):
         return self._pad_fft_bc(u)
 
 
+def is_stock(problem, cls, names=("rhs", "fourier_symbol", "spectral_form")):
+    """True if `problem` is a `cls` whose listed members are the ones defined by `cls` itself.
+    The fused kernels implement exactly those; a subclass that overrides one of them (say an
+    rhs with a source term) must go through its own methods, as in the reference, where every
+    stepper calls problem.rhs / problem.fourier_symbol."""
+    if not isinstance(problem, cls):
+        return False
+    return all(getattr(type(problem), n, None) is getattr(cls, n, None) for n in names)
+
+
 def _is_traced(*values):
     return any(isinstance(v, torch.Tensor) and v.requires_grad for v in values)
 
@@ -153,6 +168,7 @@ def _is_traced(*values):
 @dataclass
 class CahnHilliard(SemiLinearODE):
     """dc/dt = div( D c(1-c) grad mu ),  mu = mu_hom(c) - 2 eps lap(c)."""
+    autonomous = True
     vg: VoxelGrid
     eps: float = 3.0
     D: float = 1.0
@@ -215,6 +231,7 @@ class CahnHilliard(SemiLinearODE):
 class TwoPhaseAllenCahn(SemiLinearODE):
     """dphi/dt = M [ gab ( curv lap(phi) + (1-curv) d2phi/dn2 - g(phi)/(2 eps) )
                      + 3/eps phi (1-phi) force ]."""
+    autonomous = True
     vg: VoxelGrid
     eps: float = 2.0
     gab: float = 1.0
@@ -293,6 +310,7 @@ class ReactionDiffusion(SemiLinearODE):
     _fourier_symbol: Any = field(init=False, repr=False, default=None)
 
     def __post_init__(self):
+        self.autonomous = self.f is None      # a user source term f(t, u, lib) may depend on t
         if self.f is None:
             self.f = lambda c=None, t=None, lib=None: 0
         self.initialize_boundary_conditions()
@@ -329,6 +347,7 @@ class CoupledReactionDiffusion(SemiLinearODE):
     like the reference (the class has no `bc` field).  With the default interaction
     u0*u1**2 the whole right-hand side is ONE fused kernel (`evx_rd2_rhs_*`); a user
     `interaction` closure is evaluated with torch and handed to the same kernel as a field."""
+    autonomous = True
     vg: VoxelGrid
     D_A: float = 1.0
     D_B: float = 0.5

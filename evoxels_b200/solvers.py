@@ -59,7 +59,11 @@ class BaseSolver(ABC):
         if self.problem_cls is None or self.timestepper_cls is None:
             raise ValueError("Either provide step_fn or both problem_cls and timestepper_cls")
         self.problem = self.problem_cls(self.vg, **(problem_kwargs or {}))
-        self._graph_ok = bool(jit) and self.vg.device.type == "cuda"
+        # A captured graph replays step(0.0, u): legal only if rhs ignores t (ODE.autonomous).
+        # Everything else - ReactionDiffusion with a source f(t, u), user problem classes,
+        # user step_fn - runs the eager loop with the real time, like the reference.
+        self._graph_ok = (bool(jit) and self.vg.device.type == "cuda"
+                          and getattr(self.problem, "autonomous", False) is True)
         return self.timestepper_cls(self.problem, time_increment).step
 
     @abstractmethod
@@ -105,7 +109,9 @@ class BaseSolver(ABC):
         device-side NaN reduction run on a side stream into pinned memory while the solver
         keeps stepping; the frame is committed to `vf.fields` - and a
         NaN aborts the run - when the next frame is submitted, at the end of the run, or
-        immediately if files are written."""
+        immediately if files are written.  Consequence: while solve() runs, `vf.fields` lags
+        one frame behind, and a run that went NaN keeps stepping for up to `max_iters//frames`
+        more iterations before it exits."""
         if u.device.type != "cuda":
             raise RuntimeError("evoxels_b200 has no CPU path: the state must be a CUDA tensor")
         if getattr(self, "_exporter", None) is None:
@@ -118,9 +124,10 @@ class BaseSolver(ABC):
                                   field_names=self.fieldnames)
 
     def _commit_frame(self, host, has_nan, frame, time):
-        arr = host.numpy()
-        for i, name in enumerate(self.fieldnames):
-            self.vf.set_field(name, arr[i].copy())     # the pinned buffer is reused
+        # through _export_fields, so that subclasses overriding it (the reference's
+        # MultiPhaseSolver pattern) see every frame; `host` is the pinned staging buffer,
+        # which is reused - hand out a pageable copy (to_numpy() of a CPU tensor is a view)
+        self._export_fields(torch.empty_like(host, pin_memory=False).copy_(host))
         if has_nan:
             print(f"NaN detected in frame {frame} at time {time}. Aborting simulation.")
             sys.exit(1)
@@ -147,7 +154,9 @@ class _FrameExporter:
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             self.host.copy_(u, non_blocking=True)
-            self.flag.copy_(torch.isnan(u).any().reshape(1), non_blocking=True)
+            # amin propagates NaN and needs no full-size temporary (isnan(u) would allocate
+            # a bool field: 1 GB at 1024^3)
+            self.flag.copy_(torch.isnan(torch.amin(u)).reshape(1), non_blocking=True)
             done = self.stream.record_event()
         u.record_stream(self.stream)                    # keep u's memory until the copy is done
         self.pending = (done, frame, time, commit)

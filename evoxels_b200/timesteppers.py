@@ -20,8 +20,6 @@ and not provided.
 """
 from __future__ import annotations
 
-import os
-import warnings
 from abc import ABC, abstractmethod
 from dataclasses import dataclass
 from typing import Any
@@ -29,7 +27,7 @@ from typing import Any
 import torch
 
 from . import _native
-from .problem_definition import ODE, CahnHilliard, SemiLinearODE
+from .problem_definition import ODE, CahnHilliard, SemiLinearODE, is_stock
 
 State = Any
 
@@ -92,6 +90,17 @@ class RungeKutta4(TimeStepper):
         return acc
 
 
+def _defining_class(obj, name):
+    for klass in type(obj).__mro__:
+        if name in vars(klass):
+            return klass
+    return None
+
+
+def _symbol_matches_form(problem):
+    return _defining_class(problem, "spectral_form") is _defining_class(problem, "fourier_symbol")
+
+
 @dataclass
 class PseudoSpectralIMEX(TimeStepper):
     """First-order semi-implicit Fourier spectral scheme (Zhu & Chen 1999):
@@ -127,38 +136,6 @@ class PseudoSpectralIMEX(TimeStepper):
             self._plans[key] = _native.ImexPlan(shape, dtype, device, code)
         return self._plans[key]
 
-    # Launch schedule of the native pipeline (see include/evoxels_b200.h,
-    # evx_imex_plan_set_schedule): like an FFT library's "measure" planning, the first large
-    # periodic CH step times the L2-blocked schedules against the one-launch-per-pass baseline
-    # and keeps the fastest one whose result is bit-identical.  EVX_TUNE=0 keeps the baseline,
-    # EVX_SCHEDULE="planes,streams,flags" forces a schedule.
-    TUNE_MIN_VOXELS = 1 << 24
-
-    def _choose_schedule(self, plan, u3, spacing):
-        prob = self.problem
-        forced = os.environ.get("EVX_SCHEDULE")
-        if plan.backend != _native.FFT_NATIVE:
-            plan.tuned = True
-            return
-        if forced:
-            plan.set_schedule(*[int(v) for v in forced.split(",")])
-            plan.tuned = True
-            return
-        if os.environ.get("EVX_TUNE", "1") == "0" or u3.numel() < self.TUNE_MIN_VOXELS:
-            plan.tuned = True
-            return
-        if torch.cuda.is_current_stream_capturing():
-            return                       # no timing inside a graph capture; try again later
-        try:
-            log = print if os.environ.get("EVX_TUNE_VERBOSE") else None
-            _, plan.tune_report = plan.tune_ch_step(u3, spacing, self.dt, prob.eps, prob.D, prob.A,
-                                                    log=log)
-        except Exception as exc:          # keep stepping with the baseline schedule
-            plan.tuned = True
-            warnings.warn(f"evoxels_b200: schedule tuning failed ({exc!r}); "
-                          "keeping one launch per pass")
-            plan.set_schedule(0, 1, 0)
-
     def step(self, t, u):
         _native.require_cuda(u)
         prob = self.problem
@@ -173,11 +150,9 @@ class PseudoSpectralIMEX(TimeStepper):
         periodic = prob.bc_type == ("periodic",) * 3
         out = torch.empty_like(u)
 
-        if isinstance(prob, CahnHilliard) and periodic:
+        if periodic and is_stock(prob, CahnHilliard, ("rhs", "fourier_symbol", "spectral_form", "hom_field")):
             plan = self._plan(u.shape[1:], u.dtype, u.device)
             hom = prob.hom_field(u)
-            if not plan.tuned and hom is None:
-                self._choose_schedule(plan, u[0], spacing)
             for ch in range(u.shape[0]):
                 plan.ch_step(u[ch], out[ch], spacing, self.dt, prob.eps, prob.D, prob.A,
                              hom=None if hom is None else hom[ch])
@@ -190,7 +165,10 @@ class PseudoSpectralIMEX(TimeStepper):
         (kind_flag: 0 = IMEX prefactor, FILTER_ETD1 = exponential-Euler weight)."""
         prob = self.problem
         spacing = prob.vg.spacing
-        form = prob.spectral_form()
+        # the closed form stands in for problem.fourier_symbol: only trust it when the class
+        # that defines spectral_form also defines the symbol (a subclass overriding one of the
+        # two falls back to the stored-array path, which reads problem.fourier_symbol)
+        form = prob.spectral_form() if _symbol_matches_form(prob) else None
         r = self.pad(prob.rhs(t, u)).contiguous()
         if form is None:
             # user-defined symbol: stored weight array, cuFFT through torch
@@ -234,9 +212,10 @@ class ExponentialEuler(PseudoSpectralIMEX):
     # the reference bakes this array in __post_init__ (timesteppers.py:153); built on demand
     @property
     def phi_1_k_squared(self):
-        if self._prefac is None:
-            self._prefac = self.phi1(self.dt * self.problem.fourier_symbol)
-        return self._prefac
+        # own cache: `_prefac` belongs to the inherited IMEX prefactor
+        if getattr(self, "_phi1_cache", None) is None:
+            self._phi1_cache = self.phi1(self.dt * self.problem.fourier_symbol)
+        return self._phi1_cache
 
     def step(self, t, u):
         _native.require_cuda(u)

@@ -149,26 +149,6 @@ int evx_imex_plan_backend(const evx_imex_plan* plan);   /* EVX_FFT_CUFFT|NATIVE|
 /* bytes of caller-provided scratch every apply/step call needs (256-byte aligned) */
 int evx_imex_plan_workspace_bytes(const evx_imex_plan* plan, size_t* bytes);
 
-/* L2-blocked launch schedule of the EVX_FFT_NATIVE back end (others: EVX_ERR_UNSUPPORTED).
- * chunk_planes = 0 (default): every pass is one launch over the whole grid and the spectrum
- * crosses HBM between any two passes.  chunk_planes = X > 0: the z and y passes of each
- * direction run pairwise on chunks of X x-planes, so that the second pass of a pair reads the
- * chunk the first one wrote from L2 (X * ny * nz * 8 B should stay well below the 126 MB L2).
- *   streams  1; or 2: the second pass of chunk i is enqueued on a stream owned by the plan,
- *            next to the first pass of chunk i+1 (forked from / joined to `stream` with events;
- *            legal inside CUDA-graph capture); or 3 (with EVX_SCHED_CHUNK_RHS, else like 2):
- *            rhs, z forward and y forward of three consecutive chunks run next to each other
- *   flags    EVX_SCHED_RING_INV: the inverse y pass writes a two-slot ring in the workspace
- *            instead of the spectrum (no write-back of data that is read exactly once);
- *            EVX_SCHED_CHUNK_RHS: evx_ch_imex_step_f32 also evaluates the rhs per chunk.
- * Results are bit-identical for every schedule (same kernels on sub-ranges).  The setting is
- * part of the plan; do not change it while work of this plan is being enqueued elsewhere. */
-#define EVX_SCHED_RING_INV 1
-#define EVX_SCHED_CHUNK_RHS 2
-int evx_imex_plan_set_schedule(evx_imex_plan* plan, int chunk_planes, int streams, int flags);
-int evx_imex_plan_get_schedule(const evx_imex_plan* plan, int* chunk_planes, int* streams,
-                               int* flags);
-
 /* out = u + irfftn( P * rfftn(r) ).  `r` is preserved, `out` may alias `u` but not `r`;
  * u == NULL gives the update alone (out = irfftn(P * rfftn(r))).
  * CH: coef = 2*eps*D*A, power = 2 (problem_definition.py:303).  AC / reaction-diffusion:
@@ -231,11 +211,6 @@ int evx_dist_plan_sizes(const evx_dist_plan* plan, size_t* spec_bytes, int* pitc
 /* cap the persistent grid of the peer-store launches (they are NVLink-bound; leaving SMs free
  * lets the next chunk's rhs / z pass run concurrently on another stream); 0 = fill the GPU */
 int evx_dist_plan_set_p2p_ctas(evx_dist_plan* plan, int ctas);
-/* L2 blocking of the local transform pairs (default 0 = off): forward calls run z then y, and
- * evx_dist_backward_f32 runs y then z (+u), on sub-chunks of `planes` local x planes, so that the
- * chunk's spectrum is still in L2 when the second pass of the pair reads it (cf.
- * evx_imex_plan_set_schedule).  Same kernels on sub-ranges: results are bit-identical. */
-int evx_dist_plan_set_l2_planes(evx_dist_plan* plan, int planes);
 int evx_dist_forward_f32(evx_dist_plan* plan, const float* r_local, void* spec, void* send,
                          void* stream);
 int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double dt, double coef,
@@ -310,10 +285,6 @@ int evx_ch_adjoint_combine_f32(const float* u, const float* z, const float* m,
 int evx_ch_adjoint_combine_f64(const double* u, const double* z, const double* m,
                                const double* lam_in, double* lam_out, double* deps_acc, int nx,
                                int ny, int nz, const double* h, double eps, void* stream);
-
-/* measurement aid: the global load/store pattern of a strided FFT pass (512-point lines, tiles
- * of kz_cols columns) without the transform - the bandwidth ceiling of that access pattern */
-int evx_debug_strided_copy(void* data, int nx, int ny, int P, int along_x, int kz_cols, void* stream);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long evx_launch_count(void);

@@ -38,17 +38,6 @@ for name, code in (("cufft", _native.FFT_CUFFT), ("native", _native.FFT_NATIVE))
         del plan
     except Exception as exc:
         res[f"imex_apply_{name}_ms"] = str(exc)
-if n == 512:
-    lib = _native.load_library()
-    P = 264
-    spec = torch.zeros((n, n, P), dtype=torch.complex64, device=dev)
-    import ctypes
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for along_x in (0, 1):
-        for kz in (4, 8, 16):
-            ms = timed(lambda: lib.evx_debug_strided_copy(ctypes.c_void_p(spec.data_ptr()), n, n, P, along_x, kz, st))
-            res[f"probe_copy_{'x' if along_x else 'y'}_kz{kz}_ms"] = round(ms, 4)
-    del spec
 # two-species reaction-diffusion (16 B/voxel rhs) and the ETD1 step
 u2 = torch.stack([torch.rand((n, n, n), device=dev), 0.5 * torch.rand((n, n, n), device=dev)])
 ms = timed(lambda: _native.rd2_rhs(u2, (1, 1, 1), 1.0, 0.5, 0.055, 0.117), reps=10)

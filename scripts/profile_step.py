@@ -16,7 +16,6 @@ u = 0.5 + 0.1 * torch.rand((1, n, n, n), device="cuda")
 for _ in range(3):
     u = ts.step(0.0, u)
 torch.cuda.synchronize()
-print("schedule", next(iter(ts._plans.values())).schedule())
 torch.cuda.profiler.start()
 u = ts.step(0.0, u)
 torch.cuda.synchronize()

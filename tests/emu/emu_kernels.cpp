@@ -226,8 +226,55 @@ static void run_pipe(const StridedParams& p, int nblocks) {
   }
 }
 
+// TMA-tiled strided pass (fft_line_core.h) replayed with `nblocks` resident blocks: tensor
+// copies are restated by host_tile_load / host_tile_store (swizzled tile image, zero fill and
+// no write-back outside the valid columns); groups are replayed one after the other through
+// all phases of a tile, i.e. with NO ordering between different groups - exactly what the
+// kernel guarantees - and two tile buffers alternate like on the device.
+#include "../../evoxels_b200/csrc/fft_line_core.h"
+template <int KZ, int MODE>
+static void run_line(LineParams p, int nblocks) {
+  using Prog = StridedLine<512, KZ, MODE>;
+  p.tiles_per_row = (p.ncols_valid + KZ - 1) / KZ;
+  p.ntiles = (long long)(p.along_x ? p.ny : p.nx) * p.tiles_per_row;
+  std::vector<typename Prog::Regs> regs(Prog::NTHREADS);
+  std::vector<unsigned char> tiles(2 * (size_t)Prog::TILE_BYTES, 0xff);
+  std::vector<cf> xall((size_t)Prog::NG * Prog::XG, cf{std::nanf(""), std::nanf("")});
+  for (int t = 0; t < Prog::NTHREADS; ++t) Prog::init(regs[t], t);
+  for (int blk = 0; blk < nblocks; ++blk) {
+    int it = 0;
+    for (long long tile = blk; tile < p.ntiles; tile += nblocks, ++it) {
+      unsigned char* tb = tiles.data() + (it & 1) * Prog::TILE_BYTES;
+      const int row = (int)(tile / p.tiles_per_row), kz0 = (int)(tile % p.tiles_per_row) * KZ;
+      Prog::host_tile_load(p, row, kz0, tb);
+      for (int g = Prog::NG - 1; g >= 0; --g) {        // any group order must do
+        cf* xg = xall.data() + (size_t)g * Prog::XG;
+        for (int k = 0; k < Prog::NPHASES; ++k)
+          for (int t = g * Prog::GT; t < (g + 1) * Prog::GT; ++t) {
+            if (k == 0) Prog::set_tile(regs[t], row, kz0);
+            Prog::phase(k, regs[t], tb, xg, p);
+          }
+      }
+      Prog::host_tile_store(p, row, kz0, tb);
+    }
+  }
+}
+
+static int g_emu_line_kz = 0;       // 8 / 16: 512-point strided passes through the TMA-tiled program
 static int g_emu_xkz = 8;           // columns per tile of the x pass (8 or 16; 16 may straddle y groups)
 static int g_emu_pipe_blocks = 0;   // 0: one block per tile (StridedPass), >0: pipelined with that many blocks
+
+// plain single-domain layouts only (what fft_native.cu routes to the TMA-tiled passes)
+template <int MODE>
+static bool try_line(int L, const StridedParams& p, int nx, int ny) {
+  if (!g_emu_line_kz || L != 512 || p.use_peers || p.in != p.out) return false;
+  LineParams lp;
+  lp.spec = p.out; lp.tw = p.tw; lp.nx = nx; lp.ny = ny; lp.P = p.P; lp.ncols_valid = p.ncols_valid;
+  lp.along_x = pass_is_xmid(MODE) ? 1 : 0; lp.filt = p.filt;
+  const int nb = g_emu_pipe_blocks > 0 ? g_emu_pipe_blocks : 5;
+  if (g_emu_line_kz == 16) run_line<16, MODE>(lp, nb); else run_line<8, MODE>(lp, nb);
+  return true;
+}
 
 template <int KZ, int MODE>
 static int dispatch_strided(int L, StridedParams p) {
@@ -289,6 +336,7 @@ static int dispatch_z(int M, const ZParams& p) {
 extern "C" {
 
 void emu_set_pipe_blocks(int n) { g_emu_pipe_blocks = n; }
+void emu_set_line_columns(int kz) { g_emu_line_kz = kz; }
 void emu_set_xpass_columns(int kz) { g_emu_xkz = kz; }
 
 // out = u + irfftn(P * rfftn(r)) through the five native passes; spec is scratch
@@ -311,7 +359,8 @@ int emu_native_apply(const float* u, const float* r, float* out, float* spec_out
   // y pass: columns (x, kz), line stride P, group stride ny*P
   sp.tw = twy.data(); sp.src = sp.dst = yio;
   sp.ncols_total = (long long)nx * P;
-  if (dispatch_strided<KZ, PASS_FWD>(ny, sp)) return -2;
+  sp.filt = FilterParams{};
+  if (!try_line<PASS_FWD>(ny, sp, nx, ny) && dispatch_strided<KZ, PASS_FWD>(ny, sp)) return -2;
   if (spec_out) {   // forward-only check: finish x forward and return the spectrum
     sp.tw = twx.data(); sp.src = sp.dst = xio;
     sp.ncols_total = (long long)ny * P;
@@ -325,11 +374,13 @@ int emu_native_apply(const float* u, const float* r, float* out, float* spec_out
   sp.tw = twx.data(); sp.src = sp.dst = xio;
   sp.ncols_total = (long long)ny * P;
   if (sp.filt.kind == FILTER_ETD1) {
-    if (dispatch_strided<KZ, PASS_XMID_ETD1>(nx, sp)) return -3;
+    if (!try_line<PASS_XMID_ETD1>(nx, sp, nx, ny) && dispatch_strided<KZ, PASS_XMID_ETD1>(nx, sp)) return -3;
+  } else if (try_line<PASS_XMID>(nx, sp, nx, ny)) {
   } else if (g_emu_xkz == 16 ? dispatch_strided<16, PASS_XMID>(nx, sp) : dispatch_strided<KZ, PASS_XMID>(nx, sp)) return -3;
   sp.tw = twy.data(); sp.src = sp.dst = yio;
   sp.ncols_total = (long long)nx * P;
-  if (dispatch_strided<KZ, PASS_INV>(ny, sp)) return -4;
+  sp.filt = FilterParams{};
+  if (!try_line<PASS_INV>(ny, sp, nx, ny) && dispatch_strided<KZ, PASS_INV>(ny, sp)) return -4;
   zp.real_in = u; zp.real_out = out;
   if (dispatch_z<true>(M, zp)) return -5;
   return 0;
@@ -380,70 +431,6 @@ extern "C" long long emu_prefetch_mismatches(int L, int KZ, int layout, int grou
 }
 
 // -------------------------------------------------------------------------------------
-// L2-blocked schedule: the operation list of native_schedule.h executed serially (issue order)
-// -------------------------------------------------------------------------------------
-#include "../../evoxels_b200/csrc/native_schedule.h"
-extern "C" {
-
-// kind, stream, x0, nxc, slot, event per op (6 ints each); returns the number of ops
-int emu_schedule_ops(int nx, int chunk_planes, int streams, int flags, int ring_planes, int with_rhs,
-                     int* out, int capacity) {
-  std::vector<SchedOp> ops;
-  build_schedule(nx, chunk_planes, streams, flags, ring_planes, with_rhs != 0, ops);
-  if ((int)ops.size() > capacity) return -(int)ops.size();
-  for (size_t i = 0; i < ops.size(); ++i) {
-    const SchedOp& o = ops[i];
-    int* q = out + 6 * i;
-    q[0] = o.kind; q[1] = o.stream; q[2] = o.x0; q[3] = o.nxc; q[4] = o.slot; q[5] = o.event;
-  }
-  return (int)ops.size();
-}
-
-// out = u + irfftn(P * rfftn(r)) with r = CahnHilliard.rhs(u) when with_rhs (eps, D), else the
-// given r, through the scheduled pipeline.  Scratch is poisoned with NaN so that any read of a
-// chunk or ring slot that was not produced first shows up in the result.
-int emu_native_sched(const float* u, const float* r_in, float* out, int nx, int ny, int nz,
-                     const double* h, double dt, double coef, int power, double eps, double D,
-                     int with_rhs, int chunk_planes, int streams, int flags, int ring_planes) {
-  const int M = nz / 2, P = ((M + 1 + 7) / 8) * 8;
-  const NativeDims d{nx, ny, nz, M, P};
-  const float nanv = std::nanf("");
-  std::vector<cf> spec((size_t)nx * ny * P, cf{nanv, nanv});
-  std::vector<cf> ring(2 * (size_t)(ring_planes > 0 ? ring_planes : 1) * ny * P, cf{nanv, nanv});
-  std::vector<float> rhs((size_t)nx * ny * nz, nanv);
-  auto twx = make_roots(nx, nx), twy = make_roots(ny, ny), twz = make_roots(M, M),
-       twr = make_roots(nz, M + 1);
-  NativeBufs b;
-  b.u = u; b.r = with_rhs ? rhs.data() : r_in; b.out = out; b.spec = spec.data();
-  b.ring = ring_planes > 0 ? ring.data() : nullptr;
-  b.ring_slot_elems = (long long)ring_planes * ny * P;
-  const int X = (chunk_planes > 0 && chunk_planes < nx) ? chunk_planes : nx;
-  b.rhs_slot_elems = (long long)X * ny * nz;
-  b.twx = twx.data(); b.twy = twy.data(); b.twz = twz.data(); b.twr = twr.data();
-  std::vector<SchedOp> ops;
-  build_schedule(nx, chunk_planes, streams, flags, ring_planes, with_rhs != 0, ops);
-  const int per[3] = {BC_PERIODIC, BC_PERIODIC, BC_PERIODIC};
-  for (const SchedOp& o : ops) {
-    switch (o.kind) {
-      case OP_RHS: {
-        const RhsChunk k = rhs_chunk(d, u, rhs.data(), b.rhs_slot_elems, o);
-        if (emu_ch<float>(k.c, nullptr, k.out, o.nxc, ny, nz, h, eps, D, per, nullptr, k.halo_lo,
-                          k.halo_hi, o.nxc, nz % 4 == 0 ? 1 : 0)) return -10;
-        break;
-      }
-      case OP_ZFWD: if (dispatch_z<false>(M, z_chunk_params(d, b, o))) return -1; break;
-      case OP_ZINV: if (dispatch_z<true>(M, z_chunk_params(d, b, o))) return -5; break;
-      case OP_YFWD: if (dispatch_strided<8, PASS_FWD>(ny, y_chunk_params(d, b, o))) return -2; break;
-      case OP_YINV: if (dispatch_strided<8, PASS_INV>(ny, y_chunk_params(d, b, o))) return -4; break;
-      case OP_XMID: if (dispatch_strided<8, PASS_XMID>(nx, x_params(d, b, h, dt, coef, power))) return -3; break;
-      default: break;   // RECORD / WAIT: the serial replay is one legal order
-    }
-  }
-  return 0;
-}
-}
-
-// -------------------------------------------------------------------------------------
 // x-slab distributed pipeline: W virtual ranks through the parameters of dist_params.h
 // -------------------------------------------------------------------------------------
 #include "../../evoxels_b200/csrc/dist_params.h"
@@ -453,9 +440,9 @@ extern "C" {
 // ranks (x slabs).  transport 0: local send buffer + all-to-all (NCCL path), 1: local block
 // buffers with the self block written in place + block copies (copy-engine path), 2: stores
 // straight into the peers' buffers (peer-store path).  fwd_chunks / mid_chunks: pipeline chunks
-// of the host orchestration; l2_planes: evx_dist_plan_set_l2_planes.
+// of the host orchestration.
 int emu_dist_apply(const float* u, const float* r, float* out, int nx, int ny, int nz, int world,
-                   int transport, int fwd_chunks, int mid_chunks, int l2_planes, const double* h,
+                   int transport, int fwd_chunks, int mid_chunks, const double* h,
                    double dt, double coef, int power) {
   if (nx % world || ny % world || world > 8) return -1;
   std::vector<DistDims> dims;
@@ -475,7 +462,6 @@ int emu_dist_apply(const float* u, const float* r, float* out, int nx, int ny, i
     B[k].assign((size_t)world * blk, cf{nanv, nanv});
   }
   auto bounds = [](int n, int chunks, int i) { return (int)std::lround((double)i * n / chunks); };
-  std::vector<DistChunk> chunks;
   // ---- forward: z + y passes, blocks into the peers' B -------------------------------------
   for (int k = 0; k < world; ++k) {
     const DistDims& d = dims[k];
@@ -488,11 +474,8 @@ int emu_dist_apply(const float* u, const float* r, float* out, int nx, int ny, i
     for (int i = 0; i < fwd_chunks; ++i) {
       const int x0 = bounds(nxl, fwd_chunks, i), x1 = bounds(nxl, fwd_chunks, i + 1);
       if (x1 <= x0) continue;
-      dist_forward_chunks(x0, x1 - x0, l2_planes, chunks);
-      for (const DistChunk& c : chunks) {
-        if (dispatch_z<false>(M, dist_zfwd_params(d, t, r_local, spec[k].data(), c.x0, c.nxc))) return -2;
-        if (dispatch_strided<8, PASS_FWD>(ny, dist_yfwd_params(d, t, spec[k].data(), send, peers, 0, c.x0, c.nxc))) return -3;
-      }
+      if (dispatch_z<false>(M, dist_zfwd_params(d, t, r_local, spec[k].data(), x0, x1 - x0))) return -2;
+      if (dispatch_strided<8, PASS_FWD>(ny, dist_yfwd_params(d, t, spec[k].data(), send, peers, 0, x0, x1 - x0))) return -3;
     }
   }
   if (transport != 2)   // all-to-all / block copies: block j of rank k's A -> block k of rank j's B
@@ -528,13 +511,9 @@ int emu_dist_apply(const float* u, const float* r, float* out, int nx, int ny, i
   for (int k = 0; k < world; ++k) {
     const DistDims& d = dims[k];
     std::fill(spec[k].begin(), spec[k].end(), cf{nanv, nanv});
-    dist_backward_chunks(nxl, l2_planes, chunks);
-    for (const DistChunk& c : chunks) {
-      cf* sc = dist_backward_spec(d, spec[k].data(), l2_planes, c);
-      if (dispatch_strided<8, PASS_INV>(ny, dist_yinv_params(d, t, A[k].data(), sc, c.x0, c.nxc))) return -5;
-      if (dispatch_z<true>(M, dist_zinv_params(d, t, sc, u ? u + k * slab_real : nullptr,
-                                               out + k * slab_real, c.x0, c.nxc))) return -6;
-    }
+    if (dispatch_strided<8, PASS_INV>(ny, dist_yinv_params(d, t, A[k].data(), spec[k].data(), 0, nxl))) return -5;
+    if (dispatch_z<true>(M, dist_zinv_params(d, t, spec[k].data(), u ? u + k * slab_real : nullptr,
+                                             out + k * slab_real, 0, nxl))) return -6;
   }
   return 0;
 }

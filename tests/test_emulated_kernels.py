@@ -201,6 +201,57 @@ def test_native_fft_pipeline(emu, shape, pipe_blocks, xkz):
     assert rel_l2(out, want) < 1e-6
 
 
+@pytest.mark.parametrize("kz", [8, 16])
+@pytest.mark.parametrize("shape,blocks,power", [((8, 512, 16), 3, 2), ((512, 8, 16), 2, 2),
+                                                ((512, 512, 16), 7, 2), ((512, 8, 32), 5, 1 | 0x100)])
+def test_tma_tiled_strided_passes_are_bit_identical(emu, shape, blocks, power, kz):
+    """The TMA-tiled program of the 512-point strided passes (fft_line_core.h: two-line groups,
+    swizzled tile image, exchanges through X and through the tile itself) replayed on the CPU
+    gives the very same bits as the cp.async passes - y forward, x forward*weight*inverse (IMEX
+    and exponential-Euler weight) and y inverse, 64- and 128-byte tile rows, including the
+    partly out-of-range last tile of every row (nz/2+1 is not a multiple of the tile width)."""
+    nx, ny, nz = shape
+    rng = np.random.default_rng(5)
+    r = rng.standard_normal(shape).astype(np.float32)
+    u = rng.random(shape).astype(np.float32)
+    h = (ctypes.c_double * 3)(1.0, 0.5, 2.0)
+    d = ctypes.c_double
+    want = np.zeros(shape, np.float32)
+    emu.emu_set_line_columns(0)
+    assert emu.emu_native_apply(_p(u), _p(r), _p(want), None, nx, ny, nz, h, d(0.1), d(1.5), power) == 0
+    got = np.full(shape, np.nan, np.float32)
+    emu.emu_set_line_columns(kz)
+    emu.emu_set_pipe_blocks(blocks)
+    try:
+        assert emu.emu_native_apply(_p(u), _p(r), _p(got), None, nx, ny, nz, h, d(0.1), d(1.5), power) == 0
+    finally:
+        emu.emu_set_line_columns(0)
+        emu.emu_set_pipe_blocks(0)
+    assert np.array_equal(got, want)
+
+
+def test_tma_tile_image_is_conflict_free():
+    """Shared-memory bank check of the TMA-tiled pass on the index formulas of fft_line_core.h:
+    every 64-bit access pattern of a half-warp (8 consecutive t x the 2 lines of a group) hits
+    16 distinct 8-byte bank pairs - tile image with the 64-/128-byte TMA swizzle (natural order
+    and stage-1 output order) and the padded exchange buffer (natural and stage-0 order)."""
+    T = 64
+    pad = lambda i: i + (i >> 3)
+    for kz in (8, 16):
+        rowb = 8 * kz
+        swz = (lambda r: ((r >> 1) & 3) << 4) if kz == 8 else (lambda r: (r & 7) << 4)
+        tile = lambda r, c: r * rowb + ((c * 8) ^ swz(r))
+        for g in range(kz // 2):
+            for t0 in range(0, T, 8):
+                lanes = [(t, 2 * g + c2) for t in range(t0, t0 + 8) for c2 in (0, 1)]
+                for e in range(8):
+                    nat = {(tile(t + e * T, c) // 8) % 16 for t, c in lanes}
+                    st1 = {(tile(64 * (t // 8) + t % 8 + 8 * e, c) // 8) % 16 for t, c in lanes}
+                    xn = {(pad(t + e * T) * 2 + c % 2) % 16 for t, c in lanes}
+                    xs = {(pad(8 * t + e) * 2 + c % 2) % 16 for t, c in lanes}
+                    assert len(nat) == len(st1) == len(xn) == len(xs) == 16, (kz, g, t0, e)
+
+
 @pytest.mark.parametrize("shape", [(8, 8, 16), (16, 32, 64), (8, 16, 256)])
 def test_native_fft_pipeline_etd1_weight(emu, shape):
     """Same pipeline with the exponential-Euler weight (EVX_FILTER_ETD1) against the oracle's
@@ -296,168 +347,6 @@ def test_ch_rhs_adjoint_against_autograd(emu):
         assert abs(float((R.detach()[0] * torch.from_numpy(w)).sum() / 1.3) - float(gD)) < 1e-10 * max(1.0, abs(float(gD)))
 
 
-# ------------------------------------------------------------------------------------------
-# L2-blocked launch schedule (evoxels_b200/csrc/native_schedule.h)
-# ------------------------------------------------------------------------------------------
-OP = {"rhs": 0, "zfwd": 1, "yfwd": 2, "xmid": 3, "yinv": 4, "zinv": 5, "record": 6, "wait": 7}
-SCHEDULES = [(0, 1, 0), (4, 1, 0), (4, 1, 1), (4, 2, 0), (4, 2, 1), (4, 2, 3), (4, 1, 3), (6, 2, 3),
-             (5, 2, 3), (2, 2, 3), (8, 2, 1), (16, 2, 3), (3, 1, 2), (31, 2, 3), (7, 1, 3),
-             (4, 3, 3), (4, 3, 2), (5, 3, 3), (8, 3, 1), (16, 3, 3), (2, 3, 3), (31, 3, 3)]
-
-
-def _ops(emu, nx, chunk, streams, flags, ring, with_rhs):
-    buf = (ctypes.c_int * (6 * 4096))()
-    n = emu.emu_schedule_ops(nx, chunk, streams, flags, ring, int(with_rhs), buf, 4096)
-    assert n > 0
-    return [tuple(buf[6 * i:6 * i + 6]) for i in range(n)]
-
-
-def _footprint(op, nx, ring_used, rhs_slot_used):
-    """(reads, writes) of a compute op as sets of (buffer, index) cells."""
-    kind, _, x0, nxc, slot, _ = op
-    planes = range(x0, x0 + nxc)
-    S = {("spec", x) for x in planes}
-    if kind == OP["rhs"]:
-        rd = {("u", (x0 + k) % nx) for k in range(-2, nxc + 2)}
-        wr = {("rhs_slot", slot)} if slot >= 0 else {("rhs", x) for x in planes}
-        return rd, wr
-    if kind == OP["zfwd"]:
-        return ({("rhs_slot", slot)} if slot >= 0 else {("rhs", x) for x in planes}), S
-    if kind == OP["yfwd"]:
-        return S, S
-    if kind == OP["xmid"]:
-        return S, S
-    if kind == OP["yinv"]:
-        return S, ({("ring", slot)} if slot >= 0 else S)
-    if kind == OP["zinv"]:
-        rd = ({("ring", slot)} if slot >= 0 else S) | {("u", x) for x in planes}
-        return rd, {("out", x) for x in planes}
-    raise AssertionError(kind)
-
-
-def _check_ordering(ops, nx):
-    """Every pair of compute ops with a read/write or write/write overlap must be ordered by
-    stream order or by a record -> wait edge (a wait refers to the LAST record of its event
-    issued before it, the CUDA rule).  Two consecutive applications are checked back to back
-    so that hazards across steps (ring slots, side stream) are covered."""
-    seq = list(ops) + list(ops)
-    n = len(seq)
-    preds = [set() for _ in range(n)]          # direct happens-before predecessors
-    last_on_stream = {}
-    last_record = {}
-    for i, op in enumerate(seq):
-        kind, stream, *_rest, event = op
-        if stream in last_on_stream:
-            preds[i].add(last_on_stream[stream])
-        last_on_stream[stream] = i
-        if kind == OP["record"]:
-            last_record[event] = i
-        elif kind == OP["wait"]:
-            assert event in last_record, "wait on an event that was never recorded"
-            preds[i].add(last_record[event])
-    before = [set() for _ in range(n)]          # transitive closure (issue order is topological)
-    for i in range(n):
-        for p in preds[i]:
-            before[i] |= before[p] | {p}
-    comp = [i for i, op in enumerate(seq) if op[0] < OP["record"]]
-    fp = {i: _footprint(seq[i], nx, None, None) for i in comp}
-    for a_idx, a in enumerate(comp):
-        for b in comp[a_idx + 1:]:
-            ra, wa = fp[a]
-            rb, wb = fp[b]
-            if (wa & (rb | wb)) or (ra & wb):
-                assert a in before[b], f"ops {seq[a]} and {seq[b]} conflict but are unordered"
-    # everything enqueued on the side streams is joined to the caller's stream at the end
-    tail = max(i for i, op in enumerate(seq) if op[1] == 0)
-    for i in comp:
-        assert i == tail or i in before[tail], f"op {seq[i]} is not joined to the caller's stream"
-    # ... and explicitly so (stream capture wants the LAST operation of every forked stream to be
-    # an event record that the origin stream waits for)
-    for side in {op[1] for op in ops} - {0}:
-        last = max(i for i, op in enumerate(ops) if op[1] == side)
-        assert ops[last][0] == OP["record"], f"stream {side} ends with {ops[last]}"
-        waits = [i for i, op in enumerate(ops)
-                 if i > last and op[0] == OP["wait"] and op[1] == 0 and op[5] == ops[last][5]]
-        assert waits, f"stream {side} is not joined explicitly"
-
-
-@pytest.mark.parametrize("with_rhs", [False, True])
-@pytest.mark.parametrize("nx", [8, 16, 33, 64, 512])
-def test_schedule_orders_every_conflict(emu, nx, with_rhs):
-    for chunk, streams, flags in SCHEDULES + [(32, 2, 3), (26, 2, 3), (17, 3, 3)]:
-        if nx // max(chunk, 1) > 64:          # the pairwise check is quadratic in the op count
-            continue
-        for ring in (0, 4, 32):
-            ops = _ops(emu, nx, chunk, streams, flags, ring, with_rhs)
-            kinds = [o[0] for o in ops]
-            # each x plane is transformed exactly once per pass
-            for k in ("zfwd", "yfwd", "yinv", "zinv"):
-                cover = sorted(x for o in ops if o[0] == OP[k] for x in range(o[2], o[2] + o[3]))
-                assert cover == list(range(nx))
-            assert kinds.count(OP["xmid"]) == 1
-            if with_rhs:
-                cover = sorted(x for o in ops if o[0] == OP["rhs"] for x in range(o[2], o[2] + o[3]))
-                assert cover == list(range(nx))
-            _check_ordering(ops, nx)
-
-
-@pytest.mark.parametrize("shape", [(16, 8, 16), (32, 16, 64), (64, 8, 16)])
-def test_scheduled_pipeline_is_bit_identical(emu, shape):
-    """The chunked / ring / two-stream schedules replayed on the CPU (scratch poisoned with NaN)
-    give the very same bits as the one-launch-per-pass schedule, for the plain application and
-    for the fused CH step with the rhs evaluated per chunk through halo pointers."""
-    emu.emu_set_pipe_blocks(0)
-    nx, ny, nz = shape
-    rng = np.random.default_rng(5)
-    r = rng.standard_normal(shape).astype(np.float32)
-    u = (0.5 + 0.6 * (rng.random(shape) - 0.5)).astype(np.float32)
-    sp = (1.0, 0.5, 2.0)
-    h = (ctypes.c_double * 3)(*sp)
-    d = ctypes.c_double
-
-    def run(with_rhs, chunk, streams, flags, ring):
-        out = np.full(shape, np.nan, np.float32)
-        rc = emu.emu_native_sched(_p(u), _p(r), _p(out), nx, ny, nz, h, d(0.1), d(1.5), 2, d(3.0),
-                                  d(1.0), int(with_rhs), chunk, streams, flags, ring)
-        assert rc == 0
-        assert np.isfinite(out).all()
-        return out
-
-    for with_rhs in (False, True):
-        base = run(with_rhs, 0, 1, 0, 0)
-        if not with_rhs:
-            ref = np.zeros(shape, np.float32)
-            assert emu.emu_native_apply(_p(u), _p(r), _p(ref), None, nx, ny, nz, h, d(0.1), d(1.5), 2) == 0
-            assert np.array_equal(base, ref)
-        else:
-            want = O.CHOracle(shape, sp, 0.1, 3.0, 1.0, 0.25).step(torch.from_numpy(u)[None])[0].numpy()
-            assert rel_l2(base, want) < 1e-6
-        for chunk, streams, flags in SCHEDULES:
-            got = run(with_rhs, chunk, streams, flags, 4)
-            assert np.array_equal(got, base), (with_rhs, chunk, streams, flags)
-
-
-def test_schedule_checker_detects_a_missing_wait(emu):
-    """The ordering check is not vacuous: dropping the side stream's wait for 'ring slot
-    consumed' (or the per-chunk 'z forward done' wait) is reported as an unordered conflict."""
-    ops = _ops(emu, 64, 8, 2, 3, 32, True)
-    _check_ordering(ops, 64)
-    for ev in (1, 3, 4):
-        broken = [o for o in ops if not (o[0] == OP["wait"] and o[5] == ev)]
-        assert len(broken) < len(ops)
-        with pytest.raises(AssertionError):
-            _check_ordering(broken, 64)
-    # three streams: rhs / z forward / y forward of consecutive chunks overlap
-    ops = _ops(emu, 64, 8, 3, 3, 32, True)
-    assert {o[1] for o in ops if o[0] == OP["zfwd"]} == {2} and {o[4] for o in ops if o[0] == OP["rhs"]} == {0, 1}
-    _check_ordering(ops, 64)
-    for ev in (6, 8, 9, 10, 2):
-        broken = [o for o in ops if not (o[0] == OP["wait"] and o[5] == ev)]
-        assert len(broken) < len(ops)
-        with pytest.raises(AssertionError):
-            _check_ordering(broken, 64)
-
-
 @pytest.mark.parametrize("L,KZ", [(64, 8), (128, 8), (256, 8), (512, 8), (512, 16), (1024, 8), (2048, 4),
                                   (64, 16), (256, 16)])
 def test_tile_prefetch_forms_agree(emu, L, KZ):
@@ -482,7 +371,7 @@ def test_distributed_pipeline_virtual_ranks(emu, shape, world, pipe_blocks):
     """The x-slab pipeline replayed for W virtual ranks with the launch parameters of
     dist_params.h (block-layout y passes, global ky offset in the x pass, peer tables) gives the
     single-domain result bit for bit - for the all-to-all, block-copy and peer-store transports,
-    with and without pipeline chunks and with the L2 sub-chunking of the transform pairs."""
+    with and without pipeline chunks."""
     emu.emu_set_pipe_blocks(pipe_blocks)
     emu.emu_set_xpass_columns(8)
     nx, ny, nz = shape
@@ -494,18 +383,17 @@ def test_distributed_pipeline_virtual_ranks(emu, shape, world, pipe_blocks):
     want = np.zeros(shape, np.float32)
     assert emu.emu_native_apply(_p(u), _p(r), _p(want), None, nx, ny, nz, h, d(0.1), d(1.5), 2) == 0
     nxl = nx // world
-    cases = [(tr, fc, mc, l2) for tr in (0, 1, 2) for fc, mc in ((1, 1), (4, 2)) for l2 in (0, 2, 4)
-             if fc <= nxl]
-    for transport, fwd_chunks, mid_chunks, l2 in cases:
+    cases = [(tr, fc, mc) for tr in (0, 1, 2) for fc, mc in ((1, 1), (4, 2)) if fc <= nxl]
+    for transport, fwd_chunks, mid_chunks in cases:
         got = np.full(shape, np.nan, np.float32)
         rc = emu.emu_dist_apply(_p(u), _p(r), _p(got), nx, ny, nz, world, transport, fwd_chunks,
-                                mid_chunks, l2, h, d(0.1), d(1.5), 2)
+                                mid_chunks, h, d(0.1), d(1.5), 2)
         assert rc == 0
-        assert np.array_equal(got, want), (transport, fwd_chunks, mid_chunks, l2)
+        assert np.array_equal(got, want), (transport, fwd_chunks, mid_chunks)
     # update only (u = NULL) with the exponential-Euler weight
     want = np.zeros(shape, np.float32)
     assert emu.emu_native_apply(None, _p(r), _p(want), None, nx, ny, nz, h, d(0.3), d(0.7), 1 | 0x100) == 0
     got = np.full(shape, np.nan, np.float32)
-    assert emu.emu_dist_apply(None, _p(r), _p(got), nx, ny, nz, world, 1, 2, 2, 2, h, d(0.3), d(0.7), 1 | 0x100) == 0
+    assert emu.emu_dist_apply(None, _p(r), _p(got), nx, ny, nz, world, 1, 2, 2, h, d(0.3), d(0.7), 1 | 0x100) == 0
     assert np.array_equal(got, want)
     emu.emu_set_pipe_blocks(0)

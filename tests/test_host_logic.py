@@ -154,123 +154,47 @@ def test_solver_rejects_other_backends():
         TimeDependentSolver(vf, "a", backend="jax", step_fn=lambda t, u: u, device="cpu")
 
 
-class _FakeClock:
-    now = 0.0
+def test_kernel_wrappers_refuse_inputs_that_require_grad():
+    """The ctypes kernels record no autograd node: with grad mode on they must raise instead
+    of returning a detached result (round-1 advisor finding)."""
+    x = torch.zeros(2, requires_grad=True)
+    with pytest.raises(NotImplementedError, match="without a backward pass"):
+        _native.refuse_grad("probe", None, x)
+    with torch.no_grad():
+        _native.refuse_grad("probe", x)
+    _native.refuse_grad("probe", torch.zeros(2), None)
 
 
-class _FakeEvent:
-    def __init__(self, enable_timing=False):
-        self.t = None
+def test_graph_replay_and_fused_paths_are_gated_on_the_stock_classes():
+    from evoxels_b200.problem_definition import CoupledReactionDiffusion, is_stock
+    from evoxels_b200.timesteppers import _symbol_matches_form
+    vg = host_grid()
+    assert CahnHilliard(vg).autonomous and TwoPhaseAllenCahn(vg).autonomous
+    assert CoupledReactionDiffusion(vg).autonomous
+    assert ReactionDiffusion(vg, D=1.0).autonomous
+    assert not ReactionDiffusion(vg, D=1.0, f=lambda t, c, lib: t * c).autonomous
 
-    def record(self):
-        self.t = _FakeClock.now
+    class WithSource(CahnHilliard):
+        def rhs(self, t, c):
+            return super().rhs(t, c) + 1.0
 
-    def synchronize(self):
-        pass
+    class OtherSymbol(CahnHilliard):
+        @property
+        def fourier_symbol(self):
+            return -self.k_squared()
 
-    def elapsed_time(self, other):
-        return other.t - self.t
-
-
-def _fake_plan(monkeypatch, cost, wrong=()):
-    """An ImexPlan whose ch_step is a stand-in: it costs cost(schedule) fake milliseconds and
-    writes a schedule-independent field, except for the schedules in `wrong`."""
-    plan = object.__new__(_native.ImexPlan)
-    plan._handle = None
-    plan.shape = (512, 512, 512)
-    plan.backend = _native.FFT_NATIVE
-    plan.device = torch.device("cpu")
-    plan.tuned = False
-    plan.tune_report = None
-    plan.current = (0, 1, 0)
-    plan.log = []
-
-    def set_schedule(chunk_planes=0, streams=1, flags=0):
-        plan.current = (chunk_planes, streams, flags)
-        plan.log.append(plan.current)
-
-    def ch_step(u, out, spacing, dt, eps, D, A, hom=None):
-        _FakeClock.now += cost(plan.current)
-        out.copy_(u * 2 + (1 if plan.current in wrong else 0))
-        return out
-
-    plan.set_schedule, plan.ch_step, plan.schedule = set_schedule, ch_step, lambda: plan.current
-    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
-    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda dev=None: (1 << 40, 1 << 40))
-
-    class Props:
-        multi_processor_count = 148
-    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda dev=None: Props)
-    return plan
+    assert is_stock(CahnHilliard(vg), CahnHilliard)
+    assert not is_stock(WithSource(vg), CahnHilliard)
+    assert not is_stock(OtherSymbol(vg), CahnHilliard)
+    assert _symbol_matches_form(CahnHilliard(vg)) and _symbol_matches_form(WithSource(vg))
+    assert not _symbol_matches_form(OtherSymbol(vg))
 
 
-def test_schedule_tuner_picks_the_fastest_bit_identical_candidate(monkeypatch):
-    u = torch.rand(4, 4, 4)
-    R, C = _native.SCHED_RING_INV, _native.SCHED_CHUNK_RHS
-    fast, faster_but_wrong = (17, 2, 0), (26, 2, R)
-    cost = lambda s: {fast: 1.2, (17, 2, R): 1.3, faster_but_wrong: 0.9, (0, 1, 0): 1.8}.get(s, 1.5 + 0.01 * s[0])
-    plan = _fake_plan(monkeypatch, cost, wrong={faster_but_wrong})
-    assert plan.schedule_sizes() == [8, 9, 11, 12, 16, 17, 18, 23, 24, 26, 27, 32]
-    best, report = plan.tune_ch_step(u, (1, 1, 1), 0.1, 3.0, 1.0, 0.25)
-    # phase 1 finds size 17 through its ring variant, phase 2 then finds the faster no-ring form
-    assert best == fast and plan.current == fast and plan.tuned
-    assert report["chosen"] == fast and abs(report["baseline_ms"] - 1.8) < 1e-9
-    rejected = [c for c in report["candidates"] if not c["bit_identical"]]
-    assert [c["schedule"] for c in rejected] == [faster_but_wrong]
-    tried = {c["schedule"] for c in report["candidates"]}
-    assert (17, 1, R | C) in tried and (17, 3, R | C) in tried and (26, 2, 0) not in tried   # phase 2 skips rejected sizes
-    # a gain below the threshold keeps the one-launch-per-pass schedule
-    plan = _fake_plan(monkeypatch, lambda s: 1.0 if s == (0, 1, 0) else 0.99)
-    best, _ = plan.tune_ch_step(u, (1, 1, 1), 0.1, 3.0, 1.0, 0.25)
-    assert best == (0, 1, 0) and plan.current == (0, 1, 0)
-    # large grids: only chunks whose spectrum fits L2 are candidates; too small grids: none
-    plan = _fake_plan(monkeypatch, lambda s: 120.0 if s == (0, 1, 0) else 100.0)
-    plan.shape = (2048, 2048, 2048)
-    assert plan.schedule_sizes() == [2, 3]
-    best, report = plan.tune_ch_step(u, (1, 1, 1), 0.1, 3.0, 1.0, 0.25)
-    assert best[0] in (2, 3) and len(report["candidates"]) <= 16
-    plan.shape = (1024, 1024, 1024)
-    assert plan.schedule_sizes() == [8, 9, 11, 12]
-    plan.shape = (4, 64, 64)
-    plan.current = (0, 1, 0)
-    assert plan.schedule_sizes() == []
-    best, report = plan.tune_ch_step(u, (1, 1, 1), 0.1, 3.0, 1.0, 0.25)
-    assert best == (0, 1, 0) and report["skipped"] == "grid too small"
-
-
-def test_stepper_schedule_policy(monkeypatch):
-    """Small grids and EVX_TUNE=0 keep the baseline without measuring, EVX_SCHEDULE forces a
-    schedule, and a failing tuner falls back to the baseline with a warning."""
-    ts = PseudoSpectralIMEX(CahnHilliard(host_grid()), 0.1)
-    calls = []
-
-    def tune(*a, **k):
-        calls.append(a)
-        return (8, 2, 1), {"chosen": (8, 2, 1)}
-    plan = _fake_plan(monkeypatch, lambda s: 1.0)
-    plan.tune_ch_step = tune
-    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
-    small, large = torch.rand(8, 8, 8), torch.empty(0).new_empty((1 << 24,))
-    ts._choose_schedule(plan, small, (1, 1, 1))
-    assert plan.tuned and not calls and not plan.log
-    plan.tuned = False
-    monkeypatch.setenv("EVX_TUNE", "0")
-    ts._choose_schedule(plan, large, (1, 1, 1))
-    assert plan.tuned and not calls
-    monkeypatch.delenv("EVX_TUNE")
-    plan.tuned = False
-    monkeypatch.setenv("EVX_SCHEDULE", "16,2,3")
-    ts._choose_schedule(plan, small, (1, 1, 1))
-    assert plan.current == (16, 2, 3) and plan.tuned and not calls
-    monkeypatch.delenv("EVX_SCHEDULE")
-    plan.tuned = False
-    ts._choose_schedule(plan, large, (1, 1, 1))
-    assert len(calls) == 1 and plan.tune_report == {"chosen": (8, 2, 1)}
-
-    def broken(*a, **k):
-        raise RuntimeError("boom")
-    plan.tune_ch_step = broken
-    plan.tuned = False
-    with pytest.warns(UserWarning, match="schedule tuning failed"):
-        ts._choose_schedule(plan, large, (1, 1, 1))
-    assert plan.tuned and plan.current == (0, 1, 0)
+def test_etd1_and_imex_weights_do_not_share_a_cache():
+    from evoxels_b200.timesteppers import ExponentialEuler
+    vg = host_grid((8, 8, 8))
+    ts = ExponentialEuler(ReactionDiffusion(vg, D=1.0), 0.5)
+    a = ts.phi_1_k_squared
+    b = ts._fft_prefac
+    assert not torch.equal(a, b)
+    assert torch.equal(ts.phi_1_k_squared, a) and torch.equal(ts._fft_prefac, b)
