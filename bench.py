@@ -32,16 +32,31 @@ UNIT = "voxel-updates/s"
 CH = dict(eps=3.0, D=1.0, A=0.25, dt=0.1)
 B_ALG_STEP = 60.0       # algorithmic bytes / voxel / step
 B_ALG_RHS = 8.0         # fused rhs kernel: read c, write rhs
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at 512^3 from the committed
-# `ncu --set full` capture (profiles/r01_ncu_full_summary_final.txt); bytes
-NCU_TRAFFIC_512 = {
-    "ch_rhs_kernel": 0.5411e9 + 0.5019e9,
-    "fft_z_forward (ZPass fwd)": 0.5446e9 + 0.5025e9,
-    "fft_y_forward (StridedPipe FWD)": 0.5540e9 + 0.4933e9,
-    "fft_x_fwd*filter*inv (StridedPipe XMID)": 0.5537e9 + 0.4871e9,
-    "fft_y_inverse (StridedPipe INV)": 0.5540e9 + 0.4933e9,
-    "fft_z_inverse+u (ZPass inv)": 1.091e9 + 0.5084e9,
-}
+
+
+def workload_string(size, world):
+    """One string for both arms (the driver compares them)."""
+    if world == 1:
+        return f"CH IMEX {size}^3 fp32 periodic dt=0.1"
+    sh = weak_scaling_shape(size, world)
+    return f"CH IMEX {sh[0]}x{sh[1]}x{sh[2]} fp32 periodic dt=0.1 ({size}^3 voxels per GPU)"
+
+
+def ncu_traffic(kernel_name, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the
+    committed `ncu --set full` capture (profiles/r02_ncu_traffic.json, written by
+    scripts/ncu_traffic.py from the raw export).  None if the capture has no such kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
+            tab = json.load(f)
+        if int(tab.get("size", 0)) != n:
+            return None, None
+        for key, v in tab["kernels"].items():
+            if key in kernel_name or kernel_name.split(" ")[0] == v.get("bench_name"):
+                return float(v["dram_bytes"]), tab.get("source")
+    except Exception:
+        pass
+    return None, None
 
 
 def measured_peaks():
@@ -54,62 +69,102 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML from a thread of this process, every
+    few milliseconds, so that even a 30 ms timed region is covered by samples (an `nvidia-smi
+    -lms` child needs ~0.5 s to start and cannot see it).  `mark()` brackets the timed region;
+    samples taken while the GPU is busy before / after it (ramp-up steps, clock-probe steps) are
+    reported next to the in-region ones."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index=0):
-        self.gpu = gpu_index
-        self.proc = None
-        self.path = None
+    def __init__(self, gpu_index=0, period_s=0.002):
+        self.gpu, self.period = gpu_index, period_s
+        self.samples = []          # (t, sm_mhz, reasons_mask, power_w)
+        self.marks = []
+        self._stop = threading.Event()
+        self._thread = None
+        self.error = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES if it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            try:
+                ids = [int(x) for x in vis.split(",") if x.strip() != ""]
+                if ids:
+                    idx = ids[self.gpu]
+            except (ValueError, IndexError):
+                pass
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                try:
+                    mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    mask = int(get_reasons(h))
+                    try:
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    except Exception:
+                        pw = None
+                    self.samples.append((time.perf_counter(), mhz, mask, pw))
+                except Exception as exc:      # keep sampling
+                    self.error = repr(exc)
+                time.sleep(self.period)
+        except Exception as exc:
+            self.error = repr(exc)
 
     def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.gpu)],
-                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        self.max_mhz = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_mhz", None), "reasons": [],
+               "samples": 0, "samples_in_timed_region": 0, "sm_mhz_timed_region": None,
+               "source": "NVML, in-process thread, %.0f ms period; busy GPU from ramp-up steps "
+                         "before to clock-probe steps after the timed region" % (self.period * 1e3)}
+        if self.error:
+            out["error"] = self.error
+        if not self.samples:
             return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-        except Exception:
-            try:
-                self.proc.kill()
-            except Exception:
-                pass
-        try:
-            sm, mx, reasons = [], [], set()
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for line in open(self.path):
-                p = [x.strip() for x in line.split(",")]
-                if len(p) < 9:
-                    continue
-                try:
-                    sm.append(float(p[1]))
-                    mx.append(float(p[2]))
-                except ValueError:
-                    continue
-                for nm, val in zip(names, p[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
-            os.unlink(self.path)
-            if sm:
-                out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx),
-                           reasons=sorted(reasons), samples=len(sm))
-        except Exception:
-            pass
+        t0, t1 = (self.marks + [None, None])[:2]
+        inside = [x for x in self.samples if t0 is not None and t1 is not None and t0 <= x[0] <= t1]
+        mask = 0
+        for x in self.samples:
+            mask |= x[2]
+        pw = [x[3] for x in self.samples if x[3] is not None]
+        out.update(sm_mhz=statistics.median(x[1] for x in self.samples), samples=len(self.samples),
+                   sm_mhz_min=min(x[1] for x in self.samples),
+                   reasons=sorted(n for b, n in self.REASONS.items() if mask & b),
+                   samples_in_timed_region=len(inside), power_w_max=max(pw) if pw else None)
+        if inside:
+            out["sm_mhz_timed_region"] = statistics.median(x[1] for x in inside)
+            m = 0
+            for x in inside:
+                m |= x[2]
+            out["reasons_timed_region"] = sorted(n for b, n in self.REASONS.items() if m & b)
         return out
 
+
+def busy_for(step_fn, u, seconds, dev):
+    """Keep the GPU busy with untimed steps for about `seconds` (clock ramp-up / clock probe)."""
+    import torch
+    t_end = time.perf_counter() + seconds
+    while time.perf_counter() < t_end:
+        for _ in range(20):
+            u = step_fn(u)
+        torch.cuda.synchronize(dev)
+    return u
 
 
 def e2e_pipelined(step_fn, h_in, h_outs, dev, nsteps):
@@ -156,49 +211,195 @@ def e2e_pipelined(step_fn, h_in, h_outs, dev, nsteps):
     torch.cuda.synchronize(dev)
     return t0.elapsed_time(t1)
 
-def time_cpu_port(size, steps, warmup):
-    """Oracle port of the reference step on the host cores. Returns (vox/s, s/step, threads)."""
-    import torch
-    from oracle import evx_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    shape = (size, size, size)
-    orc = O.CHOracle(shape, (1.0, 1.0, 1.0), CH["dt"], CH["eps"], CH["D"], CH["A"])
-    u = O.noise_field(shape, seed=0)
-    for _ in range(warmup):
-        u = orc.step(u)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        u = orc.step(u)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return size ** 3 / dt, dt, torch.get_num_threads()
+def time_reference(problem, size, steps, warmup, device="cpu", jit=False, budget_s=0.0, timeout_s=600):
+    """oracle/time_reference.py in a subprocess: the UNMODIFIED reference (from baseline/_ref or
+    /root/reference, kind "reference") or, where neither exists, the oracle port (kind "port")."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "time_reference.py"), "--problem", problem,
+           "--size", str(size), "--steps", str(steps), "--warmup", str(warmup), "--device", device]
+    if jit:
+        cmd.append("--jit")
+    if budget_s:
+        cmd += ["--budget-s", str(budget_s)]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+        lines = [l for l in res.stdout.strip().splitlines() if l.startswith("{")]
+        if not lines:
+            return {"kind": "failed", "error": (res.stderr or res.stdout)[-300:]}
+        return json.loads(lines[-1])
+    except subprocess.TimeoutExpired:
+        return {"kind": "timeout", "error": f"no result within {timeout_s} s"}
+    except Exception as exc:
+        return {"kind": "failed", "error": repr(exc)[:300]}
+
+
+def cpu_baseline_record(size, steps, warmup, budget_s=40.0):
+    r = time_reference("ch", size, steps, warmup, "cpu", budget_s=budget_s)
+    if "vox_per_s" not in r:
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": r.get("kind", "failed"),
+                "sample": "failed: " + str(r.get("error"))}
+    what = ("unmodified reference (evoxels PseudoSpectralIMEX.step, torch CPU eager, through oracle/ref_shim.py)"
+            if r["kind"] == "reference" else "oracle port of the reference (torch CPU eager)")
+    return {"value": r["vox_per_s"], "unit": UNIT, "cores": r["threads"], "kind": r["kind"],
+            "sample": f"{r['steps']} steps of {size}^3 after {warmup} warm-up, {what}",
+            "s_per_step": r["s_per_step"]}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     # bounded sample: the largest cube whose (K+W) steps fit ~150 s on these cores
-    _, t128, _ = time_cpu_port(128, 1, 1)
+    probe = time_reference("ch", 128, 1, 1, "cpu")
+    t128 = probe.get("s_per_step", 1.0)
     total = args.steps + args.warmup
     size = 128
     for cand, factor in ((512, 64 * 3.0), (256, 8 * 2.5)):   # voxel ratio x cache penalty
         if t128 * factor * total <= 150.0:
             size = cand
             break
-    vps, spstep, threads = time_cpu_port(size, args.steps, args.warmup)
+    r = time_reference("ch", size, args.steps, args.warmup, "cpu")
+    vps, spstep = r.get("vox_per_s"), r.get("s_per_step", 0.0)
+    kind = r.get("kind", "failed")
     line = {
         "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": spstep * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"CH IMEX {size}^3 fp32 periodic dt=0.1 (CPU, bounded sample of the 512^3 workload)",
-                   **CH},
-        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps of {size}^3 after {args.warmup} warm-up, torch CPU eager"},
+        "config": {"workload": workload_string(args.size, world), **CH,
+                   "sample": f"{size}^3 cube of that workload on the host cores (the CPU path cannot "
+                             f"hold K+W steps of the full grid within minutes)" if size != args.size or world > 1
+                             else "full workload"},
+        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": r.get("threads"), "kind": kind,
+                         "sample": f"{args.steps} steps of {size}^3 after {args.warmup} warm-up, "
+                                   + ("unmodified reference, torch CPU eager" if kind == "reference"
+                                      else "oracle port, torch CPU eager")},
         "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if "error" in r:
+        line["error"] = r["error"]
     print(json.dumps(line), flush=True)
+
+
+# ---- other BASELINE configs, timed outside the headline region -------------------------------
+def extra_configs(dev):
+    """config 1 (README 100^3), config 3 (Allen-Cahn 1024^3 Neumann, one GPU) and config 5
+    (inversion: forward + backward through 100 steps at 256^3) - one number each."""
+    import torch
+    import evoxels_b200 as evo
+    from evoxels_b200.problem_definition import CahnHilliard, TwoPhaseAllenCahn
+    from evoxels_b200.timesteppers import ForwardEuler, PseudoSpectralIMEX
+    from evoxels_b200.voxelgrid import VoxelGridTorch
+    peak, _ = measured_peaks()
+    out = {}
+
+    def events(fn):
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b)
+
+    try:   # config 1
+        n = 100
+        vf = evo.VoxelFields((n, n, n), (float(n),) * 3)
+        vg = VoxelGridTorch(vf.grid_info(), device=str(dev))
+        ts = PseudoSpectralIMEX(CahnHilliard(vg, eps=3.0, D=1.0), 0.1)
+        u = 0.5 + 0.1 * torch.rand((1, n, n, n), device=dev)
+        state = {"u": u}
+
+        def run(k):
+            v = state["u"]
+            for _ in range(k):
+                v = ts.step(0.0, v)
+            state["u"] = v
+        run(20)
+        ms = events(lambda: run(1000))
+        out["config1_ch_100^3_readme"] = {
+            "us_per_step": ms, "steps": 1000, "voxel_updates_per_s": n ** 3 * 1000 / (ms * 1e-3),
+            "fft_backend": next(iter(ts._plans.values())).backend_name,
+            "note": "eager step loop (no CUDA graph), 1000 steps as in the README example"}
+        del ts, u, state
+    except Exception as exc:
+        out["config1_ch_100^3_readme"] = {"error": repr(exc)[:200]}
+    try:   # config 3
+        n = 1024
+        vf = evo.VoxelFields((n, n, n), (float(n),) * 3)
+        vg = VoxelGridTorch(vf.grid_info(), device=str(dev))
+        ts = ForwardEuler(TwoPhaseAllenCahn(vg), 0.05)
+        state = {"u": torch.rand((1, n, n, n), device=dev)}
+
+        def run(k):
+            v = state["u"]
+            for _ in range(k):
+                v = ts.step(0.0, v)
+            state["u"] = v
+        run(3)
+        ms = events(lambda: run(10)) / 10
+        out["config3_ac_1024^3_neumann_1gpu"] = {
+            "ms_per_step": ms, "voxel_updates_per_s": n ** 3 / (ms * 1e-3),
+            "achieved_GBs_at_8B_per_voxel": 8 * n ** 3 / (ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": 8 * n ** 3 / (ms * 1e-3) / 1e9 / peak,
+            "finite": bool(torch.isfinite(state["u"][0, ::64]).all())}
+        del ts, state
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out["config3_ac_1024^3_neumann_1gpu"] = {"error": repr(exc)[:200]}
+    try:   # config 5
+        n, steps = 256, 100
+        vf = evo.VoxelFields((n, n, n), (float(n),) * 3)
+        vg = VoxelGridTorch(vf.grid_info(), device=str(dev))
+        u0 = 0.5 + 0.1 * torch.rand((1, n, n, n), device=dev)
+        obs_at = {steps // 3, 2 * steps // 3, steps}
+        with torch.no_grad():
+            ts = PseudoSpectralIMEX(CahnHilliard(vg, eps=3.0, D=1.0), 0.1)
+            v, obs = u0, {}
+            for i in range(1, steps + 1):
+                v = ts.step(0.0, v)
+                if i in obs_at:
+                    obs[i] = v.clone()
+
+        def fwd_bwd():
+            D = torch.tensor(2.0, dtype=torch.float64, device=dev, requires_grad=True)
+            eps = torch.tensor(2.0, dtype=torch.float64, device=dev, requires_grad=True)
+            tsg = PseudoSpectralIMEX(CahnHilliard(vg, eps=eps, D=D), 0.1)
+            w, loss = u0.clone().requires_grad_(True), 0.0
+            for i in range(1, steps + 1):
+                w = tsg.step(0.0, w)
+                if i in obs_at:
+                    loss = loss + ((w - obs[i]) ** 2).sum()
+            return torch.autograd.grad(loss, (D, eps))
+        fwd_bwd()
+        ms = events(fwd_bwd)
+        out["config5_inversion_256^3_x100"] = {
+            "ms_forward_plus_backward": ms, "ms_per_step": ms / steps,
+            "achieved_GBs_at_160B_per_voxel": 160 * n ** 3 * steps / (ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": 160 * n ** 3 * steps / (ms * 1e-3) / 1e9 / peak}
+    except Exception as exc:
+        out["config5_inversion_256^3_x100"] = {"error": repr(exc)[:200]}
+    torch.cuda.empty_cache()
+    return out
+
+
+def reference_gpu_record(n):
+    """The reference's own GPU path on this B200 (eager, and torch.compile(step) as
+    evoxels/solvers.py:64-70 does with jit=True): the number the kernels have to beat."""
+    out = {}
+    for tag, jit, tmo in (("eager", False, 240), ("torch_compile", True, 420)):
+        r = time_reference("ch", n, 5, 2, "cuda", jit=jit, timeout_s=tmo)
+        if "s_per_step" in r:
+            out[tag] = {"ms_per_step": r["s_per_step"] * 1e3, "voxel_updates_per_s": r["vox_per_s"],
+                        "kind": r["kind"], "peak_mem_GB": r.get("peak_mem_GB")}
+        else:
+            out[tag] = {"kind": r.get("kind"), "error": r.get("error")}
+    out["cite"] = "evoxels/solvers.py:64-70, voxelgrid.py:203-207 (step = timestepper.step, optionally torch.compile'd)"
+    return out
 
 
 def run_ours(args):
@@ -238,28 +439,31 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput -----------------------------------------------------
+    step1 = lambda v: ts.step(0.0, v)      # noqa: E731
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     u = u0
     for _ in range(max(args.warmup, 3)):
         u = ts.step(0.0, u)
     plan = next(iter(ts._plans.values()))
-    sampler = ClockSampler(local)
+    u = busy_for(step1, u, 0.5, dev)       # clock ramp-up under the sampler, untimed
     barrier()
-    if rank == 0:
-        sampler.start()
     l0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         u = ts.step(0.0, u)
     e1.record()
     barrier()
+    sampler.mark()
     launches = _native.launch_count() - l0
     ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    u_end = u
+    busy_for(step1, u, 0.7, dev)           # clock probe: same kernels, >= 1 s of samples in total
     clocks = sampler.stop() if rank == 0 else {}
+    u = u_end
     ms_step = ms / args.steps
     value = world * nvox * args.steps / (ms * 1e-3)
     mass_drift = abs(float(u.double().mean()) - float(u0.double().mean()))
@@ -303,13 +507,23 @@ def run_ours(args):
     kernels["ch_rhs_kernel"] = (
         timed(lambda: _native.ch_rhs(u0[0], rhs_buf[0], vg.spacing, CH["eps"], CH["D"], per)), 8.0)
     if plan.backend_name == "native":
-        names = ["fft_z_forward (ZPass fwd)", "fft_y_forward (StridedPipe FWD)",
-                 "fft_x_fwd*filter*inv (StridedPipe XMID)", "fft_y_inverse (StridedPipe INV)",
-                 "fft_z_inverse+u (ZPass inv)"]
-        bpv = [4 + 4 * half, 8 * half, 8 * half, 8 * half, 4 * half + 8]
-        for which, (nm, bb) in enumerate(zip(names, bpv)):
-            kernels[nm] = (timed(lambda w=which: plan.native_pass(
-                w, u0[0], rhs_buf[0], out_buf[0], vg.spacing, CH["dt"], coef, 2)), bb)
+        def one_pass(w):
+            return lambda: plan.native_pass(w, u0[0], rhs_buf[0], out_buf[0], vg.spacing, CH["dt"], coef, 2)
+        try:
+            one_pass(5)()
+            chained = True
+        except Exception:
+            chained = False
+        if chained:      # one persistent kernel per z/y pair, the pair's intermediate stays in L2
+            passes = [(5, "fft_zy_forward (chained ZPass + StridedLine FWD)", 4 + 4 * half),
+                      (2, "fft_x_fwd*filter*inv (StridedLine XMID)", 8 * half),
+                      (6, "fft_yz_inverse+u (chained StridedLine INV + ZPass)", 4 * half + 8)]
+        else:
+            passes = [(0, "fft_z_forward (ZPass fwd)", 4 + 4 * half), (1, "fft_y_forward (strided FWD)", 8 * half),
+                      (2, "fft_x_fwd*filter*inv (strided XMID)", 8 * half),
+                      (3, "fft_y_inverse (strided INV)", 8 * half), (4, "fft_z_inverse+u (ZPass inv)", 4 * half + 8)]
+        for w, nm, bb in passes:
+            kernels[nm] = (timed(one_pass(w)), bb)
     else:
         kernels["spectral_apply (cuFFT + filter + add kernels)"] = (
             timed(lambda: plan.apply(u0[0], rhs_buf[0], out_buf[0], vg.spacing, CH["dt"], coef, 2)), 52.0)
@@ -319,8 +533,8 @@ def run_ours(args):
     gbs_step = B_ALG_STEP * nvox / (ms_step * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
-        "frac": dom_gbs / peak, "traffic": NCU_TRAFFIC_512.get(dom) if n == 512 else None,
-        "traffic_source": "profiles/r01_ncu_full_summary_final.txt (ncu --set full, per launch)",
+        "frac": dom_gbs / peak, "traffic": ncu_traffic(dom, n)[0],
+        "traffic_source": ncu_traffic(dom, n)[1],
         "peak_source": peak_src, "ms": dom_ms,
         "bytes_per_voxel": dom_bpv,
         "step": {"bytes_per_voxel": B_ALG_STEP, "achieved": gbs_step, "frac": gbs_step / peak,
@@ -335,24 +549,22 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) -------------------------
+    # ---- beside it, outside the timed regions (rank 0, N = 1 only; bounded samples) --------------
+    extras = None if args.no_extras else extra_configs(dev)
+    del rhs_buf, out_buf, h_in, h_outs
+    torch.cuda.empty_cache()
     cpu = None
-    if world == 1 and not args.no_cpu:
-        try:
-            cs = 512 if n >= 512 else n
-            vps, spstep, threads = time_cpu_port(cs, 2, 1)
-            cpu = {"value": vps, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"2 steps of {cs}^3 after 1 warm-up (oracle port of the reference, torch CPU eager)",
-                   "s_per_step": spstep}
-        except Exception as exc:  # pragma: no cover
-            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"failed: {exc}"}
+    ref_gpu = None
+    if not args.no_cpu:
+        cs = 512 if n >= 512 else n
+        cpu = cpu_baseline_record(cs, 3, 1)
+        ref_gpu = reference_gpu_record(n)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CH IMEX {n}^3 fp32 periodic dt=0.1 per GPU", **CH,
+        "config": {"workload": workload_string(n, 1), **CH,
                    "fft_backend": plan.backend_name,
                    "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
                    "l2": "field (%.0f MB) larger than L2 (126 MB), no flush needed" % (field_bytes / 1e6)},
@@ -366,6 +578,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "reference_gpu": ref_gpu,
+        "other_configs": extras,
         "mass_drift": mass_drift,
     }
     print(json.dumps(line), flush=True)
@@ -378,6 +592,80 @@ def weak_scaling_shape(n, world):
     1: n^3, 2: (2n,n,n), 4: (2n,2n,n), 8: (2n,2n,2n)."""
     f = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
     return tuple(n * k for k in f)
+
+
+def distributed_parity(world, rank, dev, transport):
+    """Distributed step == single-GPU step on the same 256^3 global field (every rank computes
+    the single-GPU step of the whole field itself and compares its own slab), for every
+    transport, plus bit equality across the transports.  Runs before the timed region; the
+    caller exits non-zero when rel-L2 exceeds 1e-6."""
+    import torch
+    import torch.distributed as dist
+    from evoxels_b200 import _native
+    from evoxels_b200.distributed import DistributedCahnHilliardIMEX
+    shape = (256, 256, 256)
+    gen = torch.Generator(device=dev).manual_seed(1234)      # same stream on every rank
+    ug = 0.5 + 0.1 * torch.rand(shape, device=dev, generator=gen)
+    plan = _native.ImexPlan(shape, torch.float32, dev, _native.FFT_NATIVE)
+    ref = torch.empty_like(ug)
+    plan.ch_step(ug, ref, (1.0, 1.0, 1.0), CH["dt"], CH["eps"], CH["D"], CH["A"])
+    outs, rec = {}, {}
+    for tr in dict.fromkeys([transport, "ce", "p2p", "nccl"]):
+        try:
+            st = DistributedCahnHilliardIMEX(shape, (1.0, 1.0, 1.0), CH["dt"], CH["eps"], CH["D"], CH["A"],
+                                             device=dev, transport=tr)
+            ul = st.slab.take(ug).contiguous()
+            out = st.step(ul)
+            torch.cuda.synchronize(dev)
+            rl = st.slab.take(ref)
+            sums = torch.stack([((out - rl).double() ** 2).sum(), (rl.double() ** 2).sum(),
+                                ((rl - ul).double() ** 2).sum()])
+            dist.all_reduce(sums)
+            rec[tr] = {"rel_l2": float((sums[0] / sums[1]).sqrt()),
+                       "update_rel_l2": float((sums[0] / sums[2]).sqrt())}
+            outs[tr] = out
+            del st
+        except Exception as exc:
+            rec[tr] = {"error": repr(exc)[:200]}
+    keys = [k for k in outs]
+    same = torch.tensor([1.0 if keys and all(torch.equal(outs[keys[0]], outs[k]) for k in keys[1:]) else 0.0],
+                        device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    main = rec.get(transport, {})
+    return {"grid": "256^3 global", "vs": "single-GPU evx_ch_imex_step_f32 of the whole field",
+            "rel_l2": main.get("rel_l2"), "update_rel_l2": main.get("update_rel_l2"),
+            "bit_equal_across_transports": bool(same.item() == 1.0) and len(keys) > 1,
+            "transports": rec}
+
+
+def distributed_ac_config3(world, rank, dev):
+    """BASELINE config 3: Allen-Cahn forward Euler, 1024^3, Neumann, x slabs over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from evoxels_b200.distributed import DistributedAllenCahnEuler
+    n = 1024
+    st = DistributedAllenCahnEuler((n, n, n), (1.0, 1.0, 1.0), 0.05, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    phi = torch.rand(st.slab.local_shape, device=dev, generator=gen)
+    for _ in range(3):
+        phi = st.step(phi)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        phi = st.step(phi)
+    b.record()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([a.elapsed_time(b) / 20], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    peak, _ = measured_peaks()
+    return {"ms_per_step": ms, "voxel_updates_per_s": n ** 3 / (ms * 1e-3),
+            "achieved_GBs_per_gpu_at_8B_per_voxel": 8 * n ** 3 / world / (ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak_per_gpu": 8 * n ** 3 / world / (ms * 1e-3) / 1e9 / peak,
+            "finite": bool(torch.isfinite(phi[::16]).all())}
 
 
 def run_ours_distributed(args, world, rank, local, dev):
@@ -407,24 +695,42 @@ def run_ours_distributed(args, world, rank, local, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    parity = None
+    if not args.no_extras:
+        parity = distributed_parity(world, rank, dev, args.transport)
+        if parity["rel_l2"] is None or not parity["rel_l2"] <= 1e-6:
+            if rank == 0:
+                print(json.dumps({"error": "distributed step does not match the single-GPU step", "parity": parity}),
+                      flush=True)
+            dist.destroy_process_group()
+            raise SystemExit(3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     u = u0
     for _ in range(max(args.warmup, 3)):
         u = stepper.step(u)
     m_start = stepper.total_mass(u0)
-    sampler = ClockSampler(local)
+    for _ in range(100):                    # clock ramp-up under the sampler, untimed
+        u = stepper.step(u)
     barrier()
-    if rank == 0:
-        sampler.start()
     l0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         u = stepper.step(u)
     e1.record()
     barrier()
+    sampler.mark()
     launches = _native.launch_count() - l0
     ms = reduce_max(e0.elapsed_time(e1))
+    u_end = u
+    for _ in range(200):                    # clock probe
+        u = stepper.step(u)
+    torch.cuda.synchronize(dev)
     clocks = sampler.stop() if rank == 0 else {}
+    u = u_end
     mass_drift = abs(stepper.total_mass(u) - m_start) / abs(m_start)
 
     e2e_steps = max(6, min(args.steps, 20))
@@ -436,6 +742,14 @@ def run_ours_distributed(args, world, rank, local, dev):
     barrier()
     ms_e2e = reduce_max(e2e_pipelined(stepper.step, h_in, h_outs, dev, e2e_steps))
     barrier()
+    ac3 = None
+    if not args.no_extras:
+        del h_in, h_outs, u, u_end
+        torch.cuda.empty_cache()
+        try:
+            ac3 = distributed_ac_config3(world, rank, dev)
+        except Exception as exc:
+            ac3 = {"error": repr(exc)[:200]}
     if rank == 0:
         peak, peak_src = measured_peaks()
         ms_step = ms / args.steps
@@ -446,8 +760,7 @@ def run_ours_distributed(args, world, rank, local, dev):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"CH IMEX {shape[0]}x{shape[1]}x{shape[2]} fp32 periodic dt=0.1 "
-                                   f"({args.size}^3 voxels per GPU)", **CH, "fft_backend": "native",
+            "config": {"workload": workload_string(args.size, world), **CH, "fft_backend": "native",
                        "parallelism": f"x-slab over {world} GPUs: 2-plane halos ("
                                       + ("DMA writes into the neighbours' symmetric-memory slots" if args.transport == "ce"
                                          else "NCCL send/recv") + ") + slab<->pencil "
@@ -466,7 +779,8 @@ def run_ours_distributed(args, world, rank, local, dev):
             "roofline": {"bound": "hbm", "kernel": "whole step per GPU (60 B/voxel)", "achieved": gbs,
                          "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
                          "peak_source": peak_src},
-            "cpu_baseline": None, "mass_drift": mass_drift,
+            "cpu_baseline": None, "mass_drift": mass_drift, "parity": parity,
+            "other_configs": {"config3_ac_1024^3_neumann": ac3},
         }
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
@@ -480,7 +794,8 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fft", default="auto", choices=["auto", "cufft", "native"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and reference-on-GPU legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 1 / 3 / 5 sub-records")
     ap.add_argument("--p2p-ctas", type=int, default=148,
                     help="grid cap of the NVLink-bound peer-store launches (0 = fill the GPU)")
     ap.add_argument("--overlap-chunks", type=int, default=4,

@@ -54,7 +54,7 @@ inline ZParams dist_zfwd_params(const DistDims& d, const DistTables& t, const fl
   ZParams zp;
   zp.real_in = r_local + (long long)x0 * d.ny * d.nz; zp.real_out = nullptr;
   zp.spec = spec + (long long)x0 * d.ny * d.P; zp.tw = t.twz; zp.twr = t.twr;
-  zp.rows = (long long)nxc * d.ny; zp.nz = d.nz; zp.P = d.P;
+  zp.rows = (long long)nxc * d.ny; zp.nz = d.nz; zp.P = d.P; zp.pf_blocks = 0;
   return zp;
 }
 // peers != null: block `rank` of every peer's buffer is written directly (peer stores)
@@ -111,7 +111,7 @@ inline ZParams dist_zinv_params(const DistDims& d, const DistTables& t, cf* spec
   ZParams zp;
   zp.real_in = u_local ? u_local + real_off : nullptr; zp.real_out = out_local + real_off;
   zp.spec = spec_chunk; zp.tw = t.twz; zp.twr = t.twr;
-  zp.rows = (long long)nxc * d.ny; zp.nz = d.nz; zp.P = d.P;
+  zp.rows = (long long)nxc * d.ny; zp.nz = d.nz; zp.P = d.P; zp.pf_blocks = 0;
   return zp;
 }
 

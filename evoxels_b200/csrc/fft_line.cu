@@ -14,49 +14,9 @@
 #include "evx_internal.h"
 #include "fft_line_core.h"
 #include "fft_line.h"
+#include "tma_ptx.h"
 
 namespace evx {
-
-// ---- PTX wrappers -------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// bounded wait: a pipeline bug must end in a trap, not in a hung GPU
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  const unsigned addr = smem_u32(bar);
-  const long long t0 = clock64();
-  for (unsigned spin = 0;; ++spin) {
-    unsigned ok;
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (ok) return;
-    if ((spin & 1023u) == 1023u && clock64() - t0 > 4000000000LL) __trap();   // ~2 s
-  }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void group_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar,
-                                            int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)),
-        "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(src)),
-                 "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---- kernel -------------------------------------------------------------------------
 template <class Prog>
@@ -90,6 +50,16 @@ __global__ void __launch_bounds__(Prog::NTHREADS, Prog::NTHREADS <= 512 ? 2 : 1)
       else tma_load_3d(dst + h * Prog::BOX_ROWS * Prog::ROWB, &tmap, &full[buf], kz0, h * Prog::BOX_ROWS, row);
     }
   };
+  // L2 prefetch of a tile that will be loaded `p.l2_ahead` hand-overs later: deepens the
+  // memory pipeline beyond the two shared-memory buffers without costing shared memory
+  auto prefetch_tile = [&](long long tile) {
+    const int row = (int)(tile / tpr), kz0 = (int)(tile - (long long)row * tpr) * Prog::COLS;
+#pragma unroll
+    for (int h = 0; h < 512 / Prog::BOX_ROWS; ++h) {
+      if (p.along_x) tma_prefetch_3d(&tmap, kz0, row, h * Prog::BOX_ROWS);
+      else tma_prefetch_3d(&tmap, kz0, h * Prog::BOX_ROWS, row);
+    }
+  };
   auto store_tile = [&](long long tile, int buf) {
     const int row = (int)(tile / tpr), kz0 = (int)(tile - (long long)row * tpr) * Prog::COLS;
     const unsigned char* src = tiles + buf * Prog::TILE_BYTES;
@@ -113,6 +83,8 @@ __global__ void __launch_bounds__(Prog::NTHREADS, Prog::NTHREADS <= 512 ? 2 : 1)
   if (tid == 0) {
     if ((long long)blockIdx.x < ntiles) load_tile(blockIdx.x, 0);
     if ((long long)blockIdx.x + nblk < ntiles) load_tile((long long)blockIdx.x + nblk, 1);
+    for (int a = 0; a < p.l2_ahead; ++a)
+      if ((long long)blockIdx.x + (2LL + a) * nblk < ntiles) prefetch_tile((long long)blockIdx.x + (2LL + a) * nblk);
   }
 
   // tile cursor: (row, tcol) advanced by nblk tiles per iteration without dividing
@@ -133,7 +105,11 @@ __global__ void __launch_bounds__(Prog::NTHREADS, Prog::NTHREADS <= 512 ? 2 : 1)
         group_sync(1 + r.g, Prog::GT);
         if (k == 1 && pending_buf >= 0) {       // deferred half of the previous tile's hand-over
           tma_store_wait_read();
-          if (pending_tile >= 0) load_tile(pending_tile, pending_buf);
+          if (pending_tile >= 0) {
+            load_tile(pending_tile, pending_buf);
+            const long long ahead = pending_tile + (long long)p.l2_ahead * nblk;
+            if (p.l2_ahead > 0 && ahead < ntiles) prefetch_tile(ahead);
+          }
           pending_buf = -1;
         }
       }

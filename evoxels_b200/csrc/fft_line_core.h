@@ -38,6 +38,7 @@ struct LineParams {
   int tiles_per_row;        // ceil(ncols_valid / KZ)
   long long ntiles;         // (along_x ? ny : nx) * tiles_per_row
   int along_x;              // 0: lines run along y (tile row index = x), 1: along x (row index = y)
+  int l2_ahead;             // tiles prefetched into L2 ahead of the shared-memory loads (0 = none)
   FilterParams filt;        // XMID only; n0 = nx
 };
 
@@ -121,18 +122,7 @@ struct StridedLine {
   }
 
   EVX_HD static void apply_filter(Regs& r, const LineParams& p) {
-    const FilterParams& f = p.filt;
-    const float k1 = wavenumber(signed_freq(r.kother, f.n1), f.inv_len1);
-    const float k2 = wavenumber(r.kz, f.inv_len2);
-    const float k12 = k1 * k1 + k2 * k2;
-    const float s0 = 6.283185307179586f * f.inv_len0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float k0 = s0 * (float)signed_freq(r.t + e * T, f.n0);
-      const float kk = k0 * k0 + k12;
-      const float w = (MODE == PASS_XMID_ETD1 ? etd1_weight(kk, f) : imex_prefactor_fast(kk, f)) * f.scale;
-      r.v[e] = cscale(r.v[e], w);
-    }
+    xmid_apply_filter<MODE, T>(r.v, r.t, r.kother, r.kz, p.filt);
   }
 
   EVX_HD static void fetch_tw(Regs& r, const LineParams& p, int stage) {

@@ -9,6 +9,8 @@
 #include "spectral_plan.h"
 #include "fft_pass_core.h"
 #include "fft_line.h"
+#include "fft_chain.h"
+#include "tma_ptx.h"
 #include "dist_params.h"
 
 namespace evx {
@@ -20,12 +22,29 @@ constexpr int kPitchAlign = 8;   // spectrum rows are padded to a multiple of 8 
 // threads per line) - the phases then only need warp-level synchronisation, the eight warps of
 // a block drift apart and their load, exchange and arithmetic phases overlap
 // (512^3: inverse z pass 279 -> 256 us, forward 228 -> 224 us; profiles/r02_exp_passes.json)
+// L2 prefetch of the contiguous input rows of the block that will run `pf_blocks` blocks later
+// (one bulk prefetch per array and block, issued by one thread): the z passes load straight
+// into registers, so their memory pipeline is only as deep as the resident warps - the
+// prefetch turns the DRAM latency of a later block into an L2 hit.
+template <class Prog>
+__device__ __forceinline__ void pass_prefetch(const ZParams& p, long long block) {
+  if (p.pf_blocks <= 0 || threadIdx.x != 0) return;
+  constexpr int NL = Prog::NTHREADS / Prog::T;
+  const long long row = (block + p.pf_blocks) * NL;
+  if (row + NL > p.rows) return;
+  if (p.real_in) bulk_prefetch_l2(p.real_in + row * p.nz, (unsigned)(NL * p.nz * sizeof(float)));
+  if (p.real_out) bulk_prefetch_l2(p.spec + row * p.P, (unsigned)(NL * p.P * sizeof(cf)));
+}
+template <class Prog>
+__device__ __forceinline__ void pass_prefetch(const StridedParams&, long long) {}
+
 template <class Prog, class Params, int MINB = 0, bool WARP_LINES = false>
 __global__ void __launch_bounds__(Prog::NTHREADS, MINB ? MINB : (Prog::NTHREADS <= 256 ? 4 : (Prog::NTHREADS <= 512 ? 2 : 1))) fft_pass_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf* smem = reinterpret_cast<cf*>(smem_raw);
   typename Prog::Regs r;
   Prog::init(r, p, threadIdx.x, (long long)blockIdx.x);
+  pass_prefetch<Prog>(p, (long long)blockIdx.x);
 #pragma unroll
   for (int k = 0; k < Prog::NPHASES; ++k) {
     if (k) { if (WARP_LINES) __syncwarp(); else __syncthreads(); }
@@ -179,7 +198,10 @@ int native_plan_init(evx_imex_plan* p) {
   const int M = p->nz / 2;
   p->spec_pitch = ((M + 1 + kPitchAlign - 1) / kPitchAlign) * kPitchAlign;
   p->spec_bytes = ((size_t)p->nx * p->ny * p->spec_pitch * sizeof(cf) + 255) & ~(size_t)255;
-  p->work_bytes = 0;
+  // scratch behind the spectrum: per-plane completion counters of the chained z/y passes
+  // (+ a debug area for per-block cycle counters at the very end, EVX_FFT_CHAIN_STATS)
+  p->work_bytes = chain_supported(p->nx, p->ny, p->nz)
+                      ? (((size_t)p->nx * sizeof(unsigned) + 255) & ~(size_t)255) + kChainStatsBytes : 0;
   // tables: W_nx | W_ny | W_M | W_nz[0..M]
   const size_t total = (size_t)p->nx + p->ny + M + (M + 1);
   std::vector<cf> host(total);
@@ -203,6 +225,7 @@ void native_plan_free(evx_imex_plan* p) {
 struct NativeView {
   int nx, ny, nz, M, P;
   cf* spec;
+  void* flags;             // work area behind the spectrum (null if the plan has none)
   const cf *twx, *twy, *twz, *twr;
 };
 
@@ -210,6 +233,7 @@ static NativeView view_of(const evx_imex_plan* p, void* workspace) {
   NativeView v;
   v.nx = p->nx; v.ny = p->ny; v.nz = p->nz; v.M = p->nz / 2; v.P = p->spec_pitch;
   v.spec = reinterpret_cast<cf*>((char*)workspace + p->real_bytes);
+  v.flags = p->work_bytes ? (void*)((char*)workspace + p->real_bytes + p->spec_bytes) : nullptr;
   v.twx = (const cf*)p->twiddles;
   v.twy = v.twx + p->nx;
   v.twz = v.twy + p->ny;
@@ -230,6 +254,12 @@ static int line_kz() {
   return (e && atoi(e) == 16) ? 16 : 8;
 }
 
+static int line_l2_ahead() {
+  const char* e = getenv("EVX_FFT_TMA_PF");
+  const int v = e ? atoi(e) : 0;
+  return v < 0 ? 0 : (v > 8 ? 8 : v);
+}
+
 // tensor maps are keyed by the spectrum's address (the caller owns the workspace and may pass
 // a different one per call; encoding is a host-side table fill of about a microsecond)
 static int line_tmaps(evx_imex_plan* p, const NativeView& v) {
@@ -242,10 +272,17 @@ static int line_tmaps(evx_imex_plan* p, const NativeView& v) {
   return EVX_OK;
 }
 
+static int z_pf_blocks() {
+  const char* e = getenv("EVX_FFT_Z_PF");
+  const int v = e ? atoi(e) : 0;
+  return v < 0 ? 0 : v;
+}
+
 static ZParams z_params(const NativeView& v, const float* real_in, float* real_out) {
   ZParams zp;
   zp.real_in = real_in; zp.real_out = real_out; zp.spec = v.spec; zp.tw = v.twz; zp.twr = v.twr;
   zp.rows = (long long)v.nx * v.ny; zp.nz = v.nz; zp.P = v.P;
+  zp.pf_blocks = z_pf_blocks();
   return zp;
 }
 
@@ -276,6 +313,7 @@ static int strided_pass(evx_imex_plan* p, const NativeView& v, int which, const 
     lp.spec = v.spec; lp.tw = along_x ? v.twx : v.twy;
     lp.nx = v.nx; lp.ny = v.ny; lp.P = v.P; lp.ncols_valid = v.M + 1;
     lp.tiles_per_row = 0; lp.ntiles = 0; lp.along_x = along_x ? 1 : 0;
+    lp.l2_ahead = line_l2_ahead();
     lp.filt = along_x ? filter_of(v, h, dt, coef, power) : FilterParams{};
     const int mode = which == 1 ? PASS_FWD
                                 : (which == 3 ? PASS_INV
@@ -292,9 +330,37 @@ static int strided_pass(evx_imex_plan* p, const NativeView& v, int which, const 
   return launch_xmid(v.nx, sp, st);
 }
 
+// Chained z/y passes (fft_chain.cu): one persistent kernel per direction whose second stage
+// reads the first stage's output from L2.  EVX_FFT_CHAIN=0 keeps one kernel per pass.
+static bool use_chain(const evx_imex_plan* p, const NativeView& v) {
+  const char* e = getenv("EVX_FFT_CHAIN");
+  return e && atoi(e) != 0 && v.flags && chain_supported(v.nx, v.ny, v.nz);   // opt-in until it beats the separate passes
+}
+static int chain_tmap(evx_imex_plan* p, const NativeView& v) {
+  if (p->tmap_chain_spec == (void*)v.spec) return EVX_OK;
+  const int rc = line_make_tmap(p->tmap_chain, v.spec, v.nx, v.ny, v.P, v.M + 1, 0, 8);
+  p->tmap_chain_spec = rc ? nullptr : (void*)v.spec;
+  return rc;
+}
+static int chain_pass(evx_imex_plan* p, const NativeView& v, bool inverse, const float* real_in,
+                      float* real_out, cudaStream_t st) {
+  if (int rc = chain_tmap(p, v)) return rc;
+  ChainArgs a;
+  a.nx = v.nx; a.ny = v.ny; a.nz = v.nz; a.P = v.P;
+  a.real_in = real_in; a.real_out = real_out; a.spec = v.spec;
+  a.twz = v.twz; a.twr = v.twr; a.twy = v.twy; a.flags = v.flags;
+  a.stats = (char*)v.flags + p->work_bytes - kChainStatsBytes;
+  return chain_launch(inverse, a, p->tmap_chain, st);
+}
+
 int native_apply(evx_imex_plan* p, const float* u, const float* r, float* out, void* workspace,
                  const double* h, double dt, double coef, int power, cudaStream_t st) {
   const NativeView v = view_of(p, workspace);
+  if (use_chain(p, v)) {
+    if (int rc = chain_pass(p, v, false, r, nullptr, st)) return rc;
+    if (int rc = strided_pass(p, v, 2, h, dt, coef, power, st)) return rc;
+    return chain_pass(p, v, true, u, out, st);
+  }
   if (int rc = launch_z<false>(v.M, z_params(v, r, nullptr), st)) return rc;
   for (int which = 1; which <= 3; ++which)
     if (int rc = strided_pass(p, v, which, h, dt, coef, power, st)) return rc;
@@ -310,6 +376,12 @@ int native_single_pass(evx_imex_plan* p, int which, const float* u, const float*
   if (which == 0) return launch_z<false>(v.M, z_params(v, r, nullptr), st);
   if (which >= 1 && which <= 3) return strided_pass(p, v, which, h, dt, coef, power, st);
   if (which == 4) return launch_z<true>(v.M, z_params(v, u, out), st);
+  // 5: chained z + y forward, 6: chained y + z inverse (EVX_ERR_UNSUPPORTED where the plan
+  // runs one kernel per pass)
+  if (which == 5 || which == 6) {
+    if (!use_chain(p, v)) return EVX_ERR_UNSUPPORTED;
+    return which == 5 ? chain_pass(p, v, false, r, nullptr, st) : chain_pass(p, v, true, u, out, st);
+  }
   return EVX_ERR_ARG;
 }
 

@@ -98,6 +98,21 @@ inline void finalize_strided(StridedParams& p, int L) {
   for (int it = 0; it < 4; ++it) p.src_pf_step[it] = strided_step(p.src, it * (L / 4));
 }
 
+// weight of the fused x pass applied to the 8 points t + e*T of a line (kother: index along the
+// other strided axis, kz: column); shared by every form of the pass so that they agree bit for bit
+template <int MODE, int T>
+EVX_HD void xmid_apply_filter(cf* v, int t, int kother, int kz, const FilterParams& f) {
+  const float k1 = wavenumber(signed_freq(kother, f.n1), f.inv_len1);
+  const float k2 = wavenumber(kz, f.inv_len2);
+  const float k12 = fma_rn(k1, k1, fmul_rn(k2, k2));
+  const float s0 = 6.283185307179586f * f.inv_len0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float k0 = fmul_rn(s0, (float)signed_freq(t + e * T, f.n0));
+    v[e] = cscale(v[e], xpass_weight<MODE == PASS_XMID_ETD1>(k0, k12, f));
+  }
+}
+
 template <int L, int KZ, int MODE>
 struct StridedPass {
   static constexpr int T = L / 8;
@@ -172,18 +187,7 @@ struct StridedPass {
     for (int e = 0; e < 8; ++e) base[p.dst_step[e]] = r.v[e];
   }
   EVX_HD static void apply_filter(Regs& r, const StridedParams& p) {
-    const FilterParams& f = p.filt;
-    const float k1 = wavenumber(signed_freq(r.kother, f.n1), f.inv_len1);
-    const float k2 = wavenumber(r.kz, f.inv_len2);
-    const float k12 = k1 * k1 + k2 * k2;
-    const float s0 = 6.283185307179586f * f.inv_len0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float k0 = s0 * (float)signed_freq(r.t + e * T, f.n0);
-      const float kk = k0 * k0 + k12;
-      const float w = (MODE == PASS_XMID_ETD1 ? etd1_weight(kk, f) : imex_prefactor_fast(kk, f)) * f.scale;
-      r.v[e] = cscale(r.v[e], w);
-    }
+    xmid_apply_filter<MODE, T>(r.v, r.t, r.kother, r.kz, p.filt);
   }
 
   // transform step q of the pass: FWD/INV: stage q; XMID: q < S forward stage q, else inverse q-S
@@ -370,6 +374,7 @@ struct ZParams {
   const cf* twr;           // W_nz[k], k = 0..M (untangle roots)
   long long rows;          // nx*ny
   int nz, P;
+  int pf_blocks;           // > 0: L2 prefetch distance of the z kernels, in blocks (device only)
 };
 
 template <int M, int NL, bool INVERSE>

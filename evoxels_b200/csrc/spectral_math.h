@@ -40,6 +40,14 @@ EVX_HD float fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 EVX_HD float frcp_rn(float a) { volatile float r = 1.0f / a; return r; }
 #endif
 
+#if defined(__CUDA_ARCH__)
+EVX_HD float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+EVX_HD float fdiv_fast(float a, float b) { return __fdividef(a, b); }
+#else
+EVX_HD float fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
+EVX_HD float fdiv_fast(float a, float b) { return a / b; }
+#endif
+
 EVX_HD float wavenumber(int idx, float inv_len) {
   return fmul_rn(6.283185307179586f, fmul_rn((float)idx, inv_len));
 }
@@ -87,6 +95,20 @@ EVX_HD float etd1_weight(float k2, const FilterParams& f) {
     phi = (expf(z) - 1.0f) / z;
   }
   return fmul_rn(f.dt, phi);
+}
+
+// Weight of one coefficient inside the fused x pass, FFT normalisation included: k0 is the
+// wavenumber along the transformed axis, k12 = k1^2 + k2^2 of the other two.  Every operation is
+// an explicit round-to-nearest intrinsic, so all kernels that inline this (cp.async passes,
+// TMA-tiled passes, distributed passes) produce the same bits - nvcc's mul/add contraction
+// otherwise depends on the surrounding code.
+template <bool ETD1>
+EVX_HD float xpass_weight(float k0, float k12, const FilterParams& f) {
+  const float kk = fma_rn(k0, k0, k12);
+  if (ETD1) return fmul_rn(etd1_weight(kk, f), f.scale);
+  const float kp = f.power == 2 ? fmul_rn(kk, kk) : kk;
+  const float den = fma_rn(f.dt, fmul_rn(f.coef, kp), 1.0f);
+  return fmul_rn(fdiv_fast(f.dt, den), f.scale);
 }
 
 // weight applied to one spectral coefficient (without the FFT normalisation)

@@ -24,6 +24,9 @@ struct evx_imex_plan {
   alignas(64) unsigned char tmap_x[128];
   void* tmap_spec = nullptr;
   int tmap_kz = 0;
+  // tensor map of the chained z/y passes ([8 x 256 x 1] boxes along y), same keying
+  alignas(64) unsigned char tmap_chain[128];
+  void* tmap_chain_spec = nullptr;
 };
 
 namespace evx {

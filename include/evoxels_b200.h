@@ -178,7 +178,9 @@ int evx_ch_imex_step_f64(evx_imex_plan* plan, const double* u, const double* hom
 
 /* Measurement aid (bench.py per-kernel roofline): run ONE pass of the native pipeline on the
  * plan's scratch - which = 0 z forward (r -> spectrum), 1 y forward, 2 x forward*filter*inverse,
- * 3 y inverse, 4 z inverse (+u -> out).  Native back end only. */
+ * 3 y inverse, 4 z inverse (+u -> out); 5 = the chained z+y forward kernel, 6 = the chained y+z
+ * inverse kernel (EVX_ERR_UNSUPPORTED when the plan runs one kernel per pass).  Native back
+ * end only. */
 int evx_imex_native_pass_f32(evx_imex_plan* plan, int which, const float* u, const float* r,
                              float* out, void* workspace, const double* h, double dt, double coef,
                              int power, void* stream);

@@ -56,19 +56,21 @@ def main():
            "threads": torch.get_num_threads()}
     root = find_reference()
     if root is None:
-        if cuda:
-            out.update(kind="unavailable", note="reference sources not found on this box")
-            print(json.dumps(out))
-            return
+        # no reference sources on this box: time the restatement (same torch calls in the same
+        # order, oracle/evx_oracle.py) - on the GPU too, where it stands for the reference's
+        # own eager-CUDA path (evoxels/solvers.py:64-70, voxelgrid.py:203-207)
         from oracle import evx_oracle as O
         out["kind"] = "port"
         if args.problem == "ch":
             orc = O.CHOracle(shape, (1.0, 1.0, 1.0), 0.1, 3.0, 1.0, 0.25)
-            u = O.noise_field(shape, seed=0)
+            orc.prefac = orc.prefac.to(args.device)
+            u = O.noise_field(shape, seed=0).to(args.device)
         else:
             orc = O.ACOracle(shape, (1.0, 1.0, 1.0), 0.05)
-            u = O.noise_field(shape, seed=1, lo=0.0, amp=1.0)
+            u = O.noise_field(shape, seed=1, lo=0.0, amp=1.0).to(args.device)
         step = lambda t, v: orc.step(v)      # noqa: E731
+        if args.jit:
+            step = torch.compile(step)
     else:
         os.environ["EVOXELS_REFERENCE"] = root
         from oracle.ref_shim import load_reference

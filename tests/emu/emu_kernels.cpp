@@ -644,3 +644,59 @@ int emu_generic_apply_f64(const double* u, const double* r, double* out, int nx,
   return emu_generic_apply<double>(u, r, out, nx, ny, nz, h, dt, coef, power, W, nthreads);
 }
 }
+
+// -------------------------------------------------------------------------------------
+// Chained z/y passes: the work list of fft_chain_core.h replayed with `blocks` resident
+// blocks.  Checks that every (stage, plane, idx) occurs exactly once, that every dependency
+// points to a smaller item number, and that blocks walking their items in order - a stage-1
+// item may only start once all stage-0 items of its plane have finished - always make
+// progress.  Returns 0 if all holds; *waits = stage-1 items that found their plane unfinished
+// when every block advances one item per sweep (how often the kernel would spin).
+// -------------------------------------------------------------------------------------
+#include "../../evoxels_b200/csrc/fft_chain_core.h"
+extern "C" int emu_chain_schedule_check(int nplanes, int lag, int n0, int n1, int blocks,
+                                        long long* waits) {
+  const ChainSchedule s = make_chain_schedule(nplanes, lag, n0, n1);
+  if (s.total != (long long)nplanes * (n0 + n1)) return 1;
+  std::vector<int> seen0((size_t)nplanes * n0, 0), seen1((size_t)nplanes * n1, 0);
+  std::vector<long long> last0(nplanes, -1);
+  for (long long i = 0; i < s.total; ++i) {
+    const ChainItem it = chain_decode(s, i);
+    if (it.plane < 0 || it.plane >= nplanes) return 2;
+    if (it.stage == 0) {
+      if (it.idx < 0 || it.idx >= n0 || seen0[(size_t)it.plane * n0 + it.idx]++) return 3;
+      last0[it.plane] = i;
+    } else if (it.stage == 1) {
+      if (it.idx < 0 || it.idx >= n1 || seen1[(size_t)it.plane * n1 + it.idx]++) return 4;
+      if (last0[it.plane] < 0) return 5;
+      for (int k = 0; k < n0; ++k)
+        if (!seen0[(size_t)it.plane * n0 + k]) return 6;      // a dependency with a larger number
+    } else {
+      return 7;
+    }
+  }
+  for (int v : seen0) if (v != 1) return 8;
+  for (int v : seen1) if (v != 1) return 9;
+  // progress: sweep over the blocks, each runs its next item if it can
+  std::vector<long long> next(blocks);
+  std::vector<int> done0(nplanes, 0);
+  for (int b = 0; b < blocks; ++b) next[b] = b;
+  long long finished = 0, w = 0;
+  while (finished < s.total) {
+    bool progress = false;
+    std::vector<int> inc(nplanes, 0);          // completions become visible after the sweep
+    for (int b = 0; b < blocks; ++b) {
+      if (next[b] >= s.total) continue;
+      const ChainItem it = chain_decode(s, next[b]);
+      if (it.stage == 1 && done0[it.plane] < n0) { ++w; continue; }
+      if (it.stage == 0) ++inc[it.plane];
+      next[b] += blocks;
+      ++finished;
+      progress = true;
+    }
+    for (int x = 0; x < nplanes; ++x) done0[x] += inc[x];
+    if (!progress) return 10;                  // deadlock
+  }
+  if (waits) *waits = w;
+  return 0;
+}

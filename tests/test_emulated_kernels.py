@@ -397,3 +397,17 @@ def test_distributed_pipeline_virtual_ranks(emu, shape, world, pipe_blocks):
     assert emu.emu_dist_apply(None, _p(r), _p(got), nx, ny, nz, world, 1, 2, 2, h, d(0.3), d(0.7), 1 | 0x100) == 0
     assert np.array_equal(got, want)
     emu.emu_set_pipe_blocks(0)
+
+
+@pytest.mark.parametrize("nplanes,lag,n0,n1,blocks", [
+    (512, 12, 32, 33, 296), (512, 12, 33, 32, 296), (8, 12, 32, 33, 296), (16, 1, 32, 33, 296),
+    (64, 3, 32, 33, 7), (512, 1, 32, 33, 296), (33, 5, 2, 3, 4), (9, 9, 4, 1, 50)])
+def test_chain_schedule_covers_everything_in_dependency_order(emu, nplanes, lag, n0, n1, blocks):
+    """Work list of the chained z/y kernels (fft_chain_core.h): complete, every dependency has a
+    smaller item number, blocks walking their items in order never deadlock; with the shipped
+    lag a stage-1 item practically never finds its plane unfinished."""
+    waits = ctypes.c_longlong(-1)
+    rc = emu.emu_chain_schedule_check(nplanes, lag, n0, n1, blocks, ctypes.byref(waits))
+    assert rc == 0
+    if lag >= 12 and nplanes >= 512:
+        assert waits.value == 0

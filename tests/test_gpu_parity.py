@@ -581,3 +581,38 @@ def test_tma_tiled_passes_match_the_cp_async_passes_bit_for_bit(cuda_device, mon
         assert torch.equal(a, b)
     ref = O.CHOracle(shape, (1.0, 1.0, 1.0), 0.1).step(u.cpu()[None])[0]
     assert rel_l2(outs["1"][2].cpu(), ref) <= 1e-5
+
+
+@pytest.mark.parametrize("shape", [(32, 512, 512), (8, 512, 512), (512, 512, 512)])
+def test_chained_zy_passes_match_one_kernel_per_pass_bit_for_bit(cuda_device, monkeypatch, shape):
+    """fft_chain.cu: z lines and y tiles of a plane run inside one persistent kernel per
+    direction (the plane's half spectrum goes through L2).  Same arithmetic as the stand-alone
+    passes, so update and fused CH step must be bit-identical - also when the planes are fewer
+    than the schedule's lag - and repeatable (no dependence on how the blocks interleave)."""
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    u = 0.5 + 0.1 * torch.rand(shape, device="cuda", generator=gen)
+    r = torch.randn(shape, device="cuda", generator=gen)
+    plan = _native.ImexPlan(shape, torch.float32, "cuda", _native.FFT_NATIVE)
+    outs = {}
+    for chain in ("0", "1", "1"):
+        monkeypatch.setenv("EVX_FFT_CHAIN", chain)
+        res = []
+        out = torch.full_like(u, float("nan"))
+        plan.apply(u, r, out, (1.0, 0.5, 2.0), 0.1, 1.5, 2)
+        res.append(out)
+        out = torch.full_like(u, float("nan"))
+        plan.apply(None, r, out, (1.0, 0.5, 2.0), 0.1, 1.5, 2)
+        res.append(out)
+        out = torch.full_like(u, float("nan"))
+        plan.ch_step(u, out, (1.0, 1.0, 1.0), 0.1, 3.0, 1.0, 0.25)
+        res.append(out)
+        torch.cuda.synchronize()
+        outs.setdefault(chain, []).append(res)
+    base = outs["0"][0]
+    for run in outs["1"]:
+        for a, b in zip(base, run):
+            assert torch.isfinite(b).all()
+            assert torch.equal(a, b)
+    if shape[0] <= 32:
+        ref = O.CHOracle(shape, (1.0, 1.0, 1.0), 0.1).step(u.cpu()[None])[0]
+        assert rel_l2(outs["1"][0][2].cpu(), ref) <= 1e-5
