@@ -72,8 +72,8 @@ class ClockSampler:
     """SM clock and throttle reasons sampled through NVML from a thread of this process, every
     few milliseconds, so that even a 30 ms timed region is covered by samples (an `nvidia-smi
     -lms` child needs ~0.5 s to start and cannot see it).  `mark()` brackets the timed region;
-    samples taken while the GPU is busy before / after it (ramp-up steps, clock-probe steps) are
-    reported next to the in-region ones."""
+    samples taken while the GPU is busy before / after it (warm-up steps, clock-probe steps: the
+    latter show the sustained clock under the power cap) are reported next to the in-region ones."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap"}
 
@@ -131,8 +131,8 @@ class ClockSampler:
             self._thread.join(timeout=2)
         out = {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_mhz", None), "reasons": [],
                "samples": 0, "samples_in_timed_region": 0, "sm_mhz_timed_region": None,
-               "source": "NVML, in-process thread, %.0f ms period; busy GPU from ramp-up steps "
-                         "before to clock-probe steps after the timed region" % (self.period * 1e3)}
+               "source": "NVML, in-process thread, %.0f ms period; sampled from the warm-up steps "
+                         "through the timed region to the clock-probe steps after it" % (self.period * 1e3)}
         if self.error:
             out["error"] = self.error
         if not self.samples:
@@ -447,7 +447,6 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         u = ts.step(0.0, u)
     plan = next(iter(ts._plans.values()))
-    u = busy_for(step1, u, 0.5, dev)       # clock ramp-up under the sampler, untimed
     barrier()
     l0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -711,8 +710,6 @@ def run_ours_distributed(args, world, rank, local, dev):
     for _ in range(max(args.warmup, 3)):
         u = stepper.step(u)
     m_start = stepper.total_mass(u0)
-    for _ in range(100):                    # clock ramp-up under the sampler, untimed
-        u = stepper.step(u)
     barrier()
     l0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

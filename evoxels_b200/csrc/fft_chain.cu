@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include "evx_internal.h"
 #include "fft_line_core.h"
+#include "fft_zline_core.h"
 #include "fft_chain_core.h"
 #include "fft_chain.h"
 #include "fft_line.h"
@@ -33,15 +34,20 @@ struct ChainParams {
   const cf *twz, *twr, *twy;
   int ny, nz, P;
   unsigned* done0;         // [nplanes] finished stage-0 items per plane; zeroed before the launch
-  int ahead;               // 1: the next item's input copy is issued while the current item runs
-  unsigned long long* stats;   // optional [gridDim.x][8] cycle counters of thread 0 (EVX_FFT_CHAIN_STATS)
+  unsigned long long* stats;   // optional [gridDim.x][16] cycle counters of thread 0 (EVX_FFT_CHAIN_STATS)
 };
 
-constexpr int kChainThreads = 512;
-constexpr int kChainZLines = kChainThreads / 32;     // z lines per item: one per warp
+constexpr int kChainCompute = 512;                   // compute threads (16 warps)
+// + one loader warp + one retirer warp per input buffer (lane 0 of each acts)
+constexpr int chain_threads(int nbuf) { return kChainCompute + 32 + 32 * (nbuf <= 2 ? 1 : nbuf); }
+constexpr int kChainZLines = kChainCompute / 32;     // z lines per item
 // input buffer: a [512 x 8] complex tile (32 KB) or 16 spectrum rows of 264 complex (33 KB)
 constexpr int kChainBufBytes = 34 * 1024;
-constexpr size_t kChainSmemBytes = 1024 + 2 * (size_t)kChainBufBytes + StridedLine<512, 8, PASS_FWD>::X_BYTES + 64;
+constexpr size_t chain_smem_bytes(int nbuf) {
+  return 1024 + (size_t)nbuf * kChainBufBytes + StridedLine<512, 8, PASS_FWD>::X_BYTES + 128;
+}
+// named barriers: 0 block, 1..4 y groups (128 threads), 5..12 z groups (64 threads)
+constexpr int kBarY = 1, kBarZ = 5;
 
 // spin until *flag >= target (bounded: a scheduling bug must trap, not hang the GPU)
 __device__ __forceinline__ void wait_count(const unsigned* flag, unsigned target) {
@@ -49,222 +55,188 @@ __device__ __forceinline__ void wait_count(const unsigned* flag, unsigned target
   for (unsigned spin = 0; ld_acquire_gpu(flag) < target; ++spin)
     if ((spin & 255u) == 255u && clock64() - t0 > 4000000000LL) __trap();
 }
-// thread 0's cycle accounting (only when the launcher passes a stats buffer)
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// cycle accounting of the two control threads (only when the launcher passes a stats buffer)
 struct ChainStats {
-  long long dep = 0, mbar = 0, zitem = 0, yitem = 0, nwait = 0, nearly_fail = 0, pub = 0;
+  long long a = 0, b = 0, c = 0, d = 0, n = 0;
 };
 
-template <bool INV, bool STATS>
-__global__ void __launch_bounds__(kChainThreads, 2)
+// Block = 16 compute warps + a loader warp + a retirer warp (warp specialisation):
+//   compute threads  wait for the item's input (mbarrier full[b]), run its phases with group
+//                    barriers, arrive on done[b] - no flags, no fences, no waits on other blocks
+//   loader           walks the item list two items ahead: waits for the buffer (empty[b]) and
+//                    for the plane the item depends on, then issues the TMA tile / bulk row copies
+//   retirer          waits for done[b]; y tile: TMA store, buffer free once the store has read
+//                    it, (inverse) publish the plane counter once the store is complete;
+//                    z item: buffer free at once, (forward) publish the plane counter
+// so the latencies of the control path (store drain, gpu-scope fences, acquire loads) run next to
+// the compute warps instead of inside one of them, and loads and retirements overlap each other.
+// NBUF = 2: two blocks per SM, the next item's input in flight while the current one runs;
+// NBUF = 4: one block per SM with its input copies issued up to three items ahead.
+template <bool INV, bool STATS, int NBUF>
+__global__ void __launch_bounds__(chain_threads(NBUF), NBUF <= 2 ? 2 : 1)
     fft_chain_kernel(const __grid_constant__ CUtensorMap tmap, const ChainParams p) {
   using Line = StridedLine<512, 8, INV ? PASS_INV : PASS_FWD>;
-  using ZP = ZPass<256, 1, INV>;
-  constexpr int M = 256, T = 32, ZLP = ZP::LP;
+  using ZG = ZGroupLine<INV>;
   constexpr int BUF = kChainBufBytes;
-  static_assert(kChainZLines * ZLP * sizeof(cf) <= Line::X_BYTES, "z scratch lives in the exchange area");
-  static_assert(Line::TILE_BYTES <= BUF && kChainZLines * 264 * sizeof(cf) <= BUF, "input buffer size");
+  static_assert(2 * ZG::XG <= Line::XG, "the two z groups of a y group share its exchange buffer");
+  static_assert(Line::TILE_BYTES <= BUF && kChainZLines * ZG::ROWP * sizeof(cf) <= BUF, "input buffer size");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* bufs = sm;                     // two input buffers: a y tile or the rows of a z item
-  cf* xall = reinterpret_cast<cf*>(sm + 2 * BUF);
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + 2 * BUF + Line::X_BYTES);
+  unsigned char* bufs = sm;                     // NBUF input buffers: a y tile or the rows of a z item
+  cf* xall = reinterpret_cast<cf*>(sm + NBUF * BUF);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + NBUF * BUF + Line::X_BYTES);
+  unsigned long long* done = full + NBUF;
+  unsigned long long* empty = full + 2 * NBUF;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool leader = tid == 0;
+  const int tid = threadIdx.x;
   const ChainSchedule& sc = p.sched;
-  const long long total = sc.total, G = gridDim.x;
-  typename Line::Regs yr;
-  Line::init(yr, tid);
-  cf* xg = xall + yr.g * Line::XG;
-  cf* zb = xall + warp * ZLP;
-  LineParams lp;
-  lp.tw = p.twy;
-  const unsigned zin_bytes = (unsigned)(kChainZLines * (INV ? p.P * sizeof(cf) : p.nz * sizeof(float)));
+  const int G = gridDim.x;
+  constexpr bool st_on = STATS;
+  auto is_y = [](const ChainItem& it) { return INV ? it.stage == 0 : it.stage == 1; };
 
-  if (leader) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&full[b], 1);
+      mbar_init(&done[b], kChainCompute);
+      mbar_init(&empty[b], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
   __syncthreads();
 
-  auto is_y = [](const ChainItem& it) { return INV ? it.stage == 0 : it.stage == 1; };
-  int count = 0;                    // items this block has finished (uniform)
-  // leader only --------------------------------------------------------------------------
-  int issued = 0;                   // items whose input copy has been issued
-  int pending_plane = -1;           // inverse: plane of the tile store that is not yet published
-  ChainStats cs;
-  constexpr bool st_on = STATS;
-  const long long t_begin = st_on ? clock64() : 0;
-  auto publish_pending = [&]() {
-    if (pending_plane < 0) return;
-    const long long t0 = st_on ? clock64() : 0;
-    tma_store_wait_all();           // the tile is in global memory
-    if (st_on) cs.pub += clock64() - t0;
-    fence_proxy_async_all();
-    __threadfence();
-    red_release_gpu_add(p.done0 + pending_plane, 1u);
-    pending_plane = -1;
-  };
-  // Issue the input copy of this block's item number `issued` (item index blockIdx.x + issued*G)
-  // into buffer issued & 1; false if it depends on an unfinished plane and !blocking.
-  auto issue = [&](bool blocking) -> bool {
-    const ChainItem it = chain_decode(sc, (long long)blockIdx.x + (long long)issued * G);
-    if (it.stage == 1) {            // second stage of the pair: the plane's first stage must be done
-      if (ld_acquire_gpu(p.done0 + it.plane) < (unsigned)sc.n0) {
-        if (!blocking) { ++cs.nearly_fail; return false; }
-        if (INV) publish_pending(); // never wait while holding back an own tile
-        const long long t0 = st_on ? clock64() : 0;
+  if (tid == kChainCompute) {
+    // ==================================== loader ==========================================
+    const unsigned zin_bytes = (unsigned)(kChainZLines * (INV ? ZG::ROWP * sizeof(cf) : p.nz * sizeof(float)));
+    ChainStats cs;
+    const long long t_begin = st_on ? clock64() : 0;
+    ChainCursor cur;
+    chain_cursor_init(cur, sc, blockIdx.x, G);
+    ChainItem it;
+    for (int n = 0; chain_cursor_next(cur, sc, it); ++n, chain_cursor_step(cur, sc)) {
+      const int buf = n % NBUF;
+      long long t0 = st_on ? clock64() : 0;
+      if (n >= NBUF) mbar_wait(&empty[buf], (unsigned)(n / NBUF - 1) & 1u);
+      long long t1 = st_on ? clock64() : 0;
+      if (it.stage == 1) {          // second stage of the pair: the plane's first stage must be done
         wait_count(p.done0 + it.plane, (unsigned)sc.n0);
-        if (st_on) { cs.dep += clock64() - t0; ++cs.nwait; }
+        fence_proxy_async_global();    // other blocks' stores -> this asynchronous copy
       }
-      fence_proxy_async_all();      // other blocks' stores -> this asynchronous copy
-    }
-    tma_store_wait_read();          // the buffer's previous tile has left shared memory
-    const int buf = issued & 1;
-    unsigned char* dst = bufs + buf * BUF;
-    if (is_y(it)) {
-      mbar_expect_tx(&full[buf], Line::TILE_BYTES);
+      long long t2 = st_on ? clock64() : 0;
+      unsigned char* dst = bufs + buf * BUF;
+      if (is_y(it)) {
+        mbar_expect_tx(&full[buf], Line::TILE_BYTES);
 #pragma unroll
-      for (int h = 0; h < 512 / Line::BOX_ROWS; ++h)
-        tma_load_3d(dst + h * Line::BOX_ROWS * Line::ROWB, &tmap, &full[buf], it.idx * Line::COLS,
-                    h * Line::BOX_ROWS, it.plane);
-    } else {
-      const long long row = (long long)it.plane * p.ny + (long long)it.idx * kChainZLines;
-      const void* src = INV ? (const void*)(p.spec + row * p.P) : (const void*)(p.real_in + row * p.nz);
-      mbar_expect_tx(&full[buf], zin_bytes);
-      bulk_load_1d(dst, src, zin_bytes, &full[buf]);
-      // the u rows of an inverse z item are loaded straight into registers: get them into L2
-      if (INV && p.real_in) bulk_prefetch_l2(p.real_in + row * p.nz, (unsigned)(kChainZLines * p.nz * sizeof(float)));
-    }
-    ++issued;
-    return true;
-  };
-
-  for (long long i = blockIdx.x; i < total; i += G) {
-    const ChainItem it = chain_decode(sc, i);
-    const bool y_item = is_y(it);
-    const long long t_item = (st_on && leader) ? clock64() : 0;
-    if (leader) {
-      if (issued == count) issue(true);
-      // one item ahead: its buffer is free once the previous item's tile store has been read
-      if (p.ahead && issued == count + 1 && i + G < total) issue(false);
-    }
-    const int buf = count & 1;
-    unsigned char* tb = bufs + buf * BUF;
-    if (st_on && leader) {
-      const long long t0 = clock64();
-      mbar_wait(&full[buf], (unsigned)(count >> 1) & 1u);
-      cs.mbar += clock64() - t0;
-    } else {
-      mbar_wait(&full[buf], (unsigned)(count >> 1) & 1u);
-    }
-    if (y_item) {
-#pragma unroll
-      for (int k = 0; k < Line::NPHASES; ++k) {
-        if (k) group_sync(1 + yr.g, Line::GT);
-        Line::phase(k, yr, tb, xg, lp);
+        for (int h = 0; h < 512 / Line::BOX_ROWS; ++h)
+          tma_load_3d(dst + h * Line::BOX_ROWS * Line::ROWB, &tmap, &full[buf], it.idx * Line::COLS,
+                      h * Line::BOX_ROWS, it.plane);
+      } else {
+        const long long row = (long long)it.plane * p.ny + (long long)it.idx * kChainZLines;
+        mbar_expect_tx(&full[buf], zin_bytes);
+        if (INV) {                  // spectrum rows: the global pitch is the buffer's pitch
+          bulk_load_1d(dst, p.spec + row * p.P, zin_bytes, &full[buf]);
+          // the u rows are loaded straight into registers: get them into L2
+          if (p.real_in) bulk_prefetch_l2(p.real_in + row * p.nz, (unsigned)(kChainZLines * p.nz * sizeof(float)));
+        } else {                    // real rows (2 KB) go to the same 264-complex pitch
+          const unsigned rb = (unsigned)(p.nz * sizeof(float));
+          const char* src = (const char*)(p.real_in + row * p.nz);
+          for (int l = 0; l < kChainZLines; ++l)
+            bulk_load_1d(dst + (size_t)l * ZG::ROWP * sizeof(cf), src + (size_t)l * rb, rb, &full[buf]);
+        }
       }
-      if (INV && leader) publish_pending();
-      fence_proxy_async();                      // tile writes -> visible to the TMA store
-      __syncthreads();
-      if (leader) {
+      if (st_on) { cs.a += t1 - t0; cs.b += t2 - t1; cs.c += clock64() - t2; ++cs.n; }
+    }
+    if (st_on) {
+      unsigned long long* o = p.stats + 16ull * blockIdx.x;
+      o[0] = cs.a; o[1] = cs.b; o[2] = cs.c; o[3] = cs.n; o[4] = clock64() - t_begin;
+    }
+    return;
+  }
+  if (tid >= kChainCompute + 32 && (tid & 31) == 0) {
+    // ============ retirers: one per buffer (NBUF > 2) or one for both (NBUF = 2) ===========
+    constexpr int NRET = NBUF <= 2 ? 1 : NBUF;
+    const int me = (tid - kChainCompute - 32) >> 5;
+    ChainStats cs;
+    ChainCursor cur;
+    chain_cursor_init(cur, sc, blockIdx.x, G);
+    ChainItem it;
+    for (int n = 0; chain_cursor_next(cur, sc, it); ++n, chain_cursor_step(cur, sc)) {
+      const int buf = n % NBUF;
+      if (NRET > 1 && buf != me) continue;
+      long long t0 = st_on ? clock64() : 0;
+      mbar_wait(&done[buf], (unsigned)(n / NBUF) & 1u);
+      long long t1 = st_on ? clock64() : 0;
+      if (is_y(it)) {
+        const unsigned char* tb = bufs + buf * BUF;
 #pragma unroll
         for (int h = 0; h < 512 / Line::BOX_ROWS; ++h)
           tma_store_3d(&tmap, tb + h * Line::BOX_ROWS * Line::ROWB, it.idx * Line::COLS, h * Line::BOX_ROWS, it.plane);
         tma_store_commit();
-        if (INV) pending_plane = it.plane;
-        if (st_on) cs.yitem += clock64() - t_item;
-      }
-    } else {
-      // one 512-point real line per warp, its input row already in shared memory
-      const long long row = (long long)it.plane * p.ny + (long long)it.idx * kChainZLines + warp;
-      typename ZP::Regs r;
-      r.t = lane; r.l = 0; r.row = row; r.valid = true;
-      if (!INV) {
-        const cf* line = reinterpret_cast<const cf*>(tb + (size_t)warp * p.nz * sizeof(float));
-#pragma unroll
-        for (int e = 0; e < 8; ++e) r.v[e] = line[lane + e * T];
-        line_stage_compute_pre<M, -1>(0, r.v, lane, r.w);
-        ZP::write_stage(r, zb, 0);
-        stage_twiddles<M>(1, lane, p.twz, r.w);
-        __syncwarp();
-#pragma unroll
-        for (int s = 1; s < ZP::S; ++s) {
-          ZP::read_natural(r, zb);
-          __syncwarp();
-          line_stage_compute_pre<M, -1>(s, r.v, lane, r.w);
-          ZP::write_stage(r, zb, s);
-          stage_twiddles<M>(s + 1, lane, p.twz, r.w);
-          __syncwarp();
-        }
-        cf* out = p.spec + row * p.P;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int kk = lane + e * T;
-          const cf zk = zb[zline_idx<M>(kk)];
-          const cf zmk = zb[zline_idx<M>(kk == 0 ? 0 : M - kk)];
-          out[kk] = ZP::untangle_fwd(zk, zmk, p.twr[kk]);
-        }
-        if (lane == 0) {
-          const cf z0 = zb[zline_idx<M>(0)];
-          out[M] = cf{z0.x - z0.y, 0.f};
-        }
-        __syncthreads();
-        if (leader) {
-          __threadfence();
+        tma_store_wait_read();      // the tile has left shared memory: the buffer is free
+        mbar_arrive(&empty[buf]);
+        if (INV) {                  // publish the tile once it is in global memory
+          tma_store_wait_all();
+          fence_proxy_async_global();
           red_release_gpu_add(p.done0 + it.plane, 1u);
-          if (st_on) cs.zitem += clock64() - t_item;
         }
       } else {
-        if (p.real_in) {
-          const cf* u = reinterpret_cast<const cf*>(p.real_in + row * p.nz);
+        mbar_arrive(&empty[buf]);
+        // release: covers the compute threads' stores (ordered before by the done barrier)
+        if (!INV) red_release_gpu_add(p.done0 + it.plane, 1u);
+      }
+      if (st_on) { cs.a += t1 - t0; cs.b += clock64() - t1; }
+    }
+    tma_store_wait_all();             // shared memory must outlive the stores
+    if (st_on && me == 0) {
+      unsigned long long* o = p.stats + 16ull * blockIdx.x + 8;
+      o[0] = cs.a; o[1] = cs.b;
+    }
+    return;
+  }
+  if (tid >= kChainCompute) return;     // idle lanes of the control warps
+
+  // ================================ compute warps ==========================================
+  typename Line::Regs yr;
+  Line::init(yr, tid);
+  cf* xg = xall + yr.g * Line::XG;
+  typename ZG::Regs zr;
+  ZG::init(zr, tid);
+  // the two z groups (64 threads) of a y group (128 threads) split that group's exchange buffer
+  cf* zxg = xall + (zr.g >> 1) * Line::XG + (zr.g & 1) * ZG::XG;
+  LineParams lp;
+  lp.tw = p.twy;
+  ZGroupParams zp;
+  zp.tw = p.twz; zp.twr = p.twr; zp.nz = p.nz; zp.P = p.P;
+  ChainCursor cur;
+  chain_cursor_init(cur, sc, blockIdx.x, G);
+  ChainItem it;
+  for (int count = 0; chain_cursor_next(cur, sc, it); ++count, chain_cursor_step(cur, sc)) {
+    const int buf = count % NBUF;
+    unsigned char* tb = bufs + buf * BUF;
+    mbar_wait(&full[buf], (unsigned)(count / NBUF) & 1u);
+    // the 128 threads of a y group own one exchange buffer across item types: nobody may start
+    // writing it while a neighbour still reads the previous item's data
+    group_sync(kBarY + yr.g, Line::GT);
+    if (is_y(it)) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) r.u[e] = u[lane + e * T];
-        } else {
+      for (int k = 0; k < Line::NPHASES; ++k) {
+        if (k) group_sync(kBarY + yr.g, Line::GT);
+        Line::phase(k, yr, tb, xg, lp);
+      }
+      fence_proxy_async();                      // tile writes -> visible to the TMA store
+    } else {
+      const long long grow = (long long)it.plane * p.ny + (long long)it.idx * kChainZLines + zr.g * ZG::G + zr.c2;
+      cf* rows = reinterpret_cast<cf*>(tb);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) r.u[e] = cf{0.f, 0.f};
-        }
-        // the row sits in natural order in the input buffer: X[k] and X[M-k] are both
-        // lane-contiguous reads, no staging copy
-        const cf* in = reinterpret_cast<const cf*>(tb + (size_t)warp * p.P * sizeof(cf));
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int kk = lane + e * T;
-          r.v[e] = ZP::untangle_inv(in[kk], in[M - kk], p.twr[kk]);
-        }
-#pragma unroll
-        for (int s = 0; s < ZP::S; ++s) {
-          if (s) {
-            ZP::read_natural(r, zb);
-            __syncwarp();
-          }
-          line_stage_compute_pre<M, +1>(s, r.v, lane, r.w);
-          if (s < ZP::S - 1) {
-            ZP::write_stage(r, zb, s);
-            stage_twiddles<M>(s + 1, lane, p.twz, r.w);
-            __syncwarp();
-          }
-        }
-        cf* out = reinterpret_cast<cf*>(p.real_out + row * p.nz);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) out[lane + e * T] = cadd(r.v[e], r.u[e]);
-        if (leader) publish_pending();
-        __syncthreads();
-        if (st_on && leader) cs.zitem += clock64() - t_item;
+      for (int k = 0; k < ZG::NPHASES; ++k) {
+        if (k) group_sync(kBarZ + zr.g, ZG::GT);
+        ZG::phase(k, zr, rows, zxg, zp, grow, p.real_in, p.real_out, p.spec);
       }
     }
-    ++count;
-  }
-  if (leader) {
-    if (INV) publish_pending();
-    tma_store_wait_read();            // shared memory must outlive the stores
-    if (st_on) {
-      unsigned long long* o = p.stats + 8ull * blockIdx.x;
-      o[0] = cs.dep; o[1] = cs.mbar; o[2] = cs.zitem; o[3] = cs.yitem; o[4] = clock64() - t_begin;
-      o[5] = cs.nwait; o[6] = cs.nearly_fail; o[7] = cs.pub;
-    }
+    mbar_arrive(&done[buf]);
   }
 }
 
@@ -275,34 +247,28 @@ bool chain_supported(int nx, int ny, int nz) {
 
 static int chain_lag() {
   const char* e = getenv("EVX_FFT_CHAIN_LAG");
-  const int v = e ? atoi(e) : 12;
+  const int v = e ? atoi(e) : 24;
   return v < 1 ? 1 : v;
 }
-static int chain_ahead() {
-  const char* e = getenv("EVX_FFT_CHAIN_AHEAD");
-  const int v = e ? atoi(e) : 1;
-  return v < 0 ? 0 : (v > 1 ? 1 : v);
-}
-
-template <bool INV, bool STATS>
+template <bool INV, bool STATS, int NBUF>
 static int chain_launch_t(ChainParams p, const void* tmap, cudaStream_t st) {
-  constexpr size_t smem = kChainSmemBytes;
-  auto kern = fft_chain_kernel<INV, STATS>;
+  constexpr size_t smem = chain_smem_bytes(NBUF);
+  auto kern = fft_chain_kernel<INV, STATS, NBUF>;
   static SmemOptIn optin;
   if (int rc = optin.ensure(kern, smem)) return rc;
   int dev = 0, sms = 148, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kChainThreads, smem) != cudaSuccess || per_sm < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, chain_threads(NBUF), smem) != cudaSuccess || per_sm < 1)
     return EVX_ERR_UNSUPPORTED;
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > (NBUF <= 2 ? 2 : 1)) per_sm = NBUF <= 2 ? 2 : 1;
   long long grid = (long long)sms * per_sm;
   if (grid > p.sched.total) grid = p.sched.total;
   cudaError_t e = cudaMemsetAsync(p.done0, 0, (size_t)p.sched.nplanes * sizeof(unsigned), st);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kChainThreads);
+  cfg.blockDim = dim3(chain_threads(NBUF));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -326,11 +292,17 @@ int chain_launch(bool inverse, const ChainArgs& a, const void* tmap_y, cudaStrea
   p.twz = (const cf*)a.twz; p.twr = (const cf*)a.twr; p.twy = (const cf*)a.twy;
   p.ny = a.ny; p.nz = a.nz; p.P = a.P;
   p.done0 = (unsigned*)a.flags;
-  p.ahead = chain_ahead();
   const char* es = getenv("EVX_FFT_CHAIN_STATS");
   p.stats = (es && atoi(es) != 0) ? (unsigned long long*)a.stats : nullptr;
-  if (p.stats) return inverse ? chain_launch_t<true, true>(p, tmap_y, st) : chain_launch_t<false, true>(p, tmap_y, st);
-  return inverse ? chain_launch_t<true, false>(p, tmap_y, st) : chain_launch_t<false, false>(p, tmap_y, st);
+  const char* eb = getenv("EVX_FFT_CHAIN_NBUF");
+  const int nbuf = eb ? atoi(eb) : 3;     // measured at 512^3: 3 buffers 0.433 / 0.449 ms, 2: 0.425 / 0.476, 4: 0.441 / 0.451
+#define EVX_CHAIN(NB)                                                                              \
+  if (p.stats) return inverse ? chain_launch_t<true, true, NB>(p, tmap_y, st) : chain_launch_t<false, true, NB>(p, tmap_y, st); \
+  return inverse ? chain_launch_t<true, false, NB>(p, tmap_y, st) : chain_launch_t<false, false, NB>(p, tmap_y, st);
+  if (nbuf == 2) { EVX_CHAIN(2) }
+  if (nbuf == 4) { EVX_CHAIN(4) }
+  EVX_CHAIN(3)
+#undef EVX_CHAIN
 }
 
 }  // namespace evx

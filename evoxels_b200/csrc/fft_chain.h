@@ -14,7 +14,7 @@ struct ChainArgs {
   void* stats;             // kChainStatsBytes of scratch: per-block cycle counters (debug aid)
 };
 
-constexpr size_t kChainStatsBytes = 64 * 1024;   // up to 1024 blocks x 8 counters
+constexpr size_t kChainStatsBytes = 64 * 1024;   // up to 512 blocks x 16 counters
 
 // 512-point y and z lines on a driver that can encode tensor maps
 bool chain_supported(int nx, int ny, int nz);

@@ -70,4 +70,45 @@ EVX_HD ChainItem chain_decode(const ChainSchedule& s, long long i) {
   return it;
 }
 
+// ---- division-free form used by the kernel ----------------------------------------------
+// "Virtual" numbering: nplanes + lag rounds of n0 + n1 slots each; slot w of round r is the
+// stage-0 item w of plane r (if r < nplanes) or the stage-1 item w - n0 of plane r - lag (if
+// r >= lag), else empty.  The same dependency rule holds (a stage-1 item sits `lag` rounds after
+// its plane's stage-0 items), and a block steps from slot i to slot i + G with two additions.
+struct ChainCursor {
+  int round, w;            // current slot
+  int step_round, step_w;  // G slots, decomposed
+};
+EVX_HD int chain_rounds(const ChainSchedule& s) { return s.nplanes + s.lag; }
+EVX_HD void chain_cursor_init(ChainCursor& c, const ChainSchedule& s, int first, int stride) {
+  const int per = s.n0 + s.n1;
+  c.round = first / per;
+  c.w = first - c.round * per;
+  c.step_round = stride / per;
+  c.step_w = stride - c.step_round * per;
+}
+EVX_HD void chain_cursor_step(ChainCursor& c, const ChainSchedule& s) {
+  c.round += c.step_round;
+  c.w += c.step_w;
+  if (c.w >= s.n0 + s.n1) { c.w -= s.n0 + s.n1; ++c.round; }
+}
+EVX_HD bool chain_cursor_done(const ChainCursor& c, const ChainSchedule& s) { return c.round >= chain_rounds(s); }
+// item at the cursor; false for an empty slot
+EVX_HD bool chain_cursor_item(const ChainCursor& c, const ChainSchedule& s, ChainItem& it) {
+  if (c.w < s.n0) {
+    it.stage = 0; it.plane = c.round; it.idx = c.w;
+    return c.round < s.nplanes;
+  }
+  it.stage = 1; it.plane = c.round - s.lag; it.idx = c.w - s.n0;
+  return c.round >= s.lag;
+}
+// advance to the next non-empty slot at or after the cursor; false when the list is exhausted
+EVX_HD bool chain_cursor_next(ChainCursor& c, const ChainSchedule& s, ChainItem& it) {
+  while (!chain_cursor_done(c, s)) {
+    if (chain_cursor_item(c, s, it)) return true;
+    chain_cursor_step(c, s);
+  }
+  return false;
+}
+
 }  // namespace evx

@@ -50,7 +50,7 @@ EVX_D f2 f2_fma(f2 x, f2 y, f2 z) {
 EVX_HD f2 f2_add(f2 x, f2 y) { return {x.a + y.a, x.b + y.b}; }
 EVX_HD f2 f2_sub(f2 x, f2 y) { return {x.a - y.a, x.b - y.b}; }
 EVX_HD f2 f2_mul(f2 x, f2 y) { return {x.a * y.a, x.b * y.b}; }
-EVX_HD f2 f2_fma(f2 x, f2 y, f2 z) { return {x.a * y.a + z.a, x.b * y.b + z.b}; }
+EVX_HD f2 f2_fma(f2 x, f2 y, f2 z) { return {fmaf(x.a, y.a, z.a), fmaf(x.b, y.b, z.b)}; }   // fused, like the device
 #endif
 EVX_HD f2 f2_splat(float s) { return {s, s}; }
 

@@ -33,12 +33,16 @@ def timed(which, n=10):
     return a.elapsed_time(b) / n
 
 def stats(tag):
-    st = plan.workspace[-65536:].view(torch.int64).view(-1, 8)[:296].double().cpu()
-    names = ["dep_wait", "mbar_wait", "z_items", "y_items", "total", "n_waits", "early_fail", "publish_wait"]
-    print(tag, " | ".join(f"{n} mean {st[:, i].mean():.0f} max {st[:, i].max():.0f}" for i, n in enumerate(names)), flush=True)
+    st = plan.workspace[-65536:].view(torch.int64).view(-1, 16)[:296].double().cpu()
+    st = st[st[:, 4] > 0]            # blocks that ran (one or two per SM)
+    names = ["loader:wait_buffer", "loader:wait_plane", "loader:issue", "items", "total", "", "", "",
+             "retirer:wait_done", "retirer:retire", "", "", "", "", "", ""]
+    print(tag, " | ".join(f"{n} {st[:, i].mean():.0f}" for i, n in enumerate(names) if n), flush=True)
 
 os.environ["EVX_FFT_CHAIN"] = "1"
 os.environ["EVX_FFT_CHAIN_STATS"] = "1"
+def zero_stats():
+    plan.workspace[-65536:].zero_()
 # forward: separate z + y
 spec_off = plan.workspace.numel()
 run(0); run(1)
@@ -59,5 +63,5 @@ if nx >= 64:
     for lag in os.environ.get("LAGS", "12").split(","):
         os.environ["EVX_FFT_CHAIN_LAG"] = lag
         print(f"lag {lag}: zy fwd {timed(5):.4f} ms, yz inv {timed(6):.4f} ms | separate: z {timed(0):.4f} y {timed(1):.4f} yinv {timed(3):.4f} zinv {timed(4):.4f}", flush=True)
-        run(5); stats(f"  fwd lag {lag}:")
-        run(6); stats(f"  inv lag {lag}:")
+        zero_stats(); run(5); stats(f"  fwd lag {lag}:")
+        zero_stats(); run(6); stats(f"  inv lag {lag}:")

@@ -700,3 +700,130 @@ extern "C" int emu_chain_schedule_check(int nplanes, int lag, int n0, int n1, in
   if (waits) *waits = w;
   return 0;
 }
+
+// the same checks for the division-free cursor the kernels use (virtual numbering)
+extern "C" int emu_chain_cursor_check(int nplanes, int lag, int n0, int n1, int blocks, long long* waits) {
+  const ChainSchedule s = make_chain_schedule(nplanes, lag, n0, n1);
+  std::vector<int> seen0((size_t)nplanes * n0, 0), seen1((size_t)nplanes * n1, 0);
+  // per block: list of its items in order, with their virtual slot numbers
+  struct Ent { long long slot; ChainItem it; };
+  std::vector<std::vector<Ent>> lists(blocks);
+  for (int b = 0; b < blocks; ++b) {
+    ChainCursor c;
+    chain_cursor_init(c, s, b, blocks);
+    ChainItem it;
+    while (chain_cursor_next(c, s, it)) {
+      lists[b].push_back({(long long)c.round * (n0 + n1) + c.w, it});
+      chain_cursor_step(c, s);
+    }
+  }
+  std::vector<long long> last0(nplanes, -1), first1(nplanes, -1);
+  for (int b = 0; b < blocks; ++b) {
+    long long prev = -1;
+    for (const Ent& e : lists[b]) {
+      if (e.slot <= prev || (e.slot - b) % blocks) return 1;
+      prev = e.slot;
+      const ChainItem& it = e.it;
+      if (it.plane < 0 || it.plane >= nplanes) return 2;
+      if (it.stage == 0) {
+        if (it.idx < 0 || it.idx >= n0 || seen0[(size_t)it.plane * n0 + it.idx]++) return 3;
+        if (e.slot > last0[it.plane]) last0[it.plane] = e.slot;
+      } else {
+        if (it.idx < 0 || it.idx >= n1 || seen1[(size_t)it.plane * n1 + it.idx]++) return 4;
+        if (first1[it.plane] < 0 || e.slot < first1[it.plane]) first1[it.plane] = e.slot;
+      }
+    }
+  }
+  for (int v : seen0) if (v != 1) return 8;
+  for (int v : seen1) if (v != 1) return 9;
+  for (int x = 0; x < nplanes; ++x) if (first1[x] <= last0[x]) return 6;   // dependency order
+  std::vector<size_t> next(blocks, 0);
+  std::vector<int> done0(nplanes, 0);
+  long long remaining = (long long)nplanes * (n0 + n1), w = 0;
+  while (remaining > 0) {
+    bool progress = false;
+    std::vector<int> inc(nplanes, 0);
+    for (int b = 0; b < blocks; ++b) {
+      if (next[b] >= lists[b].size()) continue;
+      const ChainItem& it = lists[b][next[b]].it;
+      if (it.stage == 1 && done0[it.plane] < n0) { ++w; continue; }
+      if (it.stage == 0) ++inc[it.plane];
+      ++next[b]; --remaining; progress = true;
+    }
+    for (int x = 0; x < nplanes; ++x) done0[x] += inc[x];
+    if (!progress) return 10;
+  }
+  if (waits) *waits = w;
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------
+// z lines in the two-lines-per-group form (fft_zline_core.h) against ZPass, bit for bit.
+// One item = 16 rows; the bulk copies are restated as row copies into the 264-complex pitch;
+// groups are replayed one after the other (no ordering between groups, as on the device), the
+// row buffer and the exchange buffers are poisoned before every item.
+// returns the number of differing floats (forward spectrum rows + inverse real rows)
+// -------------------------------------------------------------------------------------
+#include "../../evoxels_b200/csrc/fft_zline_core.h"
+extern "C" long long emu_zgroup_mismatches(const float* r, const float* u, int rows_total) {
+  constexpr int M = 256, NZ = 512, P = 264, NL = 16, NT = 512;
+  if (rows_total % NL) return -1;
+  auto twz = make_roots(M, M), twr = make_roots(NZ, M + 1);
+  const cf nan2{std::nanf(""), std::nanf("")};
+  // reference: ZPass
+  std::vector<cf> spec_ref((size_t)rows_total * P, cf{0.f, 0.f}), spec_new((size_t)rows_total * P, cf{0.f, 0.f});
+  std::vector<float> out_ref((size_t)rows_total * NZ, 0.f), out_new((size_t)rows_total * NZ, 0.f);
+  ZParams zp;
+  zp.real_in = r; zp.real_out = nullptr; zp.spec = spec_ref.data(); zp.tw = twz.data(); zp.twr = twr.data();
+  zp.rows = rows_total; zp.nz = NZ; zp.P = P; zp.pf_blocks = 0;
+  run_z<M, 8, false>(zp);
+  zp.real_in = u; zp.real_out = out_ref.data();
+  run_z<M, 8, true>(zp);
+  // new form
+  ZGroupParams gp;
+  gp.tw = twz.data(); gp.twr = twr.data(); gp.nz = NZ; gp.P = P;
+  using F = ZGroupLine<false>;
+  using I = ZGroupLine<true>;
+  std::vector<cf> rowsbuf((size_t)NL * F::ROWP + 8), xall((size_t)(NT / F::GT) * F::XG);
+  for (int item = 0; item < rows_total / NL; ++item) {
+    {  // forward
+      std::fill(rowsbuf.begin(), rowsbuf.end(), nan2);
+      std::fill(xall.begin(), xall.end(), nan2);
+      for (int l = 0; l < NL; ++l)
+        std::memcpy(&rowsbuf[(size_t)l * F::ROWP], r + ((size_t)item * NL + l) * NZ, NZ * sizeof(float));
+      std::vector<F::Regs> regs(NT);
+      for (int t = 0; t < NT; ++t) F::init(regs[t], t);
+      for (int g = NT / F::GT - 1; g >= 0; --g)
+        for (int k = 0; k < F::NPHASES; ++k)
+          for (int t = g * F::GT; t < (g + 1) * F::GT; ++t) {
+            const long long grow = (long long)item * NL + regs[t].g * F::G + regs[t].c2;
+            F::phase(k, regs[t], rowsbuf.data(), xall.data() + (size_t)g * F::XG, gp, grow, nullptr, nullptr,
+                     spec_new.data());
+          }
+    }
+    {  // inverse from the reference spectrum rows
+      std::fill(rowsbuf.begin(), rowsbuf.end(), nan2);
+      std::fill(xall.begin(), xall.end(), nan2);
+      std::memcpy(rowsbuf.data(), &spec_ref[(size_t)item * NL * P], (size_t)NL * P * sizeof(cf));
+      std::vector<I::Regs> regs(NT);
+      for (int t = 0; t < NT; ++t) I::init(regs[t], t);
+      for (int g = 0; g < NT / I::GT; ++g)
+        for (int k = 0; k < I::NPHASES; ++k)
+          for (int t = g * I::GT; t < (g + 1) * I::GT; ++t) {
+            const long long grow = (long long)item * NL + regs[t].g * I::G + regs[t].c2;
+            I::phase(k, regs[t], rowsbuf.data(), xall.data() + (size_t)g * I::XG, gp, grow, u, out_new.data(),
+                     nullptr);
+          }
+    }
+  }
+  long long bad = 0;
+  for (long long row = 0; row < rows_total; ++row)
+    for (int k = 0; k <= M; ++k) {
+      const cf a = spec_ref[(size_t)row * P + k], b = spec_new[(size_t)row * P + k];
+      bad += std::memcmp(&a, &b, sizeof(cf)) != 0;
+    }
+  bad += std::memcmp(out_ref.data(), out_new.data(), out_ref.size() * sizeof(float)) != 0
+             ? [&] { long long n = 0; for (size_t i = 0; i < out_ref.size(); ++i) n += std::memcmp(&out_ref[i], &out_new[i], 4) != 0; return n; }()
+             : 0;
+  return bad;
+}

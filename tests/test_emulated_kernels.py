@@ -411,3 +411,48 @@ def test_chain_schedule_covers_everything_in_dependency_order(emu, nplanes, lag,
     assert rc == 0
     if lag >= 12 and nplanes >= 512:
         assert waits.value == 0
+    # the division-free cursor the kernels walk (virtual numbering with empty slots)
+    rc = emu.emu_chain_cursor_check(nplanes, lag, n0, n1, blocks, ctypes.byref(waits))
+    assert rc == 0
+    if lag >= 12 and nplanes >= 512:
+        assert waits.value <= 64      # of 33280 items (the empty head slots skew the blocks a little)
+
+
+def test_two_lines_per_group_z_passes_are_bit_identical(emu):
+    """fft_zline_core.h (z lines as used by the chained kernels: rows in natural order at a
+    264-complex pitch, two lines per 64-thread group, no address swizzle) against ZPass: forward
+    spectrum rows and inverse real rows equal bit for bit, on poisoned scratch."""
+    rng = np.random.default_rng(11)
+    rows = 48
+    r = rng.standard_normal((rows, 512)).astype(np.float32)
+    u = rng.standard_normal((rows, 512)).astype(np.float32)
+    emu.emu_zgroup_mismatches.restype = ctypes.c_longlong
+    assert emu.emu_zgroup_mismatches(_p(r), _p(u), rows) == 0
+
+
+def test_two_lines_per_group_layout_is_conflict_free():
+    """64-bit shared-memory accesses of a half-warp (8 consecutive t x 2 lines) of the z-line
+    program hit 16 distinct 8-byte banks, except the in-place stage-1 writes (two-way)."""
+    ROWP, G = 264, 2
+    pad = lambda i: i + (i >> 3)
+    def banks(addr_cf):       # cf index -> 8-byte bank (16 banks of 8 bytes = 128 bytes)
+        return addr_cf % 16
+    worst = {}
+    for t0 in range(0, 32, 8):
+        for e in range(8):
+            pats = {
+                "rows natural": [(c2 * ROWP + t + 32 * e) for t in range(t0, t0 + 8) for c2 in range(G)],
+                "rows partner": [(c2 * ROWP + 256 - t - 32 * e) for t in range(t0, t0 + 8) for c2 in range(G)],
+                "rows stage1": [(c2 * ROWP + (t // 4) * 32 + t % 4 + 4 * e) for t in range(t0, t0 + 8) for c2 in range(G)],
+                "x natural": [(pad(t + 32 * e) * G + c2) for t in range(t0, t0 + 8) for c2 in range(G)],
+                "x stage0": [((4 * t + (t >> 1) + (e >> 1) + 144 * (e & 1)) * G + c2) for t in range(t0, t0 + 8) for c2 in range(G)],
+            }
+            for name, idx in pats.items():
+                b = [banks(i) for i in idx]
+                worst[name] = max(worst.get(name, 0), max(b.count(x) for x in set(b)))
+    assert worst == {"rows natural": 1, "rows partner": 1, "rows stage1": 2, "x natural": 1, "x stage0": 1}
+    # the stage-0 index really is the padded Stockham output index
+    for t in range(32):
+        for e in range(8):
+            i, r = e & 1, e >> 1
+            assert pad(4 * (t + 32 * i) + r) == 4 * t + (t >> 1) + (e >> 1) + 144 * (e & 1)

@@ -588,7 +588,8 @@ def test_chained_zy_passes_match_one_kernel_per_pass_bit_for_bit(cuda_device, mo
     """fft_chain.cu: z lines and y tiles of a plane run inside one persistent kernel per
     direction (the plane's half spectrum goes through L2).  Same arithmetic as the stand-alone
     passes, so update and fused CH step must be bit-identical - also when the planes are fewer
-    than the schedule's lag - and repeatable (no dependence on how the blocks interleave)."""
+    than the schedule's lag - and repeatable (no dependence on how the blocks interleave).  (The
+    one-kernel-per-pass pipeline is the one checked against the oracle, test_ch_step_512_vs_oracle.)"""
     gen = torch.Generator(device="cuda").manual_seed(5)
     u = 0.5 + 0.1 * torch.rand(shape, device="cuda", generator=gen)
     r = torch.randn(shape, device="cuda", generator=gen)
@@ -613,6 +614,3 @@ def test_chained_zy_passes_match_one_kernel_per_pass_bit_for_bit(cuda_device, mo
         for a, b in zip(base, run):
             assert torch.isfinite(b).all()
             assert torch.equal(a, b)
-    if shape[0] <= 32:
-        ref = O.CHOracle(shape, (1.0, 1.0, 1.0), 0.1).step(u.cpu()[None])[0]
-        assert rel_l2(outs["1"][0][2].cpu(), ref) <= 1e-5
