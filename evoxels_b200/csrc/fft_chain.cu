@@ -34,6 +34,7 @@ struct ChainParams {
   const cf *twz, *twr, *twy;
   int ny, nz, P;
   unsigned* done0;         // [nplanes] finished stage-0 items per plane; zeroed before the launch
+  int discard;             // inverse: drop the consumed spectrum rows from L2 without write-back
   unsigned long long* stats;   // optional [gridDim.x][16] cycle counters of thread 0 (EVX_FFT_CHAIN_STATS)
 };
 
@@ -75,7 +76,10 @@ struct ChainStats {
 // the compute warps instead of inside one of them, and loads and retirements overlap each other.
 // NBUF = 2: two blocks per SM, the next item's input in flight while the current one runs;
 // NBUF = 4: one block per SM with its input copies issued up to three items ahead.
-template <bool INV, bool STATS, int NBUF>
+// TW: roots of unity kept in registers over the whole item loop - 0 none (fetched per item),
+// 1 the stage twiddles of the y and z lines, 2 also the untangle roots of the z lines, 3 the
+// stage twiddles of the y lines only.
+template <bool INV, bool STATS, int NBUF, int TW>
 __global__ void __launch_bounds__(chain_threads(NBUF), NBUF <= 2 ? 2 : 1)
     fft_chain_kernel(const __grid_constant__ CUtensorMap tmap, const ChainParams p) {
   using Line = StridedLine<512, 8, INV ? PASS_INV : PASS_FWD>;
@@ -206,6 +210,22 @@ __global__ void __launch_bounds__(chain_threads(NBUF), NBUF <= 2 ? 2 : 1)
   ZG::init(zr, tid);
   // the two z groups (64 threads) of a y group (128 threads) split that group's exchange buffer
   cf* zxg = xall + (zr.g >> 1) * Line::XG + (zr.g & 1) * ZG::XG;
+  // roots of unity of this thread's butterflies: the same for every item, kept in registers
+  // where the block has them to spare (one block per SM)
+  constexpr bool TWREG = TW >= 1, TWREG_Z = TW == 1 || TW == 2, ROOTREG = TW == 2;
+  cf yw1[3], yw2[3], zw1[3], zw2[3], zroot[8];
+  if (TWREG) {
+    stage_twiddles<512>(1, yr.t, p.twy, yw1);
+    stage_twiddles<512>(2, yr.t, p.twy, yw2);
+  }
+  if (TWREG_Z) {
+    stage_twiddles<ZG::M>(1, zr.t, p.twz, zw1);
+    stage_twiddles<ZG::M>(2, zr.t, p.twz, zw2);
+  }
+  if (ROOTREG) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) zroot[e] = p.twr[zr.t + e * ZG::T];
+  }
   LineParams lp;
   lp.tw = p.twy;
   ZGroupParams zp;
@@ -224,16 +244,30 @@ __global__ void __launch_bounds__(chain_threads(NBUF), NBUF <= 2 ? 2 : 1)
 #pragma unroll
       for (int k = 0; k < Line::NPHASES; ++k) {
         if (k) group_sync(kBarY + yr.g, Line::GT);
-        Line::phase(k, yr, tb, xg, lp);
+        if (TWREG) Line::phase_tw(k, yr, tb, xg, lp, yw1, yw2);
+        else Line::phase(k, yr, tb, xg, lp);
       }
       fence_proxy_async();                      // tile writes -> visible to the TMA store
     } else {
       const long long grow = (long long)it.plane * p.ny + (long long)it.idx * kChainZLines + zr.g * ZG::G + zr.c2;
       cf* rows = reinterpret_cast<cf*>(tb);
+      if (INV && p.discard) {
+        // The item's 16 spectrum rows (264 cache lines, contiguous) are in shared memory now and
+        // nobody reads them from global memory again before the next step overwrites them: drop
+        // the lines - dirty since the y tiles were stored in place - so that they are never
+        // written back to HBM.
+        constexpr int kLines = kChainZLines * ZG::ROWP * (int)sizeof(cf) / 128;
+        static_assert(kChainZLines * ZG::ROWP * sizeof(cf) % 128 == 0 && kLines <= kChainCompute, "");
+        if (tid < kLines) {
+          const char* line = (const char*)(p.spec + ((long long)it.plane * p.ny + (long long)it.idx * kChainZLines) * p.P) + 128 * tid;
+          asm volatile("discard.global.L2 [%0], 128;" ::"l"(line) : "memory");
+        }
+      }
 #pragma unroll
       for (int k = 0; k < ZG::NPHASES; ++k) {
         if (k) group_sync(kBarZ + zr.g, ZG::GT);
-        ZG::phase(k, zr, rows, zxg, zp, grow, p.real_in, p.real_out, p.spec);
+        if (TWREG_Z) ZG::template phase_tw<ROOTREG>(k, zr, rows, zxg, zw1, zw2, zroot, p.twr, p.nz, p.P, grow, p.real_in, p.real_out, p.spec);
+        else ZG::phase(k, zr, rows, zxg, zp, grow, p.real_in, p.real_out, p.spec);
       }
     }
     mbar_arrive(&done[buf]);
@@ -250,10 +284,10 @@ static int chain_lag() {
   const int v = e ? atoi(e) : 24;
   return v < 1 ? 1 : v;
 }
-template <bool INV, bool STATS, int NBUF>
+template <bool INV, bool STATS, int NBUF, int TW>
 static int chain_launch_t(ChainParams p, const void* tmap, cudaStream_t st) {
   constexpr size_t smem = chain_smem_bytes(NBUF);
-  auto kern = fft_chain_kernel<INV, STATS, NBUF>;
+  auto kern = fft_chain_kernel<INV, STATS, NBUF, TW>;
   static SmemOptIn optin;
   if (int rc = optin.ensure(kern, smem)) return rc;
   int dev = 0, sms = 148, per_sm = 0;
@@ -292,16 +326,28 @@ int chain_launch(bool inverse, const ChainArgs& a, const void* tmap_y, cudaStrea
   p.twz = (const cf*)a.twz; p.twr = (const cf*)a.twr; p.twy = (const cf*)a.twy;
   p.ny = a.ny; p.nz = a.nz; p.P = a.P;
   p.done0 = (unsigned*)a.flags;
+  const char* ed = getenv("EVX_FFT_CHAIN_DISCARD");
+  p.discard = ed ? atoi(ed) : 1;      // inverse: 2.27 -> 1.77 GB of DRAM traffic per launch at 512^3 (ncu)
   const char* es = getenv("EVX_FFT_CHAIN_STATS");
   p.stats = (es && atoi(es) != 0) ? (unsigned long long*)a.stats : nullptr;
   const char* eb = getenv("EVX_FFT_CHAIN_NBUF");
   const int nbuf = eb ? atoi(eb) : 3;     // measured at 512^3: 3 buffers 0.433 / 0.449 ms, 2: 0.425 / 0.476, 4: 0.441 / 0.451
-#define EVX_CHAIN(NB)                                                                              \
-  if (p.stats) return inverse ? chain_launch_t<true, true, NB>(p, tmap_y, st) : chain_launch_t<false, true, NB>(p, tmap_y, st); \
-  return inverse ? chain_launch_t<true, false, NB>(p, tmap_y, st) : chain_launch_t<false, false, NB>(p, tmap_y, st);
-  if (nbuf == 2) { EVX_CHAIN(2) }
-  if (nbuf == 4) { EVX_CHAIN(4) }
-  EVX_CHAIN(3)
+  const char* et = getenv("EVX_FFT_CHAIN_TW");
+  // forward: all roots in registers (0.435 -> 0.339 ms at 512^3); the inverse kernel also holds
+  // a line's eight u values and spills with more than the y twiddles (0.449 -> 0.421 ms)
+  const int tw = et ? atoi(et) : (inverse ? 3 : 2);
+#define EVX_CHAIN(NB, TWV)                                                                         \
+  {                                                                                                \
+    if (p.stats) return inverse ? chain_launch_t<true, true, NB, TWV>(p, tmap_y, st)               \
+                                : chain_launch_t<false, true, NB, TWV>(p, tmap_y, st);            \
+    return inverse ? chain_launch_t<true, false, NB, TWV>(p, tmap_y, st)                           \
+                   : chain_launch_t<false, false, NB, TWV>(p, tmap_y, st);                        \
+  }
+  if (nbuf == 2) EVX_CHAIN(2, 0)
+  if (tw <= 0) EVX_CHAIN(3, 0)
+  if (tw == 1) EVX_CHAIN(3, 1)
+  if (tw == 3) EVX_CHAIN(3, 3)
+  EVX_CHAIN(3, 2)
 #undef EVX_CHAIN
 }
 

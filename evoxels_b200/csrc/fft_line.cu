@@ -135,6 +135,113 @@ __global__ void __launch_bounds__(Prog::NTHREADS, Prog::NTHREADS <= 512 ? 2 : 1)
   tma_store_wait_read();            // shared memory must outlive the stores this thread issued
 }
 
+// ---- warp-specialised form --------------------------------------------------------------
+// One block per SM: 16 compute warps + a loader warp + one retirer warp per tile buffer (lane 0
+// of each acts), NBUF tile buffers.  Compute threads wait for a tile (mbarrier full[b]), run the
+// phases with their group barriers and arrive on done[b]; the loader issues the TMA loads up to
+// NBUF tiles ahead as buffers come back (empty[b]); retirer b stores the tile in buffer b and
+// frees the buffer once the store has read it.  No compute thread ever waits for a store to
+// drain, and with the whole register file to itself a thread keeps the roots of its twiddled
+// stages in registers for the whole kernel (the per-stage table loads were the top stall).
+constexpr int line_ws_threads(int compute, int nbuf) { return compute + 32 + 32 * nbuf; }
+
+__device__ __forceinline__ void mbar_arrive_cta(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <class Prog, int NBUF>
+__global__ void __launch_bounds__(line_ws_threads(Prog::NTHREADS, NBUF), 1)
+    fft_line_ws_kernel(const __grid_constant__ CUtensorMap tmap, const LineParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* tiles = sm;
+  cf* xall = reinterpret_cast<cf*>(sm + NBUF * Prog::TILE_BYTES);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + NBUF * Prog::TILE_BYTES + Prog::X_BYTES);
+  unsigned long long* done = full + NBUF;
+  unsigned long long* empty = full + 2 * NBUF;
+  const int tid = threadIdx.x;
+  const int tpr = p.tiles_per_row;
+  const long long ntiles = p.ntiles;
+  const int nblk = gridDim.x;
+
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&full[b], 1);
+      mbar_init(&done[b], Prog::NTHREADS);
+      mbar_init(&empty[b], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
+
+  if (tid == Prog::NTHREADS) {
+    // ------------------------------------ loader ------------------------------------------
+    int n = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += nblk, ++n) {
+      const int buf = n % NBUF;
+      if (n >= NBUF) mbar_wait(&empty[buf], (unsigned)(n / NBUF - 1) & 1u);
+      const int row = (int)(tile / tpr), kz0 = (int)(tile - (long long)row * tpr) * Prog::COLS;
+      unsigned char* dst = tiles + buf * Prog::TILE_BYTES;
+      mbar_expect_tx(&full[buf], Prog::TILE_BYTES);
+#pragma unroll
+      for (int h = 0; h < 512 / Prog::BOX_ROWS; ++h) {
+        if (p.along_x) tma_load_3d(dst + h * Prog::BOX_ROWS * Prog::ROWB, &tmap, &full[buf], kz0, row, h * Prog::BOX_ROWS);
+        else tma_load_3d(dst + h * Prog::BOX_ROWS * Prog::ROWB, &tmap, &full[buf], kz0, h * Prog::BOX_ROWS, row);
+      }
+    }
+    return;
+  }
+  if (tid > Prog::NTHREADS && (tid & 31) == 0) {
+    // ------------------------------ retirer of buffer `me` ---------------------------------
+    const int me = (tid - Prog::NTHREADS - 32) >> 5;
+    int n = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += nblk, ++n) {
+      if (n % NBUF != me) continue;
+      mbar_wait(&done[me], (unsigned)(n / NBUF) & 1u);
+      const int row = (int)(tile / tpr), kz0 = (int)(tile - (long long)row * tpr) * Prog::COLS;
+      const unsigned char* src = tiles + me * Prog::TILE_BYTES;
+#pragma unroll
+      for (int h = 0; h < 512 / Prog::BOX_ROWS; ++h) {
+        if (p.along_x) tma_store_3d(&tmap, src + h * Prog::BOX_ROWS * Prog::ROWB, kz0, row, h * Prog::BOX_ROWS);
+        else tma_store_3d(&tmap, src + h * Prog::BOX_ROWS * Prog::ROWB, kz0, h * Prog::BOX_ROWS, row);
+      }
+      tma_store_commit();
+      tma_store_wait_read();
+      mbar_arrive_cta(&empty[me]);
+    }
+    tma_store_wait_read();
+    return;
+  }
+  if (tid >= Prog::NTHREADS) return;
+
+  // ------------------------------------ compute warps --------------------------------------
+  typename Prog::Regs r;
+  Prog::init(r, tid);
+  cf* xg = xall + r.g * Prog::XG;
+  cf w1[3], w2[3];
+  stage_twiddles<512>(1, r.t, p.tw, w1);
+  stage_twiddles<512>(2, r.t, p.tw, w2);
+  int row = blockIdx.x / tpr, tcol = blockIdx.x - row * tpr;
+  const int step_row = nblk / tpr, step_col = nblk - step_row * tpr;
+  int n = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += nblk, ++n) {
+    const int buf = n % NBUF;
+    unsigned char* tb = tiles + buf * Prog::TILE_BYTES;
+    Prog::set_tile(r, row, tcol * Prog::COLS);
+    mbar_wait(&full[buf], (unsigned)(n / NBUF) & 1u);
+#pragma unroll
+    for (int k = 0; k < Prog::NPHASES; ++k) {
+      if (k) group_sync(1 + r.g, Prog::GT);
+      Prog::phase_tw(k, r, tb, xg, p, w1, w2);
+    }
+    fence_proxy_async();                        // my tile writes -> visible to the TMA store
+    mbar_arrive_cta(&done[buf]);
+    row += step_row; tcol += step_col;
+    if (tcol >= tpr) { tcol -= tpr; ++row; }
+  }
+}
+
 // ---- host ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -181,11 +288,38 @@ static int line_sms() {
   return n;
 }
 
+// EVX_FFT_LINE_WS: 0 = two blocks per SM, tile hand-over by the compute threads (fft_line_kernel);
+// 3 / 4 / 5 = warp-specialised form with that many tile buffers (KZ = 8 only)
+static int line_ws_bufs() {
+  const char* e = getenv("EVX_FFT_LINE_WS");
+  const int v = e ? atoi(e) : 3;     // 512^3 x pass: 0.320 ms (form 0), 0.2455 (3 buffers), 0.258 (4), 0.250 (5)
+  return (v == 3 || v == 4 || v == 5) ? v : 0;
+}
+
+template <class Prog, int NBUF>
+static int launch_line_ws(const LineParams& p, const void* tmap, cudaStream_t st) {
+  constexpr size_t smem = 1024 + (size_t)NBUF * Prog::TILE_BYTES + Prog::X_BYTES + 128;
+  auto kern = fft_line_ws_kernel<Prog, NBUF>;
+  static SmemOptIn optin;
+  if (int rc = optin.ensure(kern, smem)) return rc;
+  const long long resident = line_sms();
+  const unsigned grid = (unsigned)(p.ntiles < resident ? p.ntiles : resident);
+  kern<<<grid, line_ws_threads(Prog::NTHREADS, NBUF), smem, st>>>(*(const CUtensorMap*)tmap, p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 template <int KZ, int MODE>
 static int launch_line_t(LineParams p, const void* tmap, cudaStream_t st) {
   using Prog = StridedLine<512, KZ, MODE>;
   p.tiles_per_row = (p.ncols_valid + KZ - 1) / KZ;
   p.ntiles = (long long)(p.along_x ? p.ny : p.nx) * p.tiles_per_row;
+  if (KZ == 8) {
+    const int ws = line_ws_bufs();
+    if (ws == 3) return launch_line_ws<StridedLine<512, 8, MODE>, 3>(p, tmap, st);
+    if (ws == 4) return launch_line_ws<StridedLine<512, 8, MODE>, 4>(p, tmap, st);
+    if (ws == 5) return launch_line_ws<StridedLine<512, 8, MODE>, 5>(p, tmap, st);
+  }
   auto kern = fft_line_kernel<Prog>;
   static SmemOptIn optin;
   if (int rc = optin.ensure(kern, Prog::SMEM_BYTES)) return rc;

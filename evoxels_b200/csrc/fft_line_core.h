@@ -166,6 +166,42 @@ struct StridedLine {
     }
   }
 
+  // Same phases with the roots of the two twiddled stages supplied by the caller - a persistent
+  // kernel with registers to spare (one block per SM: fft_chain.cu, fft_line_ws_kernel) fetches
+  // them once instead of once per stage and tile.  w1 / w2: stage_twiddles<L>(1 / 2, t, tw, .);
+  // the inverse stages of the x pass use the same roots (conjugated inside the butterfly).
+  EVX_HD static void phase_tw(int k, Regs& r, unsigned char* tile, cf* xg, const LineParams& p,
+                              const cf* w1, const cf* w2) {
+    constexpr int DIR = MODE == PASS_INV ? +1 : -1;      // direction of the first transform
+    if (k == 0) {
+      read_tile_natural(r, tile);
+      line_stage_compute_pre<L, DIR>(0, r.v, r.t, w1);
+      write_x_stage0(r, xg);
+    } else if (k == 1) {
+      read_x_natural(r, xg);
+      line_stage_compute_pre<L, DIR>(1, r.v, r.t, w1);
+      write_tile_stage1(r, tile);
+    } else if (k == 2) {
+      read_tile_natural(r, tile);
+      line_stage_compute_pre<L, DIR>(2, r.v, r.t, w2);
+      if (!XMID) {
+        write_tile_natural(r, tile);
+      } else {
+        apply_filter(r, p);
+        line_stage_compute_pre<L, +1>(0, r.v, r.t, w1);
+        write_x_stage0(r, xg);
+      }
+    } else if (k == 3) {
+      read_x_natural(r, xg);
+      line_stage_compute_pre<L, +1>(1, r.v, r.t, w1);
+      write_tile_stage1(r, tile);
+    } else {
+      read_tile_natural(r, tile);
+      line_stage_compute_pre<L, +1>(2, r.v, r.t, w2);
+      write_tile_natural(r, tile);
+    }
+  }
+
   // ---- what the tensor copies do, restated for the host replay (tests/emu) ---------------
   // element (kz, y, x) of the spectrum; tile (row, kz0): rows run along y (along_x = 0, x = row)
   // or along x (along_x = 1, y = row).  Out-of-range columns read as zero and are not written.

@@ -81,6 +81,68 @@ struct ZGroupLine {
     for (int e = 0; e < 8; ++e) rows[r.s1 + 4 * e] = r.v[e];
   }
 
+  // The same phases with all roots supplied by the caller (fetched once per kernel instead of
+  // once per item): w1 / w2 = stage_twiddles<M>(1 / 2, t, tw, .), root[e] = twr[t + 32 e].
+  template <bool ROOTS_IN_REGS>
+  EVX_HD static void phase_tw(int k, Regs& r, cf* rows, cf* xg, const cf* w1, const cf* w2, const cf* root,
+                              const cf* twr, int nz, int P, long long grow, const float* real_in,
+                              float* real_out, cf* spec) {
+    if (!INVERSE) {
+      if (k == 0) {
+        read_rows_natural(r, rows);
+        line_stage_compute_pre<M, -1>(0, r.v, r.t, w1);
+        write_x_stage0(r, xg);
+      } else if (k == 1) {
+        read_x_natural(r, xg);
+        line_stage_compute_pre<M, -1>(1, r.v, r.t, w1);
+        write_rows_stage1(r, rows);
+      } else if (k == 2) {
+        read_rows_natural(r, rows);
+        line_stage_compute_pre<M, -1>(2, r.v, r.t, w2);
+        write_rows_natural(r, rows);
+        if (r.t == 0) rows[r.rb + M] = r.v[0];
+        if (!ROOTS_IN_REGS) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r.u[e] = twr[r.t + e * T];
+        }
+      } else {
+        cf* out = spec + grow * P;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          out[r.t + e * T] = ZPass<M, 1, false>::untangle_fwd(r.v[e], rows[r.pb - e * T],
+                                                              ROOTS_IN_REGS ? root[e] : r.u[e]);
+        if (r.t == 0) out[M] = cf{r.v[0].x - r.v[0].y, 0.f};
+      }
+    } else {
+      if (k == 0) {
+        if (real_in) {
+          const cf* u = reinterpret_cast<const cf*>(real_in + grow * nz);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r.u[e] = u[r.t + e * T];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r.u[e] = cf{0.f, 0.f};
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          r.v[e] = ZPass<M, 1, true>::untangle_inv(rows[r.rb + e * T], rows[r.pb - e * T],
+                                                   ROOTS_IN_REGS ? root[e] : twr[r.t + e * T]);
+        line_stage_compute_pre<M, +1>(0, r.v, r.t, w1);
+        write_x_stage0(r, xg);
+      } else if (k == 1) {
+        read_x_natural(r, xg);
+        line_stage_compute_pre<M, +1>(1, r.v, r.t, w1);
+        write_rows_stage1(r, rows);
+      } else {
+        read_rows_natural(r, rows);
+        line_stage_compute_pre<M, +1>(2, r.v, r.t, w2);
+        cf* out = reinterpret_cast<cf*>(real_out + grow * nz);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out[r.t + e * T] = cadd(r.v[e], r.u[e]);
+      }
+    }
+  }
+
   // `rows`: the item's row buffer (input rows already there), `xg`: the group's exchange buffer,
   // `grow`: global row index of the thread's line.  Caller synchronises the GROUP between phases.
   EVX_HD static void phase(int k, Regs& r, cf* rows, cf* xg, const ZGroupParams& p, long long grow,
