@@ -667,6 +667,70 @@ def distributed_ac_config3(world, rank, dev):
             "finite": bool(torch.isfinite(phi[::16]).all())}
 
 
+def config4_record(world, rank, dev):
+    """BASELINE config 4 (opt-in, `--config4`): Cahn-Hilliard 2048^3 on all ranks of this run, then
+    the same grid on rank 0 alone (137 GB of HBM) for the scaling ratio the north star states."""
+    import torch
+    import torch.distributed as dist
+    from evoxels_b200 import _native
+    from evoxels_b200.distributed import DistributedCahnHilliardIMEX
+    n = 2048
+    rec = {"grid": f"{n}^3", "n_gpus": world}
+    st = DistributedCahnHilliardIMEX((n, n, n), (1.0, 1.0, 1.0), CH["dt"], CH["eps"], CH["D"], CH["A"],
+                                     device=dev, transport="ce")
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    u = torch.empty(st.slab.local_shape, device=dev)
+    for i in range(0, u.shape[0], 32):
+        u[i:i + 32] = 0.5 + 0.1 * torch.rand((min(32, u.shape[0] - i), n, n), device=dev, generator=gen)
+    m0 = st.total_mass(u)
+    for _ in range(2):
+        u = st.step(u)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        u = st.step(u)
+    b.record()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([a.elapsed_time(b) / 5], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    rec["ms_per_step"] = float(t.item())
+    rec["voxel_updates_per_s"] = n ** 3 / (rec["ms_per_step"] * 1e-3)
+    rec["mass_drift"] = abs(st.total_mass(u) - m0) / abs(m0)
+    del st, u
+    torch.cuda.empty_cache()
+    dist.barrier()
+    if rank == 0:
+        try:
+            plan = _native.ImexPlan((n, n, n), torch.float32, dev, _native.FFT_NATIVE)
+            v = torch.empty((n, n, n), device=dev)
+            for i in range(0, n, 32):
+                v[i:i + 32] = 0.5 + 0.1 * torch.rand((32, n, n), device=dev, generator=gen)
+            w = torch.empty_like(v)
+            for _ in range(2):
+                plan.ch_step(v, w, (1, 1, 1), CH["dt"], CH["eps"], CH["D"], CH["A"])
+                v, w = w, v
+            torch.cuda.synchronize(dev)
+            a.record()
+            for _ in range(3):
+                plan.ch_step(v, w, (1, 1, 1), CH["dt"], CH["eps"], CH["D"], CH["A"])
+                v, w = w, v
+            b.record()
+            torch.cuda.synchronize(dev)
+            one = a.elapsed_time(b) / 3
+            rec["one_gpu_ms_per_step"] = one
+            rec["speedup_vs_one_gpu"] = one / rec["ms_per_step"]
+            rec["one_gpu_peak_mem_GB"] = torch.cuda.max_memory_allocated(dev) / 1e9
+            del plan, v, w
+        except Exception as exc:
+            rec["one_gpu_error"] = repr(exc)[:200]
+        torch.cuda.empty_cache()
+    dist.barrier()
+    return rec
+
+
 def run_ours_distributed(args, world, rank, local, dev):
     """N > 1: ONE global Cahn-Hilliard problem, x-slab decomposed over the ranks (weak
     scaling: args.size^3 voxels per GPU): halo planes and slab<->pencil transposes over
@@ -747,6 +811,14 @@ def run_ours_distributed(args, world, rank, local, dev):
             ac3 = distributed_ac_config3(world, rank, dev)
         except Exception as exc:
             ac3 = {"error": repr(exc)[:200]}
+    cfg4 = None
+    if args.config4:
+        del stepper
+        torch.cuda.empty_cache()
+        try:
+            cfg4 = config4_record(world, rank, dev)
+        except Exception as exc:
+            cfg4 = {"error": repr(exc)[:200]}
     if rank == 0:
         peak, peak_src = measured_peaks()
         ms_step = ms / args.steps
@@ -777,7 +849,7 @@ def run_ours_distributed(args, world, rank, local, dev):
                          "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
                          "peak_source": peak_src},
             "cpu_baseline": None, "mass_drift": mass_drift, "parity": parity,
-            "other_configs": {"config3_ac_1024^3_neumann": ac3},
+            "other_configs": {"config3_ac_1024^3_neumann": ac3, "config4_ch_2048^3": cfg4},
         }
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
@@ -793,6 +865,8 @@ def main():
     ap.add_argument("--fft", default="auto", choices=["auto", "cufft", "native"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and reference-on-GPU legs")
     ap.add_argument("--no-extras", action="store_true", help="skip the config 1 / 3 / 5 sub-records")
+    ap.add_argument("--config4", action="store_true",
+                    help="N > 1: also time Cahn-Hilliard 2048^3 on all ranks and on rank 0 alone (config 4)")
     ap.add_argument("--p2p-ctas", type=int, default=148,
                     help="grid cap of the NVLink-bound peer-store launches (0 = fill the GPU)")
     ap.add_argument("--overlap-chunks", type=int, default=4,

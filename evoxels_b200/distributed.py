@@ -151,32 +151,43 @@ class PeerBuffers:
 class PeerHalos:
     """Stencil halos through symmetric memory: every rank owns a [2][width][ny][nz] buffer
     (slot 0 = planes below the slab, slot 1 = planes above); `exchange` has the DMA engines
-    write this rank's boundary planes straight into the ring neighbours' slots and enqueues
-    one cross-rank barrier - no NCCL call, no staging copies.  Periodic ring only."""
+    write this rank's boundary planes straight into the neighbours' slots and enqueues one
+    cross-rank barrier - no NCCL call, no staging copies.  `periodic=False`: the domain ends get
+    no halo (None is returned there and the kernels apply the Neumann / Dirichlet ghost rule)."""
 
     def __init__(self, width, ny, nz, device, group, world, rank):
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
         self.width, self.world, self.rank = width, world, rank
-        self.buf = symm_mem.empty(2, width, ny, nz, dtype=torch.float32, device=device)
+        # two sets of slots used alternately: a neighbour may write the halos of step k+1 while
+        # this rank's kernel of step k still reads its own (one barrier per step orders a write
+        # only against the reads of the step before last)
+        self.buf = symm_mem.empty(2, 2, width, ny, nz, dtype=torch.float32, device=device)
         self.handle = symm_mem.rendezvous(self.buf, group=group)
         self.ptrs = [int(x) for x in self.handle.buffer_ptrs]
         self.slot_bytes = width * ny * nz * 4
+        self.parity = 0
 
-    def exchange(self, u_local):
+    def exchange(self, u_local, periodic=True):
         W, r, w = self.world, self.rank, self.width
         if u_local.shape[0] < w:
             raise ValueError("slab thinner than the halo width")
         st = torch.cuda.current_stream(u_local.device)
         lo, hi = (r - 1) % W, (r + 1) % W
+        has_lo, has_hi = periodic or r > 0, periodic or r < W - 1
         plane = u_local.stride(0) * 4
+        par = self.parity
+        self.parity ^= 1
+        base = par * 2 * self.slot_bytes
         # my first planes are the lower neighbour's "above" halo, my last planes the upper
         # neighbour's "below" halo
-        _native.copy_async(self.ptrs[lo] + self.slot_bytes, u_local.data_ptr(), self.slot_bytes, st)
-        _native.copy_async(self.ptrs[hi], u_local.data_ptr() + (u_local.shape[0] - w) * plane,
-                           self.slot_bytes, st)
+        if has_lo:
+            _native.copy_async(self.ptrs[lo] + base + self.slot_bytes, u_local.data_ptr(), self.slot_bytes, st)
+        if has_hi:
+            _native.copy_async(self.ptrs[hi] + base, u_local.data_ptr() + (u_local.shape[0] - w) * plane,
+                               self.slot_bytes, st)
         self.handle.barrier(channel=0)
-        return self.buf[0], self.buf[1]
+        return (self.buf[par, 0] if has_lo else None), (self.buf[par, 1] if has_hi else None)
 
 
 class CudaOps:
@@ -218,6 +229,10 @@ class CudaOps:
 
     def ch_rhs(self, u, out, eps, D, bc, halo_lo, halo_hi):
         _native.ch_rhs(u, out, self.spacing, eps, D, bc, halo_lo=halo_lo, halo_hi=halo_hi)
+
+    def ch_rhs_hom(self, c, out, eps, D, bc, hom):
+        """rhs with a caller-evaluated potential field (no x halos: the caller extends the slab)."""
+        _native.ch_rhs(c, out, self.spacing, eps, D, bc, hom=hom)
 
     def ac_stage(self, phi, out, params, bc, dt, halo_lo, halo_hi):
         _native.ac_stage(phi, self.spacing, params["eps"], params["gab"], params["M"],
@@ -405,7 +420,10 @@ class DistributedCahnHilliardIMEX:
 
     def __init__(self, global_shape, spacing, dt, eps=3.0, D=1.0, A=0.25, group=None,
                  device=None, ops=None, transport="ce", overlap_chunks=4, p2p_ctas=148,
-                 copier=None, scatter_ctas=None, mid_chunks=None):
+                 copier=None, scatter_ctas=None, mid_chunks=None, hom_fn=None):
+        # hom_fn: user potential, [1, n, ny, nz] raw c -> mu_hom(clip(c)) (CahnHilliard.hom_field);
+        # None = the default double well, evaluated inside the rhs kernel
+        self.hom_fn = hom_fn
         self.comm = Comm(group)
         self.slab = Slab(tuple(global_shape), self.comm.world, self.comm.rank)
         self.spacing, self.dt, self.eps, self.D, self.A = tuple(spacing), dt, eps, D, A
@@ -458,9 +476,42 @@ class DistributedCahnHilliardIMEX:
         times = {ev[i][0]: ev[i - 1][1].elapsed_time(ev[i][1]) for i in range(1, len(ev))}
         return out, times
 
+    def _step_user_potential(self, u_local):
+        """Custom mu_hom: the potential is a caller-evaluated field, which the fused kernel
+        accepts only without x halos - so the rhs runs on the slab extended by its two halo
+        planes per side (periodic in x inside the kernel: the wrap only reaches the four outer
+        planes, which are dropped) and the update goes through the un-pipelined transposes."""
+        ops, comm = self.ops, self.comm
+        halo_lo, halo_hi = comm.exchange_halos(u_local, 2, periodic=True)
+        if halo_lo is None:            # one rank: the kernel wraps by index arithmetic
+            ops.ch_rhs_hom(u_local, self.rhs, self.eps, self.D, self.bc,
+                           self.hom_fn(u_local[None])[0].contiguous())
+        else:
+            ext = torch.cat([halo_lo, u_local, halo_hi], 0).contiguous()
+            hom = self.hom_fn(ext[None])[0].contiguous()
+            rhs_ext = torch.empty_like(ext)
+            ops.ch_rhs_hom(ext, rhs_ext, self.eps, self.D, self.bc, hom)
+            self.rhs.copy_(rhs_ext[2:-2])
+        coef = 2.0 * self.eps * self.D * self.A
+        out = ops.new_field()
+        if getattr(ops, "transport", "nccl") in ("p2p", "ce") and ops.peers is not None:
+            ops.spectral_forward_p2p(self.rhs)
+            a = ops.spectral_middle_p2p(self.dt, coef, 2)
+            ops.spectral_backward(a, u_local, out)
+            return out
+        a, b = ops.exchange_buffers()
+        send = ops.spectral_forward(self.rhs)
+        comm.all_to_all_blocks(send, b)
+        ops.spectral_middle(b, self.dt, coef, 2)
+        comm.all_to_all_blocks(b, a)
+        ops.spectral_backward(a, u_local, out)
+        return out
+
     def step(self, u_local):
         ops, comm = self.ops, self.comm
         u_local = u_local.contiguous()
+        if self.hom_fn is not None:
+            return self._step_user_potential(u_local)
         transport = getattr(ops, "transport", "nccl")
         if transport == "ce":
             halo_lo, halo_hi = ops.halos.exchange(u_local)
@@ -517,11 +568,26 @@ class DistributedAllenCahnEuler:
         self.bc = normalize_bc(bc)
         self.ops = ops if ops is not None else CudaOps(self.slab, spacing, device or "cuda",
                                                        spectral=False)
+        # halos as DMA writes into the neighbours' symmetric-memory slots where that exists
+        # (CUDA ranks of one NVSwitch box); otherwise torch.distributed send / recv
+        self.halos = None
+        if ops is None and self.slab.world > 1:
+            try:
+                _, ny, nz = self.slab.global_shape
+                self.halos = PeerHalos(1, ny, nz, torch.device(device or "cuda"), group, self.slab.world,
+                                       self.slab.rank)
+            except Exception as exc:
+                import warnings
+                warnings.warn(f"torch symmetric memory is not available ({exc}); Allen-Cahn halos use "
+                              "send / recv")
 
     def step(self, phi_local):
         phi_local = phi_local.contiguous()
         periodic = self.bc[0][0] == "periodic"
-        halo_lo, halo_hi = self.comm.exchange_halos(phi_local, 1, periodic=periodic)
+        if self.halos is not None:
+            halo_lo, halo_hi = self.halos.exchange(phi_local, periodic=periodic)
+        else:
+            halo_lo, halo_hi = self.comm.exchange_halos(phi_local, 1, periodic=periodic)
         out = torch.empty_like(phi_local)
         self.ops.ac_stage(phi_local, out, self.params, self.bc, self.dt, halo_lo, halo_hi)
         return out

@@ -35,13 +35,16 @@ class BaseSolver(ABC):
     timestepper_cls: Type[TimeStepper] | None = None
     step_fn: Callable | None = None
     device: str = "cuda"
+    # multi-GPU: under an initialised torch.distributed group the grid is x-slab decomposed and
+    # every rank solves its slab (VoxelGridTorch); False keeps each rank on the whole grid
+    distributed: Any = "auto"
 
     def __post_init__(self):
         if self.backend != "torch":
             raise ValueError(f"Unsupported backend: {self.backend} "
                              "(evoxels_b200 drives CUDA through torch only)")
         self.vg = VoxelGridTorch(self.vf.grid_info(), precision=self.vf.precision,
-                                 device=self.device)
+                                 device=self.device, distributed=self.distributed)
         self.fieldnames = [self.fieldnames] if isinstance(self.fieldnames, str) \
             else list(self.fieldnames)
         self.problem = None
@@ -62,8 +65,10 @@ class BaseSolver(ABC):
         # A captured graph replays step(0.0, u): legal only if rhs ignores t (ODE.autonomous).
         # Everything else - ReactionDiffusion with a source f(t, u), user problem classes,
         # user step_fn - runs the eager loop with the real time, like the reference.
+        # (the multi-GPU step runs on several streams with cross-rank barriers: eager only)
         self._graph_ok = (bool(jit) and self.vg.device.type == "cuda"
-                          and getattr(self.problem, "autonomous", False) is True)
+                          and getattr(self.problem, "autonomous", False) is True
+                          and getattr(self.vg, "slab", None) is None)
         return self.timestepper_cls(self.problem, time_increment).step
 
     @abstractmethod
@@ -116,6 +121,8 @@ class BaseSolver(ABC):
             raise RuntimeError("evoxels_b200 has no CPU path: the state must be a CUDA tensor")
         if getattr(self, "_exporter", None) is None:
             self._exporter = _FrameExporter(u.device)
+        if getattr(self.vg, "slab", None) is not None:
+            u = self.vg.gather_slabs(u)      # x-slab run: every rank exports the global field
         self._exporter.submit(u, frame, time, self._commit_frame)
         if vtk_out:
             self._exporter.finish()

@@ -53,6 +53,8 @@ class ForwardEuler(TimeStepper):
         return 1
 
     def step(self, t, u):
+        if getattr(self.problem.vg, "slab", None) is not None:
+            return _distributed_ac_euler(self, u)
         stage = getattr(self.problem, "fused_stage", None)
         if stage is None or u.requires_grad:
             return u + self.dt * self.problem.rhs(t, u)
@@ -88,6 +90,52 @@ class RungeKutta4(TimeStepper):
         stage(yb, base=u, alpha=dt, y_out=ya, acc_in=acc, beta=dt / 3, acc_out=acc)
         stage(ya, acc_in=acc, beta=dt / 6, acc_out=acc)
         return acc
+
+
+# ---- x-slab decomposed grids (VoxelGridTorch.slab): the stock problem / stepper pairs run the
+# distributed kernels of distributed.py behind the same step(t, u) call -----------------------
+def _require_no_grad_distributed(u):
+    if u.requires_grad:
+        raise NotImplementedError("backprop through the multi-GPU step is not available; "
+                                  "run the inversion on one GPU")
+
+
+def _distributed_ac_euler(ts, u):
+    from .distributed import DistributedAllenCahnEuler
+    from .problem_definition import TwoPhaseAllenCahn, is_stock
+    prob = ts.problem
+    _require_no_grad_distributed(u)
+    if not is_stock(prob, TwoPhaseAllenCahn, ("rhs",)) or not getattr(prob, "_default_potential", False):
+        raise NotImplementedError("on an x-slab decomposed grid ForwardEuler steps the stock "
+                                  "TwoPhaseAllenCahn (default potential) only")
+    if getattr(ts, "_dist", None) is None:
+        vg = prob.vg
+        ts._dist = DistributedAllenCahnEuler(vg.shape, vg.spacing, ts.dt, eps=float(prob.eps), gab=float(prob.gab),
+                                             M=float(prob.M), force=float(prob.force),
+                                             curvature=float(prob.curvature), bc=prob.bc, device=vg.device)
+    return torch.stack([ts._dist.step(ch) for ch in u.contiguous()], 0)
+
+
+def _distributed_ch_imex(ts, u):
+    from .distributed import DistributedCahnHilliardIMEX
+    prob = ts.problem
+    _require_no_grad_distributed(u)
+    periodic = prob.bc_type == ("periodic",) * 3
+    if not (periodic and is_stock(prob, CahnHilliard, ("rhs", "fourier_symbol", "spectral_form", "hom_field"))):
+        raise NotImplementedError("on an x-slab decomposed grid PseudoSpectralIMEX steps the stock, "
+                                  "fully periodic CahnHilliard only")
+    if getattr(ts, "_dist", None) is None:
+        vg = prob.vg
+        try:
+            ts._dist = DistributedCahnHilliardIMEX(vg.shape, vg.spacing, ts.dt, eps=float(prob.eps),
+                                                   D=float(prob.D), A=float(prob.A), device=vg.device,
+                                                   hom_fn=None if prob._default_mu else prob.hom_field)
+        except _native.NativeLibraryError as exc:
+            raise NotImplementedError(
+                f"the multi-GPU spectral step needs power-of-two extents (8..2048) divisible by the number "
+                f"of ranks along x and y; grid {vg.shape}: {exc}.  Build the grid with distributed=False "
+                "to let every rank solve the whole problem.") from exc
+    return torch.stack([ts._dist.step(ch) for ch in u.contiguous()], 0)
 
 
 def _defining_class(obj, name):
@@ -139,6 +187,8 @@ class PseudoSpectralIMEX(TimeStepper):
     def step(self, t, u):
         _native.require_cuda(u)
         prob = self.problem
+        if getattr(prob.vg, "slab", None) is not None:
+            return _distributed_ch_imex(self, u)
         traced = u.requires_grad or any(
             isinstance(v, torch.Tensor) and v.requires_grad
             for v in (getattr(prob, "eps", None), getattr(prob, "D", None)))

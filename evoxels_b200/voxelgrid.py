@@ -106,7 +106,15 @@ class VoxelGrid(FDStencils):
 
 
 class VoxelGridTorch(VoxelGrid):
-    def __init__(self, grid: Grid, precision="float32", device: str = "cuda"):
+    """`distributed`: under an initialised `torch.distributed` process group with more than
+    one rank the grid is x-slab decomposed: `init_scalar_field` hands out this
+    rank's slab of the (replicated) host array, `export_scalar_field_to_numpy` gathers the
+    global field on every rank, `shape` stays the GLOBAL shape, and the stock steppers route
+    `step(t, u_slab)` to the distributed kernels (timesteppers.py).  "auto" (default) does
+    that whenever a group exists and its size divides nx and ny; False keeps every rank on
+    its own full copy; True insists (raises where the decomposition does not fit)."""
+
+    def __init__(self, grid: Grid, precision="float32", device: str = "cuda", distributed="auto"):
         self.torch = torch
         self.device = torch.device(device)
         if self.device.type == "cuda":
@@ -122,6 +130,43 @@ class VoxelGridTorch(VoxelGrid):
         # user callbacks creating tensors (custom mu_hom, forcing terms) land on the GPU
         torch.set_default_device(self.device)
         super().__init__(grid, torch)
+        self.slab = None
+        self.group = None
+        if distributed not in (False, None):
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                from .distributed import Slab
+                try:
+                    self.slab = Slab(self.shape, dist.get_world_size(), dist.get_rank())
+                except ValueError:
+                    if distributed is True:
+                        raise
+                    import warnings
+                    warnings.warn(f"grid {self.shape} does not decompose over {dist.get_world_size()} "
+                                  "ranks; every rank keeps the whole grid")
+            elif distributed is True:
+                raise RuntimeError("distributed=True needs an initialised process group with > 1 rank")
+
+    # fields: slab of a replicated host array in, gathered global field out ------------------
+    def init_scalar_field(self, array):
+        if self.slab is not None:
+            array = np.ascontiguousarray(self.slab.take(np.asarray(array)))
+        return super().init_scalar_field(array)
+
+    def gather_slabs(self, field):
+        """[C, nx/W, ny, nz] on every rank -> the global [C, nx, ny, nz] on every rank."""
+        if self.slab is None:
+            return field
+        import torch.distributed as dist
+        field = field.contiguous()
+        parts = [torch.empty_like(field) for _ in range(self.slab.world)]
+        dist.all_gather(parts, field)
+        return torch.cat(parts, dim=1)
+
+    def export_scalar_field_to_numpy(self, field):
+        if self.slab is not None and field.shape[1] == self.slab.nxl and self.slab.nxl != self.shape[0]:
+            field = self.gather_slabs(field)
+        return super().export_scalar_field_to_numpy(field)
 
     # conversions ----------------------------------------------------------------------
     def to_backend(self, np_arr):

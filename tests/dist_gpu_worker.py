@@ -18,6 +18,45 @@ from evoxels_b200.timesteppers import ForwardEuler, PseudoSpectralIMEX  # noqa: 
 from evoxels_b200.voxelgrid import VoxelGridTorch  # noqa: E402
 
 
+def api_drop_in(dev, rank, world):
+    """The reference's own entry points under torchrun: run_cahn_hilliard_solver /
+    run_allen_cahn_solver / a user potential decompose the grid over the ranks by themselves and
+    must leave the SAME global fields in `vf` on every rank as a one-GPU run of the same call."""
+    import numpy as np
+    from evoxels_b200.solvers import TimeDependentSolver
+    shape = (64, 32, 64)         # the distributed FFT plan wants power-of-two extents
+    rng = np.random.default_rng(5)
+    c0 = (0.5 + 0.1 * rng.random(shape)).astype(np.float32)
+    mu = lambda c, lib=None: 4.0 * c * (1 - c) * (1 - 2 * c) + 0.3 * c      # noqa: E731
+
+    def fields(distributed, problem_cls, stepper_cls, kw, dt):
+        vf = evo.VoxelFields(shape, tuple(float(n) for n in shape))
+        vf.add_field("c", c0.copy())
+        s = TimeDependentSolver(vf, "c", "torch", problem_cls=problem_cls, timestepper_cls=stepper_cls,
+                                device=str(dev), distributed=distributed)
+        s.solve(time_increment=dt, frames=2, max_iters=6, problem_kwargs=kw, jit=True, verbose=False)
+        assert (s.vg.slab is not None) == bool(distributed)
+        return vf.fields["c"]
+
+    for cls, ts, kw, dt, tol in ((CahnHilliard, PseudoSpectralIMEX, dict(eps=3.0, D=1.0), 0.1, 1e-6),
+                                 (CahnHilliard, PseudoSpectralIMEX, dict(eps=3.0, D=1.0, mu_hom=mu), 0.1, 1e-6),
+                                 (TwoPhaseAllenCahn, ForwardEuler, dict(), 0.05, 0.0)):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            one = fields(False, cls, ts, kw, dt)
+            many = fields("auto", cls, ts, kw, dt)
+        assert one.shape == many.shape == shape
+        err = float(np.linalg.norm(many - one) / np.linalg.norm(one))
+        assert err <= tol, (cls.__name__, kw.keys(), rank, err)
+    # the precompiled driver with the reference's signature
+    vf = evo.VoxelFields(shape, tuple(float(n) for n in shape))
+    vf.add_field("c", c0.copy())
+    solver = evo.run_cahn_hilliard_solver(vf, "c", backend="torch", device=str(dev), time_increment=0.1,
+                                          frames=2, max_iters=4, verbose=False)
+    assert solver.vg.slab is not None and vf.fields["c"].shape == shape and np.isfinite(vf.fields["c"]).all()
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -33,7 +72,7 @@ def main():
         u = 0.5 + 0.1 * torch.rand(shape, device=dev, generator=gen)
         dom = tuple(float(n * h) for n, h in zip(shape, spacing))
         vf = evo.VoxelFields(shape, dom)
-        vg = VoxelGridTorch(vf.grid_info(), device=str(dev))
+        vg = VoxelGridTorch(vf.grid_info(), device=str(dev), distributed=False)
         single = PseudoSpectralIMEX(CahnHilliard(vg), 0.1)
         slab = Slab(shape, world, rank)
         results = {}
@@ -64,6 +103,7 @@ def main():
             for _ in range(2):
                 v, w = euler.step(0.0, v), ac.step(w)
             assert torch.equal(w, slab.take(v[0])), (shape, bc, rank)   # same kernel, same inputs
+    api_drop_in(dev, rank, world)
     t = torch.tensor([worst], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

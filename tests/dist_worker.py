@@ -48,6 +48,14 @@ class OracleOps:
         r = O.ch_rhs(ext[None], self.spacing, eps, D, bc)[0]
         out.copy_(r[a:r.shape[0] - b])
 
+    user_mu = None
+
+    def ch_rhs_hom(self, c, out, eps, D, bc, hom):
+        # the stand-in re-evaluates the potential inside the oracle (same function the test
+        # handed to the stepper as hom_fn) and checks that the caller's field is that function
+        assert torch.allclose(hom, self.user_mu(torch.clip(c, 0, 1)))
+        out.copy_(O.ch_rhs(c[None], self.spacing, eps, D, bc, self.user_mu)[0])
+
     def ac_stage(self, phi, out, params, bc, dt, halo_lo, halo_hi):
         ext, a, b = self._extended(phi, halo_lo, halo_hi, 1)
         kw = dict(params)
@@ -102,6 +110,21 @@ def run(rank, world, port, shape):
     assert abs(stepper.total_mass(w) - m0) < 1e-3 * abs(m0) * 1e-3
     assert abs(m0 - float(u.double().sum())) < 1e-6 * abs(m0)
 
+    # Cahn-Hilliard with a user potential (caller-evaluated field on the halo-extended slab)
+    if slab.nxl >= 2:
+        mu = lambda c, lib=None: 4.0 * c * (1 - c) * (1 - 2 * c) + 0.3 * c     # noqa: E731
+        ops = OracleOps(slab, spacing, 0.1, (1.5, 2))
+        ops.user_mu = mu
+        stepper = DistributedCahnHilliardIMEX(shape, spacing, 0.1, ops=ops,
+                                              hom_fn=lambda c: mu(torch.clip(c, 0, 1)))
+        orc = O.CHOracle(shape, spacing, 0.1, mu_hom=mu)
+        v, w = u[None], slab.take(u).clone()
+        for _ in range(2):
+            v, w = orc.step(v), stepper.step(w)
+        ref = slab.take(v[0])
+        err = float((w - ref).norm() / ref.norm())
+        assert err < 2e-6, f"CH user potential rank {rank}: {err}"
+
     # Allen-Cahn Euler with three BC layouts along x
     for bc in (("neumann",) * 3, ("periodic",) * 3, (("dirichlet", (0.0, 1.0)), "neumann", "periodic")):
         phi = O.noise_field(shape, seed=1, lo=0.0, amp=1.0)[0]
@@ -114,6 +137,22 @@ def run(rank, world, port, shape):
         ref = slab.take(v[0])
         err = float((w - ref).norm() / ref.norm())
         assert err < 1e-6, f"AC {bc} rank {rank}: {err}"
+    # the grid object under a process group: slab in, gathered global field out (host-side
+    # bookkeeping only - a CPU grid runs no kernels)
+    import evoxels_b200 as evo
+    from evoxels_b200.voxelgrid import VoxelGridTorch
+    vf = evo.VoxelFields(shape, tuple(float(n) for n in shape))
+    vg = VoxelGridTorch(vf.grid_info(), device="cpu")
+    a = np.random.default_rng(9).random(shape).astype(np.float32)
+    f = vg.init_scalar_field(a)
+    if world > 1:
+        assert vg.slab is not None and tuple(f.shape) == (1,) + slab.local_shape
+        assert np.array_equal(f[0].numpy(), a[slab.x0:slab.x0 + slab.nxl])
+    else:
+        assert vg.slab is None and tuple(f.shape) == (1,) + tuple(shape)
+    assert np.array_equal(vg.export_scalar_field_to_numpy(f), a)
+    assert VoxelGridTorch(vf.grid_info(), device="cpu", distributed=False).slab is None
+    torch.set_default_device("cpu")
     dist.barrier()
     dist.destroy_process_group()
 
