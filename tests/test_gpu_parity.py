@@ -614,3 +614,29 @@ def test_chained_zy_passes_match_one_kernel_per_pass_bit_for_bit(cuda_device, mo
         for a, b in zip(base, run):
             assert torch.isfinite(b).all()
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("ws", ["0", "3", "4", "5"])
+def test_line_pass_forms_agree_bit_for_bit(cuda_device, monkeypatch, ws):
+    """TMA-tiled strided passes: the two-blocks-per-SM form (tile hand-over by the compute
+    threads) and the warp-specialised form with 3 / 4 / 5 tile buffers (loader + retirer warps,
+    roots in registers) against the cp.async passes - separate passes, so the y passes go
+    through the line kernels as well."""
+    shape = (512, 512, 64)
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    u = 0.5 + 0.1 * torch.rand(shape, device="cuda", generator=gen)
+    r = torch.randn(shape, device="cuda", generator=gen)
+    plan = _native.ImexPlan(shape, torch.float32, "cuda", _native.FFT_NATIVE)
+    monkeypatch.setenv("EVX_FFT_CHAIN", "0")
+    outs = []
+    for tma, form in (("0", "0"), ("1", ws)):
+        monkeypatch.setenv("EVX_FFT_TMA", tma)
+        monkeypatch.setenv("EVX_FFT_LINE_WS", form)
+        out = torch.full_like(u, float("nan"))
+        plan.apply(u, r, out, (1.0, 0.5, 2.0), 0.1, 1.5, 2)
+        etd = torch.full_like(u, float("nan"))
+        plan.apply(u, r, etd, (1.0, 0.5, 2.0), 0.5, 1.0, 1 | _native.FILTER_ETD1)
+        torch.cuda.synchronize()
+        outs.append((out, etd))
+    for a, b in zip(*outs):
+        assert torch.isfinite(b).all() and torch.equal(a, b)
