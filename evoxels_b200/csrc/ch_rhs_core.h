@@ -248,8 +248,11 @@ struct ChRhsProgram {
   // the cell keeps a finite don't-care value)
   EVX_HD static void fetch_next(Regs& t, Smem& s, const P& p, int cell) {
     constexpr int B = (int)sizeof(Vt);
+    // fully periodic instantiation: every plane of c exists (own slab, x halo or periodic
+    // image), so the pointers are never null and the ghost-plane branches compile away
+    constexpr bool NEVER_NULL = !GHOSTS;
     if (t.has_pos) {
-      if (t.pn) async_copy_bytes<B>(&s.stage[cell][t.tid], t.pn);
+      if (NEVER_NULL || t.pn) async_copy_bytes<B>(&s.stage[cell][t.tid], t.pn);
       else s.stage[cell][t.tid] = vec_splat<T, V>(T(0));
       if (HOM) {
         if (t.ph) async_copy_bytes<B>(&s.stage_h[cell][t.tid], t.ph);
@@ -257,7 +260,7 @@ struct ChRhsProgram {
       }
     }
     if (t.has_extra) {
-      if (t.pe) async_copy_bytes<B>(&s.stage_e[cell][t.tid - N_INT], t.pe);
+      if (NEVER_NULL || t.pe) async_copy_bytes<B>(&s.stage_e[cell][t.tid - N_INT], t.pe);
       else s.stage_e[cell][t.tid - N_INT] = vec_splat<T, V>(T(0));
     }
     async_copy_commit();

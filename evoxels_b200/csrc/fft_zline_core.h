@@ -115,14 +115,6 @@ struct ZGroupLine {
       }
     } else {
       if (k == 0) {
-        if (real_in) {
-          const cf* u = reinterpret_cast<const cf*>(real_in + grow * nz);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) r.u[e] = u[r.t + e * T];
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) r.u[e] = cf{0.f, 0.f};
-        }
 #pragma unroll
         for (int e = 0; e < 8; ++e)
           r.v[e] = ZPass<M, 1, true>::untangle_inv(rows[r.rb + e * T], rows[r.pb - e * T],
@@ -134,6 +126,14 @@ struct ZGroupLine {
         line_stage_compute_pre<M, +1>(1, r.v, r.t, w1);
         write_rows_stage1(r, rows);
       } else {
+        if (real_in) {
+          const cf* u = reinterpret_cast<const cf*>(real_in + grow * nz);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r.u[e] = u[r.t + e * T];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r.u[e] = cf{0.f, 0.f};
+        }
         read_rows_natural(r, rows);
         line_stage_compute_pre<M, +1>(2, r.v, r.t, w2);
         cf* out = reinterpret_cast<cf*>(real_out + grow * nz);
@@ -178,14 +178,6 @@ struct ZGroupLine {
       }
     } else {
       if (k == 0) {
-        if (real_in) {
-          const cf* u = reinterpret_cast<const cf*>(real_in + grow * p.nz);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) r.u[e] = u[r.t + e * T];
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) r.u[e] = cf{0.f, 0.f};
-        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int kk = r.t + e * T;
@@ -200,6 +192,16 @@ struct ZGroupLine {
         write_rows_stage1(r, rows);
         stage_twiddles<M>(2, r.t, p.tw, r.w);
       } else {
+        // the u row comes from L2 (the loader prefetches it when it issues the item); fetched
+        // here, first thing of the last phase, its eight values are live for this phase only
+        if (real_in) {
+          const cf* u = reinterpret_cast<const cf*>(real_in + grow * p.nz);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r.u[e] = u[r.t + e * T];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r.u[e] = cf{0.f, 0.f};
+        }
         read_rows_natural(r, rows);
         line_stage_compute_pre<M, +1>(2, r.v, r.t, r.w);
         cf* out = reinterpret_cast<cf*>(real_out + grow * p.nz);

@@ -640,3 +640,19 @@ def test_line_pass_forms_agree_bit_for_bit(cuda_device, monkeypatch, ws):
         outs.append((out, etd))
     for a, b in zip(*outs):
         assert torch.isfinite(b).all() and torch.equal(a, b)
+
+
+def test_cuda_graph_replay_of_the_chained_step(cuda_device, recwarn):
+    """The 512-point path (cooperative chained kernels, warp-specialised x pass, two memsets per
+    step) inside the solver's CUDA-graph replay: same fields as the eager loop, and the capture
+    must really have happened (no fall-back warning)."""
+    shape = (16, 512, 512)
+    res = {}
+    for jit in (False, True):
+        vf = evo.VoxelFields(shape, tuple(float(n) for n in shape))
+        vf.add_field("c", 0.5 + 0.1 * np.random.default_rng(3).random(shape).astype(np.float32))
+        evo.run_cahn_hilliard_solver(vf, "c", backend="torch", device="cuda", jit=jit, frames=2,
+                                     max_iters=20, time_increment=0.1, verbose=False)
+        res[jit] = vf.fields["c"].copy()
+    assert np.isfinite(res[True]).all() and np.array_equal(res[False], res[True])
+    assert not [w for w in recwarn.list if "CUDA-graph capture" in str(w.message)]
