@@ -825,7 +825,7 @@ def run_ours_distributed(args, world, rank, local, dev):
         except Exception as exc:
             ac3 = {"error": repr(exc)[:200]}
     cfg4 = None
-    if args.config4:
+    if args.config4 or (world == 8 and not args.no_extras):
         del stepper
         torch.cuda.empty_cache()
         try:
@@ -879,7 +879,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and reference-on-GPU legs")
     ap.add_argument("--no-extras", action="store_true", help="skip the config 1 / 3 / 5 sub-records")
     ap.add_argument("--config4", action="store_true",
-                    help="N > 1: also time Cahn-Hilliard 2048^3 on all ranks and on rank 0 alone (config 4)")
+                    help="N > 1: also time Cahn-Hilliard 2048^3 on all ranks and on rank 0 alone (config 4); "
+                         "on by default at N = 8, the configuration BASELINE.json names")
     ap.add_argument("--p2p-ctas", type=int, default=148,
                     help="grid cap of the NVLink-bound peer-store launches (0 = fill the GPU)")
     ap.add_argument("--overlap-chunks", type=int, default=4,
