@@ -36,4 +36,8 @@ int ch_rhs_impl(const T* c, const T* hom, T* rhs, int nx, int ny, int nz, const 
                 double eps, double D, const int* bc_kind, const double* bc_val,
                 const T* halo_lo, const T* halo_hi, cudaStream_t st);
 
+// ch_rhs_tma.cu: warp-specialised fp32 form; EVX_ERR_UNSUPPORTED when the shape is not covered
+template <typename T> struct ChParams;
+int ch_rhs_tma_f32(ChParams<float> p, cudaStream_t st);
+
 }  // namespace evx

@@ -93,6 +93,12 @@ int ch_rhs_impl(const T* c, const T* hom, T* rhs, int nx, int ny, int nz, const 
   const bool vec = nz % VW == 0 && aligned16(c) && aligned16(rhs) && aligned16(hom) &&
                    aligned16(halo_lo) && aligned16(halo_hi);
   if (vec) {
+    if constexpr (sizeof(T) == 4) {
+      // warp-specialised form (loader warp + bulk copies, ch_rhs_tma.cu); it declines shapes
+      // it does not cover
+      const int e = ch_rhs_tma_f32(p, st);
+      if (e != EVX_ERR_UNSUPPORTED) return e;
+    }
     // tile height: 14 rows x 16 groups = 7 interior warps + 2 ring warps = 288 threads
     return launch_ch<T, VW, 14, 16>(p, st);
   }
