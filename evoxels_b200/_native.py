@@ -65,6 +65,8 @@ SIGNATURES = {
     "evx_ch_adjoint_flux_f64": [_c_void_p] * 5 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
     "evx_ch_adjoint_combine_f32": [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
     "evx_ch_adjoint_combine_f64": [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_void_p],
+    "evx_ch_adjoint_combine_range_f32": [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_int, _c_int, _c_void_p],
+    "evx_ch_adjoint_combine_range_f64": [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _dptr, _c_double, _c_int, _c_int, _c_void_p],
     "evx_dist_plan_create": [ctypes.POINTER(_c_void_p), _c_int, _c_int, _c_int, _c_int, _c_int],
     "evx_dist_plan_destroy": [_c_void_p],
     "evx_dist_plan_set_p2p_ctas": [_c_void_p, _c_int],
@@ -374,9 +376,10 @@ class ImexPlan:
             pass
 
 
-def ch_rhs_vjp(u, w, spacing, eps, D, lam_in=None):
+def ch_rhs_vjp(u, w, spacing, eps, D, lam_in=None, deps_planes=None):
     """Vector-Jacobian product of the periodic CH rhs at state `u` with cotangent `w`.
-    Returns (dL/du [+ lam_in], dL/deps as a 0-dim float64 CUDA tensor).  Three kernels."""
+    Returns (dL/du [+ lam_in], dL/deps as a 0-dim float64 CUDA tensor).  Three kernels.
+    deps_planes = (x_lo, x_hi): only those planes enter dL/deps (x-slab extended by halos)."""
     require_cuda(u, w, lam_in)
     lib = load_library()
     sfx = _suffix(u)
@@ -391,9 +394,14 @@ def ch_rhs_vjp(u, w, spacing, eps, D, lam_in=None):
         check(getattr(lib, "evx_ch_adjoint_flux_" + sfx)(_ptr(u), _ptr(mu), _ptr(_field3(w)), _ptr(z),
                                                          _ptr(m), nx, ny, nz, h, float(D), st),
               "evx_ch_adjoint_flux")
-        check(getattr(lib, "evx_ch_adjoint_combine_" + sfx)(_ptr(u), _ptr(z), _ptr(m), _ptr(lam_in),
-                                                            _ptr(lam), _ptr(deps), nx, ny, nz, h,
-                                                            float(eps), st), "evx_ch_adjoint_combine")
+        if deps_planes is None:
+            check(getattr(lib, "evx_ch_adjoint_combine_" + sfx)(_ptr(u), _ptr(z), _ptr(m), _ptr(lam_in),
+                                                                _ptr(lam), _ptr(deps), nx, ny, nz, h,
+                                                                float(eps), st), "evx_ch_adjoint_combine")
+        else:
+            check(getattr(lib, "evx_ch_adjoint_combine_range_" + sfx)(
+                _ptr(u), _ptr(z), _ptr(m), _ptr(lam_in), _ptr(lam), _ptr(deps), nx, ny, nz, h, float(eps),
+                int(deps_planes[0]), int(deps_planes[1]), st), "evx_ch_adjoint_combine_range")
     return lam, deps
 
 

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) ch_adjoint_kernel(const AdjParams<T> p) {
       } else {
         double term;
         p.out0[i] = adj_combine(p, x, y, z, term);
-        acc += term;
+        if (x >= p.red_x0 && x < p.red_x1) acc += term;
       }
     }
   }
@@ -44,9 +44,11 @@ __global__ void __launch_bounds__(256) ch_adjoint_kernel(const AdjParams<T> p) {
 template <typename T>
 static int launch_adjoint(int op, const T* u, const T* mu, const T* w, const T* z, const T* m,
                           const T* lam_in, T* out0, T* out1, double* red, int nx, int ny, int nz,
-                          const double* h, double eps, double D, cudaStream_t st) {
+                          const double* h, double eps, double D, cudaStream_t st, int red_x0 = 0,
+                          int red_x1 = 2147483647) {
   if (!u || !out0 || !h || nx < 1 || ny < 1 || nz < 1) return EVX_ERR_ARG;
   AdjParams<T> p;
+  p.red_x0 = red_x0; p.red_x1 = red_x1;
   p.u = u; p.mu = mu; p.w = w; p.z = z; p.m = m; p.lam_in = lam_in; p.out0 = out0; p.out1 = out1;
   p.red = red; p.nx = nx; p.ny = ny; p.nz = nz;
   p.ihx2 = T(1.0 / (h[0] * h[0])); p.ihy2 = T(1.0 / (h[1] * h[1])); p.ihz2 = T(1.0 / (h[2] * h[2]));
@@ -107,6 +109,23 @@ int evx_ch_adjoint_combine_f64(const double* u, const double* z, const double* m
                                int ny, int nz, const double* h, double eps, void* stream) {
   return launch_adjoint<double>(2, u, nullptr, nullptr, z, m, lam_in, lam_out, nullptr, deps_acc,
                                 nx, ny, nz, h, eps, 1.0, (cudaStream_t)stream);
+}
+
+int evx_ch_adjoint_combine_range_f32(const float* u, const float* z, const float* m,
+                                     const float* lam_in, float* lam_out, double* deps_acc, int nx,
+                                     int ny, int nz, const double* h, double eps, int x_lo, int x_hi,
+                                     void* stream) {
+  if (x_lo < 0 || x_hi > nx || x_lo > x_hi) return EVX_ERR_ARG;
+  return launch_adjoint<float>(2, u, nullptr, nullptr, z, m, lam_in, lam_out, nullptr, deps_acc,
+                               nx, ny, nz, h, eps, 1.0, (cudaStream_t)stream, x_lo, x_hi);
+}
+int evx_ch_adjoint_combine_range_f64(const double* u, const double* z, const double* m,
+                                     const double* lam_in, double* lam_out, double* deps_acc, int nx,
+                                     int ny, int nz, const double* h, double eps, int x_lo, int x_hi,
+                                     void* stream) {
+  if (x_lo < 0 || x_hi > nx || x_lo > x_hi) return EVX_ERR_ARG;
+  return launch_adjoint<double>(2, u, nullptr, nullptr, z, m, lam_in, lam_out, nullptr, deps_acc,
+                                nx, ny, nz, h, eps, 1.0, (cudaStream_t)stream, x_lo, x_hi);
 }
 
 }  // extern "C"

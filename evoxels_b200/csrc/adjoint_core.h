@@ -29,6 +29,8 @@ struct AdjParams {
   T* out0;         // op 0: mu      op 1: z      op 2: dL/du
   T* out1;         //               op 1: m
   double* red;     // op 2: device accumulator for dL/deps (atomicAdd of block partials)
+  int red_x0, red_x1;   // op 2: planes whose integrand enters `red` (an x-slab extended by its
+                        // halo planes passes the slab's own planes; default: all)
   int nx, ny, nz;
   T ihx2, ihy2, ihz2;   // 1/h^2
   T eps, D;

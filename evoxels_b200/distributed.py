@@ -239,6 +239,13 @@ class CudaOps:
                          params["force"], params["curvature"], bc, base=phi, y_out=out, alpha=dt,
                          halo_lo=halo_lo, halo_hi=halo_hi)
 
+    def ch_rhs_vjp_ext(self, u_ext, w_ext, lam_in_ext, eps, D, x_lo, x_hi):
+        """Adjoint stencil kernels on a halo-extended slab (periodic inside the kernels: the wrap
+        only reaches the outer halo planes, which the caller drops); only the planes
+        [x_lo, x_hi) enter the dL/deps partial sum.  Returns (lam_ext, deps)."""
+        return _native.ch_rhs_vjp(u_ext, w_ext, self.spacing, eps, D, lam_in=lam_in_ext,
+                                  deps_planes=(x_lo, x_hi))
+
     def spectral_forward(self, r):
         self.plan.forward(r, self.spec, self.buf_a)
         return self.buf_a
@@ -554,6 +561,96 @@ class DistributedCahnHilliardIMEX:
     def total_mass(self, u_local):
         s = u_local.double().sum().reshape(1)
         return float(self.comm.all_reduce_sum(s).item())
+
+    # ---- adjoint of one step (last row: same partitioning, parameter-gradient
+    # partial sums all-reduced once) ---------------------------------------------------------
+    ADJ_HALO = 4      # planes per side of the extended slab the adjoint stencil runs on
+
+    def spectral_filter(self, r_local):
+        """G r = F^-1[ dt / (1 + dt s) F r ] of a slab-decomposed field (self-adjoint: the same
+        call serves the forward update and w = G lam+ of the backward pass)."""
+        ops, comm = self.ops, self.comm
+        coef = 2.0 * self.eps * self.D * self.A
+        out = ops.new_field()
+        r_local = r_local.contiguous()
+        if getattr(ops, "transport", "nccl") in ("p2p", "ce") and ops.peers is not None:
+            ops.spectral_forward_p2p(r_local)
+            a = ops.spectral_middle_p2p(self.dt, coef, 2)
+            ops.spectral_backward(a, None, out)
+            return out
+        a, b = ops.exchange_buffers()
+        send = ops.spectral_forward(r_local)
+        comm.all_to_all_blocks(send, b)
+        ops.spectral_middle(b, self.dt, coef, 2)
+        comm.all_to_all_blocks(b, a)
+        ops.spectral_backward(a, None, out)
+        return out
+
+    def _extend(self, f_local, width):
+        lo, hi = self.comm.exchange_halos(f_local, width, periodic=True)
+        if lo is None:                       # one rank: the kernels wrap by index arithmetic
+            return f_local, 0
+        return torch.cat([lo, f_local, hi], 0).contiguous(), width
+
+    def step_vjp(self, u_local, u_plus_local, lam_plus_local):
+        """Backward pass of `step` on this rank's slab: given lam+ = dL/du+ returns
+        (dL/du, dL/dD, dL/deps) - the field gradient of the slab, the two parameter gradients
+        ALREADY summed over all ranks (one all-reduce of a 2-vector).  Same formulas as the
+        single-GPU adjoint (autograd._CHImexStepFn):
+            w = G lam+ (distributed filter), lam = lam+ + dR/du^T w (stencil kernels on the slab
+            extended by ADJ_HALO planes of u and w per side),
+            dL/dD = <w, u+ - u> / (dt D),  dL/deps = <z, dmu/deps> + <w/dt - lam+, u+ - u> / eps."""
+        if self.hom_fn is not None:
+            raise NotImplementedError("the hand-written adjoint supports the default mu_hom only")
+        u_local, lam_plus_local = u_local.contiguous(), lam_plus_local.contiguous()
+        if self.slab.world > 1 and self.slab.nxl < self.ADJ_HALO:
+            raise ValueError("slab thinner than the adjoint halo")
+        w = self.spectral_filter(lam_plus_local)
+        u_ext, h = self._extend(u_local, self.ADJ_HALO)
+        w_ext, _ = self._extend(w, self.ADJ_HALO)
+        n = u_local.shape[0]
+        if h:
+            lam_in = torch.zeros_like(u_ext)
+            lam_in[h:h + n] = lam_plus_local
+        else:
+            lam_in = lam_plus_local
+        lam_ext, deps = self.ops.ch_rhs_vjp_ext(u_ext, w_ext, lam_in, self.eps, self.D, h, h + n)
+        lam = lam_ext[h:h + n].contiguous() if h else lam_ext
+        du = (u_plus_local - u_local).double()
+        wd = w.double()
+        g_D = (wd * du).sum() / (self.dt * self.D)
+        g_eps = deps.double() + ((wd / self.dt - lam_plus_local.double()) * du).sum() / self.eps
+        g = self.comm.all_reduce_sum(torch.stack([g_D, g_eps]))
+        return lam, g[0], g[1]
+
+    def step_autograd(self, u_local, D=None, eps=None):
+        """Differentiable `step`: u_local (and optionally 0-dim tensors D, eps that carry
+        requires_grad) -> u+ of the slab, with `step_vjp` as the backward pass.  Every rank
+        must call it (and later backward) collectively."""
+        like = u_local
+        D_t = D if isinstance(D, torch.Tensor) else torch.tensor(float(self.D), dtype=torch.float64, device=like.device)
+        e_t = eps if isinstance(eps, torch.Tensor) else torch.tensor(float(self.eps), dtype=torch.float64, device=like.device)
+        return _DistCHImexStepFn.apply(u_local.contiguous(), D_t, e_t, self)
+
+
+class _DistCHImexStepFn(torch.autograd.Function):
+    """One node per distributed step; saves (u, u+) of the slab only."""
+
+    @staticmethod
+    def forward(ctx, u, D, eps, stepper):
+        stepper.D, stepper.eps = float(D), float(eps)
+        out = stepper.step(u.detach())
+        ctx.save_for_backward(u, out, D, eps)
+        ctx.stepper = stepper
+        return out
+
+    @staticmethod
+    def backward(ctx, lam_plus):
+        u, u_plus, D, eps = ctx.saved_tensors
+        st = ctx.stepper
+        st.D, st.eps = float(D), float(eps)
+        lam, g_D, g_eps = st.step_vjp(u.detach(), u_plus, lam_plus)
+        return lam, g_D.to(D.dtype), g_eps.to(eps.dtype), None
 
 
 class DistributedAllenCahnEuler:

@@ -119,7 +119,8 @@ def _distributed_ac_euler(ts, u):
 def _distributed_ch_imex(ts, u):
     from .distributed import DistributedCahnHilliardIMEX
     prob = ts.problem
-    _require_no_grad_distributed(u)
+    traced = u.requires_grad or any(isinstance(v, torch.Tensor) and v.requires_grad
+                                    for v in (getattr(prob, "eps", None), getattr(prob, "D", None)))
     periodic = prob.bc_type == ("periodic",) * 3
     if not (periodic and is_stock(prob, CahnHilliard, ("rhs", "fourier_symbol", "spectral_form", "hom_field"))):
         raise NotImplementedError("on an x-slab decomposed grid PseudoSpectralIMEX steps the stock, "
@@ -135,6 +136,13 @@ def _distributed_ch_imex(ts, u):
                 f"the multi-GPU spectral step needs power-of-two extents (8..2048) divisible by the number "
                 f"of ranks along x and y; grid {vg.shape}: {exc}.  Build the grid with distributed=False "
                 "to let every rank solve the whole problem.") from exc
+    if traced:
+        # backward = the distributed adjoint (slab gradient; dL/dD, dL/deps all-reduced)
+        if not prob._default_mu:
+            raise NotImplementedError("the hand-written adjoint supports the default mu_hom only")
+        D = prob.D if isinstance(prob.D, torch.Tensor) else None
+        eps = prob.eps if isinstance(prob.eps, torch.Tensor) else None
+        return torch.stack([ts._dist.step_autograd(ch, D, eps) for ch in u.contiguous()], 0)
     return torch.stack([ts._dist.step(ch) for ch in u.contiguous()], 0)
 
 

@@ -287,6 +287,17 @@ int evx_ch_adjoint_combine_f32(const float* u, const float* z, const float* m,
 int evx_ch_adjoint_combine_f64(const double* u, const double* z, const double* m,
                                const double* lam_in, double* lam_out, double* deps_acc, int nx,
                                int ny, int nz, const double* h, double eps, void* stream);
+/* x-slab form (multi-GPU adjoint, SURVEY 8e last row): the arrays are the slab extended by halo
+ * planes; lam_out is formed on every plane, *deps_acc only takes the planes [x_lo, x_hi) - the
+ * slab's own - so that the partial sums of the ranks add up to the single-GPU value. */
+int evx_ch_adjoint_combine_range_f32(const float* u, const float* z, const float* m,
+                                     const float* lam_in, float* lam_out, double* deps_acc, int nx,
+                                     int ny, int nz, const double* h, double eps, int x_lo, int x_hi,
+                                     void* stream);
+int evx_ch_adjoint_combine_range_f64(const double* u, const double* z, const double* m,
+                                     const double* lam_in, double* lam_out, double* deps_acc, int nx,
+                                     int ny, int nz, const double* h, double eps, int x_lo, int x_hi,
+                                     void* stream);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long evx_launch_count(void);

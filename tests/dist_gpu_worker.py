@@ -57,6 +57,43 @@ def api_drop_in(dev, rank, world):
     assert solver.vg.slab is not None and vf.fields["c"].shape == shape and np.isfinite(vf.fields["c"]).all()
 
 
+def adjoint(dev, rank, world):
+    """Backprop through two distributed steps (last row): the slab of dL/du and the
+    all-reduced dL/dD, dL/deps against the single-GPU hand-written adjoint on the whole field."""
+    shape, spacing = (64, 32, 128), (1.0, 0.5, 2.0)
+    if shape[0] % world or shape[1] % world or shape[0] // world < DistributedCahnHilliardIMEX.ADJ_HALO:
+        return
+    gen = torch.Generator(device=dev).manual_seed(3)
+    u0 = 0.5 + 0.3 * torch.rand(shape, device=dev, generator=gen)
+    tgt = 0.5 + 0.1 * torch.rand(shape, device=dev, generator=gen)
+    dom = tuple(float(n * h) for n, h in zip(shape, spacing))
+    vf = evo.VoxelFields(shape, dom)
+    vg = VoxelGridTorch(vf.grid_info(), device=str(dev), distributed=False)
+    D1 = torch.tensor(1.3, dtype=torch.float64, device=dev, requires_grad=True)
+    e1 = torch.tensor(2.5, dtype=torch.float64, device=dev, requires_grad=True)
+    single = PseudoSpectralIMEX(CahnHilliard(vg, eps=e1, D=D1), 0.1)
+    v = u0[None].clone().requires_grad_(True)
+    x = v
+    for _ in range(2):
+        x = single.step(0.0, x)
+    ((x[0] - tgt) ** 2).sum().backward()
+    slab = Slab(shape, world, rank)
+    for transport in ("nccl", "ce"):
+        D2 = torch.tensor(1.3, dtype=torch.float64, device=dev, requires_grad=True)
+        e2 = torch.tensor(2.5, dtype=torch.float64, device=dev, requires_grad=True)
+        st = DistributedCahnHilliardIMEX(shape, spacing, 0.1, eps=2.5, D=1.3, device=dev, transport=transport)
+        w = slab.take(u0).contiguous().requires_grad_(True)
+        y = w
+        for _ in range(2):
+            y = st.step_autograd(y, D2, e2)
+        ((y - slab.take(tgt)) ** 2).sum().backward()
+        ref = slab.take(v.grad[0])
+        err = float((w.grad - ref).norm() / ref.norm())
+        assert err < 1e-5, ("adjoint dL/du", transport, rank, err)
+        assert abs(float(D2.grad) - float(D1.grad)) <= 1e-5 * abs(float(D1.grad)), (float(D2.grad), float(D1.grad))
+        assert abs(float(e2.grad) - float(e1.grad)) <= 1e-5 * abs(float(e1.grad)), (float(e2.grad), float(e1.grad))
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -104,6 +141,7 @@ def main():
                 v, w = euler.step(0.0, v), ac.step(w)
             assert torch.equal(w, slab.take(v[0])), (shape, bc, rank)   # same kernel, same inputs
     api_drop_in(dev, rank, world)
+    adjoint(dev, rank, world)
     t = torch.tensor([worst], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

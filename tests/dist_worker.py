@@ -84,7 +84,24 @@ class OracleOps:
     def spectral_backward(self, buf, u, out):
         s = torch.cat([buf[j] for j in range(self.slab.world)], dim=1)   # [nxl, ny, nzh]
         upd = torch.fft.irfft(torch.fft.ifft(s, dim=1), n=self.slab.global_shape[2], dim=2)
-        out.copy_(u + upd)
+        out.copy_(upd if u is None else u + upd)
+
+    def ch_rhs_vjp_ext(self, u_ext, w_ext, lam_in_ext, eps, D, x_lo, x_hi):
+        """Stand-in for the adjoint stencil kernels: autograd through the oracle's rhs on the
+        extended slab (float64).  dL/du takes the full cotangent; the dL/deps partial sum takes
+        the cotangent of the slab's own planes only (partition by rhs site: the ranks' partial
+        sums add up to the global value just like the kernels' partition by mu site)."""
+        per = ("periodic",) * 3
+        with torch.enable_grad():        # called from inside an autograd backward
+            u = u_ext.double().clone().requires_grad_(True)
+            e = torch.tensor(float(eps), dtype=torch.float64, requires_grad=True)
+            R = O.ch_rhs(u[None], self.spacing, e, float(D), per)[0]
+            wd = w_ext.double()
+            lam, = torch.autograd.grad((R * wd).sum(), u, retain_graph=True)
+            mask = torch.zeros_like(wd)
+            mask[x_lo:x_hi] = 1.0
+            deps, = torch.autograd.grad((R * wd * mask).sum(), e)
+        return (lam + lam_in_ext.double()).float(), deps
 
 
 def run(rank, world, port, shape):
@@ -124,6 +141,29 @@ def run(rank, world, port, shape):
         ref = slab.take(v[0])
         err = float((w - ref).norm() / ref.norm())
         assert err < 2e-6, f"CH user potential rank {rank}: {err}"
+
+    # adjoint of one Cahn-Hilliard step: slab gradient and the all-reduced parameter gradients
+    # against float64 autograd through the single-domain oracle
+    if world == 1 or slab.nxl >= DistributedCahnHilliardIMEX.ADJ_HALO:
+        tgt = O.noise_field(shape, seed=6, lo=0.45, amp=0.1)[0]
+        v = u[None].double().clone().requires_grad_(True)
+        Dt = torch.tensor(1.3, dtype=torch.float64, requires_grad=True)
+        et = torch.tensor(2.5, dtype=torch.float64, requires_grad=True)
+        loss = ((O.ch_imex_step(v, spacing, 0.1, et, Dt, 0.25) - tgt[None].double()) ** 2).sum()
+        gu, gD, ge = torch.autograd.grad(loss, (v, Dt, et))
+        ops = OracleOps(slab, spacing, 0.1, (1.5, 2))
+        stepper = DistributedCahnHilliardIMEX(shape, spacing, 0.1, eps=2.5, D=1.3, A=0.25, ops=ops)
+        w = slab.take(u).clone().requires_grad_(True)
+        Dl = torch.tensor(1.3, dtype=torch.float64, requires_grad=True)
+        el = torch.tensor(2.5, dtype=torch.float64, requires_grad=True)
+        out = stepper.step_autograd(w, Dl, el)
+        local = ((out.double() - slab.take(tgt).double()) ** 2).sum()    # this rank's share of the loss
+        local.backward()
+        ref = slab.take(gu[0])
+        err = float((w.grad.double() - ref).norm() / ref.norm())
+        assert err < 2e-4, f"adjoint dL/du rank {rank}: {err}"
+        assert abs(float(Dl.grad) - float(gD)) < 2e-4 * abs(float(gD)), (float(Dl.grad), float(gD))
+        assert abs(float(el.grad) - float(ge)) < 2e-4 * abs(float(ge)), (float(el.grad), float(ge))
 
     # Allen-Cahn Euler with three BC layouts along x
     for bc in (("neumann",) * 3, ("periodic",) * 3, (("dirichlet", (0.0, 1.0)), "neumann", "periodic")):

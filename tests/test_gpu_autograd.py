@@ -111,3 +111,50 @@ def test_rhs_alone_is_differentiable(cuda_device):
     assert rel_l2(gu[0].cpu().numpy(), ru[0].numpy()) <= 1e-11
     assert abs(float(gD) - float(rD)) <= 1e-9 * abs(float(rD))
     assert abs(float(ge) - float(re)) <= 1e-9 * abs(float(re))
+
+
+def test_slab_form_of_the_adjoint_kernels(cuda_device):
+    """The x-slab form of the backward pass on one GPU: (a) DistributedCahnHilliardIMEX with one
+    rank reproduces the single-GPU autograd step; (b) the stencil adjoint on a slab extended by
+    ADJ_HALO periodic image planes with the dL/deps sum restricted to the slab's own planes
+    (evx_ch_adjoint_combine_range) - the slabs' fields tile the full-domain dL/du and their
+    partial sums add up to the full-domain dL/deps."""
+    from evoxels_b200 import _native
+    from evoxels_b200.distributed import DistributedCahnHilliardIMEX
+    shape, spacing = (32, 16, 64), (1.0, 0.5, 2.0)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    u = -0.05 + 1.1 * torch.rand(shape, device="cuda", generator=gen)
+    w = torch.randn(shape, device="cuda", generator=gen)
+    lam_ref, deps_ref = _native.ch_rhs_vjp(u, w, spacing, 2.5, 1.3)
+    H = DistributedCahnHilliardIMEX.ADJ_HALO
+    nxl, total = 8, 0.0
+    for a in range(0, shape[0], nxl):
+        idx = torch.arange(a - H, a + nxl + H, device="cuda") % shape[0]
+        lam, deps = _native.ch_rhs_vjp(u[idx].contiguous(), w[idx].contiguous(), spacing, 2.5, 1.3,
+                                       deps_planes=(H, H + nxl))
+        assert torch.allclose(lam[H:H + nxl], lam_ref[a:a + nxl], rtol=0, atol=1e-6 * float(lam_ref.abs().max()))
+        total += float(deps)
+    assert abs(total - float(deps_ref)) <= 1e-9 * abs(float(deps_ref)) + 1e-12
+    # (a) one rank
+    tgt = 0.5 + 0.1 * torch.rand(shape, device="cuda", generator=gen)
+    D1 = torch.tensor(1.3, dtype=torch.float64, device="cuda", requires_grad=True)
+    e1 = torch.tensor(2.5, dtype=torch.float64, device="cuda", requires_grad=True)
+    st = DistributedCahnHilliardIMEX(shape, spacing, 0.1, eps=2.5, D=1.3, device="cuda")
+    x = u.clone().requires_grad_(True)
+    y = st.step_autograd(st.step_autograd(x, D1, e1), D1, e1)
+    ((y - tgt) ** 2).sum().backward()
+    import evoxels_b200 as evo
+    from evoxels_b200.problem_definition import CahnHilliard
+    from evoxels_b200.timesteppers import PseudoSpectralIMEX
+    from evoxels_b200.voxelgrid import VoxelGridTorch
+    vf = evo.VoxelFields(shape, tuple(float(n * h) for n, h in zip(shape, spacing)))
+    vg = VoxelGridTorch(vf.grid_info(), device="cuda")
+    D2 = torch.tensor(1.3, dtype=torch.float64, device="cuda", requires_grad=True)
+    e2 = torch.tensor(2.5, dtype=torch.float64, device="cuda", requires_grad=True)
+    ts = PseudoSpectralIMEX(CahnHilliard(vg, eps=e2, D=D2), 0.1, fft_backend="native")
+    x2 = u[None].clone().requires_grad_(True)
+    y2 = ts.step(0.0, ts.step(0.0, x2))
+    ((y2[0] - tgt) ** 2).sum().backward()
+    assert float((x.grad - x2.grad[0]).norm() / x2.grad.norm()) < 1e-6
+    assert abs(float(D1.grad) - float(D2.grad)) <= 1e-6 * abs(float(D2.grad))
+    assert abs(float(e1.grad) - float(e2.grad)) <= 1e-6 * abs(float(e2.grad))
