@@ -40,45 +40,11 @@
 #include "evx_params.h"
 #include "packed_f32.h"
 #include "tma_ptx.h"
+#include "stencil_tma.h"
 
 namespace evx {
 namespace chtma {
-
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ float sat(float a) { return __saturatef(a); }
-
-__device__ __forceinline__ bool mbar_try(unsigned addr, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-  return ok != 0;
-}
-// slow path of a wait, out of line: bounded (a pipeline bug must end in a trap, not in a hang)
-__device__ __noinline__ void mbar_wait_slow(unsigned addr, unsigned parity) {
-  const long long t0 = clock64();
-  for (unsigned spin = 0;; ++spin) {
-    if (mbar_try(addr, parity)) return;
-    if ((spin & 255u) == 255u && clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-// consumers: the plane has normally landed long ago - one probe, no clock read
-__device__ __forceinline__ void wait_full(unsigned long long* bar, unsigned parity) {
-  const unsigned addr = smem_u32(bar);
-  if (!mbar_try(addr, parity)) mbar_wait_slow(addr, parity);
-}
-// loader: it is normally ahead of the consumers and polls; sleep between probes so that the
-// polling does not take issue slots from the compute warps
-__device__ __forceinline__ void wait_empty(unsigned long long* bar, unsigned parity) {
-  const unsigned addr = smem_u32(bar);
-  const long long t0 = clock64();
-  for (unsigned spin = 0; !mbar_try(addr, parity); ++spin) {
-    __nanosleep(100);
-    if ((spin & 255u) == 255u && clock64() - t0 > 4000000000LL) __trap();
-  }
-}
+using namespace stma;
 
 struct Consts {
   float k2ps, km3ps, kpl;     // g(c) + l0 c = c (kpl + c (km3ps + k2ps c)),  kpl = 18/eps + l0
@@ -157,12 +123,6 @@ __device__ __forceinline__ void ld4sat(float* r, const float* s) {
 __device__ __forceinline__ void st4(float* s, const float* r) {
   *reinterpret_cast<float4*>(s) = make_float4(r[0], r[1], r[2], r[3]);
 }
-
-// tensor maps of one launch: [array: c, halo_lo, halo_hi][box: tile (128 x TY), row pair
-// (128 x 2), column (4 x TY), corner (4 x 1)]
-struct Maps {
-  CUtensorMap m[3][4];
-};
 
 template <int NWI, int NS, bool GHOSTS, bool DEC>
 struct Prog {
@@ -779,67 +739,6 @@ __global__ void __maxnreg__(MAXREG)
   }
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
-// ---- tensor maps ----------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = [] {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      sym = nullptr;
-    return (EncodeTiledFn)sym;
-  }();
-  return fn;
-}
-
-// the four boxes over one [nplanes, ny, nz] fp32 array; encoding is pure host arithmetic, the
-// last few arrays are remembered (a stepper alternates between two or three fields)
-static bool make_maps(CUtensorMap out[4], const float* base, int nplanes, int ny, int nz, int ty) {
-  struct Entry {
-    const float* base = nullptr;
-    int nplanes = 0, ny = 0, nz = 0, ty = 0;
-    CUtensorMap m[4];
-  };
-  constexpr int NE = 8;
-  thread_local Entry cache[NE];
-  thread_local int next = 0;
-  for (int i = 0; i < NE; ++i) {
-    const Entry& e = cache[i];
-    if (e.base == base && e.nplanes == nplanes && e.ny == ny && e.nz == nz && e.ty == ty) {
-      for (int k = 0; k < 4; ++k) out[k] = e.m[k];
-      return true;
-    }
-  }
-  EncodeTiledFn enc = encode_fn();
-  if (!enc) return false;
-  const cuuint64_t dims[3] = {(cuuint64_t)nz, (cuuint64_t)ny, (cuuint64_t)nplanes};
-  const cuuint64_t strides[2] = {(cuuint64_t)nz * sizeof(float), (cuuint64_t)ny * nz * sizeof(float)};
-  const cuuint32_t boxes[4][3] = {{128, (cuuint32_t)ty, 1}, {128, 2, 1}, {4, (cuuint32_t)ty, 1}, {4, 1, 1}};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  Entry e;
-  e.base = base; e.nplanes = nplanes; e.ny = ny; e.nz = nz; e.ty = ty;
-  for (int k = 0; k < 4; ++k) {
-    const CUresult rc = enc(&e.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, boxes[k],
-                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                            k < 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) return false;
-  }
-  cache[next] = e;
-  next = (next + 1) % NE;
-  for (int k = 0; k < 4; ++k) out[k] = e.m[k];
-  return true;
-}
-
 template <int NWI, int NS, bool GHOSTS, int MAXREG, bool DEC = false>
 static int launch(ChParams<float> p, cudaStream_t st) {
   using P = Prog<NWI, NS, GHOSTS, DEC>;
@@ -849,9 +748,9 @@ static int launch(ChParams<float> p, cudaStream_t st) {
   const size_t smem = sizeof(typename P::Smem) + 128;
   if (int e = optin.ensure(kern, smem)) return e;
   Maps maps;
-  if (!make_maps(maps.m[0], p.c, p.nx, p.ny, p.nz, P::TY)) return EVX_ERR_UNSUPPORTED;
-  if (p.halo_lo && !make_maps(maps.m[1], p.halo_lo, 2, p.ny, p.nz, P::TY)) return EVX_ERR_UNSUPPORTED;
-  if (p.halo_hi && !make_maps(maps.m[2], p.halo_hi, 2, p.ny, p.nz, P::TY)) return EVX_ERR_UNSUPPORTED;
+  if (!make_maps(maps.m[0], p.c, p.nx, p.ny, p.nz, P::TY, 2)) return EVX_ERR_UNSUPPORTED;
+  if (p.halo_lo && !make_maps(maps.m[1], p.halo_lo, 2, p.ny, p.nz, P::TY, 2)) return EVX_ERR_UNSUPPORTED;
+  if (p.halo_hi && !make_maps(maps.m[2], p.halo_hi, 2, p.ny, p.nz, P::TY, 2)) return EVX_ERR_UNSUPPORTED;
   if (!p.halo_lo) for (int k = 0; k < 4; ++k) maps.m[1][k] = maps.m[0][k];
   if (!p.halo_hi) for (int k = 0; k < 4; ++k) maps.m[2][k] = maps.m[0][k];
   const int tiles_z = (p.nz + P::TZ - 1) / P::TZ;
