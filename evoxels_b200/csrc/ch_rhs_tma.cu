@@ -765,7 +765,7 @@ static int launch(ChParams<float> p, cudaStream_t st) {
     // prefer a chunk count whose block count is just below a multiple of the resident set
     double best = -1.0;
     int best_c = chunks;
-    for (int c = chunks; c <= 2 * chunks && c <= p.nx; ++c) {
+    for (int c = chunks; (c <= 2 * chunks || c * 8 <= p.nx) && c <= p.nx && c <= 64; ++c) {
       const double waves = (double)(tiles * c) / (double)resident;
       const double eff = waves / (double)(long long)(waves + 0.999999);
       const double over = 1.0 + 4.0 * c / (double)p.nx;      // re-read planes
