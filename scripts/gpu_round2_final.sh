@@ -23,8 +23,9 @@ echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 300 --csv --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 1 --no-cpu --no-extras > $OUT/bench_under_ncu.log 2>&1
 python scripts/summarize_launches.py $OUT/launches.csv | tee $OUT/launches_summary.txt | head -8
 echo "== ncu full capture"
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'ch_rhs_kernel|fft_pass_kernel|fft_pipe_kernel|fft_line_kernel|fft_line_ws_kernel|fft_chain_kernel|ac_tile_kernel|rd_rhs_kernel' -f -o $OUT/prof python scripts/profile_kernels.py 512 > $OUT/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'ch_rhs_kernel|ch_rhs_tma_kernel|fft_pass_kernel|fft_pipe_kernel|fft_line_kernel|fft_line_ws_kernel|fft_chain_kernel|ac_tile_kernel|rd_rhs_kernel' -f -o $OUT/prof python scripts/profile_kernels.py 512 > $OUT/ncu_full.log 2>&1
 tail -2 $OUT/ncu_full.log
 ncu -i $OUT/prof.ncu-rep --page raw --csv > $OUT/prof_raw.csv 2>/dev/null
 python scripts/ncu_summary.py $OUT/prof_raw.csv | tee $OUT/prof_summary.txt
+python scripts/ncu_traffic.py $OUT/prof_raw.csv "profiles/r02_ncu_full_summary_final.txt (ncu --set full --clock-control none, one launch per kernel, scripts/profile_kernels.py 512; scripts/gpu_round2_final.sh)" > /dev/null
 echo "== done"

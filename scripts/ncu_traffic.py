@@ -8,7 +8,7 @@ hdr, units = rows[0], rows[1]
 kn, rd, wr, tm = (hdr.index(x) for x in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum",
                                          "gpu__time_duration.sum"))
 U = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-names = {"ch_rhs_kernel<float, 4, 14, 16, 0, 0, 3>": "ch_rhs_kernel", "fft_chain_kernel<0, 0, 3, 2>": "fft_zy_forward",
+names = {"ch_rhs_tma_kernel<4, 4, 0, 168, 0>": "ch_rhs_kernel", "fft_chain_kernel<0, 0, 3, 2>": "fft_zy_forward",
          "fft_chain_kernel<1, 0, 3, 3>": "fft_yz_inverse+u", "fft_line_ws_kernel<StridedLine<512, 8, 2>, 3>": "fft_x_fwd*filter*inv"}
 out = {"size": 512, "source": sys.argv[2] if len(sys.argv) > 2 else sys.argv[1], "kernels": {}}
 val = lambda r, i: float(r[i].replace(",", "")) * U[units[i]]
