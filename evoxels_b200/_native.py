@@ -40,6 +40,9 @@ _FILTER_ARGS = [_c_void_p, _c_int, _c_int, _c_int, _dptr, _c_double, _c_double, 
                 _c_double, _c_void_p]
 
 FILTER_ETD1 = 0x100      # EVX_FILTER_ETD1: OR into `power` for the exponential-Euler weight
+FILTER_MIRROR_EVEN = 0x200   # EVX_FILTER_MIRROR_EVEN / _ODD: non-periodic x axis, the mirror image of
+FILTER_MIRROR_ODD = 0x400    # every x line is synthesised inside the x pass (un-extended arrays)
+ERR_UNSUPPORTED = -2
 
 SIGNATURES = {
     "evx_version": [],
@@ -119,7 +122,9 @@ def load_library():
 def check(code: int, what: str):
     if code != 0:
         msg = load_library().evx_strerror(code).decode()
-        raise NativeLibraryError(f"{what} failed with code {code}: {msg}")
+        err = NativeLibraryError(f"{what} failed with code {code}: {msg}")
+        err.code = code
+        raise err
 
 
 def launch_count() -> int:

@@ -76,11 +76,13 @@ static void fill_roots_r(std::vector<gcplx<R>>& w, size_t off, int n) {
 
 template <typename R>
 static int generic_tables(evx_imex_plan* p) {
-  const size_t total = (size_t)p->nx + p->ny + p->nz;
+  // W_nx | W_ny | W_nz | W_2nx (x pass of a mirrored, non-periodic x axis)
+  const size_t total = (size_t)p->nx + p->ny + p->nz + 2 * (size_t)p->nx;
   std::vector<gcplx<R>> host(total);
   fill_roots_r<R>(host, 0, p->nx);
   fill_roots_r<R>(host, p->nx, p->ny);
   fill_roots_r<R>(host, (size_t)p->nx + p->ny, p->nz);
+  fill_roots_r<R>(host, (size_t)p->nx + p->ny + p->nz, 2 * p->nx);
   cudaError_t e = cudaMalloc(&p->twiddles, total * sizeof(gcplx<R>));
   if (e != cudaSuccess) return (int)e;
   e = cudaMemcpy(p->twiddles, host.data(), total * sizeof(gcplx<R>), cudaMemcpyHostToDevice);
@@ -104,8 +106,12 @@ int generic_apply(evx_imex_plan* pl, const R* u, const R* r, R* out, void* works
   const gcplx<R>* twx = (const gcplx<R>*)pl->twiddles;
   const gcplx<R>* twy = twx + nx;
   const gcplx<R>* twz = twy + ny;
+  const int mirror = filter_mirror(power);
+  const int nxl = mirror ? 2 * nx : nx;       // points of an x line
+  const gcplx<R>* twx2 = twz + nz;
   LineDesc lx, ly, lz;
-  if (!factor_line(nx, lx) || !factor_line(ny, ly) || !factor_line(nz, lz)) return EVX_ERR_UNSUPPORTED;
+  if (!factor_line(nxl, lx) || !factor_line(ny, ly) || !factor_line(nz, lz)) return EVX_ERR_UNSUPPORTED;
+  if (nxl > 4096) return EVX_ERR_UNSUPPORTED;
   const size_t esz = sizeof(R);
   int rc;
 
@@ -125,10 +131,11 @@ int generic_apply(evx_imex_plan* pl, const R* u, const R* r, R* out, void* works
 
   // x forward * weight * x inverse: columns (y, kz)
   GenericParams<R> x = p;
-  x.mode = GEN_XMID; x.line = lx; x.tw = twx; x.W = lines_per_block(nx, esz);
+  x.mode = GEN_XMID; x.line = lx; x.tw = mirror ? twx2 : twx; x.W = lines_per_block(nxl, esz);
   x.line_stride = (long long)ny * P; x.group_stride = P; x.ncols_total = (long long)ny * P;
-  const int n[3] = {nx, ny, nz};
-  x.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nx * ny * nz));
+  x.mirror = mirror;
+  const int n[3] = {nxl, ny, nz};
+  x.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)nxl * ny * nz));
   if ((rc = launch_generic<R>(x, (x.ncols_total + x.W - 1) / x.W, st))) return rc;
 
   // y inverse

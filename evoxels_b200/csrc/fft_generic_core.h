@@ -99,6 +99,9 @@ struct GenericParams {
   long long line_stride, group_stride, ncols_total;
   int ncols_valid;          // kz < ncols_valid is data, the rest of a row is padding
   FilterParams filt;        // GEN_XMID: n0 = this axis, n1 = the group axis, n2 = nz
+  // GEN_XMID on a non-periodic axis: the array holds N/2 rows, row i >= N/2 of the line is
+  // mirror * row (N-1-i) and is not stored (+1 even, -1 odd, 0 periodic)
+  int mirror;
 };
 
 template <typename R>
@@ -279,6 +282,16 @@ struct GenericProgram {
     return p.spec + (g * p.group_stride + kz);
   }
 
+  // element i of a strided line (mirror mode: the upper half is the reversed lower half)
+  EVX_HD static C line_element(const P& p, const C* src, int i) {
+    if (!src) return C{R(0), R(0)};
+    if (p.mirror && 2 * i >= p.line.N) {
+      const C v = src[(long long)(p.line.N - 1 - i) * p.line_stride];
+      return p.mirror > 0 ? v : C{-v.x, -v.y};
+    }
+    return src[(long long)i * p.line_stride];
+  }
+
   EVX_HD static void load(const P& p, C* b, long long block, int tid, int nthreads) {
     const int N = p.line.N, W = p.W;
     if (p.mode == GEN_Z_FWD || p.mode == GEN_Z_INV) {
@@ -311,14 +324,12 @@ struct GenericProgram {
     if (nthreads % W == 0) {            // the launch configuration: one column per thread
       const int c = tid % W;
       const C* src = column(p, block, c);
-      for (int i = tid / W; i < N; i += nthreads / W)
-        b[i * W + c] = src ? src[(long long)i * p.line_stride] : C{R(0), R(0)};
+      for (int i = tid / W; i < N; i += nthreads / W) b[i * W + c] = line_element(p, src, i);
       return;
     }
     for (int item = tid; item < N * W; item += nthreads) {
       const int i = item / W, c = item - i * W;       // columns fastest
-      const C* src = column(p, block, c);
-      b[i * W + c] = src ? src[(long long)i * p.line_stride] : C{R(0), R(0)};
+      b[i * W + c] = line_element(p, column(p, block, c), i);
     }
   }
 
@@ -354,12 +365,13 @@ struct GenericProgram {
           p.real_out[rb * p.nz + i] = p.real_in ? p.real_in[rb * p.nz + i] + z.y : z.y;
       }
     } else if (nthreads % W == 0) {
-      const int c = tid % W;
+      const int c = tid % W, nst = p.mirror ? N / 2 : N;
       C* dst = column(p, block, c);
       if (dst)
-        for (int i = tid / W; i < N; i += nthreads / W) dst[(long long)i * p.line_stride] = b[i * W + c];
+        for (int i = tid / W; i < nst; i += nthreads / W) dst[(long long)i * p.line_stride] = b[i * W + c];
     } else {
-      for (int item = tid; item < N * W; item += nthreads) {
+      const int nst = p.mirror ? N / 2 : N;
+      for (int item = tid; item < nst * W; item += nthreads) {
         const int i = item / W, c = item - i * W;
         C* dst = column(p, block, c);
         if (dst) dst[(long long)i * p.line_stride] = b[i * W + c];

@@ -154,7 +154,7 @@ static int launch_strided(int L, StridedParams p, cudaStream_t st) {
 #define EVX_CASE(N)                                                                   \
   case N: {                                                                           \
     constexpr int KZ = StridedCfg<N, MODE>::KZ;                                       \
-    if (N >= 64 && use_pipeline()) return launch_pipe<StridedPipe<N, KZ, MODE>>(p, st); \
+    if (N >= 64 && use_pipeline() && !p.mirror) return launch_pipe<StridedPipe<N, KZ, MODE>>(p, st); \
     return launch_pass<StridedPass<N, KZ, MODE>, StridedParams>(                      \
         p, (p.ncols_total + KZ - 1) / KZ, st);                                        \
   }
@@ -202,13 +202,14 @@ int native_plan_init(evx_imex_plan* p) {
   // (+ a debug area for per-block cycle counters at the very end, EVX_FFT_CHAIN_STATS)
   p->work_bytes = chain_supported(p->nx, p->ny, p->nz)
                       ? (((size_t)p->nx * sizeof(unsigned) + 255) & ~(size_t)255) + kChainStatsBytes : 0;
-  // tables: W_nx | W_ny | W_M | W_nz[0..M]
-  const size_t total = (size_t)p->nx + p->ny + M + (M + 1);
+  // tables: W_nx | W_ny | W_M | W_nz[0..M] | W_2nx (x pass of a mirrored, non-periodic x axis)
+  const size_t total = (size_t)p->nx + p->ny + M + (M + 1) + 2 * (size_t)p->nx;
   std::vector<cf> host(total);
   fill_roots(host, 0, p->nx, p->nx);
   fill_roots(host, p->nx, p->ny, p->ny);
   fill_roots(host, (size_t)p->nx + p->ny, M, M);
   fill_roots(host, (size_t)p->nx + p->ny + M, p->nz, M + 1);
+  fill_roots(host, (size_t)p->nx + p->ny + M + (M + 1), 2 * p->nx, 2 * p->nx);
   cudaError_t e = cudaMalloc(&p->twiddles, total * sizeof(cf));
   if (e != cudaSuccess) return (int)e;
   e = cudaMemcpy(p->twiddles, host.data(), total * sizeof(cf), cudaMemcpyHostToDevice);
@@ -226,7 +227,7 @@ struct NativeView {
   int nx, ny, nz, M, P;
   cf* spec;
   void* flags;             // work area behind the spectrum (null if the plan has none)
-  const cf *twx, *twy, *twz, *twr;
+  const cf *twx, *twy, *twz, *twr, *twx2;
 };
 
 static NativeView view_of(const evx_imex_plan* p, void* workspace) {
@@ -238,6 +239,7 @@ static NativeView view_of(const evx_imex_plan* p, void* workspace) {
   v.twy = v.twx + p->nx;
   v.twz = v.twy + p->ny;
   v.twr = v.twz + v.M;
+  v.twx2 = v.twr + (v.M + 1);
   return v;
 }
 
@@ -307,6 +309,19 @@ static int strided_pass(evx_imex_plan* p, const NativeView& v, int which, const 
                         double coef, int power, cudaStream_t st) {
   const bool along_x = which == 2;
   const int L = along_x ? v.nx : v.ny;
+  const int mirror = along_x ? filter_mirror(power) : 0;
+  if (mirror) {
+    // non-periodic x: lines of 2 nx points, the upper half synthesised from the lower one
+    if (2 * v.nx > 2048) return EVX_ERR_UNSUPPORTED;
+    StridedParams sp = y_params(v);
+    sp.tw = v.twx2;
+    sp.src = sp.dst = plain_io((long long)v.ny * v.P, v.P, 2 * v.nx);
+    sp.ncols_total = (long long)v.ny * v.P;
+    sp.mirror = mirror;
+    const int n[3] = {2 * v.nx, v.ny, v.nz};
+    sp.filt = make_filter(n, h, dt, coef, power, 1.0 / (2.0 * v.nx * v.ny * v.nz));
+    return launch_xmid(2 * v.nx, sp, st);
+  }
   if (use_line_pass(L)) {
     if (int rc = line_tmaps(p, v)) return rc;
     LineParams lp;

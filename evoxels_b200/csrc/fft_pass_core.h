@@ -70,6 +70,9 @@ struct StridedParams {
   long long dst_peer_base;
   int use_peers;
   int max_ctas;            // > 0: cap of the persistent grid (NVLink-bound launches leave SMs free)
+  // XMID on a non-periodic axis: the array holds L/2 rows; row i >= L/2 of the transformed line
+  // is mirror * row (L-1-i) on load and is not stored (mirror = +1 even, -1 odd, 0 periodic)
+  int mirror = 0;
 };
 
 inline StridedIO plain_io(long long line_stride, long long plane_stride, int L) {
@@ -151,6 +154,7 @@ struct StridedPass {
     bool valid;
     long long grp;
     long long src_base, dst_base;
+    long long src_base_m;  // mirror mode: offset of row T-1-t (rows L-1-(t+eT) = (7-e)T + T-1-t)
     int kz, kother;
   };
 
@@ -172,6 +176,7 @@ struct StridedPass {
     r.valid = c < p.ncols_total && r.kz < p.ncols_valid;
     r.src_base = strided_base(p.src, grp, r.kz, r.t);
     r.dst_base = strided_base(p.dst, grp, r.kz, r.t);
+    r.src_base_m = p.mirror ? strided_base(p.src, grp, r.kz, T - 1 - r.t) : 0;
   }
 
   template <int DIR>
@@ -187,12 +192,29 @@ struct StridedPass {
   }
   EVX_HD static void load_global(Regs& r, const StridedParams& p) {
     const cf* base = p.in + r.src_base;
+    if (p.mirror) {          // lower half from memory, upper half = +- the lower half reversed
+      const cf* mbase = p.in + r.src_base_m;
+      const float sg = (float)p.mirror;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        r.v[e] = r.valid ? base[p.src_step[e]] : cf{0.f, 0.f};
+        const cf m = r.valid ? mbase[p.src_step[3 - e]] : cf{0.f, 0.f};
+        r.v[4 + e] = cf{sg * m.x, sg * m.y};
+      }
+      return;
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e)
       r.v[e] = r.valid ? base[p.src_step[e]] : cf{0.f, 0.f};
   }
   EVX_HD static void store_global(Regs& r, const StridedParams& p) {
     if (!r.valid) return;
+    if (p.mirror) {          // the mirror image of the result is implied, only rows < L/2 exist
+      cf* base = p.out + r.dst_base;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) base[p.dst_step[e]] = r.v[e];
+      return;
+    }
     if (p.use_peers) {
       const long long within = p.dst_peer_base + r.grp * p.dst.plane_stride + r.kz;
 #pragma unroll

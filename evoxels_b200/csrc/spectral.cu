@@ -215,6 +215,7 @@ int imex_apply_impl(evx_imex_plan* p, const T* u, const T* r, T* out, void* work
                         power, st);
   if (p->backend == EVX_FFT_NATIVE_MIXED)
     return generic_apply<T>(p, u, r, out, workspace, h, dt, coef, power, st);
+  if (filter_mirror(power)) return EVX_ERR_UNSUPPORTED;   // the caller extends the field itself
   return apply_cufft<T>(p, u, r, out, workspace, h, dt, coef, power, st);
 }
 

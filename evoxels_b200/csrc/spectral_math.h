@@ -24,10 +24,20 @@ struct FilterParams {
 
 // The `power` argument of the C ABI carries the filter kind in bit 8 (EVX_FILTER_ETD1 in
 // include/evoxels_b200.h): weight = dt / (1 + dt c |k|^2p)  or  dt * phi1(-dt c |k|^2p).
-enum : int { FILTER_IMEX = 0, FILTER_ETD1 = 1, FILTER_KIND_BIT = 0x100 };
+// Bits 9 / 10 (EVX_FILTER_MIRROR_EVEN / _ODD): the x axis is not periodic - the x pass
+// transforms every line together with its even (zero-flux) or odd (Dirichlet) mirror image,
+// synthesised on the fly, as ONE line of 2 nx points (reference boundary_conditions.py:65-71
+// concatenates the flipped field in memory before rfftn).
+enum : int { FILTER_IMEX = 0, FILTER_ETD1 = 1, FILTER_KIND_BIT = 0x100, FILTER_MIRROR_EVEN = 0x200,
+             FILTER_MIRROR_ODD = 0x400, FILTER_FLAG_BITS = 0x700 };
 inline bool valid_filter_spec(int power) {
-  const int pw = power & ~FILTER_KIND_BIT;
+  const int pw = power & ~FILTER_FLAG_BITS;
+  if ((power & FILTER_MIRROR_EVEN) && (power & FILTER_MIRROR_ODD)) return false;
   return pw == 1 || pw == 2;
+}
+// +1 even mirror, -1 odd mirror, 0 periodic
+inline int filter_mirror(int power) {
+  return (power & FILTER_MIRROR_EVEN) ? 1 : ((power & FILTER_MIRROR_ODD) ? -1 : 0);
 }
 
 #if defined(__CUDA_ARCH__)

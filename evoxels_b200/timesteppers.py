@@ -168,6 +168,7 @@ class PseudoSpectralIMEX(TimeStepper):
     def __post_init__(self):
         self.problem.verify_fft_bc_config()
         self.pad = self.problem.pad_fft_bc
+        self._no_native_mirror = False
         self._plans = {}
         self._prefac = None
 
@@ -227,7 +228,26 @@ class PseudoSpectralIMEX(TimeStepper):
         # that defines spectral_form also defines the symbol (a subclass overriding one of the
         # two falls back to the stored-array path, which reads problem.fourier_symbol)
         form = prob.spectral_form() if _symbol_matches_form(prob) else None
-        r = self.pad(prob.rhs(t, u)).contiguous()
+        rhs = prob.rhs(t, u)
+        # non-periodic x with the stock mirror padding (boundary_conditions.py:65-71): the native
+        # x pass synthesises the mirror image of every line in shared memory, so the transforms
+        # run on the un-extended field - no concatenated 2 Nx array, half the y / z work
+        mirror = {"neumann": _native.FILTER_MIRROR_EVEN, "dirichlet": _native.FILTER_MIRROR_ODD}.get(
+            prob.bc_type[0], 0)
+        if (form is not None and mirror and not getattr(self, "_no_native_mirror", False)
+                and _defining_class(prob, "pad_fft_bc") is SemiLinearODE):
+            coef, power = form
+            plan = self._plan(u.shape[1:], u.dtype, u.device)
+            r = rhs.contiguous()
+            try:
+                for ch in range(u.shape[0]):
+                    plan.apply(u[ch], r[ch], out[ch], spacing, self.dt, coef, power | kind_flag | mirror)
+                return out
+            except _native.NativeLibraryError as exc:
+                if getattr(exc, "code", None) != _native.ERR_UNSUPPORTED:
+                    raise
+                self._no_native_mirror = True      # cuFFT back end / extents beyond the native x pass
+        r = self.pad(rhs).contiguous()
         if form is None:
             # user-defined symbol: stored weight array, cuFFT through torch
             upd = torch.fft.irfftn(stored_weight() * torch.fft.rfftn(r, s=r.shape), s=r.shape)

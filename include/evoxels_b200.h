@@ -158,6 +158,14 @@ int evx_imex_plan_workspace_bytes(const evx_imex_plan* plan, size_t* bytes);
  * i.e. ExponentialEuler.step / phi1 / phiPade (evoxels/timesteppers.py:137-202).  The flag
  * is accepted wherever a `power` argument appears. */
 #define EVX_FILTER_ETD1 0x100
+/* Non-periodic x axis (zero-flux / Dirichlet; reference boundary_conditions.py:61-71 and
+ * voxelgrid.py:116-124 mirror the field to 2 nx planes before rfftn): OR one of these into `power`
+ * and pass the UN-extended [nx,ny,nz] arrays.  The y and z transforms then run on nx planes and the
+ * x pass transforms each line together with its even / odd mirror image as one 2 nx-point line in
+ * shared memory - the 2 nx array never exists in device memory.  Native back ends only (the
+ * cuFFT back end answers EVX_ERR_UNSUPPORTED and the caller extends the field itself). */
+#define EVX_FILTER_MIRROR_EVEN 0x200
+#define EVX_FILTER_MIRROR_ODD 0x400
 int evx_imex_apply_f32(evx_imex_plan* plan, const float* u, const float* r, float* out,
                        void* workspace, const double* h, double dt, double coef, int power,
                        void* stream);

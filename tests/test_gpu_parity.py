@@ -710,3 +710,39 @@ def test_ch_rhs_warp_specialised_form_with_x_halos(cuda_device, monkeypatch, bc)
         _native.ch_rhs(sl, out, (1.0, 0.5, 2.0), 3.0, 1.0, bc, halo_lo=lo, halo_hi=hi)
         torch.cuda.synchronize()
         assert rel_l2(out.cpu().numpy(), ref[a:b].cpu().numpy()) <= 5e-7
+
+
+@pytest.mark.parametrize("shape,dtype", [((64, 32, 64), torch.float32), ((16, 8, 16), torch.float32),
+                                         ((512, 16, 32), torch.float32), ((1024, 8, 16), torch.float32),
+                                         ((50, 12, 14), torch.float32), ((9, 7, 5), torch.float32),
+                                         ((30, 10, 12), torch.float64)])
+@pytest.mark.parametrize("flag", ["even", "odd"])
+def test_mirrored_x_pass_equals_the_extended_transform(cuda_device, shape, dtype, flag):
+    """Non-periodic x (reference boundary_conditions.py:65-71: rfftn of the field concatenated with
+    its flipped / negated copy): the x pass that synthesises the mirror image of every line in
+    shared memory (EVX_FILTER_MIRROR_EVEN / _ODD on the un-extended arrays) against the same plan
+    applied to the explicitly extended 2 Nx field - radix-8 passes (powers of two, up to 2 Nx =
+    2048), mixed-radix passes (incl. odd extents and float64), IMEX and exponential-Euler weight."""
+    nx, ny, nz = shape
+    gen = torch.Generator(device="cuda").manual_seed(12)
+    u = torch.rand(shape, device="cuda", generator=gen, dtype=dtype)
+    r = torch.randn(shape, device="cuda", generator=gen, dtype=dtype)
+    sign = 1.0 if flag == "even" else -1.0
+    mflag = _native.FILTER_MIRROR_EVEN if flag == "even" else _native.FILTER_MIRROR_ODD
+    sp = (1.0, 0.5, 2.0)
+    plan = _native.ImexPlan(shape, dtype, "cuda", _native.FFT_AUTO)
+    ext_shape = (2 * nx, ny, nz)
+    plan2 = _native.ImexPlan(ext_shape, dtype, "cuda", _native.FFT_AUTO)
+    if plan.backend_name == "cufft":
+        pytest.skip("extents beyond the native passes")
+    r_ext = torch.cat([r, sign * torch.flip(r, [0])], 0).contiguous()
+    for power in (2, 1 | _native.FILTER_ETD1):
+        got = torch.full_like(u, float("nan"))
+        plan.apply(u, r, got, sp, 0.1, 1.5, power | mflag)
+        upd = torch.empty_like(r_ext)
+        plan2.apply(None, r_ext, upd, sp, 0.1, 1.5, power)
+        ref = u + upd[:nx]
+        torch.cuda.synchronize()
+        tol = 1e-12 if dtype == torch.float64 else 2e-6
+        scale = float(upd.abs().max())
+        assert float((got - ref).abs().max()) <= tol * max(scale, 1.0), (power, float((got - ref).abs().max()), scale)
