@@ -12,9 +12,13 @@ dist.init_process_group("nccl", device_id=dev)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 shape = {1: (n, n, n), 2: (2 * n, n, n), 4: (2 * n, 2 * n, n), 8: (2 * n, 2 * n, 2 * n)}[world]
 res = {}
+STEPS = 20 if n <= 512 else 8
 u0 = 0.5 + 0.1 * torch.rand(Slab(shape, world, rank).local_shape, device=dev)
 ref = None
-for chunks, mid, last in ((4, 4, 0), (4, 4, 24), (2, 4, 24), (2, 2, 24), (4, 2, 24), (4, 4, 48), (3, 3, 24), (8, 4, 24)):
+CFGS = ((4, 4, 0), (4, 4, 24), (2, 4, 24), (2, 2, 24), (4, 2, 24), (4, 4, 48), (3, 3, 24), (8, 4, 24))
+if len(sys.argv) > 2:
+    CFGS = tuple(tuple(int(v) for v in c.split(",")) for c in sys.argv[2:])
+for chunks, mid, last in CFGS:
     st = DistributedCahnHilliardIMEX(shape, (1.0, 1.0, 1.0), 0.1, device=dev, transport="ce",
                                      overlap_chunks=chunks, mid_chunks=mid)
     st.ops.last_chunk_ctas = last
@@ -28,10 +32,10 @@ for chunks, mid, last in ((4, 4, 0), (4, 4, 24), (2, 4, 24), (2, 2, 24), (4, 2, 
     torch.cuda.synchronize(); dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(20):
+    for _ in range(STEPS):
         u = st.step(u)
     b.record(); torch.cuda.synchronize()
-    t = torch.tensor([a.elapsed_time(b) / 20], device=dev)
+    t = torch.tensor([a.elapsed_time(b) / STEPS], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     res[f"fwd{chunks}_mid{mid}_last{last}"] = (round(float(t), 4), same)
     del st
