@@ -242,6 +242,111 @@ __global__ void __launch_bounds__(line_ws_threads(Prog::NTHREADS, NBUF), 1)
   }
 }
 
+
+// ---- 1024-point lines: warp-specialised kernel over 4-D tensor maps -----------------------
+// Same roles as fft_line_ws_kernel (loader thread, one retirer per tile buffer, compute warps in
+// two-line groups), for the four-stage program StridedLine4: 512 compute threads, every group
+// runs two line pairs per tile.  The tensor maps are 4-D - (kz, i_lo, row, i_hi) with line index
+// i = i_hi * box_rows + i_lo - so one code path serves lines along y, lines along x, and the
+// block layout of the x-slab transposes; loads go through map_in, stores through map_out, except
+// the boxes [self_lo, self_hi) which go through map_self (the block that stays on this GPU lands
+// in the next stage's receive buffer).
+template <class Prog, int NBUF>
+__global__ void __launch_bounds__(line_ws_threads(Prog::NTHREADS, NBUF), 1)
+    fft_line4_ws_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out,
+                        const __grid_constant__ CUtensorMap map_self, const LineParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* tiles = sm;
+  cf* xall = reinterpret_cast<cf*>(sm + NBUF * Prog::TILE_BYTES);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + NBUF * Prog::TILE_BYTES + Prog::X_BYTES);
+  unsigned long long* done = full + NBUF;
+  unsigned long long* empty = full + 2 * NBUF;
+  const int tid = threadIdx.x;
+  const int tpr = p.tiles_per_row;
+  const long long ntiles = p.ntiles;
+  const int nblk = gridDim.x;
+  const int nbox = Prog::LEN / p.box_rows;
+  const int box_bytes = p.box_rows * Prog::ROWB;
+
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&full[b], 1);
+      mbar_init(&done[b], Prog::NTHREADS);
+      mbar_init(&empty[b], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
+
+  if (tid == Prog::NTHREADS) {
+    // ------------------------------------ loader ------------------------------------------
+    int n = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += nblk, ++n) {
+      const int buf = n % NBUF;
+      const int row = p.row0 + (int)(tile / tpr), kz0 = (int)(tile % tpr) * Prog::COLS;
+      if (n >= NBUF) {
+        // the buffer is still in use: pull the tile into L2 while waiting for it
+        if (p.l2_ahead)
+          for (int h = 0; h < nbox; ++h) tma_prefetch_4d(&map_in, kz0, 0, row, h);
+        mbar_wait(&empty[buf], (unsigned)(n / NBUF - 1) & 1u);
+      }
+      unsigned char* dst = tiles + buf * Prog::TILE_BYTES;
+      mbar_expect_tx(&full[buf], Prog::TILE_BYTES);
+      for (int h = 0; h < nbox; ++h) tma_load_4d(dst + h * box_bytes, &map_in, &full[buf], kz0, 0, row, h);
+    }
+    return;
+  }
+  if (tid > Prog::NTHREADS && (tid & 31) == 0) {
+    // ------------------------------ retirer of buffer `me` ---------------------------------
+    const int me = (tid - Prog::NTHREADS - 32) >> 5;
+    int n = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += nblk, ++n) {
+      if (n % NBUF != me) continue;
+      mbar_wait(&done[me], (unsigned)(n / NBUF) & 1u);
+      const int row = p.row0 + (int)(tile / tpr), kz0 = (int)(tile % tpr) * Prog::COLS;
+      const unsigned char* src = tiles + me * Prog::TILE_BYTES;
+      for (int h = 0; h < nbox; ++h)
+        tma_store_4d(h >= p.self_lo && h < p.self_hi ? &map_self : &map_out, src + h * box_bytes, kz0, 0, row, h);
+      tma_store_commit();
+      tma_store_wait_read();
+      mbar_arrive_cta(&empty[me]);
+    }
+    tma_store_wait_all();
+    return;
+  }
+  if (tid >= Prog::NTHREADS) return;
+
+  // ------------------------------------ compute warps --------------------------------------
+  typename Prog::Regs r;
+  Prog::init(r, tid);
+  cf* xg = xall + r.g * 2 * Prog::XG;
+  typename Prog::Roots w;
+  Prog::load_roots(w, r.t, p.tw);
+  int row = blockIdx.x / tpr, tcol = blockIdx.x - row * tpr;
+  const int step_row = nblk / tpr, step_col = nblk - step_row * tpr;
+  int n = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += nblk, ++n) {
+    const int buf = n % NBUF;
+    unsigned char* tb = tiles + buf * Prog::TILE_BYTES;
+    Prog::set_tile(r, p.row0 + p.kother0 + row, tcol * Prog::COLS);
+    mbar_wait(&full[buf], (unsigned)(n / NBUF) & 1u);
+#pragma unroll 1
+    for (int pass = 0; pass < Prog::NPASS; ++pass) {
+#pragma unroll
+      for (int k = 0; k < Prog::NPHASES; ++k) {
+        if (k) group_sync(1 + r.g, Prog::GT);
+        Prog::phase(pass, k, r, tb, xg, p, w);
+      }
+    }
+    fence_proxy_async();                        // my tile writes -> visible to the TMA store
+    mbar_arrive_cta(&done[buf]);
+    row += step_row; tcol += step_col;
+    if (tcol >= tpr) { tcol -= tpr; ++row; }
+  }
+}
+
 // ---- host ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -277,6 +382,57 @@ int line_make_tmap(void* out, void* spec, int nx, int ny, int P, int ncols_valid
                           kz == 8 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return rc == CUDA_SUCCESS ? EVX_OK : EVX_ERR_UNSUPPORTED;
+}
+
+static int line_sms();
+
+// 4-D tensor map (kz, i_lo, row, i_hi) over 8-byte elements; strides in elements.  Line index
+// i = i_hi * box_rows + i_lo; the box is [box_rows x 8 columns] of one row.
+int line_make_tmap4(void* out, void* base, int ncols_valid, int box_rows, long long lo_stride, int nrows,
+                    long long row_stride, int nhi, long long hi_stride) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return EVX_ERR_UNSUPPORTED;
+  if (box_rows < 1 || box_rows > 256 || nrows < 1 || nhi < 1) return EVX_ERR_ARG;
+  const cuuint64_t dims[4] = {(cuuint64_t)ncols_valid, (cuuint64_t)box_rows, (cuuint64_t)nrows, (cuuint64_t)nhi};
+  const cuuint64_t strides[3] = {(cuuint64_t)lo_stride * sizeof(cf), (cuuint64_t)row_stride * sizeof(cf),
+                                 (cuuint64_t)(nhi > 1 ? hi_stride : lo_stride * box_rows) * sizeof(cf)};
+  const cuuint32_t box[4] = {8, (cuuint32_t)box_rows, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult rc = enc((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, base, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? EVX_OK : EVX_ERR_UNSUPPORTED;
+}
+
+template <int MODE>
+static int launch_line4_t(LineParams p, const void* map_in, const void* map_out, const void* map_self,
+                          cudaStream_t st) {
+  using Prog = StridedLine4<1024, 8, MODE>;
+  constexpr int NBUF = 2;
+  p.tiles_per_row = (p.ncols_valid + 7) / 8;
+  p.ntiles = (long long)p.nrows * p.tiles_per_row;
+  if (p.ntiles < 1 || p.box_rows < 1 || 1024 % p.box_rows) return EVX_ERR_ARG;
+  constexpr size_t smem = 1024 + (size_t)NBUF * Prog::TILE_BYTES + Prog::X_BYTES + 128;
+  auto kern = fft_line4_ws_kernel<Prog, NBUF>;
+  static SmemOptIn optin;
+  if (int rc = optin.ensure(kern, smem)) return rc;
+  const long long resident = line_sms();
+  const unsigned grid = (unsigned)(p.ntiles < resident ? p.ntiles : resident);
+  kern<<<grid, line_ws_threads(Prog::NTHREADS, NBUF), smem, st>>>(
+      *(const CUtensorMap*)map_in, *(const CUtensorMap*)map_out, *(const CUtensorMap*)(map_self ? map_self : map_out), p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int line4_pass_launch(int mode, const LineParams& p, const void* map_in, const void* map_out,
+                      const void* map_self, cudaStream_t st) {
+  switch (mode) {
+    case PASS_FWD: return launch_line4_t<PASS_FWD>(p, map_in, map_out, map_self, st);
+    case PASS_INV: return launch_line4_t<PASS_INV>(p, map_in, map_out, map_self, st);
+    case PASS_XMID: return launch_line4_t<PASS_XMID>(p, map_in, map_out, map_self, st);
+    case PASS_XMID_ETD1: return launch_line4_t<PASS_XMID_ETD1>(p, map_in, map_out, map_self, st);
+    default: return EVX_ERR_ARG;
+  }
 }
 
 static int line_sms() {

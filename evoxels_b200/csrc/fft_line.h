@@ -15,4 +15,15 @@ int line_make_tmap(void* out, void* spec, int nx, int ny, int P, int ncols_valid
 // mode: PASS_FWD / PASS_INV / PASS_XMID / PASS_XMID_ETD1 of fft_pass_core.h
 int line_pass_launch(int mode, int kz, const LineParams& p, const void* tmap, cudaStream_t st);
 
+
+// ---- 1024-point lines (StridedLine4, fft_line4_ws_kernel) -------------------------------------
+// 4-D tensor map (kz, i_lo, row, i_hi), strides in complex elements: line index i = i_hi *
+// box_rows + i_lo, box = [box_rows][8 columns] of one row (box_rows <= 256, divides 1024)
+int line_make_tmap4(void* out, void* base, int ncols_valid, int box_rows, long long lo_stride, int nrows,
+                    long long row_stride, int nhi, long long hi_stride);
+// p: tw, ncols_valid, row0, nrows, kother0, box_rows, self_lo / self_hi, l2_ahead, filt; loads through
+// map_in, stores through map_out (boxes [self_lo, self_hi): map_self, may be null if the range is empty)
+int line4_pass_launch(int mode, const LineParams& p, const void* map_in, const void* map_out,
+                      const void* map_self, cudaStream_t st);
+
 }  // namespace evx

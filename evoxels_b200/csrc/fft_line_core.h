@@ -40,6 +40,11 @@ struct LineParams {
   int along_x;              // 0: lines run along y (tile row index = x), 1: along x (row index = y)
   int l2_ahead;             // tiles prefetched into L2 ahead of the shared-memory loads (0 = none)
   FilterParams filt;        // XMID only; n0 = nx
+  // 1024-point form (StridedLine4, 4-D tensor maps: kz, line index low part, row, line index
+  // high part): first tile row / number of tile rows of this launch, global index of tile row 0
+  // along the other strided axis (x-slab y-pencils), rows per TMA box, and the range of boxes
+  // whose STORE goes through the second output map (the block that stays on this GPU)
+  int row0 = 0, nrows = 0, kother0 = 0, box_rows = 256, self_lo = 0, self_hi = 0;
 };
 
 template <int L, int KZ, int MODE>
@@ -205,6 +210,165 @@ struct StridedLine {
   // ---- what the tensor copies do, restated for the host replay (tests/emu) ---------------
   // element (kz, y, x) of the spectrum; tile (row, kz0): rows run along y (along_x = 0, x = row)
   // or along x (along_x = 1, y = row).  Out-of-range columns read as zero and are not written.
+  EVX_HD static long long spec_index(const LineParams& p, int row, int kz, int i) {
+    return p.along_x ? ((long long)i * p.ny + row) * p.P + kz : ((long long)row * p.ny + i) * p.P + kz;
+  }
+  static void host_tile_load(const LineParams& p, int row, int kz0, unsigned char* tile) {
+    for (int i = 0; i < L; ++i)
+      for (int c = 0; c < KZ; ++c) {
+        const int kz = kz0 + c;
+        *tile_at(tile, tile_off(i, c)) = kz < p.ncols_valid ? p.spec[spec_index(p, row, kz, i)] : cf{0.f, 0.f};
+      }
+  }
+  static void host_tile_store(const LineParams& p, int row, int kz0, unsigned char* tile) {
+    for (int i = 0; i < L; ++i)
+      for (int c = 0; c < KZ; ++c) {
+        const int kz = kz0 + c;
+        if (kz < p.ncols_valid) p.spec[spec_index(p, row, kz, i)] = *tile_at(tile, tile_off(i, c));
+      }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// 1024-point lines: four stages (radix 2, 8, 8, 8 - the stages, roots and thread -> butterfly
+// assignment of StridedPass<1024>, hence the same bits), T = 128 threads per line.  A tile is
+// [1024 rows][8 columns] (64-byte rows, 64 KB); 1024 compute threads would leave no room for the
+// loader / retirer warps of the warp-specialised kernel, so a block has 512 compute threads = two
+// groups of 256 (two neighbouring lines each, own named barrier) and every group transforms TWO
+// line pairs of a tile one after the other (columns 2g, 2g+1, then 4+2g, 4+2g+1: the same tile
+// byte offsets with bit 5 flipped).  The tile image is touched in natural order only (first read,
+// last write: conflict-free under the 64-byte TMA swizzle); the three (XMID: six) exchanges
+// alternate between two padded buffers of the group, one barrier each.  Phase k reads the buffer
+// phase k-1 wrote and writes the other one, so the only hazard left - the first write of the next
+// line pair - is covered by starting that pair on the buffer the last phase did NOT read (4
+// phases: the pairs alternate; 7 phases: always buffer 0).
+// ---------------------------------------------------------------------------------------------
+template <int L, int KZ, int MODE>
+struct StridedLine4 {
+  static_assert(L == 1024 && KZ == 8, "four-stage TMA-tiled pass: 1024-point lines, 64-byte tile rows");
+  static constexpr int LEN = L;
+  static constexpr int COLS = KZ;
+  static constexpr int T = L / 8;
+  static constexpr int G = 2;
+  static constexpr int GT = T * G;
+  static constexpr int NPASS = 2;              // line pairs per group and tile
+  static constexpr int NG = KZ / (G * NPASS);
+  static constexpr int NTHREADS = GT * NG;
+  static constexpr int S = 4;
+  static constexpr bool XMID = pass_is_xmid(MODE);
+  static constexpr int NPHASES = XMID ? 2 * S - 1 : S;
+  static constexpr int ROWB = KZ * (int)sizeof(cf);
+  static constexpr int TILE_BYTES = L * ROWB;
+  static constexpr int LP = smem_padded_len(L);
+  static constexpr int XG = LP * G;            // cf elements of ONE exchange buffer of a group
+  static constexpr int X_BYTES = NG * 2 * XG * (int)sizeof(cf);
+
+  struct Roots { cf w[3][3]; };                // roots of stages 1, 2, 3 of this thread
+  struct Regs {
+    cf v[8];
+    int t, c2, g, col;       // position in the line, line of the pair, group, column of pair 0
+    int tb;                  // byte offset of tile element (row t, col)
+    int xn, xs[3];           // cf index in X: natural order base / output base of stages 0, 1, 2
+    int kz, kother;          // XMID: global column of pair 0 and index along the other strided axis
+  };
+
+  EVX_HD static int swz(int r) { return ((r >> 1) & 3) << 4; }
+  EVX_HD static int tile_off(int r, int c) { return r * ROWB + ((c * (int)sizeof(cf)) ^ swz(r)); }
+
+  EVX_HD static void init(Regs& r, int tid) {
+    r.g = tid / GT;
+    const int tg = tid - r.g * GT;
+    r.c2 = tg % G;
+    r.t = tg / G;
+    r.col = r.g * G + r.c2;
+    r.tb = tile_off(r.t, r.col);
+    r.xn = smem_pad(r.t) * G + r.c2;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) r.xs[s] = smem_pad(stage_out_base<L>(s, r.t)) * G + r.c2;
+  }
+  EVX_HD static void load_roots(Roots& w, int t, const cf* tw) {
+#pragma unroll
+    for (int s = 1; s < S; ++s) stage_twiddles<L>(s, t, tw, w.w[s - 1]);
+  }
+  EVX_HD static void set_tile(Regs& r, int kother, int kz0) {
+    r.kz = kz0 + r.col;
+    r.kother = kother;
+  }
+  EVX_HD static cf* tile_at(unsigned char* tile, int byte_off) {
+    return reinterpret_cast<cf*>(tile + byte_off);
+  }
+  // pair `pass` of the group: columns + 4 = byte offset bit 5 flipped
+  EVX_HD static void read_tile(Regs& r, unsigned char* tile, int pass) {
+    const int tb = r.tb ^ (pass << 5);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r.v[e] = *tile_at(tile, tb + e * T * ROWB);
+  }
+  EVX_HD static void write_tile(Regs& r, unsigned char* tile, int pass) {
+    const int tb = r.tb ^ (pass << 5);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) *tile_at(tile, tb + e * T * ROWB) = r.v[e];
+  }
+  EVX_HD static void read_x(Regs& r, const cf* xb) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r.v[e] = xb[r.xn + smem_pad(e * T) * G];
+  }
+  template <int STAGE>
+  EVX_HD static void write_x(Regs& r, cf* xb) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xb[r.xs[STAGE] + smem_pad(stage_out_const<L>(STAGE, e)) * G] = r.v[e];
+  }
+  template <int STAGE, int DIR>
+  EVX_HD static void stage(Regs& r, const Roots& w) {
+    if constexpr (STAGE == 0) line_stage_compute_pre<L, DIR>(0, r.v, r.t, nullptr);
+    else line_stage_compute_pre<L, DIR>(STAGE, r.v, r.t, w.w[STAGE - 1]);
+  }
+
+  // Phase k of line pair `pass` of a tile; the caller synchronises the GROUP between phases
+  // (not between the pairs).  xg: the group's two exchange buffers (XG elements each).
+  EVX_HD static void phase(int pass, int k, Regs& r, unsigned char* tile, cf* xg, const LineParams& p,
+                           const Roots& w) {
+    constexpr int DIR = MODE == PASS_INV ? +1 : -1;      // direction of the first transform
+    const int b0 = XMID ? 0 : (pass & 1);
+    cf* xw = xg + ((b0 ^ (k & 1)) ? XG : 0);             // written by phase k
+    const cf* xr = xg + ((b0 ^ (k & 1)) ? 0 : XG);       // written by phase k - 1
+    if (k == 0) {
+      read_tile(r, tile, pass);
+      stage<0, DIR>(r, w);
+      write_x<0>(r, xw);
+    } else if (k == 1) {
+      read_x(r, xr);
+      stage<1, DIR>(r, w);
+      write_x<1>(r, xw);
+    } else if (k == 2) {
+      read_x(r, xr);
+      stage<2, DIR>(r, w);
+      write_x<2>(r, xw);
+    } else if (k == 3) {
+      read_x(r, xr);
+      stage<3, DIR>(r, w);
+      if (!XMID) {
+        write_tile(r, tile, pass);
+      } else {
+        xmid_apply_filter<MODE, T>(r.v, r.t, r.kother, r.kz + pass * (G * NG), p.filt);
+        stage<0, +1>(r, w);
+        write_x<0>(r, xw);
+      }
+    } else if (k == 4) {
+      read_x(r, xr);
+      stage<1, +1>(r, w);
+      write_x<1>(r, xw);
+    } else if (k == 5) {
+      read_x(r, xr);
+      stage<2, +1>(r, w);
+      write_x<2>(r, xw);
+    } else {
+      read_x(r, xr);
+      stage<3, +1>(r, w);
+      write_tile(r, tile, pass);
+    }
+  }
+
+  // ---- the tensor copies restated for the host replay: plain [nx][ny][P] spectrum ----------
   EVX_HD static long long spec_index(const LineParams& p, int row, int kz, int i) {
     return p.along_x ? ((long long)i * p.ny + row) * p.P + kz : ((long long)row * p.ny + i) * p.P + kz;
   }

@@ -251,6 +251,13 @@ static bool use_line_pass(int L) {
   const char* e = getenv("EVX_FFT_TMA");
   return (!e || atoi(e) != 0) && L == 512 && line_pass_available();
 }
+// 1024-point lines: four-stage TMA-tiled program (StridedLine4); EVX_FFT_LINE4=0 keeps the
+// cp.async passes
+static bool use_line4(int L) {
+  const char* e = getenv("EVX_FFT_TMA");
+  const char* e4 = getenv("EVX_FFT_LINE4");
+  return (!e || atoi(e) != 0) && (!e4 || atoi(e4) != 0) && L == 1024 && line_pass_available();
+}
 static int line_kz() {
   const char* e = getenv("EVX_FFT_TMA_KZ");
   return (e && atoi(e) == 16) ? 16 : 8;
@@ -321,6 +328,25 @@ static int strided_pass(evx_imex_plan* p, const NativeView& v, int which, const 
     const int n[3] = {2 * v.nx, v.ny, v.nz};
     sp.filt = make_filter(n, h, dt, coef, power, 1.0 / (2.0 * v.nx * v.ny * v.nz));
     return launch_xmid(2 * v.nx, sp, st);
+  }
+  if (use_line4(L)) {
+    // 4-D maps (kz, i_lo, row, i_hi), i = 256 i_hi + i_lo: lines along x have rows y, along y rows x
+    alignas(64) unsigned char map[kTensorMapBytes];
+    const long long line_stride = along_x ? (long long)v.ny * v.P : v.P;
+    const long long row_stride = along_x ? v.P : (long long)v.ny * v.P;
+    LineParams lp;
+    lp.spec = v.spec; lp.tw = along_x ? v.twx : v.twy;
+    lp.nx = v.nx; lp.ny = v.ny; lp.P = v.P; lp.ncols_valid = v.M + 1;
+    lp.tiles_per_row = 0; lp.ntiles = 0; lp.along_x = along_x ? 1 : 0;
+    lp.l2_ahead = line_l2_ahead();
+    lp.nrows = along_x ? v.ny : v.nx; lp.box_rows = 256;
+    if (int rc = line_make_tmap4(map, v.spec, v.M + 1, 256, line_stride, lp.nrows, row_stride, 4, 256 * line_stride))
+      return rc;
+    lp.filt = along_x ? filter_of(v, h, dt, coef, power) : FilterParams{};
+    const int mode = which == 1 ? PASS_FWD
+                                : (which == 3 ? PASS_INV
+                                              : (lp.filt.kind == FILTER_ETD1 ? PASS_XMID_ETD1 : PASS_XMID));
+    return line4_pass_launch(mode, lp, map, map, nullptr, st);
   }
   if (use_line_pass(L)) {
     if (int rc = line_tmaps(p, v)) return rc;
@@ -477,6 +503,35 @@ int dist_middle(DistPlan* p, cf* recv, void* const* peers, const double* h, doub
                                              power, yl0, nylc), st);
 }
 
+// x pass of the y-pencils through the four-stage TMA-tiled program (1024-point x lines, local
+// stores only): in place on recv = [nx][nyl][P], except that the x range of this rank goes into
+// `self_block` (same layout) when one is given.  EVX_ERR_UNSUPPORTED: use the cp.async pass.
+static int dist_middle_line4(DistPlan* p, cf* recv, cf* self_block, const double* h, double dt, double coef,
+                             int power, cudaStream_t st, int yl0, int nylc) {
+  if (!use_line4(p->nx) || filter_mirror(power)) return EVX_ERR_UNSUPPORTED;
+  if (nylc < 0) nylc = p->nyl - yl0;
+  if (yl0 < 0 || nylc < 1 || yl0 + nylc > p->nyl) return EVX_ERR_ARG;
+  const int box = p->nxl < 256 ? p->nxl : 256;
+  if (box < 8 || p->nx % box) return EVX_ERR_UNSUPPORTED;
+  alignas(64) unsigned char map[kTensorMapBytes], map_self[kTensorMapBytes];
+  const long long line_stride = (long long)p->nyl * p->P;
+  int rc = line_make_tmap4(map, recv, p->M + 1, box, line_stride, p->nyl, p->P, p->nx / box, box * line_stride);
+  if (!rc && self_block)
+    rc = line_make_tmap4(map_self, self_block, p->M + 1, box, line_stride, p->nyl, p->P, p->nx / box,
+                         box * line_stride);
+  if (rc) return rc;
+  LineParams lp;
+  lp.spec = recv; lp.tw = tables_of(p).twx;
+  lp.nx = p->nx; lp.ny = p->nyl; lp.P = p->P; lp.ncols_valid = p->M + 1;
+  lp.tiles_per_row = 0; lp.ntiles = 0; lp.along_x = 1; lp.l2_ahead = line_l2_ahead();
+  lp.row0 = yl0; lp.nrows = nylc; lp.kother0 = p->rank * p->nyl; lp.box_rows = box;
+  if (self_block) { lp.self_lo = p->rank * (p->nxl / box); lp.self_hi = (p->rank + 1) * (p->nxl / box); }
+  const int n[3] = {p->nx, p->ny, p->nz};
+  lp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)p->nx * p->ny * p->nz));
+  return line4_pass_launch(lp.filt.kind == FILTER_ETD1 ? PASS_XMID_ETD1 : PASS_XMID, lp, map, map,
+                           self_block ? map_self : nullptr, st);
+}
+
 int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, float* out_local,
                   cudaStream_t st) {
   const DistTables t = tables_of(p);
@@ -608,6 +663,11 @@ int evx_dist_middle_chunk_f32(evx_dist_plan* plan, void* recv, void* self_block,
                               const double* h, double dt, double coef, int power, void* stream) {
   if (!plan || !recv || !h || !valid_filter_spec(power)) return EVX_ERR_ARG;
   DistPlan* dp = (DistPlan*)plan;
+  {
+    const int rc = dist_middle_line4(dp, (cf*)recv, (cf*)self_block, h, dt, coef, power, (cudaStream_t)stream,
+                                     yl0, nylc);
+    if (rc != EVX_ERR_UNSUPPORTED) return rc;
+  }
   if (!self_block)
     return dist_middle(dp, (cf*)recv, nullptr, h, dt, coef, power, (cudaStream_t)stream, yl0, nylc);
   if (dp->world > 8) return EVX_ERR_UNSUPPORTED;
@@ -644,6 +704,9 @@ int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_o
 int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double dt, double coef,
                         int power, void* stream) {
   if (!plan || !recv || !h || !valid_filter_spec(power)) return EVX_ERR_ARG;
+  const int rc = dist_middle_line4((DistPlan*)plan, (cf*)recv, nullptr, h, dt, coef, power, (cudaStream_t)stream,
+                                   0, -1);
+  if (rc != EVX_ERR_UNSUPPORTED) return rc;
   return dist_middle((DistPlan*)plan, (cf*)recv, nullptr, h, dt, coef, power, (cudaStream_t)stream);
 }
 int evx_dist_backward_f32(evx_dist_plan* plan, const void* recv, void* spec, const float* u_local,

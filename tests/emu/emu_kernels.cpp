@@ -260,6 +260,42 @@ static void run_line(LineParams p, int nblocks) {
   }
 }
 
+// 1024-point form (StridedLine4): two line pairs per group and tile, two exchange buffers per
+// group; groups (and, inside a group, the pairs) are replayed one after the other.
+template <int MODE>
+static void run_line4(LineParams p, int nblocks) {
+  using Prog = StridedLine4<1024, 8, MODE>;
+  p.tiles_per_row = (p.ncols_valid + 7) / 8;
+  if (p.nrows <= 0) p.nrows = (p.along_x ? p.ny : p.nx) - p.row0;
+  p.ntiles = (long long)p.nrows * p.tiles_per_row;
+  std::vector<typename Prog::Regs> regs(Prog::NTHREADS);
+  std::vector<typename Prog::Roots> roots(Prog::NTHREADS);
+  std::vector<unsigned char> tiles(2 * (size_t)Prog::TILE_BYTES, 0xff);
+  std::vector<cf> xall((size_t)Prog::NG * 2 * Prog::XG, cf{std::nanf(""), std::nanf("")});
+  for (int t = 0; t < Prog::NTHREADS; ++t) {
+    Prog::init(regs[t], t);
+    Prog::load_roots(roots[t], regs[t].t, p.tw);
+  }
+  for (int blk = 0; blk < nblocks; ++blk) {
+    int it = 0;
+    for (long long tile = blk; tile < p.ntiles; tile += nblocks, ++it) {
+      unsigned char* tb = tiles.data() + (it & 1) * Prog::TILE_BYTES;
+      const int row = p.row0 + (int)(tile / p.tiles_per_row), kz0 = (int)(tile % p.tiles_per_row) * 8;
+      Prog::host_tile_load(p, row, kz0, tb);
+      for (int g = Prog::NG - 1; g >= 0; --g) {
+        cf* xg = xall.data() + (size_t)g * 2 * Prog::XG;
+        for (int pass = 0; pass < Prog::NPASS; ++pass)
+          for (int k = 0; k < Prog::NPHASES; ++k)
+            for (int t = g * Prog::GT; t < (g + 1) * Prog::GT; ++t) {
+              if (k == 0) Prog::set_tile(regs[t], row + p.kother0, kz0);
+              Prog::phase(pass, k, regs[t], tb, xg, p, roots[t]);
+            }
+      }
+      Prog::host_tile_store(p, row, kz0, tb);
+    }
+  }
+}
+
 static int g_emu_line_kz = 0;       // 8 / 16: 512-point strided passes through the TMA-tiled program
 static int g_emu_xkz = 8;           // columns per tile of the x pass (8 or 16; 16 may straddle y groups)
 static int g_emu_pipe_blocks = 0;   // 0: one block per tile (StridedPass), >0: pipelined with that many blocks
@@ -267,11 +303,13 @@ static int g_emu_pipe_blocks = 0;   // 0: one block per tile (StridedPass), >0: 
 // plain single-domain layouts only (what fft_native.cu routes to the TMA-tiled passes)
 template <int MODE>
 static bool try_line(int L, const StridedParams& p, int nx, int ny) {
-  if (!g_emu_line_kz || L != 512 || p.use_peers || p.in != p.out) return false;
+  if (!g_emu_line_kz || (L != 512 && !(L == 1024 && g_emu_line_kz == 8)) || p.use_peers || p.in != p.out)
+    return false;
   LineParams lp;
   lp.spec = p.out; lp.tw = p.tw; lp.nx = nx; lp.ny = ny; lp.P = p.P; lp.ncols_valid = p.ncols_valid;
   lp.along_x = pass_is_xmid(MODE) ? 1 : 0; lp.filt = p.filt;
   const int nb = g_emu_pipe_blocks > 0 ? g_emu_pipe_blocks : 5;
+  if (L == 1024) { run_line4<MODE>(lp, nb); return true; }
   if (g_emu_line_kz == 16) run_line<16, MODE>(lp, nb); else run_line<8, MODE>(lp, nb);
   return true;
 }
