@@ -494,6 +494,22 @@ int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* co
   return EVX_OK;
 }
 
+// z pass + y pass with local stores only: the TMA-tiled y pass where it applies.  line4_only: report
+// EVX_ERR_UNSUPPORTED (before launching anything) instead of falling back to the cp.async y pass.
+static int dist_y_line4(DistPlan* p, bool inverse, cf* spec, cf* blocks, cf* self_block, int x0, int nxc,
+                        cudaStream_t st);
+static bool use_line4(int L);
+int dist_forward_local(DistPlan* p, const float* r_local, cf* spec, cf* send, cf* self_block, int x0, int nxc,
+                       cudaStream_t st, bool line4_only = false) {
+  const bool line4 = use_line4(p->ny) && p->nyl <= 256 && p->nyl >= 8;
+  if (!line4) {
+    if (line4_only) return EVX_ERR_UNSUPPORTED;
+    return dist_forward(p, r_local, spec, send, nullptr, x0, nxc, st);
+  }
+  if (int rc = dist_forward(p, r_local, spec, nullptr, nullptr, x0, nxc, st, 1)) return rc;
+  return dist_y_line4(p, false, spec, send, self_block, x0, nxc, st);
+}
+
 // [yl0, yl0+nylc): chunk of the local y-pencil rows (all x, all kz of those rows)
 int dist_middle(DistPlan* p, cf* recv, void* const* peers, const double* h, double dt, double coef,
                 int power, cudaStream_t st, int yl0 = 0, int nylc = -1) {
@@ -501,6 +517,34 @@ int dist_middle(DistPlan* p, cf* recv, void* const* peers, const double* h, doub
   if (yl0 < 0 || nylc < 1 || yl0 + nylc > p->nyl) return EVX_ERR_ARG;
   return launch_xmid(p->nx, dist_xmid_params(*p, tables_of(p), recv, peers, p->p2p_ctas, h, dt, coef,
                                              power, yl0, nylc), st);
+}
+
+// y pass of the local x planes [x0, x0+nxc) through the four-stage TMA-tiled program (1024-point y
+// lines): forward reads the plain spectrum and writes the block layout `blocks` = [W][nxl][nyl][P]
+// (block `rank` into `self_block` when given), inverse reads the block layout and writes the plain
+// spectrum.  One TMA box = the nyl rows of one block, so nyl <= 256 is required.
+static int dist_y_line4(DistPlan* p, bool inverse, cf* spec, cf* blocks, cf* self_block, int x0, int nxc,
+                        cudaStream_t st) {
+  if (!use_line4(p->ny) || p->nyl > 256 || p->nyl < 8) return EVX_ERR_UNSUPPORTED;
+  if (x0 < 0 || nxc < 1 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
+  const int box = p->nyl;
+  alignas(64) unsigned char map_plain[kTensorMapBytes], map_blk[kTensorMapBytes], map_self[kTensorMapBytes];
+  int rc = line_make_tmap4(map_plain, spec, p->M + 1, box, p->P, p->nxl, (long long)p->ny * p->P, p->world,
+                           (long long)box * p->P);
+  const long long blk = (long long)p->nxl * p->nyl * p->P;
+  if (!rc) rc = line_make_tmap4(map_blk, blocks, p->M + 1, box, p->P, p->nxl, (long long)p->nyl * p->P, p->world, blk);
+  if (!rc && self_block)
+    rc = line_make_tmap4(map_self, self_block, p->M + 1, box, p->P, p->nxl, (long long)p->nyl * p->P, p->world, blk);
+  if (rc) return rc;
+  LineParams lp;
+  lp.spec = spec; lp.tw = tables_of(p).twy;
+  lp.nx = p->nxl; lp.ny = p->ny; lp.P = p->P; lp.ncols_valid = p->M + 1;
+  lp.tiles_per_row = 0; lp.ntiles = 0; lp.along_x = 0; lp.l2_ahead = line_l2_ahead();
+  lp.row0 = x0; lp.nrows = nxc; lp.kother0 = 0; lp.box_rows = box;
+  lp.filt = FilterParams{};
+  if (self_block && !inverse) { lp.self_lo = p->rank; lp.self_hi = p->rank + 1; }
+  return inverse ? line4_pass_launch(PASS_INV, lp, map_blk, map_plain, nullptr, st)
+                 : line4_pass_launch(PASS_FWD, lp, map_plain, map_blk, self_block ? map_self : nullptr, st);
 }
 
 // x pass of the y-pencils through the four-stage TMA-tiled program (1024-point x lines, local
@@ -535,7 +579,9 @@ static int dist_middle_line4(DistPlan* p, cf* recv, cf* self_block, const double
 int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, float* out_local,
                   cudaStream_t st) {
   const DistTables t = tables_of(p);
-  int rc = launch_strided<PASS_INV>(p->ny, dist_yinv_params(*p, t, recv, spec, 0, p->nxl), st);
+  int rc = dist_y_line4(p, true, spec, const_cast<cf*>(recv), nullptr, 0, p->nxl, st);
+  if (rc == EVX_ERR_UNSUPPORTED)
+    rc = launch_strided<PASS_INV>(p->ny, dist_yinv_params(*p, t, recv, spec, 0, p->nxl), st);
   if (rc) return rc;
   return launch_z<true>(p->M, dist_zinv_params(*p, t, spec, u_local, out_local, 0, p->nxl), st);
 }
@@ -628,7 +674,7 @@ int evx_dist_forward_f32(evx_dist_plan* plan, const float* r_local, void* spec, 
                          void* stream) {
   if (!plan || !r_local || !spec || !send || spec == send) return EVX_ERR_ARG;
   DistPlan* dp = (DistPlan*)plan;
-  return dist_forward(dp, r_local, (cf*)spec, (cf*)send, nullptr, 0, dp->nxl, (cudaStream_t)stream);
+  return dist_forward_local(dp, r_local, (cf*)spec, (cf*)send, nullptr, 0, dp->nxl, (cudaStream_t)stream);
 }
 int evx_dist_forward_p2p_f32(evx_dist_plan* plan, const float* r_local, void* spec,
                              void* const* peer_recv, void* stream) {
@@ -648,6 +694,11 @@ int evx_dist_forward_chunk_f32(evx_dist_plan* plan, const float* r_local, void* 
                                void* self_block, int x0, int nxc, void* stream) {
   if (!plan || !r_local || !spec || !send || spec == send) return EVX_ERR_ARG;
   DistPlan* dp = (DistPlan*)plan;
+  {
+    const int rc = dist_forward_local(dp, r_local, (cf*)spec, (cf*)send, (cf*)self_block, x0, nxc,
+                                      (cudaStream_t)stream, true);
+    if (rc != EVX_ERR_UNSUPPORTED) return rc;
+  }
   if (!self_block)
     return dist_forward(dp, r_local, (cf*)spec, (cf*)send, nullptr, x0, nxc, (cudaStream_t)stream);
   if (dp->world > 8) return EVX_ERR_UNSUPPORTED;

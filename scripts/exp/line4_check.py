@@ -50,11 +50,19 @@ def virtual(shape, world, chunks):
         A = [p.new_buffer().fill_(float("nan")) for p in plans]
         B = [p.new_buffer().fill_(float("nan")) for p in plans]
         spec = [p.new_buffer() for p in plans]
+        xb = [round(i * nxl / chunks) for i in range(chunks + 1)]
         for k, p in enumerate(plans):
-            p.forward(r[k * nxl:(k + 1) * nxl].contiguous(), spec[k], send[k])
+            rl = r[k * nxl:(k + 1) * nxl].contiguous()
+            if chunks == 1:
+                p.forward(rl, spec[k], send[k])
+                B[k][k].copy_(send[k][k])
+            else:
+                for i in range(chunks):
+                    p.forward_chunk(rl, spec[k], send[k], xb[i], xb[i + 1] - xb[i], self_block=B[k])
         for k in range(world):
             for j in range(world):
-                B[k][j].copy_(send[j][k])
+                if j != k:
+                    B[k][j].copy_(send[j][k])
         bounds = [round(i * nyl / chunks) for i in range(chunks + 1)]
         for k, p in enumerate(plans):
             for i in range(chunks):
@@ -130,13 +138,41 @@ def time_dist_middle(shape, world):
     torch.cuda.empty_cache()
 
 
+def time_dist_fwd_bwd(shape, world):
+    """z + y forward in 4 x chunks and y + z inverse of one rank's slab, as the ce transport runs them"""
+    plan = _native.DistPlan(shape, world, 0, "cuda")
+    send, B, spec = plan.new_buffer().zero_(), plan.new_buffer().zero_(), plan.new_buffer()
+    nxl = shape[0] // world
+    rl = torch.randn((nxl,) + tuple(shape[1:]), device="cuda")
+    out = torch.empty_like(rl)
+    xb = [round(i * nxl / 4) for i in range(5)]
+    row = {}
+    for flag in ("0", "1"):
+        os.environ["EVX_FFT_LINE4"] = flag
+
+        def fwd():
+            for i in range(4):
+                plan.forward_chunk(rl, spec, send, xb[i], xb[i + 1] - xb[i], self_block=B)
+        row[f"forward_4chunks_line4={flag}_ms"] = timed(fwd)
+        row[f"backward_line4={flag}_ms"] = timed(lambda: plan.backward(B, spec, rl, out))
+    print("dist fwd/bwd", shape, "W", world, json.dumps(row), flush=True)
+    res["dist fwd/bwd %s W%d" % (shape, world)] = row
+    del plan, send, B, spec, rl, out
+    torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
     ok = True
     for shape in [(1024, 64, 32), (32, 1024, 64), (1024, 1024, 16), (1024, 8, 16)]:
         ok &= single(shape)
     for world, chunks in [(2, 1), (4, 2), (8, 3)]:
         ok &= virtual((1024, 64, 32), world, chunks)
+    for shape, world, chunks in [((64, 1024, 32), 4, 2), ((64, 1024, 32), 8, 1), ((64, 1024, 32), 2, 2),
+                                 ((1024, 1024, 16), 8, 4), ((1024, 1024, 16), 4, 1)]:
+        ok &= virtual(shape, world, chunks)
     res["bit_identical"] = bool(ok)
+    time_dist_fwd_bwd((1024, 1024, 1024), 8)
+    time_dist_fwd_bwd((1024, 1024, 512), 4)
     time_dist_middle((1024, 512, 512), 2)
     time_dist_middle((1024, 1024, 1024), 8)
     time_passes((1024, 512, 512), [2])
