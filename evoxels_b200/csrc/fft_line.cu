@@ -248,13 +248,18 @@ __global__ void __launch_bounds__(line_ws_threads(Prog::NTHREADS, NBUF), 1)
 // two-line groups), for the four-stage program StridedLine4: 512 compute threads, every group
 // runs two line pairs per tile.  The tensor maps are 4-D - (kz, i_lo, row, i_hi) with line index
 // i = i_hi * box_rows + i_lo - so one code path serves lines along y, lines along x, and the
-// block layout of the x-slab transposes; loads go through map_in, stores through map_out, except
-// the boxes [self_lo, self_hi) which go through map_self (the block that stays on this GPU lands
-// in the next stage's receive buffer).
+// block layout of the x-slab transposes; loads go through maps.in, box h of a tile is stored
+// through maps.out[h / out_div] - one map per destination block, which may live in a PEER's
+// symmetric-memory buffer: then the TMA store IS the slab<->pencil transpose (64-byte rows over
+// NVLink, issued by the retirer thread while the compute warps are already on the next tile).
+struct LineMaps {
+  CUtensorMap in;
+  CUtensorMap out[8];
+};
+
 template <class Prog, int NBUF>
 __global__ void __launch_bounds__(line_ws_threads(Prog::NTHREADS, NBUF), 1)
-    fft_line4_ws_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out,
-                        const __grid_constant__ CUtensorMap map_self, const LineParams p) {
+    fft_line4_ws_kernel(const __grid_constant__ LineMaps maps, const LineParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* tiles = sm;
@@ -289,12 +294,12 @@ __global__ void __launch_bounds__(line_ws_threads(Prog::NTHREADS, NBUF), 1)
       if (n >= NBUF) {
         // the buffer is still in use: pull the tile into L2 while waiting for it
         if (p.l2_ahead)
-          for (int h = 0; h < nbox; ++h) tma_prefetch_4d(&map_in, kz0, 0, row, h);
+          for (int h = 0; h < nbox; ++h) tma_prefetch_4d(&maps.in, kz0, 0, row, h);
         mbar_wait(&empty[buf], (unsigned)(n / NBUF - 1) & 1u);
       }
       unsigned char* dst = tiles + buf * Prog::TILE_BYTES;
       mbar_expect_tx(&full[buf], Prog::TILE_BYTES);
-      for (int h = 0; h < nbox; ++h) tma_load_4d(dst + h * box_bytes, &map_in, &full[buf], kz0, 0, row, h);
+      for (int h = 0; h < nbox; ++h) tma_load_4d(dst + h * box_bytes, &maps.in, &full[buf], kz0, 0, row, h);
     }
     return;
   }
@@ -307,8 +312,10 @@ __global__ void __launch_bounds__(line_ws_threads(Prog::NTHREADS, NBUF), 1)
       mbar_wait(&done[me], (unsigned)(n / NBUF) & 1u);
       const int row = p.row0 + (int)(tile / tpr), kz0 = (int)(tile % tpr) * Prog::COLS;
       const unsigned char* src = tiles + me * Prog::TILE_BYTES;
-      for (int h = 0; h < nbox; ++h)
-        tma_store_4d(h >= p.self_lo && h < p.self_hi ? &map_self : &map_out, src + h * box_bytes, kz0, 0, row, h);
+      for (int h = 0, m = 0, c = 0; h < nbox; ++h) {
+        tma_store_4d(&maps.out[m], src + h * box_bytes, kz0, 0, row, c);
+        if (++c == p.out_div) { c = 0; ++m; }
+      }
       tma_store_commit();
       tma_store_wait_read();
       mbar_arrive_cta(&empty[me]);
@@ -405,32 +412,36 @@ int line_make_tmap4(void* out, void* base, int ncols_valid, int box_rows, long l
 }
 
 template <int MODE>
-static int launch_line4_t(LineParams p, const void* map_in, const void* map_out, const void* map_self,
-                          cudaStream_t st) {
+static int launch_line4_t(LineParams p, const void* map_in, const void* const* maps_out, int nout, cudaStream_t st) {
   using Prog = StridedLine4<1024, 8, MODE>;
   constexpr int NBUF = 2;
   p.tiles_per_row = (p.ncols_valid + 7) / 8;
   p.ntiles = (long long)p.nrows * p.tiles_per_row;
-  if (p.ntiles < 1 || p.box_rows < 1 || 1024 % p.box_rows) return EVX_ERR_ARG;
+  if (p.ntiles < 1 || p.box_rows < 1 || 1024 % p.box_rows || p.out_div < 1) return EVX_ERR_ARG;
+  const int nbox = 1024 / p.box_rows;
+  if (nout < 1 || nout > 8 || (nbox + p.out_div - 1) / p.out_div > nout) return EVX_ERR_ARG;
   constexpr size_t smem = 1024 + (size_t)NBUF * Prog::TILE_BYTES + Prog::X_BYTES + 128;
   auto kern = fft_line4_ws_kernel<Prog, NBUF>;
   static SmemOptIn optin;
   if (int rc = optin.ensure(kern, smem)) return rc;
-  const long long resident = line_sms();
+  LineMaps maps;
+  maps.in = *(const CUtensorMap*)map_in;
+  for (int i = 0; i < 8; ++i) maps.out[i] = *(const CUtensorMap*)maps_out[i < nout ? i : 0];
+  long long resident = line_sms();
+  if (p.max_ctas > 0 && p.max_ctas < resident) resident = p.max_ctas;
   const unsigned grid = (unsigned)(p.ntiles < resident ? p.ntiles : resident);
-  kern<<<grid, line_ws_threads(Prog::NTHREADS, NBUF), smem, st>>>(
-      *(const CUtensorMap*)map_in, *(const CUtensorMap*)map_out, *(const CUtensorMap*)(map_self ? map_self : map_out), p);
+  kern<<<grid, line_ws_threads(Prog::NTHREADS, NBUF), smem, st>>>(maps, p);
   count_launch();
   return (int)cudaGetLastError();
 }
 
-int line4_pass_launch(int mode, const LineParams& p, const void* map_in, const void* map_out,
-                      const void* map_self, cudaStream_t st) {
+int line4_pass_launch(int mode, const LineParams& p, const void* map_in, const void* const* maps_out, int nout,
+                      cudaStream_t st) {
   switch (mode) {
-    case PASS_FWD: return launch_line4_t<PASS_FWD>(p, map_in, map_out, map_self, st);
-    case PASS_INV: return launch_line4_t<PASS_INV>(p, map_in, map_out, map_self, st);
-    case PASS_XMID: return launch_line4_t<PASS_XMID>(p, map_in, map_out, map_self, st);
-    case PASS_XMID_ETD1: return launch_line4_t<PASS_XMID_ETD1>(p, map_in, map_out, map_self, st);
+    case PASS_FWD: return launch_line4_t<PASS_FWD>(p, map_in, maps_out, nout, st);
+    case PASS_INV: return launch_line4_t<PASS_INV>(p, map_in, maps_out, nout, st);
+    case PASS_XMID: return launch_line4_t<PASS_XMID>(p, map_in, maps_out, nout, st);
+    case PASS_XMID_ETD1: return launch_line4_t<PASS_XMID_ETD1>(p, map_in, maps_out, nout, st);
     default: return EVX_ERR_ARG;
   }
 }

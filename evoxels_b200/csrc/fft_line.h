@@ -21,9 +21,9 @@ int line_pass_launch(int mode, int kz, const LineParams& p, const void* tmap, cu
 // box_rows + i_lo, box = [box_rows][8 columns] of one row (box_rows <= 256, divides 1024)
 int line_make_tmap4(void* out, void* base, int ncols_valid, int box_rows, long long lo_stride, int nrows,
                     long long row_stride, int nhi, long long hi_stride);
-// p: tw, ncols_valid, row0, nrows, kother0, box_rows, self_lo / self_hi, l2_ahead, filt; loads through
-// map_in, stores through map_out (boxes [self_lo, self_hi): map_self, may be null if the range is empty)
-int line4_pass_launch(int mode, const LineParams& p, const void* map_in, const void* map_out,
-                      const void* map_self, cudaStream_t st);
+// p: tw, ncols_valid, row0, nrows, kother0, box_rows, out_div, max_ctas, l2_ahead, filt; loads through
+// map_in, box h of a tile is stored through maps_out[h / out_div] at high coordinate h % out_div
+int line4_pass_launch(int mode, const LineParams& p, const void* map_in, const void* const* maps_out, int nout,
+                      cudaStream_t st);
 
 }  // namespace evx

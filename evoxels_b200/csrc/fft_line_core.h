@@ -42,9 +42,12 @@ struct LineParams {
   FilterParams filt;        // XMID only; n0 = nx
   // 1024-point form (StridedLine4, 4-D tensor maps: kz, line index low part, row, line index
   // high part): first tile row / number of tile rows of this launch, global index of tile row 0
-  // along the other strided axis (x-slab y-pencils), rows per TMA box, and the range of boxes
-  // whose STORE goes through the second output map (the block that stays on this GPU)
-  int row0 = 0, nrows = 0, kother0 = 0, box_rows = 256, self_lo = 0, self_hi = 0;
+  // along the other strided axis (x-slab y-pencils), rows per TMA box.  Box h of a tile is STORED
+  // through output map h / out_div at high coordinate h % out_div (one output map per destination
+  // block of the x-slab transposes - a peer's buffer over NVLink, or local; out_div = boxes per
+  // tile and a single map for an ordinary pass).  max_ctas > 0 caps the persistent grid (an
+  // NVLink-bound launch leaves SMs to the kernels of the next chunk).
+  int row0 = 0, nrows = 0, kother0 = 0, box_rows = 256, out_div = 4, max_ctas = 0;
 };
 
 template <int L, int KZ, int MODE>

@@ -346,7 +346,9 @@ static int strided_pass(evx_imex_plan* p, const NativeView& v, int which, const 
     const int mode = which == 1 ? PASS_FWD
                                 : (which == 3 ? PASS_INV
                                               : (lp.filt.kind == FILTER_ETD1 ? PASS_XMID_ETD1 : PASS_XMID));
-    return line4_pass_launch(mode, lp, map, map, nullptr, st);
+    lp.out_div = 4;
+    const void* outs[1] = {map};
+    return line4_pass_launch(mode, lp, map, outs, 1, st);
   }
   if (use_line_pass(L)) {
     if (int rc = line_tmaps(p, v)) return rc;
@@ -474,12 +476,92 @@ int dist_plan_create(DistPlan** out, int nx, int ny, int nz, int world, int rank
   return EVX_OK;
 }
 
+// ---- 1024-point lines of the distributed plan: four-stage TMA-tiled passes (fft_line.cu) ------
+// Destination tables follow the peer-store convention of dist_params.h: block `rank` of the
+// buffer peers[w] receives what this rank produces for rank w - a peer's symmetric-memory buffer
+// (the TMA stores of the pass ARE the slab<->pencil transpose over NVLink) or, with the table of
+// local_block_table(), this GPU's own block buffers (copy-engine / NCCL transports).
+// EVX_ERR_UNSUPPORTED (nothing launched): the caller uses the cp.async pass.
+static int line4_p2p_ctas(const DistPlan* p, bool to_peers) {
+  if (!to_peers || p->p2p_ctas <= 0) return 0;
+  const char* e = getenv("EVX_LINE4_P2P_CTAS");     // grid of an NVLink-bound launch in the pipelined plan
+  const int v = e ? atoi(e) : 64;
+  return v > 0 ? v : 0;
+}
+
+// y pass of the local x planes [x0, x0+nxc).  Forward: plain spectrum -> block `rank` of every
+// peers[w]; inverse: block layout `blocks` -> plain spectrum.  One TMA box = the nyl rows of one
+// block, hence nyl <= 256.
+static int dist_y_line4(DistPlan* p, bool inverse, cf* spec, cf* blocks, void* const* peers, bool remote,
+                        int x0, int nxc, cudaStream_t st) {
+  if (!use_line4(p->ny) || p->nyl > 256 || p->nyl < 8 || p->world > 8) return EVX_ERR_UNSUPPORTED;
+  if (x0 < 0 || nxc < 1 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
+  const int box = p->nyl;
+  const long long blk = (long long)p->nxl * p->nyl * p->P;
+  alignas(64) unsigned char map_plain[kTensorMapBytes], maps[8][kTensorMapBytes];
+  int rc = line_make_tmap4(map_plain, spec, p->M + 1, box, p->P, p->nxl, (long long)p->ny * p->P, p->world,
+                           (long long)box * p->P);
+  const void* outs[8];
+  LineParams lp;
+  if (inverse) {
+    if (!rc) rc = line_make_tmap4(maps[0], blocks, p->M + 1, box, p->P, p->nxl, (long long)p->nyl * p->P, p->world, blk);
+    outs[0] = map_plain;
+    lp.out_div = p->world;
+  } else {
+    for (int w = 0; w < p->world && !rc; ++w) {
+      rc = line_make_tmap4(maps[w], (cf*)peers[w] + (long long)p->rank * blk, p->M + 1, box, p->P, p->nxl,
+                           (long long)p->nyl * p->P, 1, blk);
+      outs[w] = maps[w];
+    }
+    lp.out_div = 1;
+  }
+  if (rc) return rc;
+  lp.spec = spec; lp.tw = tables_of(p).twy;
+  lp.nx = p->nxl; lp.ny = p->ny; lp.P = p->P; lp.ncols_valid = p->M + 1;
+  lp.tiles_per_row = 0; lp.ntiles = 0; lp.along_x = 0; lp.l2_ahead = line_l2_ahead();
+  lp.row0 = x0; lp.nrows = nxc; lp.kother0 = 0; lp.box_rows = box;
+  lp.max_ctas = line4_p2p_ctas(p, remote);
+  lp.filt = FilterParams{};
+  return inverse ? line4_pass_launch(PASS_INV, lp, maps[0], outs, 1, st)
+                 : line4_pass_launch(PASS_FWD, lp, map_plain, outs, p->world, st);
+}
+
+// x pass of the local y-pencil rows [yl0, yl0+nylc): reads recv = [nx][nyl][P], the x range of rank
+// w is stored into block `rank` of peers[w].
+static int dist_middle_line4(DistPlan* p, cf* recv, void* const* peers, bool remote, const double* h, double dt,
+                             double coef, int power, cudaStream_t st, int yl0, int nylc) {
+  if (!use_line4(p->nx) || filter_mirror(power) || p->world > 8) return EVX_ERR_UNSUPPORTED;
+  const int box = p->nxl < 256 ? p->nxl : 256;
+  if (box < 8 || p->nx % box) return EVX_ERR_UNSUPPORTED;
+  const long long line_stride = (long long)p->nyl * p->P, blk = (long long)p->nxl * p->nyl * p->P;
+  alignas(64) unsigned char map_in[kTensorMapBytes], maps[8][kTensorMapBytes];
+  int rc = line_make_tmap4(map_in, recv, p->M + 1, box, line_stride, p->nyl, p->P, p->nx / box, box * line_stride);
+  const void* outs[8];
+  for (int w = 0; w < p->world && !rc; ++w) {
+    rc = line_make_tmap4(maps[w], (cf*)peers[w] + (long long)p->rank * blk, p->M + 1, box, line_stride, p->nyl,
+                         p->P, p->nxl / box, box * line_stride);
+    outs[w] = maps[w];
+  }
+  if (rc) return rc;
+  LineParams lp;
+  lp.spec = recv; lp.tw = tables_of(p).twx;
+  lp.nx = p->nx; lp.ny = p->nyl; lp.P = p->P; lp.ncols_valid = p->M + 1;
+  lp.tiles_per_row = 0; lp.ntiles = 0; lp.along_x = 1; lp.l2_ahead = line_l2_ahead();
+  lp.row0 = yl0; lp.nrows = nylc; lp.kother0 = p->rank * p->nyl; lp.box_rows = box;
+  lp.out_div = p->nxl / box;
+  lp.max_ctas = line4_p2p_ctas(p, remote);
+  const int n[3] = {p->nx, p->ny, p->nz};
+  lp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)p->nx * p->ny * p->nz));
+  return line4_pass_launch(lp.filt.kind == FILTER_ETD1 ? PASS_XMID_ETD1 : PASS_XMID, lp, map_in, outs, p->world, st);
+}
+
 // Parameters: dist_params.h.  [x0, x0+nxc) selects a chunk of local x planes (r_local / spec /
 // send still point at the start of the full local arrays), so that several chunks can be
 // pipelined on streams: the NVLink-bound y pass of one chunk overlaps the HBM-bound z pass of
-// the next.  parts: 1 = z pass, 2 = y pass, 3 = both (then with L2 blocking if set).
+// the next.  parts: 1 = z pass, 2 = y pass, 3 = both.  `send`: local block buffer (peers null), or
+// `peers`: destination table (see above; `remote` tells whether it points at other GPUs).
 int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* const* peers,
-                 int x0, int nxc, cudaStream_t st, int parts = 3) {
+                 int x0, int nxc, cudaStream_t st, int parts = 3, bool remote = true) {
   if (x0 < 0 || nxc < 1 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
   const DistTables t = tables_of(p);
   if (parts & 1) {
@@ -487,99 +569,37 @@ int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* co
     if (rc) return rc;
   }
   if (parts & 2) {
-    const int rc = launch_strided<PASS_FWD>(
-        p->ny, dist_yfwd_params(*p, t, spec, send, peers, p->p2p_ctas, x0, nxc), st);
+    void* table[8];
+    if (!peers && p->world <= 8) local_block_table(*p, send, send, table);
+    int rc = peers ? dist_y_line4(p, false, spec, nullptr, peers, remote, x0, nxc, st)
+                   : (p->world <= 8 ? dist_y_line4(p, false, spec, nullptr, table, false, x0, nxc, st)
+                                    : EVX_ERR_UNSUPPORTED);
+    if (rc == EVX_ERR_UNSUPPORTED)
+      rc = launch_strided<PASS_FWD>(p->ny, dist_yfwd_params(*p, t, spec, send, peers, p->p2p_ctas, x0, nxc), st);
     if (rc) return rc;
   }
   return EVX_OK;
 }
 
-// z pass + y pass with local stores only: the TMA-tiled y pass where it applies.  line4_only: report
-// EVX_ERR_UNSUPPORTED (before launching anything) instead of falling back to the cp.async y pass.
-static int dist_y_line4(DistPlan* p, bool inverse, cf* spec, cf* blocks, cf* self_block, int x0, int nxc,
-                        cudaStream_t st);
-static bool use_line4(int L);
-int dist_forward_local(DistPlan* p, const float* r_local, cf* spec, cf* send, cf* self_block, int x0, int nxc,
-                       cudaStream_t st, bool line4_only = false) {
-  const bool line4 = use_line4(p->ny) && p->nyl <= 256 && p->nyl >= 8;
-  if (!line4) {
-    if (line4_only) return EVX_ERR_UNSUPPORTED;
-    return dist_forward(p, r_local, spec, send, nullptr, x0, nxc, st);
-  }
-  if (int rc = dist_forward(p, r_local, spec, nullptr, nullptr, x0, nxc, st, 1)) return rc;
-  return dist_y_line4(p, false, spec, send, self_block, x0, nxc, st);
-}
-
 // [yl0, yl0+nylc): chunk of the local y-pencil rows (all x, all kz of those rows)
 int dist_middle(DistPlan* p, cf* recv, void* const* peers, const double* h, double dt, double coef,
-                int power, cudaStream_t st, int yl0 = 0, int nylc = -1) {
+                int power, cudaStream_t st, int yl0 = 0, int nylc = -1, bool remote = true) {
   if (nylc < 0) nylc = p->nyl - yl0;
   if (yl0 < 0 || nylc < 1 || yl0 + nylc > p->nyl) return EVX_ERR_ARG;
+  void* table[8];
+  if (!peers && p->world <= 8) local_block_table(*p, recv, recv, table);
+  const int rc = peers ? dist_middle_line4(p, recv, peers, remote, h, dt, coef, power, st, yl0, nylc)
+                       : (p->world <= 8 ? dist_middle_line4(p, recv, table, false, h, dt, coef, power, st, yl0, nylc)
+                                        : EVX_ERR_UNSUPPORTED);
+  if (rc != EVX_ERR_UNSUPPORTED) return rc;
   return launch_xmid(p->nx, dist_xmid_params(*p, tables_of(p), recv, peers, p->p2p_ctas, h, dt, coef,
                                              power, yl0, nylc), st);
-}
-
-// y pass of the local x planes [x0, x0+nxc) through the four-stage TMA-tiled program (1024-point y
-// lines): forward reads the plain spectrum and writes the block layout `blocks` = [W][nxl][nyl][P]
-// (block `rank` into `self_block` when given), inverse reads the block layout and writes the plain
-// spectrum.  One TMA box = the nyl rows of one block, so nyl <= 256 is required.
-static int dist_y_line4(DistPlan* p, bool inverse, cf* spec, cf* blocks, cf* self_block, int x0, int nxc,
-                        cudaStream_t st) {
-  if (!use_line4(p->ny) || p->nyl > 256 || p->nyl < 8) return EVX_ERR_UNSUPPORTED;
-  if (x0 < 0 || nxc < 1 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
-  const int box = p->nyl;
-  alignas(64) unsigned char map_plain[kTensorMapBytes], map_blk[kTensorMapBytes], map_self[kTensorMapBytes];
-  int rc = line_make_tmap4(map_plain, spec, p->M + 1, box, p->P, p->nxl, (long long)p->ny * p->P, p->world,
-                           (long long)box * p->P);
-  const long long blk = (long long)p->nxl * p->nyl * p->P;
-  if (!rc) rc = line_make_tmap4(map_blk, blocks, p->M + 1, box, p->P, p->nxl, (long long)p->nyl * p->P, p->world, blk);
-  if (!rc && self_block)
-    rc = line_make_tmap4(map_self, self_block, p->M + 1, box, p->P, p->nxl, (long long)p->nyl * p->P, p->world, blk);
-  if (rc) return rc;
-  LineParams lp;
-  lp.spec = spec; lp.tw = tables_of(p).twy;
-  lp.nx = p->nxl; lp.ny = p->ny; lp.P = p->P; lp.ncols_valid = p->M + 1;
-  lp.tiles_per_row = 0; lp.ntiles = 0; lp.along_x = 0; lp.l2_ahead = line_l2_ahead();
-  lp.row0 = x0; lp.nrows = nxc; lp.kother0 = 0; lp.box_rows = box;
-  lp.filt = FilterParams{};
-  if (self_block && !inverse) { lp.self_lo = p->rank; lp.self_hi = p->rank + 1; }
-  return inverse ? line4_pass_launch(PASS_INV, lp, map_blk, map_plain, nullptr, st)
-                 : line4_pass_launch(PASS_FWD, lp, map_plain, map_blk, self_block ? map_self : nullptr, st);
-}
-
-// x pass of the y-pencils through the four-stage TMA-tiled program (1024-point x lines, local
-// stores only): in place on recv = [nx][nyl][P], except that the x range of this rank goes into
-// `self_block` (same layout) when one is given.  EVX_ERR_UNSUPPORTED: use the cp.async pass.
-static int dist_middle_line4(DistPlan* p, cf* recv, cf* self_block, const double* h, double dt, double coef,
-                             int power, cudaStream_t st, int yl0, int nylc) {
-  if (!use_line4(p->nx) || filter_mirror(power)) return EVX_ERR_UNSUPPORTED;
-  if (nylc < 0) nylc = p->nyl - yl0;
-  if (yl0 < 0 || nylc < 1 || yl0 + nylc > p->nyl) return EVX_ERR_ARG;
-  const int box = p->nxl < 256 ? p->nxl : 256;
-  if (box < 8 || p->nx % box) return EVX_ERR_UNSUPPORTED;
-  alignas(64) unsigned char map[kTensorMapBytes], map_self[kTensorMapBytes];
-  const long long line_stride = (long long)p->nyl * p->P;
-  int rc = line_make_tmap4(map, recv, p->M + 1, box, line_stride, p->nyl, p->P, p->nx / box, box * line_stride);
-  if (!rc && self_block)
-    rc = line_make_tmap4(map_self, self_block, p->M + 1, box, line_stride, p->nyl, p->P, p->nx / box,
-                         box * line_stride);
-  if (rc) return rc;
-  LineParams lp;
-  lp.spec = recv; lp.tw = tables_of(p).twx;
-  lp.nx = p->nx; lp.ny = p->nyl; lp.P = p->P; lp.ncols_valid = p->M + 1;
-  lp.tiles_per_row = 0; lp.ntiles = 0; lp.along_x = 1; lp.l2_ahead = line_l2_ahead();
-  lp.row0 = yl0; lp.nrows = nylc; lp.kother0 = p->rank * p->nyl; lp.box_rows = box;
-  if (self_block) { lp.self_lo = p->rank * (p->nxl / box); lp.self_hi = (p->rank + 1) * (p->nxl / box); }
-  const int n[3] = {p->nx, p->ny, p->nz};
-  lp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)p->nx * p->ny * p->nz));
-  return line4_pass_launch(lp.filt.kind == FILTER_ETD1 ? PASS_XMID_ETD1 : PASS_XMID, lp, map, map,
-                           self_block ? map_self : nullptr, st);
 }
 
 int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, float* out_local,
                   cudaStream_t st) {
   const DistTables t = tables_of(p);
-  int rc = dist_y_line4(p, true, spec, const_cast<cf*>(recv), nullptr, 0, p->nxl, st);
+  int rc = dist_y_line4(p, true, spec, const_cast<cf*>(recv), nullptr, false, 0, p->nxl, st);
   if (rc == EVX_ERR_UNSUPPORTED)
     rc = launch_strided<PASS_INV>(p->ny, dist_yinv_params(*p, t, recv, spec, 0, p->nxl), st);
   if (rc) return rc;
@@ -674,7 +694,7 @@ int evx_dist_forward_f32(evx_dist_plan* plan, const float* r_local, void* spec, 
                          void* stream) {
   if (!plan || !r_local || !spec || !send || spec == send) return EVX_ERR_ARG;
   DistPlan* dp = (DistPlan*)plan;
-  return dist_forward_local(dp, r_local, (cf*)spec, (cf*)send, nullptr, 0, dp->nxl, (cudaStream_t)stream);
+  return dist_forward(dp, r_local, (cf*)spec, (cf*)send, nullptr, 0, dp->nxl, (cudaStream_t)stream);
 }
 int evx_dist_forward_p2p_f32(evx_dist_plan* plan, const float* r_local, void* spec,
                              void* const* peer_recv, void* stream) {
@@ -694,11 +714,6 @@ int evx_dist_forward_chunk_f32(evx_dist_plan* plan, const float* r_local, void* 
                                void* self_block, int x0, int nxc, void* stream) {
   if (!plan || !r_local || !spec || !send || spec == send) return EVX_ERR_ARG;
   DistPlan* dp = (DistPlan*)plan;
-  {
-    const int rc = dist_forward_local(dp, r_local, (cf*)spec, (cf*)send, (cf*)self_block, x0, nxc,
-                                      (cudaStream_t)stream, true);
-    if (rc != EVX_ERR_UNSUPPORTED) return rc;
-  }
   if (!self_block)
     return dist_forward(dp, r_local, (cf*)spec, (cf*)send, nullptr, x0, nxc, (cudaStream_t)stream);
   if (dp->world > 8) return EVX_ERR_UNSUPPORTED;
@@ -706,7 +721,7 @@ int evx_dist_forward_chunk_f32(evx_dist_plan* plan, const float* r_local, void* 
   local_block_table(*dp, (cf*)send, (cf*)self_block, table);
   const int ctas = dp->p2p_ctas;
   dp->p2p_ctas = 0;                       // local stores: fill the GPU
-  const int rc = dist_forward(dp, r_local, (cf*)spec, nullptr, table, x0, nxc, (cudaStream_t)stream);
+  const int rc = dist_forward(dp, r_local, (cf*)spec, nullptr, table, x0, nxc, (cudaStream_t)stream, 3, false);
   dp->p2p_ctas = ctas;
   return rc;
 }
@@ -714,11 +729,6 @@ int evx_dist_middle_chunk_f32(evx_dist_plan* plan, void* recv, void* self_block,
                               const double* h, double dt, double coef, int power, void* stream) {
   if (!plan || !recv || !h || !valid_filter_spec(power)) return EVX_ERR_ARG;
   DistPlan* dp = (DistPlan*)plan;
-  {
-    const int rc = dist_middle_line4(dp, (cf*)recv, (cf*)self_block, h, dt, coef, power, (cudaStream_t)stream,
-                                     yl0, nylc);
-    if (rc != EVX_ERR_UNSUPPORTED) return rc;
-  }
   if (!self_block)
     return dist_middle(dp, (cf*)recv, nullptr, h, dt, coef, power, (cudaStream_t)stream, yl0, nylc);
   if (dp->world > 8) return EVX_ERR_UNSUPPORTED;
@@ -726,7 +736,7 @@ int evx_dist_middle_chunk_f32(evx_dist_plan* plan, void* recv, void* self_block,
   local_block_table(*dp, (cf*)recv, (cf*)self_block, table);
   const int ctas = dp->p2p_ctas;
   dp->p2p_ctas = 0;
-  const int rc = dist_middle(dp, (cf*)recv, table, h, dt, coef, power, (cudaStream_t)stream, yl0, nylc);
+  const int rc = dist_middle(dp, (cf*)recv, table, h, dt, coef, power, (cudaStream_t)stream, yl0, nylc, false);
   dp->p2p_ctas = ctas;
   return rc;
 }
@@ -755,9 +765,6 @@ int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_o
 int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double dt, double coef,
                         int power, void* stream) {
   if (!plan || !recv || !h || !valid_filter_spec(power)) return EVX_ERR_ARG;
-  const int rc = dist_middle_line4((DistPlan*)plan, (cf*)recv, nullptr, h, dt, coef, power, (cudaStream_t)stream,
-                                   0, -1);
-  if (rc != EVX_ERR_UNSUPPORTED) return rc;
   return dist_middle((DistPlan*)plan, (cf*)recv, nullptr, h, dt, coef, power, (cudaStream_t)stream);
 }
 int evx_dist_backward_f32(evx_dist_plan* plan, const void* recv, void* spec, const float* u_local,

@@ -84,6 +84,47 @@ def virtual(shape, world, chunks):
     return ok
 
 
+def virtual_p2p(shape, world, chunks):
+    """peer-store transport with W plans on one GPU: the passes write into each other's buffers"""
+    gen = torch.Generator(device="cuda").manual_seed(12)
+    r = torch.randn(shape, device="cuda", generator=gen)
+    u = torch.rand(shape, device="cuda", generator=gen)
+    os.environ["EVX_FFT_LINE4"] = "0"
+    ref = torch.empty_like(u)
+    _native.ImexPlan(shape, torch.float32, "cuda", _native.FFT_NATIVE).apply(u, r, ref, SP, 0.1, 1.5, 2)
+    nxl = shape[0] // world
+    ok = True
+    for flag in ("0", "1"):
+        os.environ["EVX_FFT_LINE4"] = flag
+        plans = [_native.DistPlan(shape, world, k, "cuda") for k in range(world)]
+        A = [p.new_buffer().fill_(float("nan")) for p in plans]
+        B = [p.new_buffer().fill_(float("nan")) for p in plans]
+        spec = [p.new_buffer() for p in plans]
+        xb = [round(i * nxl / chunks) for i in range(chunks + 1)]
+        for k, p in enumerate(plans):
+            p.set_p2p_ctas(0 if chunks == 1 else 148)
+            rl = r[k * nxl:(k + 1) * nxl].contiguous()
+            if chunks == 1:
+                p.forward_p2p(rl, spec[k], [b.data_ptr() for b in B])
+            else:
+                for i in range(chunks):
+                    p.forward_chunk_p2p(rl, spec[k], [b.data_ptr() for b in B], xb[i], xb[i + 1] - xb[i], parts=1)
+                    p.forward_chunk_p2p(rl, spec[k], [b.data_ptr() for b in B], xb[i], xb[i + 1] - xb[i], parts=2)
+        for k, p in enumerate(plans):
+            p.middle_p2p(B[k], [a.data_ptr() for a in A], SP, 0.1, 1.5, 2)
+        out = torch.empty_like(u)
+        for k, p in enumerate(plans):
+            o = torch.empty((nxl,) + tuple(shape[1:]), device="cuda")
+            p.backward(A[k], spec[k], u[k * nxl:(k + 1) * nxl].contiguous(), o)
+            out[k * nxl:(k + 1) * nxl] = o
+        torch.cuda.synchronize()
+        eq = torch.equal(out, ref)
+        print("virtual p2p", shape, "W", world, "chunks", chunks, "LINE4", flag,
+              "bit-identical" if eq else "MISMATCH", float((out - ref).abs().max()), flush=True)
+        ok = ok and eq
+    return ok
+
+
 def timed(fn, n=10):
     for _ in range(3):
         fn()
@@ -170,6 +211,9 @@ if __name__ == "__main__":
     for shape, world, chunks in [((64, 1024, 32), 4, 2), ((64, 1024, 32), 8, 1), ((64, 1024, 32), 2, 2),
                                  ((1024, 1024, 16), 8, 4), ((1024, 1024, 16), 4, 1)]:
         ok &= virtual(shape, world, chunks)
+    for shape, world, chunks in [((1024, 64, 32), 2, 1), ((1024, 1024, 16), 8, 2), ((1024, 1024, 16), 4, 1),
+                                 ((64, 1024, 32), 8, 4)]:
+        ok &= virtual_p2p(shape, world, chunks)
     res["bit_identical"] = bool(ok)
     time_dist_fwd_bwd((1024, 1024, 1024), 8)
     time_dist_fwd_bwd((1024, 1024, 512), 4)
