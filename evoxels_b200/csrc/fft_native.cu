@@ -482,10 +482,12 @@ int dist_plan_create(DistPlan** out, int nx, int ny, int nz, int world, int rank
 // (the TMA stores of the pass ARE the slab<->pencil transpose over NVLink) or, with the table of
 // local_block_table(), this GPU's own block buffers (copy-engine / NCCL transports).
 // EVX_ERR_UNSUPPORTED (nothing launched): the caller uses the cp.async pass.
-static int line4_p2p_ctas(const DistPlan* p, bool to_peers) {
+static int line4_p2p_ctas(const DistPlan* p, bool to_peers, bool mid) {
   if (!to_peers || p->p2p_ctas <= 0) return 0;
-  const char* e = getenv("EVX_LINE4_P2P_CTAS");     // grid of an NVLink-bound launch in the pipelined plan
-  const int v = e ? atoi(e) : 64;
+  // grid of an NVLink-bound launch in the pipelined plan: the y pass shares the GPU with rhs and
+  // z pass of the next chunk; nothing runs next to the x pass
+  const char* e = getenv(mid ? "EVX_LINE4_P2P_CTAS_MID" : "EVX_LINE4_P2P_CTAS");
+  const int v = e ? atoi(e) : (mid ? 0 : 64);
   return v > 0 ? v : 0;
 }
 
@@ -520,7 +522,7 @@ static int dist_y_line4(DistPlan* p, bool inverse, cf* spec, cf* blocks, void* c
   lp.nx = p->nxl; lp.ny = p->ny; lp.P = p->P; lp.ncols_valid = p->M + 1;
   lp.tiles_per_row = 0; lp.ntiles = 0; lp.along_x = 0; lp.l2_ahead = line_l2_ahead();
   lp.row0 = x0; lp.nrows = nxc; lp.kother0 = 0; lp.box_rows = box;
-  lp.max_ctas = line4_p2p_ctas(p, remote);
+  lp.max_ctas = line4_p2p_ctas(p, remote, false);
   lp.filt = FilterParams{};
   return inverse ? line4_pass_launch(PASS_INV, lp, maps[0], outs, 1, st)
                  : line4_pass_launch(PASS_FWD, lp, map_plain, outs, p->world, st);
@@ -549,7 +551,7 @@ static int dist_middle_line4(DistPlan* p, cf* recv, void* const* peers, bool rem
   lp.tiles_per_row = 0; lp.ntiles = 0; lp.along_x = 1; lp.l2_ahead = line_l2_ahead();
   lp.row0 = yl0; lp.nrows = nylc; lp.kother0 = p->rank * p->nyl; lp.box_rows = box;
   lp.out_div = p->nxl / box;
-  lp.max_ctas = line4_p2p_ctas(p, remote);
+  lp.max_ctas = line4_p2p_ctas(p, remote, true);
   const int n[3] = {p->nx, p->ny, p->nz};
   lp.filt = make_filter(n, h, dt, coef, power, 1.0 / ((double)p->nx * p->ny * p->nz));
   return line4_pass_launch(lp.filt.kind == FILTER_ETD1 ? PASS_XMID_ETD1 : PASS_XMID, lp, map_in, outs, p->world, st);

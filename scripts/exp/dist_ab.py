@@ -1,0 +1,72 @@
+"""torchrun worker: A/B of the transports of the distributed CH step on real GPUs (ms/step, max over
+ranks, 20 steps after 5), all variants inside one session; every variant is checked against the
+first one (bit-identical fields after the same number of steps)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+import torch.distributed as dist
+from evoxels_b200.distributed import DistributedCahnHilliardIMEX, Slab
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+n = 512
+shape = {1: (n, n, n), 2: (2 * n, n, n), 4: (2 * n, 2 * n, n), 8: (2 * n, 2 * n, 2 * n)}[world]
+if len(sys.argv) > 1 and "x" in sys.argv[1]:
+    shape = tuple(int(v) for v in sys.argv[1].split("x"))
+variants = [
+    ("ce4", dict(transport="ce", overlap_chunks=4), {}),
+    ("ce4_equal", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "1,1,1,1"}),
+    ("ce4_line4=0", dict(transport="ce", overlap_chunks=4), {"EVX_FFT_LINE4": "0", "EVX_CE_FWD_SPLIT": "1,1,1,1"}),
+    ("ce4_mid6", dict(transport="ce", overlap_chunks=4, mid_chunks=6), {}),
+    ("ce4_mid2", dict(transport="ce", overlap_chunks=4, mid_chunks=2), {}),
+    ("ce4_first_small", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "0.12,0.2,0.56,0.12"}),
+    ("p2p_seq", dict(transport="p2p", overlap_chunks=1), {}),
+    ("p2p_pipe4_c64", dict(transport="p2p", overlap_chunks=4), {"EVX_LINE4_P2P_CTAS": "64"}),
+    ("p2p_pipe4_c100", dict(transport="p2p", overlap_chunks=4), {"EVX_LINE4_P2P_CTAS": "100"}),
+]
+only = os.environ.get("EVX_AB_ONLY")
+if only:
+    variants = [v for v in variants if v[0] in only.split(",")]
+gen = torch.Generator(device="cuda").manual_seed(100 + rank)
+u0 = 0.5 + 0.1 * torch.rand(Slab(shape, world, rank).local_shape, device=dev, generator=gen)
+out = {}
+ref = None
+for name, kw, env in variants:
+    for k, v in env.items():
+        os.environ[k] = v
+    st = DistributedCahnHilliardIMEX(shape, (1.0, 1.0, 1.0), 0.1, device=dev, **kw)
+    u = u0.clone()
+    for _ in range(5):
+        u = st.step(u)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        u = st.step(u)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / 20], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if ref is None:
+        ref = u.clone()
+    same = torch.tensor([int(torch.equal(u, ref))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    out[name] = {"ms_per_step": round(float(ms.item()), 4), "bit_equal_to_first": bool(same.item()),
+                 "finite": bool(torch.isfinite(u).all().item())}
+    if rank == 0:
+        print(name, json.dumps(out[name]), flush=True)
+    for k in env:
+        os.environ.pop(k, None)
+    del st
+    torch.cuda.empty_cache()
+    dist.barrier()
+if rank == 0:
+    os.makedirs("gpurun_out/r02_ab", exist_ok=True)
+    json.dump({"shape": shape, "world": world, "variants": out}, open(f"gpurun_out/r02_ab/ab_n{world}.json", "w"), indent=1)
+dist.destroy_process_group()
