@@ -252,6 +252,68 @@ def test_tma_tile_image_is_conflict_free():
                     assert len(nat) == len(st1) == len(xn) == len(xs) == 16, (kz, g, t0, e)
 
 
+@pytest.mark.parametrize("shape,blocks,power", [((8, 1024, 16), 3, 2), ((1024, 8, 16), 2, 2),
+                                                ((1024, 8, 32), 5, 1 | 0x100)])
+def test_four_stage_tma_tiled_passes_are_bit_identical(emu, shape, blocks, power):
+    """1024-point lines (StridedLine4 in fft_line_core.h: two groups of 256 threads, two line
+    pairs per group and tile, exchanges alternating between two padded buffers, tile touched in
+    natural order only) replayed on the CPU against the cp.async passes: y forward, x
+    forward*weight*inverse (IMEX and exponential-Euler weight), y inverse - same bits, including
+    the partly out-of-range last tile of a row."""
+    nx, ny, nz = shape
+    rng = np.random.default_rng(5)
+    r = rng.standard_normal(shape).astype(np.float32)
+    u = rng.random(shape).astype(np.float32)
+    h = (ctypes.c_double * 3)(1.0, 0.5, 2.0)
+    d = ctypes.c_double
+    want = np.zeros(shape, np.float32)
+    emu.emu_set_line_columns(0)
+    assert emu.emu_native_apply(_p(u), _p(r), _p(want), None, nx, ny, nz, h, d(0.1), d(1.5), power) == 0
+    got = np.full(shape, np.nan, np.float32)
+    emu.emu_set_line_columns(8)
+    emu.emu_set_pipe_blocks(blocks)
+    try:
+        assert emu.emu_native_apply(_p(u), _p(r), _p(got), None, nx, ny, nz, h, d(0.1), d(1.5), power) == 0
+    finally:
+        emu.emu_set_line_columns(0)
+        emu.emu_set_pipe_blocks(0)
+    assert np.array_equal(got, want)
+
+
+def test_four_stage_tile_and_exchange_layout_is_conflict_free():
+    """Bank check of StridedLine4: 64-bit accesses of a half-warp (8 consecutive t x the 2 lines of
+    a pair) hit 16 distinct 8-byte bank pairs - natural-order tile rows under the 64-byte TMA
+    swizzle for both line pairs of a group, natural-order reads and the stage-0/1/2 output orders
+    of the padded exchange buffers."""
+    T, L = 128, 1024
+    pad = lambda i: i + (i >> 3)
+    tile = lambda r, c: r * 64 + ((c * 8) ^ (((r >> 1) & 3) << 4))
+    ns = [1, 2, 16]                                   # Ns of stages 0, 1, 2 (radix 2, 8, 8)
+    radix = [2, 8, 8]
+
+    def out_index(s, t, e):
+        q = 8 // radix[s]
+        i, r = e % q, e // q
+        jv = t + i * T
+        return (jv // ns[s]) * ns[s] * radix[s] + jv % ns[s] + r * ns[s]
+
+    for g in range(2):
+        for t0 in range(0, T, 8):
+            for e in range(8):
+                for ps in range(2):
+                    lanes = [(t, 2 * g + c2 + 4 * ps) for t in range(t0, t0 + 8) for c2 in (0, 1)]
+                    nat = {(tile(t + e * T, c) // 8) % 16 for t, c in lanes}
+                    assert len(nat) == 16, ("tile", g, t0, e, ps)
+                lanes = [(t, c2) for t in range(t0, t0 + 8) for c2 in (0, 1)]
+                assert len({(pad(t + e * T) * 2 + c2) % 16 for t, c2 in lanes}) == 16
+                for s in range(3):
+                    idx = {(pad(out_index(s, t, e)) * 2 + c2) % 16 for t, c2 in lanes}
+                    assert len(idx) == 16, ("x", s, t0, e)
+    # every line index is written exactly once per stage
+    for s in range(3):
+        assert sorted(out_index(s, t, e) for t in range(T) for e in range(8)) == list(range(L))
+
+
 @pytest.mark.parametrize("shape", [(8, 8, 16), (16, 32, 64), (8, 16, 256)])
 def test_native_fft_pipeline_etd1_weight(emu, shape):
     """Same pipeline with the exponential-Euler weight (EVX_FILTER_ETD1) against the oracle's

@@ -73,3 +73,67 @@ def test_p2p_block_addressing_with_virtual_ranks(cuda_device, world):
         p.backward(A[k], spec[k], u[k * nxl:(k + 1) * nxl].contiguous(), o)
         out[k * nxl:(k + 1) * nxl] = o
     assert torch.equal(out, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,world,chunks", [((1024, 64, 32), 2, 1), ((1024, 64, 32), 8, 3),
+                                                ((64, 1024, 32), 4, 2), ((64, 1024, 32), 2, 2),
+                                                ((1024, 1024, 16), 8, 4)])
+@pytest.mark.parametrize("transport", ["local", "p2p"])
+def test_four_stage_tma_passes_in_the_distributed_plan_with_virtual_ranks(cuda_device, monkeypatch, shape,
+                                                                            world, chunks, transport):
+    """1024-point y / x lines of the x-slab plan through the four-stage TMA-tiled kernel, W plans
+    ("virtual ranks") on ONE GPU: `local` = block buffers + explicit block exchange (what the
+    copy-engine / NCCL transports do, own block through the second buffer), `p2p` = the TMA stores
+    of the passes land in the other plans' buffers (per-destination tensor maps).  Both must equal
+    the single-GPU spectral stage bit for bit, with and without the four-stage kernel."""
+    from evoxels_b200 import _native
+    sp = (1.0, 0.5, 2.0)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    r = torch.randn(shape, device="cuda", generator=gen)
+    u = torch.rand(shape, device="cuda", generator=gen)
+    monkeypatch.setenv("EVX_FFT_LINE4", "0")
+    ref = torch.empty_like(u)
+    _native.ImexPlan(shape, torch.float32, "cuda", _native.FFT_NATIVE).apply(u, r, ref, sp, 0.1, 1.5, 2)
+    nxl, nyl = shape[0] // world, shape[1] // world
+    xb = [round(i * nxl / chunks) for i in range(chunks + 1)]
+    yb = [round(i * nyl / chunks) for i in range(chunks + 1)]
+    for flag in ("0", "1"):
+        monkeypatch.setenv("EVX_FFT_LINE4", flag)
+        plans = [_native.DistPlan(shape, world, k, "cuda") for k in range(world)]
+        send = [p.new_buffer().zero_() for p in plans]
+        A = [p.new_buffer().fill_(float("nan")) for p in plans]
+        B = [p.new_buffer().fill_(float("nan")) for p in plans]
+        spec = [p.new_buffer() for p in plans]
+        for k, p in enumerate(plans):
+            rl = r[k * nxl:(k + 1) * nxl].contiguous()
+            for i in range(chunks):
+                if transport == "p2p":
+                    p.set_p2p_ctas(148 if chunks > 1 else 0)
+                    p.forward_chunk_p2p(rl, spec[k], [b.data_ptr() for b in B], xb[i], xb[i + 1] - xb[i], parts=1)
+                    p.forward_chunk_p2p(rl, spec[k], [b.data_ptr() for b in B], xb[i], xb[i + 1] - xb[i], parts=2)
+                else:
+                    p.forward_chunk(rl, spec[k], send[k], xb[i], xb[i + 1] - xb[i], self_block=B[k])
+        if transport == "local":
+            for k in range(world):
+                for j in range(world):
+                    if j != k:
+                        B[k][j].copy_(send[j][k])
+        for k, p in enumerate(plans):
+            if transport == "p2p":
+                p.middle_p2p(B[k], [a.data_ptr() for a in A], sp, 0.1, 1.5, 2)
+            else:
+                for i in range(chunks):
+                    p.middle_chunk(B[k], yb[i], yb[i + 1] - yb[i], sp, 0.1, 1.5, 2, self_block=A[k])
+        if transport == "local":
+            for k in range(world):
+                for j in range(world):
+                    if j != k:
+                        A[j][k].copy_(B[k][j])
+        out = torch.empty_like(u)
+        for k, p in enumerate(plans):
+            o = torch.empty((nxl,) + tuple(shape[1:]), device="cuda")
+            p.backward(A[k], spec[k], u[k * nxl:(k + 1) * nxl].contiguous(), o)
+            out[k * nxl:(k + 1) * nxl] = o
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), (flag, transport)

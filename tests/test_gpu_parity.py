@@ -642,6 +642,30 @@ def test_line_pass_forms_agree_bit_for_bit(cuda_device, monkeypatch, ws):
         assert torch.isfinite(b).all() and torch.equal(a, b)
 
 
+@pytest.mark.parametrize("shape", [(1024, 64, 32), (32, 1024, 64), (1024, 1024, 16), (1024, 8, 16)])
+def test_four_stage_tma_passes_match_the_cp_async_passes_bit_for_bit(cuda_device, monkeypatch, shape):
+    """1024-point strided passes: the four-stage TMA-tiled kernel (fft_line4_ws_kernel, 4-D tensor
+    maps) against the cp.async kernels - y forward, x forward*weight*inverse (IMEX and
+    exponential-Euler weight), y inverse; the update must be bit-identical."""
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    u = 0.5 + 0.1 * torch.rand(shape, device="cuda", generator=gen)
+    r = torch.randn(shape, device="cuda", generator=gen)
+    plan = _native.ImexPlan(shape, torch.float32, "cuda", _native.FFT_NATIVE)
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("EVX_FFT_LINE4", flag)
+        res = []
+        for power in (2, 1 | _native.FILTER_ETD1):
+            out = torch.full_like(u, float("nan"))
+            plan.apply(u, r, out, (1.0, 0.5, 2.0), 0.1, 1.5, power)
+            res.append(out)
+        torch.cuda.synchronize()
+        outs[flag] = res
+    for a, b in zip(outs["0"], outs["1"]):
+        assert torch.isfinite(b).all()
+        assert torch.equal(a, b)
+
+
 def test_cuda_graph_replay_of_the_chained_step(cuda_device, recwarn):
     """The 512-point path (cooperative chained kernels, warp-specialised x pass, two memsets per
     step) inside the solver's CUDA-graph replay: same fields as the eager loop, and the capture
