@@ -35,7 +35,17 @@ struct ChainParams {
   int ny, nz, P;
   unsigned* done0;         // [nplanes] finished stage-0 items per plane; zeroed before the launch
   int discard;             // inverse: drop the consumed spectrum rows from L2 without write-back
+  int blk_mode;            // x-slab plan: the y tiles are stored to (forward) / loaded from (inverse) the
+                           // all-to-all block layout, one tensor map per 256-row box (ChainMaps::blk)
   unsigned long long* stats;   // optional [gridDim.x][16] cycle counters of thread 0 (EVX_FFT_CHAIN_STATS)
+};
+
+// tensor maps of a launch: the plain spectrum ([8 x 256 x 1] boxes along y) and, for the x-slab
+// plan with ny / W = 256, the two destination (forward) / source (inverse) blocks of the all-to-all
+// layout - local block buffers or, forward, a peer's buffer over NVLink
+struct ChainMaps {
+  CUtensorMap spec;
+  CUtensorMap blk[2];
 };
 
 constexpr int kChainCompute = 512;                   // compute threads (16 warps)
@@ -81,7 +91,7 @@ struct ChainStats {
 // stage twiddles of the y lines only.
 template <bool INV, bool STATS, int NBUF, int TW>
 __global__ void __launch_bounds__(chain_threads(NBUF), NBUF <= 2 ? 2 : 1)
-    fft_chain_kernel(const __grid_constant__ CUtensorMap tmap, const ChainParams p) {
+    fft_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   using Line = StridedLine<512, 8, INV ? PASS_INV : PASS_FWD>;
   using ZG = ZGroupLine<INV>;
   constexpr int BUF = kChainBufBytes;
@@ -134,9 +144,13 @@ __global__ void __launch_bounds__(chain_threads(NBUF), NBUF <= 2 ? 2 : 1)
       if (is_y(it)) {
         mbar_expect_tx(&full[buf], Line::TILE_BYTES);
 #pragma unroll
-        for (int h = 0; h < 512 / Line::BOX_ROWS; ++h)
-          tma_load_3d(dst + h * Line::BOX_ROWS * Line::ROWB, &tmap, &full[buf], it.idx * Line::COLS,
-                      h * Line::BOX_ROWS, it.plane);
+        for (int h = 0; h < 512 / Line::BOX_ROWS; ++h) {
+          if (INV && p.blk_mode)
+            tma_load_3d(dst + h * Line::BOX_ROWS * Line::ROWB, &maps.blk[h], &full[buf], it.idx * Line::COLS, 0, it.plane);
+          else
+            tma_load_3d(dst + h * Line::BOX_ROWS * Line::ROWB, &maps.spec, &full[buf], it.idx * Line::COLS,
+                        h * Line::BOX_ROWS, it.plane);
+        }
       } else {
         const long long row = (long long)it.plane * p.ny + (long long)it.idx * kChainZLines;
         mbar_expect_tx(&full[buf], zin_bytes);
@@ -176,8 +190,12 @@ __global__ void __launch_bounds__(chain_threads(NBUF), NBUF <= 2 ? 2 : 1)
       if (is_y(it)) {
         const unsigned char* tb = bufs + buf * BUF;
 #pragma unroll
-        for (int h = 0; h < 512 / Line::BOX_ROWS; ++h)
-          tma_store_3d(&tmap, tb + h * Line::BOX_ROWS * Line::ROWB, it.idx * Line::COLS, h * Line::BOX_ROWS, it.plane);
+        for (int h = 0; h < 512 / Line::BOX_ROWS; ++h) {
+          if (!INV && p.blk_mode)
+            tma_store_3d(&maps.blk[h], tb + h * Line::BOX_ROWS * Line::ROWB, it.idx * Line::COLS, 0, it.plane);
+          else
+            tma_store_3d(&maps.spec, tb + h * Line::BOX_ROWS * Line::ROWB, it.idx * Line::COLS, h * Line::BOX_ROWS, it.plane);
+        }
         tma_store_commit();
         tma_store_wait_read();      // the tile has left shared memory: the buffer is free
         mbar_arrive(&empty[buf]);
@@ -285,7 +303,7 @@ static int chain_lag() {
   return v < 1 ? 1 : v;
 }
 template <bool INV, bool STATS, int NBUF, int TW>
-static int chain_launch_t(ChainParams p, const void* tmap, cudaStream_t st) {
+static int chain_launch_t(ChainParams p, const ChainMaps& maps, cudaStream_t st) {
   constexpr size_t smem = chain_smem_bytes(NBUF);
   auto kern = fft_chain_kernel<INV, STATS, NBUF, TW>;
   static SmemOptIn optin;
@@ -310,14 +328,20 @@ static int chain_launch_t(ChainParams p, const void* tmap, cudaStream_t st) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, *(const CUtensorMap*)tmap, p);
+  e = cudaLaunchKernelEx(&cfg, kern, maps, p);
   count_launch();
   return (int)e;
 }
 
-int chain_launch(bool inverse, const ChainArgs& a, const void* tmap_y, cudaStream_t st) {
+int chain_launch(bool inverse, const ChainArgs& a, const void* tmap_y, cudaStream_t st, const void* tmap_blk0,
+                 const void* tmap_blk1) {
   if (!chain_supported(a.nx, a.ny, a.nz)) return EVX_ERR_UNSUPPORTED;
+  ChainMaps maps;
+  maps.spec = *(const CUtensorMap*)tmap_y;
+  maps.blk[0] = *(const CUtensorMap*)(tmap_blk0 ? tmap_blk0 : tmap_y);
+  maps.blk[1] = *(const CUtensorMap*)(tmap_blk1 ? tmap_blk1 : tmap_y);
   ChainParams p;
+  p.blk_mode = (tmap_blk0 && tmap_blk1) ? 1 : 0;
   const int ytiles = (a.nz / 2 + 1 + 7) / 8;
   const int zitems = a.ny / kChainZLines;
   p.sched = inverse ? make_chain_schedule(a.nx, chain_lag(), ytiles, zitems)
@@ -338,10 +362,10 @@ int chain_launch(bool inverse, const ChainArgs& a, const void* tmap_y, cudaStrea
   const int tw = et ? atoi(et) : (inverse ? 3 : 2);
 #define EVX_CHAIN(NB, TWV)                                                                         \
   {                                                                                                \
-    if (p.stats) return inverse ? chain_launch_t<true, true, NB, TWV>(p, tmap_y, st)               \
-                                : chain_launch_t<false, true, NB, TWV>(p, tmap_y, st);            \
-    return inverse ? chain_launch_t<true, false, NB, TWV>(p, tmap_y, st)                           \
-                   : chain_launch_t<false, false, NB, TWV>(p, tmap_y, st);                        \
+    if (p.stats) return inverse ? chain_launch_t<true, true, NB, TWV>(p, maps, st)               \
+                                : chain_launch_t<false, true, NB, TWV>(p, maps, st);            \
+    return inverse ? chain_launch_t<true, false, NB, TWV>(p, maps, st)                           \
+                   : chain_launch_t<false, false, NB, TWV>(p, maps, st);                        \
   }
   if (nbuf == 2) EVX_CHAIN(2, 0)
   if (tw <= 0) EVX_CHAIN(3, 0)

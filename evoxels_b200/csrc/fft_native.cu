@@ -445,6 +445,7 @@ int native_ch_step(evx_imex_plan* p, const float* u, const float* hom, float* ou
 struct DistPlan : DistDims {
   int p2p_ctas = 0;   // grid cap of the peer-store launches (0: fill the GPU)
   void* twiddles = nullptr;
+  void* chain_scratch = nullptr;   // plane counters (+ stats area) of the chained z/y kernels
 };
 
 static DistTables tables_of(const DistPlan* p) {
@@ -471,9 +472,46 @@ int dist_plan_create(DistPlan** out, int nx, int ny, int nz, int world, int rank
   cudaError_t e = cudaMalloc(&p->twiddles, total * sizeof(cf));
   if (e == cudaSuccess)
     e = cudaMemcpy(p->twiddles, host.data(), total * sizeof(cf), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { delete p; return (int)e; }
+  if (e == cudaSuccess && chain_supported(p->nxl, ny, nz) && world == 2)
+    e = cudaMalloc(&p->chain_scratch, (((size_t)p->nxl * sizeof(unsigned) + 255) & ~(size_t)255) + kChainStatsBytes);
+  if (e != cudaSuccess) { if (p->twiddles) cudaFree(p->twiddles); delete p; return (int)e; }
   *out = p;
   return EVX_OK;
+}
+
+// ---- chained z/y kernels in the distributed plan (2 ranks, 512-point y and z lines) -------------
+// The y tiles of the chained kernels (fft_chain.cu) are [512 x 8]; with ny / W = 256 their two
+// 256-row TMA boxes are exactly the two blocks of the all-to-all layout, so the forward pair
+// stores its tiles through one tensor map per destination block (local buffers or the peer's
+// buffer) and the inverse pair loads them from the two blocks of the receive buffer - the plane's
+// spectrum still goes through L2 only.  EVX_ERR_UNSUPPORTED (nothing launched) otherwise.
+static bool use_chain_dist(const DistPlan* p, int nxc) {
+  const char* e = getenv("EVX_FFT_CHAIN");
+  return (!e || atoi(e) != 0) && p->chain_scratch && p->world == 2 && p->nyl == 256 && chain_supported(nxc, p->ny, p->nz);
+}
+static int dist_chain(DistPlan* p, bool inverse, const float* real_in, float* real_out, cf* spec, cf* blocks,
+                      void* const* peers, int x0, int nxc, cudaStream_t st) {
+  if (!use_chain_dist(p, nxc)) return EVX_ERR_UNSUPPORTED;
+  if (x0 < 0 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
+  const long long blk = (long long)p->nxl * p->nyl * p->P, xoff = (long long)x0 * p->nyl * p->P;
+  alignas(64) unsigned char map_spec[kTensorMapBytes], map_blk[2][kTensorMapBytes];
+  cf* spec_c = spec + (long long)x0 * p->ny * p->P;
+  int rc = line_make_tmap(map_spec, spec_c, nxc, p->ny, p->P, p->M + 1, 0, 8);
+  for (int w = 0; w < 2 && !rc; ++w) {
+    cf* base = inverse ? blocks + w * blk + xoff : (cf*)peers[w] + (long long)p->rank * blk + xoff;
+    rc = line_make_tmap(map_blk[w], base, nxc, p->nyl, p->P, p->M + 1, 0, 8);
+  }
+  if (rc) return rc;
+  const DistTables t = tables_of(p);
+  const long long roff = (long long)x0 * p->ny * p->nz;
+  ChainArgs a;
+  a.nx = nxc; a.ny = p->ny; a.nz = p->nz; a.P = p->P;
+  a.real_in = real_in ? real_in + roff : nullptr;
+  a.real_out = real_out ? real_out + roff : nullptr;
+  a.spec = spec_c; a.twz = t.twz; a.twr = t.twr; a.twy = t.twy;
+  a.flags = p->chain_scratch;
+  a.stats = (char*)p->chain_scratch + (((size_t)p->nxl * sizeof(unsigned) + 255) & ~(size_t)255);
+  return chain_launch(inverse, a, map_spec, st, map_blk[0], map_blk[1]);
 }
 
 // ---- 1024-point lines of the distributed plan: four-stage TMA-tiled passes (fft_line.cu) ------
@@ -566,13 +604,17 @@ int dist_forward(DistPlan* p, const float* r_local, cf* spec, cf* send, void* co
                  int x0, int nxc, cudaStream_t st, int parts = 3, bool remote = true) {
   if (x0 < 0 || nxc < 1 || x0 + nxc > p->nxl) return EVX_ERR_ARG;
   const DistTables t = tables_of(p);
+  void* table[8];
+  if (!peers && p->world <= 8) local_block_table(*p, send, send, table);
+  if (parts == 3 && p->world <= 8) {
+    const int rc = dist_chain(p, false, r_local, nullptr, spec, nullptr, peers ? peers : table, x0, nxc, st);
+    if (rc != EVX_ERR_UNSUPPORTED) return rc;
+  }
   if (parts & 1) {
     const int rc = launch_z<false>(p->M, dist_zfwd_params(*p, t, r_local, spec, x0, nxc), st);
     if (rc) return rc;
   }
   if (parts & 2) {
-    void* table[8];
-    if (!peers && p->world <= 8) local_block_table(*p, send, send, table);
     int rc = peers ? dist_y_line4(p, false, spec, nullptr, peers, remote, x0, nxc, st)
                    : (p->world <= 8 ? dist_y_line4(p, false, spec, nullptr, table, false, x0, nxc, st)
                                     : EVX_ERR_UNSUPPORTED);
@@ -601,7 +643,9 @@ int dist_middle(DistPlan* p, cf* recv, void* const* peers, const double* h, doub
 int dist_backward(DistPlan* p, const cf* recv, cf* spec, const float* u_local, float* out_local,
                   cudaStream_t st) {
   const DistTables t = tables_of(p);
-  int rc = dist_y_line4(p, true, spec, const_cast<cf*>(recv), nullptr, false, 0, p->nxl, st);
+  int rc = dist_chain(p, true, u_local, out_local, spec, const_cast<cf*>(recv), nullptr, 0, p->nxl, st);
+  if (rc != EVX_ERR_UNSUPPORTED) return rc;
+  rc = dist_y_line4(p, true, spec, const_cast<cf*>(recv), nullptr, false, 0, p->nxl, st);
   if (rc == EVX_ERR_UNSUPPORTED)
     rc = launch_strided<PASS_INV>(p->ny, dist_yinv_params(*p, t, recv, spec, 0, p->nxl), st);
   if (rc) return rc;
@@ -677,7 +721,11 @@ int evx_dist_plan_create(evx_dist_plan** plan, int nx, int ny, int nz, int world
 }
 int evx_dist_plan_destroy(evx_dist_plan* plan) {
   DistPlan* p = (DistPlan*)plan;
-  if (p) { if (p->twiddles) cudaFree(p->twiddles); delete p; }
+  if (p) {
+    if (p->twiddles) cudaFree(p->twiddles);
+    if (p->chain_scratch) cudaFree(p->chain_scratch);
+    delete p;
+  }
   return EVX_OK;
 }
 int evx_dist_plan_set_p2p_ctas(evx_dist_plan* plan, int ctas) {

@@ -483,7 +483,9 @@ class DistributedCahnHilliardIMEX:
                                                        transport=transport, group=group)
         # x-pass pipeline depth of the 'ce' transport (measured on 8 GPUs, 512^3 per GPU:
         # 4 chunks 3.39 ms/step, 2 chunks 3.40, unchunked 3.94)
-        self.mid_chunks = mid_chunks if mid_chunks else overlap_chunks
+        # (2 GPUs, round 2: 6 chunks 1.80 ms/step, 4 chunks 1.82, 3 chunks 1.85; 8 GPUs: 4 chunks)
+        self.mid_chunks = mid_chunks if mid_chunks else (6 if self.comm.world == 2 and overlap_chunks == 4
+                                                         else overlap_chunks)
         if copier is not None:
             self.ops.copier = copier
         if scatter_ctas:

@@ -20,14 +20,12 @@ if len(sys.argv) > 1 and "x" in sys.argv[1]:
     shape = tuple(int(v) for v in sys.argv[1].split("x"))
 variants = [
     ("ce4", dict(transport="ce", overlap_chunks=4), {}),
+    ("ce4_chain=0", dict(transport="ce", overlap_chunks=4), {"EVX_FFT_CHAIN": "0"}),
     ("ce4_equal", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "1,1,1,1"}),
-    ("ce4_line4=0", dict(transport="ce", overlap_chunks=4), {"EVX_FFT_LINE4": "0", "EVX_CE_FWD_SPLIT": "1,1,1,1"}),
+    ("ce3_thin_edges", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "0.15,0.7,0.15"}),
     ("ce4_mid6", dict(transport="ce", overlap_chunks=4, mid_chunks=6), {}),
-    ("ce4_mid2", dict(transport="ce", overlap_chunks=4, mid_chunks=2), {}),
-    ("ce4_first_small", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "0.12,0.2,0.56,0.12"}),
+    ("ce4_mid3", dict(transport="ce", overlap_chunks=4, mid_chunks=3), {}),
     ("p2p_seq", dict(transport="p2p", overlap_chunks=1), {}),
-    ("p2p_pipe4_c64", dict(transport="p2p", overlap_chunks=4), {"EVX_LINE4_P2P_CTAS": "64"}),
-    ("p2p_pipe4_c100", dict(transport="p2p", overlap_chunks=4), {"EVX_LINE4_P2P_CTAS": "100"}),
 ]
 only = os.environ.get("EVX_AB_ONLY")
 if only:

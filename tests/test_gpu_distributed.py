@@ -137,3 +137,46 @@ def test_four_stage_tma_passes_in_the_distributed_plan_with_virtual_ranks(cuda_d
             out[k * nxl:(k + 1) * nxl] = o
         torch.cuda.synchronize()
         assert torch.equal(out, ref), (flag, transport)
+
+
+@pytest.mark.parametrize("transport,chunks", [("local", 1), ("local", 2), ("p2p", 1)])
+def test_chained_zy_kernels_in_the_distributed_plan_with_virtual_ranks(cuda_device, monkeypatch, transport, chunks):
+    """2 ranks, 512-point y and z lines: the chained z/y kernels write / read the all-to-all block
+    layout through one tensor map per 256-row box (fft_chain.cu, ChainMaps::blk) - local block
+    buffers with an explicit exchange, or straight into the other plan's buffer.  Bit-identical to
+    the single-GPU spectral stage and to the un-chained distributed passes."""
+    from evoxels_b200 import _native
+    shape, world, sp = (64, 512, 512), 2, (1.0, 0.5, 2.0)
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    r = torch.randn(shape, device="cuda", generator=gen)
+    u = torch.rand(shape, device="cuda", generator=gen)
+    ref = torch.empty_like(u)
+    _native.ImexPlan(shape, torch.float32, "cuda", _native.FFT_NATIVE).apply(u, r, ref, sp, 0.1, 1.5, 2)
+    nxl = shape[0] // world
+    xb = [round(i * nxl / chunks) for i in range(chunks + 1)]
+    for chain in ("0", "1"):
+        monkeypatch.setenv("EVX_FFT_CHAIN", chain)
+        plans = [_native.DistPlan(shape, world, k, "cuda") for k in range(world)]
+        send = [p.new_buffer().zero_() for p in plans]
+        A = [p.new_buffer().fill_(float("nan")) for p in plans]
+        B = [p.new_buffer().fill_(float("nan")) for p in plans]
+        spec = [p.new_buffer() for p in plans]
+        for k, p in enumerate(plans):
+            rl = r[k * nxl:(k + 1) * nxl].contiguous()
+            if transport == "p2p":
+                p.forward_p2p(rl, spec[k], [b.data_ptr() for b in B])
+            else:
+                for i in range(chunks):
+                    p.forward_chunk(rl, spec[k], send[k], xb[i], xb[i + 1] - xb[i], self_block=B[k])
+        if transport == "local":
+            for k in range(world):
+                B[k][1 - k].copy_(send[1 - k][k])
+        for k, p in enumerate(plans):
+            p.middle_p2p(B[k], [a.data_ptr() for a in A], sp, 0.1, 1.5, 2)
+        out = torch.empty_like(u)
+        for k, p in enumerate(plans):
+            o = torch.empty((nxl,) + tuple(shape[1:]), device="cuda")
+            p.backward(A[k], spec[k], u[k * nxl:(k + 1) * nxl].contiguous(), o)
+            out[k * nxl:(k + 1) * nxl] = o
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), (chain, transport, chunks)
