@@ -824,6 +824,7 @@ def run_ours_distributed(args, world, rank, local, dev):
             ac3 = distributed_ac_config3(world, rank, dev)
         except Exception as exc:
             ac3 = {"error": repr(exc)[:200]}
+    stepper_direct = int(getattr(stepper.ops, "direct_peers", 0))
     cfg4 = None
     if args.config4 or (world == 8 and not args.no_extras):
         del stepper
@@ -848,7 +849,9 @@ def run_ours_distributed(args, world, rank, local, dev):
                                          else "NCCL send/recv") + ") + slab<->pencil "
                                       + {"p2p": "transposes fused into the FFT passes as NVLink peer stores (symmetric memory)",
                                          "ce": "transposes as DMA-engine copies between symmetric-memory block buffers, "
-                                               "pipelined against the kernels of the next chunk",
+                                               "pipelined against the kernels of the next chunk"
+                                               + (f"; the blocks of {stepper_direct} of the {world - 1} peers leave the FFT passes "
+                                                  "as TMA stores into the peer's buffer over NVLink" if stepper_direct else ""),
                                          "nccl": "NCCL all-to-all"}[args.transport],
                        "l2": "slab (%.0f MB) larger than L2 (126 MB), no flush needed" % (slab_bytes / 1e6)},
             "clocks": clocks,

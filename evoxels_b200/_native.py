@@ -90,6 +90,8 @@ SIGNATURES = {
                                        _c_int, _c_int, _c_void_p],
     "evx_dist_middle_p2p_f32": [_c_void_p, _c_void_p, ctypes.POINTER(_c_void_p), _dptr, _c_double,
                                 _c_double, _c_int, _c_void_p],
+    "evx_dist_middle_chunk_p2p_f32": [_c_void_p, _c_void_p, ctypes.POINTER(_c_void_p), _c_int, _c_int, _dptr,
+                                      _c_double, _c_double, _c_int, _c_void_p],
     "evx_dist_backward_f32": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
 }
 _RESTYPES = {"evx_strerror": ctypes.c_char_p, "evx_launch_count": ctypes.c_ulonglong}
@@ -498,6 +500,15 @@ class DistPlan:
             check(load_library().evx_dist_middle_p2p_f32(self._handle, _ptr(recv), self._ptr_array(peer_ptrs),
                                                          _h3(spacing), float(dt), float(coef), int(power),
                                                          _stream(recv)), "evx_dist_middle_p2p")
+
+    def middle_chunk_p2p(self, recv, peer_ptrs, yl0, nylc, spacing, dt, coef, power):
+        """middle_p2p for the local y-pencil rows [yl0, yl0+nylc); the table may mix peer and local
+        destinations (hybrid transport)."""
+        require_cuda(recv)
+        with torch.cuda.device(self.device):
+            check(load_library().evx_dist_middle_chunk_p2p_f32(
+                self._handle, _ptr(recv), self._ptr_array(peer_ptrs), int(yl0), int(nylc), _h3(spacing),
+                float(dt), float(coef), int(power), _stream(recv)), "evx_dist_middle_chunk_p2p")
 
     def backward(self, recv, spec, u_local, out_local):
         require_cuda(recv, spec, u_local, out_local)

@@ -812,6 +812,12 @@ int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_o
   if (((DistPlan*)plan)->world > 8) return EVX_ERR_UNSUPPORTED;
   return dist_middle((DistPlan*)plan, (cf*)recv, peer_out, h, dt, coef, power, (cudaStream_t)stream);
 }
+int evx_dist_middle_chunk_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_out, int yl0, int nylc,
+                                  const double* h, double dt, double coef, int power, void* stream) {
+  if (!plan || !recv || !peer_out || !h || !valid_filter_spec(power)) return EVX_ERR_ARG;
+  if (((DistPlan*)plan)->world > 8) return EVX_ERR_UNSUPPORTED;
+  return dist_middle((DistPlan*)plan, (cf*)recv, peer_out, h, dt, coef, power, (cudaStream_t)stream, yl0, nylc);
+}
 int evx_dist_middle_f32(evx_dist_plan* plan, void* recv, const double* h, double dt, double coef,
                         int power, void* stream) {
   if (!plan || !recv || !h || !valid_filter_spec(power)) return EVX_ERR_ARG;

@@ -300,7 +300,10 @@ class CudaOps:
     # copy kernel that fills the GPU (NVLink-bound, ~700 GB/s aggregate) instead of the DMA engines
     # (measured ~420 GB/s aggregate over 7 peers for contiguous regions, ~215 GB/s for the pitched
     # regions after the x pass).  0 = DMA for every chunk.
-    last_chunk_ctas = 24
+    last_chunk_ctas = int(os.environ.get("EVX_CE_LAST_CTAS", "24"))
+    # hybrid transport: number of peers served by TMA stores from inside the y pass / x pass
+    direct_peers = int(os.environ.get("EVX_CE_DIRECT", "0"))
+    direct_peers_mid = int(os.environ.get("EVX_CE_DIRECT_MID", os.environ.get("EVX_CE_DIRECT", "0")))
 
     def _mark(self, name, stream=None):
         if self.trace is not None:
@@ -361,6 +364,15 @@ class CudaOps:
         comp.wait_stream(main)
         halo_waited = halo_event is None
         a_ptr, b_ptrs = self.buf_a.data_ptr(), self.peers.peer_ptrs[1]
+        stagger = [(me + 1 + k) % W for k in range(W - 1)]        # staggered across ranks
+        # hybrid transport: the blocks of the first `direct_peers` ranks of that order leave the y
+        # pass as TMA stores into the peer's buffer (no send-buffer round trip, no DMA copy), the
+        # others go through the local block buffer and the copy engines as before
+        direct = stagger[:max(0, min(self.direct_peers, W - 1))]
+        table = [b_ptrs[j] if j in direct else (self.buf_b.data_ptr() if j == me else a_ptr + (j - me) * blk)
+                 for j in range(W)]
+        if direct:
+            self.plan.set_p2p_ctas(0)
         for n_done, i in enumerate(order):
             x0, x1 = bounds[i], bounds[i + 1]
             with torch.cuda.stream(comp):
@@ -371,12 +383,17 @@ class CudaOps:
                 hi = halo_hi if x1 == nxl else u[x1:x1 + 2]
                 _native.ch_rhs(u[x0:x1], rhs[x0:x1], self.spacing, eps, D, bc, halo_lo=lo, halo_hi=hi)
                 self._mark(f"fwd{i} rhs", comp)
-                self.plan.forward_chunk(rhs, self.spec, self.buf_a, x0, x1 - x0, self_block=self.buf_b)
+                if direct:
+                    self.plan.forward_chunk_p2p(rhs, self.spec, table, x0, x1 - x0, parts=3)
+                else:
+                    self.plan.forward_chunk(rhs, self.spec, self.buf_a, x0, x1 - x0, self_block=self.buf_b)
                 self._mark(f"fwd{i} z+y", comp)
                 done = torch.cuda.Event()
                 done.record(comp)
-            peers_ = [(me + 1 + k) % W for k in range(W - 1)]     # staggered across ranks
+            peers_ = [j for j in stagger if j not in direct]
             last = n_done == chunks - 1 and self.last_chunk_ctas > 0 and W > 1
+            if not peers_:
+                continue
             if self.copier == "kernel" or last:
                 cs = comp if last else copies[0]
                 cs.wait_event(done)
@@ -416,16 +433,27 @@ class CudaOps:
         comp, copies = self._ce_streams()
         comp.wait_stream(main)
         b_ptr, a_ptrs = self.buf_b.data_ptr(), self.peers.peer_ptrs[0]
+        stagger = [(me + 1 + k) % W for k in range(W - 1)]
+        direct = stagger[:max(0, min(self.direct_peers_mid, W - 1))]      # see forward_ce
+        table = [a_ptrs[j] if j in direct else (self.buf_a.data_ptr() if j == me else b_ptr + (j - me) * blk)
+                 for j in range(W)]
+        if direct:
+            self.plan.set_p2p_ctas(0)
         for i in range(chunks):
             y0, y1 = bounds[i], bounds[i + 1]
             with torch.cuda.stream(comp):
-                self.plan.middle_chunk(self.buf_b, y0, y1 - y0, self.spacing, dt, coef, power,
-                                       self_block=self.buf_a)
+                if direct:
+                    self.plan.middle_chunk_p2p(self.buf_b, table, y0, y1 - y0, self.spacing, dt, coef, power)
+                else:
+                    self.plan.middle_chunk(self.buf_b, y0, y1 - y0, self.spacing, dt, coef, power,
+                                           self_block=self.buf_a)
                 self._mark(f"mid{i} x", comp)
                 done = torch.cuda.Event()
                 done.record(comp)
-            peers_ = [(me + 1 + k) % W for k in range(W - 1)]
+            peers_ = [j for j in stagger if j not in direct]
             last = i == chunks - 1 and self.last_chunk_ctas > 0 and W > 1
+            if not peers_:
+                continue
             if self.copier == "kernel" or last:
                 cs = comp if last else copies[0]
                 cs.wait_event(done)
@@ -483,9 +511,16 @@ class DistributedCahnHilliardIMEX:
                                                        transport=transport, group=group)
         # x-pass pipeline depth of the 'ce' transport (measured on 8 GPUs, 512^3 per GPU:
         # 4 chunks 3.39 ms/step, 2 chunks 3.40, unchunked 3.94)
-        # (2 GPUs, round 2: 6 chunks 1.80 ms/step, 4 chunks 1.82, 3 chunks 1.85; 8 GPUs: 4 chunks)
-        self.mid_chunks = mid_chunks if mid_chunks else (6 if self.comm.world == 2 and overlap_chunks == 4
+        # (2 GPUs, round 2: 8 chunks 1.79 ms/step, 6 chunks 1.80, 4 chunks 1.82, 3 chunks 1.85; 8 GPUs: 4 chunks)
+        self.mid_chunks = mid_chunks if mid_chunks else (8 if self.comm.world == 2 and overlap_chunks == 4
                                                          else overlap_chunks)
+        if self.comm.world >= 8 and ops is None and "EVX_CE_DIRECT" not in os.environ:
+            # 8 GPUs (copy-bound): two of the seven blocks leave the passes as TMA stores over NVLink
+            # instead of through the copy engines (3.03 -> 2.93 ms/step; 1: 2.99, 3: 3.01)
+            self.ops.direct_peers = self.ops.direct_peers_mid = 2
+        if self.comm.world == 2 and "EVX_CE_LAST_CTAS" not in os.environ and ops is None:
+            # one peer: the last slice's blocks move fastest with the whole GPU copying (1.81 -> 1.77 ms)
+            self.ops.last_chunk_ctas = 148
         if copier is not None:
             self.ops.copier = copier
         if scatter_ctas:

@@ -242,6 +242,13 @@ int evx_dist_middle_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_o
  * transfer of one chunk with the rhs / z pass of the next. */
 int evx_dist_forward_chunk_p2p_f32(evx_dist_plan* plan, const float* r_local, void* spec,
                                    void* const* peer_recv, int x0, int nxc, int parts, void* stream);
+/* middle_p2p restricted to the local y-pencil rows [yl0, yl0+nylc).  The destination tables of the
+ * *_chunk_p2p calls may mix peers' buffers with local ones (entry j - rank blocks before the local
+ * buffer's block j): the hybrid transport stores the blocks of some ranks over NVLink from inside
+ * the pass and leaves the others to the copy engines. */
+int evx_dist_middle_chunk_p2p_f32(evx_dist_plan* plan, void* recv, void* const* peer_out, int yl0,
+                                  int nylc, const double* h, double dt, double coef, int power,
+                                  void* stream);
 
 /* Copy-engine transport: the same block buffers, but the transposes are plain device-to-device
  * copies between mapped peer buffers issued on copy streams (DMA engines, no SM involved), so

@@ -18,15 +18,19 @@ n = 512
 shape = {1: (n, n, n), 2: (2 * n, n, n), 4: (2 * n, 2 * n, n), 8: (2 * n, 2 * n, 2 * n)}[world]
 if len(sys.argv) > 1 and "x" in sys.argv[1]:
     shape = tuple(int(v) for v in sys.argv[1].split("x"))
+W8 = world >= 4
 variants = [
     ("ce4", dict(transport="ce", overlap_chunks=4), {}),
-    ("ce4_chain=0", dict(transport="ce", overlap_chunks=4), {"EVX_FFT_CHAIN": "0"}),
-    ("ce4_equal", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "1,1,1,1"}),
-    ("ce3_thin_edges", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "0.15,0.7,0.15"}),
-    ("ce4_mid6", dict(transport="ce", overlap_chunks=4, mid_chunks=6), {}),
-    ("ce4_mid3", dict(transport="ce", overlap_chunks=4, mid_chunks=3), {}),
-    ("p2p_seq", dict(transport="p2p", overlap_chunks=1), {}),
-]
+    ("ce4_direct1", dict(transport="ce", overlap_chunks=4), {"direct": 1, "direct_mid": 1}),
+] + ([
+    ("ce4_direct_fwd1", dict(transport="ce", overlap_chunks=4), {"direct": 1, "direct_mid": 0}),
+    ("ce4_direct_mid1", dict(transport="ce", overlap_chunks=4), {"direct": 0, "direct_mid": 1}),
+] if not W8 else []) + ([
+    ("ce4_direct2", dict(transport="ce", overlap_chunks=4), {"direct": 2, "direct_mid": 2}),
+    ("ce4_direct3", dict(transport="ce", overlap_chunks=4), {"direct": 3, "direct_mid": 3}),
+    ("ce4_direct_1_3", dict(transport="ce", overlap_chunks=4), {"direct": 1, "direct_mid": 3}),
+    ("ce4_direct_2_4", dict(transport="ce", overlap_chunks=4), {"direct": 2, "direct_mid": 4}),
+] if W8 else [])
 only = os.environ.get("EVX_AB_ONLY")
 if only:
     variants = [v for v in variants if v[0] in only.split(",")]
@@ -35,9 +39,15 @@ u0 = 0.5 + 0.1 * torch.rand(Slab(shape, world, rank).local_shape, device=dev, ge
 out = {}
 ref = None
 for name, kw, env in variants:
+    attrs = {k: v for k, v in env.items() if not k.startswith("EVX_")}
+    env = {k: v for k, v in env.items() if k.startswith("EVX_")}
     for k, v in env.items():
         os.environ[k] = v
     st = DistributedCahnHilliardIMEX(shape, (1.0, 1.0, 1.0), 0.1, device=dev, **kw)
+    if "EVX_CE_LAST_CTAS" in env:
+        st.ops.last_chunk_ctas = int(env["EVX_CE_LAST_CTAS"])
+    if "direct" in attrs:
+        st.ops.direct_peers, st.ops.direct_peers_mid = attrs["direct"], attrs["direct_mid"]
     u = u0.clone()
     for _ in range(5):
         u = st.step(u)
