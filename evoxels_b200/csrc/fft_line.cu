@@ -411,9 +411,15 @@ int line_make_tmap4(void* out, void* base, int ncols_valid, int box_rows, long l
   return rc == CUDA_SUCCESS ? EVX_OK : EVX_ERR_UNSUPPORTED;
 }
 
-template <int MODE>
+// EVX_LINE4_G: lines per synchronisation group (2 = two groups of 256 threads, 1 = four groups of 128)
+static int line4_group_lines() {
+  const char* e = getenv("EVX_LINE4_G");
+  return (e && atoi(e) == 1) ? 1 : 2;
+}
+
+template <int MODE, int GL>
 static int launch_line4_t(LineParams p, const void* map_in, const void* const* maps_out, int nout, cudaStream_t st) {
-  using Prog = StridedLine4<1024, 8, MODE>;
+  using Prog = StridedLine4<1024, 8, MODE, GL>;
   constexpr int NBUF = 2;
   p.tiles_per_row = (p.ncols_valid + 7) / 8;
   p.ntiles = (long long)p.nrows * p.tiles_per_row;
@@ -437,11 +443,16 @@ static int launch_line4_t(LineParams p, const void* map_in, const void* const* m
 
 int line4_pass_launch(int mode, const LineParams& p, const void* map_in, const void* const* maps_out, int nout,
                       cudaStream_t st) {
+  const bool g1 = line4_group_lines() == 1;
   switch (mode) {
-    case PASS_FWD: return launch_line4_t<PASS_FWD>(p, map_in, maps_out, nout, st);
-    case PASS_INV: return launch_line4_t<PASS_INV>(p, map_in, maps_out, nout, st);
-    case PASS_XMID: return launch_line4_t<PASS_XMID>(p, map_in, maps_out, nout, st);
-    case PASS_XMID_ETD1: return launch_line4_t<PASS_XMID_ETD1>(p, map_in, maps_out, nout, st);
+    case PASS_FWD: return g1 ? launch_line4_t<PASS_FWD, 1>(p, map_in, maps_out, nout, st)
+                             : launch_line4_t<PASS_FWD, 2>(p, map_in, maps_out, nout, st);
+    case PASS_INV: return g1 ? launch_line4_t<PASS_INV, 1>(p, map_in, maps_out, nout, st)
+                             : launch_line4_t<PASS_INV, 2>(p, map_in, maps_out, nout, st);
+    case PASS_XMID: return g1 ? launch_line4_t<PASS_XMID, 1>(p, map_in, maps_out, nout, st)
+                              : launch_line4_t<PASS_XMID, 2>(p, map_in, maps_out, nout, st);
+    case PASS_XMID_ETD1: return g1 ? launch_line4_t<PASS_XMID_ETD1, 1>(p, map_in, maps_out, nout, st)
+                                   : launch_line4_t<PASS_XMID_ETD1, 2>(p, map_in, maps_out, nout, st);
     default: return EVX_ERR_ARG;
   }
 }

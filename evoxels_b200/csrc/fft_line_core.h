@@ -246,13 +246,15 @@ struct StridedLine {
 // line pair - is covered by starting that pair on the buffer the last phase did NOT read (4
 // phases: the pairs alternate; 7 phases: always buffer 0).
 // ---------------------------------------------------------------------------------------------
-template <int L, int KZ, int MODE>
+template <int L, int KZ, int MODE, int GL = 2>
 struct StridedLine4 {
   static_assert(L == 1024 && KZ == 8, "four-stage TMA-tiled pass: 1024-point lines, 64-byte tile rows");
+  static_assert(GL == 1 || GL == 2, "lines per synchronisation group");
   static constexpr int LEN = L;
   static constexpr int COLS = KZ;
   static constexpr int T = L / 8;
-  static constexpr int G = 2;
+  static constexpr int G = GL;                 // 2: conflict-free 16-byte pairs, two groups of 8 warps;
+                                               // 1: four groups of 4 warps (2-way conflicts on the tile rows)
   static constexpr int GT = T * G;
   static constexpr int NPASS = 2;              // line pairs per group and tile
   static constexpr int NG = KZ / (G * NPASS);
@@ -300,7 +302,8 @@ struct StridedLine4 {
   EVX_HD static cf* tile_at(unsigned char* tile, int byte_off) {
     return reinterpret_cast<cf*>(tile + byte_off);
   }
-  // pair `pass` of the group: columns + 4 = byte offset bit 5 flipped
+  // pair `pass` of the group: columns + 4 = byte offset bit 5 flipped (both group shapes: pass 0
+  // covers columns 0..3, pass 1 columns 4..7)
   EVX_HD static void read_tile(Regs& r, unsigned char* tile, int pass) {
     const int tb = r.tb ^ (pass << 5);
 #pragma unroll

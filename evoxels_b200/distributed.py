@@ -514,7 +514,8 @@ class DistributedCahnHilliardIMEX:
         # (2 GPUs, round 2: 8 chunks 1.79 ms/step, 6 chunks 1.80, 4 chunks 1.82, 3 chunks 1.85; 8 GPUs: 4 chunks)
         self.mid_chunks = mid_chunks if mid_chunks else (8 if self.comm.world == 2 and overlap_chunks == 4
                                                          else overlap_chunks)
-        if self.comm.world >= 8 and ops is None and "EVX_CE_DIRECT" not in os.environ:
+        if (self.comm.world >= 8 and ops is None and "EVX_CE_DIRECT" not in os.environ
+                and tuple(global_shape[:2]) == (1024, 1024)):      # measured with the TMA-store passes only
             # 8 GPUs (copy-bound): two of the seven blocks leave the passes as TMA stores over NVLink
             # instead of through the copy engines (3.03 -> 2.93 ms/step; 1: 2.99, 3: 3.01)
             self.ops.direct_peers = self.ops.direct_peers_mid = 2
