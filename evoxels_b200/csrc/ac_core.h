@@ -275,6 +275,14 @@ struct AcTileProgram {
   struct Smem {
     Vt c[4][ROWS][COLS];
     Vt stage[2][NTHREADS];   // raw planes in flight (cp.async), one cell per thread
+    // z neighbours of every interior group, kept as compact arrays next to the planes: the value
+    // left of a group (last element of the group before it) and right of it (first element of
+    // the group after it).  Read as 4-byte words straight from c[][][] these sit 16 bytes apart
+    // from lane to lane - a 4-way bank conflict on each of the ten neighbour reads of a voxel
+    // group, as many shared-memory wavefronts as all its vector reads together; here a warp (two
+    // rows of G = 16 groups) reads 32 consecutive words.
+    T zl[4][ROWS][G];
+    T zr[4][ROWS][G];
   };
   static_assert(sizeof(Vt) == 16, "the staging copy moves 16 bytes per thread");
 
@@ -312,6 +320,14 @@ struct AcTileProgram {
       v.v[0] = Base::rule(p, 2, 1, v.v[V - 1]);
     }
     return v;
+  }
+
+  // store the padded group of the own position into plane slot `sl`, and its outer elements
+  // into the neighbour arrays of the groups next to it
+  EVX_HD static void publish(Smem& s, int sl, const Regs& t, const Vt& v) {
+    s.c[sl][t.row][t.col] = v;
+    if (t.col <= G - 1) s.zl[sl][t.row][t.col] = v.v[V - 1];      // left neighbour of group col + 1
+    if (t.col >= 2) s.zr[sl][t.row][t.col - 2] = v.v[0];          // right neighbour of group col - 1
   }
 
   EVX_HD static Vt load_plane(const Regs& t, const P& p, int q, int& xside) {
@@ -371,7 +387,7 @@ struct AcTileProgram {
       for (int i = 0; i < 4; ++i) {     // planes xa-1 .. xa+2 -> slots 0..3
         int xs;
         const Vt raw = load_plane(t, p, t.xa - 1 + i, xs);
-        s.c[i][t.row][t.col] = padded(t, p, raw, xs);
+        publish(s, i, t, padded(t, p, raw, xs));
       }
       if (t.qn <= t.xb) fetch_next(t, s, p, 0);     // plane xa+3 -> cell 0
     }
@@ -382,8 +398,8 @@ struct AcTileProgram {
     const Vt c = s.c[sl][row][col];
 #pragma unroll
     for (int k = 0; k < V; ++k) w[k + 1] = c.v[k];
-    w[0] = s.c[sl][row][col - 1].v[V - 1];
-    w[V + 1] = s.c[sl][row][col + 1].v[0];
+    w[0] = s.zl[sl][row][col - 1];
+    w[V + 1] = s.zr[sl][row][col - 1];
   }
   EVX_HD static void centre_only(const Smem& s, int sl, int row, int col, T* w) {
     const Vt c = s.c[sl][row][col];
@@ -420,7 +436,7 @@ struct AcTileProgram {
     if (x + 3 <= t.xb) {
       async_copy_wait_all();
       const Vt raw = s.stage[ROT & 1][t.tid];
-      s.c[ROT % 4][t.row][t.col] = padded(t, p, raw, xside_of(p, x + 3));
+      publish(s, ROT % 4, t, padded(t, p, raw, xside_of(p, x + 3)));
       if (x + 4 <= t.xb) fetch_next(t, s, p, (ROT + 1) & 1);
     }
   }

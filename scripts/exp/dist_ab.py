@@ -18,19 +18,16 @@ n = 512
 shape = {1: (n, n, n), 2: (2 * n, n, n), 4: (2 * n, 2 * n, n), 8: (2 * n, 2 * n, 2 * n)}[world]
 if len(sys.argv) > 1 and "x" in sys.argv[1]:
     shape = tuple(int(v) for v in sys.argv[1].split("x"))
-W8 = world >= 4
 variants = [
     ("ce4", dict(transport="ce", overlap_chunks=4), {}),
+    ("ce4_thin_edges", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "0.12,0.38,0.38,0.12"}),
+    ("ce4_mid6", dict(transport="ce", overlap_chunks=4, mid_chunks=6), {}),
     ("ce4_direct1", dict(transport="ce", overlap_chunks=4), {"direct": 1, "direct_mid": 1}),
-] + ([
-    ("ce4_direct_fwd1", dict(transport="ce", overlap_chunks=4), {"direct": 1, "direct_mid": 0}),
     ("ce4_direct_mid1", dict(transport="ce", overlap_chunks=4), {"direct": 0, "direct_mid": 1}),
-] if not W8 else []) + ([
-    ("ce4_direct2", dict(transport="ce", overlap_chunks=4), {"direct": 2, "direct_mid": 2}),
-    ("ce4_direct3", dict(transport="ce", overlap_chunks=4), {"direct": 3, "direct_mid": 3}),
-    ("ce4_direct_1_3", dict(transport="ce", overlap_chunks=4), {"direct": 1, "direct_mid": 3}),
-    ("ce4_direct_2_4", dict(transport="ce", overlap_chunks=4), {"direct": 2, "direct_mid": 4}),
-] if W8 else [])
+    ("ce4_last148", dict(transport="ce", overlap_chunks=4), {"EVX_CE_LAST_CTAS": "148"}),
+    ("ce4_last_dma", dict(transport="ce", overlap_chunks=4), {"EVX_CE_LAST_CTAS": "0"}),
+    ("ce6", dict(transport="ce", overlap_chunks=4, mid_chunks=6), {"EVX_CE_FWD_SPLIT": "1,1,1,1,1,1"}),
+]
 only = os.environ.get("EVX_AB_ONLY")
 if only:
     variants = [v for v in variants if v[0] in only.split(",")]
