@@ -198,3 +198,23 @@ def test_etd1_and_imex_weights_do_not_share_a_cache():
     b = ts._fft_prefac
     assert not torch.equal(a, b)
     assert torch.equal(ts.phi_1_k_squared, a) and torch.equal(ts._fft_prefac, b)
+
+
+def test_pipeline_slice_bounds(monkeypatch):
+    """Slice bounds of the pipelined distributed stages (CudaOps._split): equal parts by default,
+    weights from the environment (any positive numbers), always a partition of the range with
+    non-empty slices; malformed or over-fine specifications fall back to equal parts."""
+    from evoxels_b200.distributed import CudaOps
+    monkeypatch.delenv("EVX_T_SPLIT", raising=False)
+    assert CudaOps._split(512, 4, "EVX_T_SPLIT") == [0, 128, 256, 384, 512]
+    assert CudaOps._split(512, 4, "EVX_T_SPLIT", "0.12,0.38,0.38,0.12") == [0, 61, 256, 451, 512]
+    monkeypatch.setenv("EVX_T_SPLIT", "1,2,1")
+    assert CudaOps._split(128, 4, "EVX_T_SPLIT") == [0, 32, 96, 128]
+    for spec, n in (("3,1", 100), ("1,1,1,1,1", 47), ("0.5,0.25,0.25", 128)):
+        monkeypatch.setenv("EVX_T_SPLIT", spec)
+        b = CudaOps._split(n, 4, "EVX_T_SPLIT")
+        assert b[0] == 0 and b[-1] == n and all(x < y for x, y in zip(b, b[1:]))
+    monkeypatch.setenv("EVX_T_SPLIT", "1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1")       # 17 slices of 64 planes: too fine
+    assert CudaOps._split(64, 4, "EVX_T_SPLIT") == [0, 16, 32, 48, 64]
+    monkeypatch.setenv("EVX_T_SPLIT", "1,-1")
+    assert CudaOps._split(64, 2, "EVX_T_SPLIT") == [0, 32, 64]
