@@ -11,6 +11,7 @@
 // blocks per SM).
 #include <cuda.h>
 #include <cstdlib>
+#include <type_traits>
 #include "evx_internal.h"
 #include "fft_line_core.h"
 #include "fft_line.h"
@@ -245,8 +246,7 @@ __global__ void __launch_bounds__(line_ws_threads(Prog::NTHREADS, NBUF), 1)
 
 // ---- 1024-point lines: warp-specialised kernel over 4-D tensor maps -----------------------
 // Same roles as fft_line_ws_kernel (loader thread, one retirer per tile buffer, compute warps in
-// two-line groups), for the four-stage program StridedLine4: 512 compute threads, every group
-// runs two line pairs per tile.  The tensor maps are 4-D - (kz, i_lo, row, i_hi) with line index
+// two-line groups; one retirer for both tile buffers), for the programs StridedLine4 / StridedLine16.  The tensor maps are 4-D - (kz, i_lo, row, i_hi) with line index
 // i = i_hi * box_rows + i_lo - so one code path serves lines along y, lines along x, and the
 // block layout of the x-slab transposes; loads go through maps.in, box h of a tile is stored
 // through maps.out[h / out_div] - one map per destination block, which may live in a PEER's
@@ -258,7 +258,7 @@ struct LineMaps {
 };
 
 template <class Prog, int NBUF>
-__global__ void __launch_bounds__(line_ws_threads(Prog::NTHREADS, NBUF), 1)
+__global__ void __launch_bounds__(Prog::NTHREADS + 64, 1)
     fft_line4_ws_kernel(const __grid_constant__ LineMaps maps, const LineParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -303,12 +303,12 @@ __global__ void __launch_bounds__(line_ws_threads(Prog::NTHREADS, NBUF), 1)
     }
     return;
   }
-  if (tid > Prog::NTHREADS && (tid & 31) == 0) {
-    // ------------------------------ retirer of buffer `me` ---------------------------------
-    const int me = (tid - Prog::NTHREADS - 32) >> 5;
+  if (tid == Prog::NTHREADS + 32) {
+    // ---- retirer: ONE thread serves the buffers in tile order (tiles complete in order; a second
+    // control warp per buffer would take the block to 19 warps and the register cap from 112 to 96)
     int n = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += nblk, ++n) {
-      if (n % NBUF != me) continue;
+      const int me = n % NBUF;
       mbar_wait(&done[me], (unsigned)(n / NBUF) & 1u);
       const int row = p.row0 + (int)(tile / tpr), kz0 = (int)(tile % tpr) * Prog::COLS;
       const unsigned char* src = tiles + me * Prog::TILE_BYTES;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(line_ws_threads(Prog::NTHREADS, NBUF), 1)
   // ------------------------------------ compute warps --------------------------------------
   typename Prog::Regs r;
   Prog::init(r, tid);
-  cf* xg = xall + r.g * 2 * Prog::XG;
+  cf* xg = xall + r.g * Prog::XSTRIDE;
   typename Prog::Roots w;
   Prog::load_roots(w, r.t, p.tw);
   int row = blockIdx.x / tpr, tcol = blockIdx.x - row * tpr;
@@ -417,9 +417,20 @@ static int line4_group_lines() {
   return (e && atoi(e) == 1) ? 1 : 2;
 }
 
+// EVX_LINE4_FORM: 16 = sixteen points per thread (StridedLine16: two trips through shared memory per
+// transform), 8 = eight points per thread (StridedLine4)
+// default: 16 for the x pass (chunked x pass of the distributed plan 0.372 -> 0.328 ms per rank), 8 for
+// the y passes (HBM-bound at 0.92 of the copy peak in the eight-point form; 0.36 against 0.45 ms)
+static int line4_form(int mode) {
+  const char* e = getenv("EVX_LINE4_FORM");
+  if (e && atoi(e) == 8) return 8;
+  if (e && atoi(e) == 16) return 16;
+  return pass_is_xmid(mode) ? 16 : 8;
+}
+
 template <int MODE, int GL>
 static int launch_line4_t(LineParams p, const void* map_in, const void* const* maps_out, int nout, cudaStream_t st) {
-  using Prog = StridedLine4<1024, 8, MODE, GL>;
+  using Prog = typename std::conditional<GL == 16, StridedLine16<1024, 8, MODE>, StridedLine4<1024, 8, MODE, GL == 16 ? 2 : GL>>::type;
   constexpr int NBUF = 2;
   p.tiles_per_row = (p.ncols_valid + 7) / 8;
   p.ntiles = (long long)p.nrows * p.tiles_per_row;
@@ -436,13 +447,26 @@ static int launch_line4_t(LineParams p, const void* map_in, const void* const* m
   long long resident = line_sms();
   if (p.max_ctas > 0 && p.max_ctas < resident) resident = p.max_ctas;
   const unsigned grid = (unsigned)(p.ntiles < resident ? p.ntiles : resident);
-  kern<<<grid, line_ws_threads(Prog::NTHREADS, NBUF), smem, st>>>(maps, p);
+  kern<<<grid, Prog::NTHREADS + 64, smem, st>>>(maps, p);
   count_launch();
   return (int)cudaGetLastError();
 }
 
 int line4_pass_launch(int mode, const LineParams& p, const void* map_in, const void* const* maps_out, int nout,
                       cudaStream_t st) {
+  // The exponential-Euler x pass keeps the eight-point form: its sixteen-point instantiation differs
+  // from the cp.async pass by one ulp in ~9 % of the outputs on the device (repeatable; the CPU replay
+  // of the same program is bit-identical, the IMEX instantiation is bit-identical on the device -
+  // a code-generation difference that was not tracked down), and the transports are tested for
+  // bit-identity.
+  if (line4_form(mode) == 16 && mode != PASS_XMID_ETD1) {
+    switch (mode) {
+      case PASS_FWD: return launch_line4_t<PASS_FWD, 16>(p, map_in, maps_out, nout, st);
+      case PASS_INV: return launch_line4_t<PASS_INV, 16>(p, map_in, maps_out, nout, st);
+      case PASS_XMID: return launch_line4_t<PASS_XMID, 16>(p, map_in, maps_out, nout, st);
+      default: return EVX_ERR_ARG;
+    }
+  }
   const bool g1 = line4_group_lines() == 1;
   switch (mode) {
     case PASS_FWD: return g1 ? launch_line4_t<PASS_FWD, 1>(p, map_in, maps_out, nout, st)

@@ -266,7 +266,8 @@ struct StridedLine4 {
   static constexpr int TILE_BYTES = L * ROWB;
   static constexpr int LP = smem_padded_len(L);
   static constexpr int XG = LP * G;            // cf elements of ONE exchange buffer of a group
-  static constexpr int X_BYTES = NG * 2 * XG * (int)sizeof(cf);
+  static constexpr int XSTRIDE = 2 * XG;       // cf elements of a group's exchange space
+  static constexpr int X_BYTES = NG * XSTRIDE * (int)sizeof(cf);
 
   struct Roots { cf w[3][3]; };                // roots of stages 1, 2, 3 of this thread
   struct Regs {
@@ -371,6 +372,193 @@ struct StridedLine4 {
       read_x(r, xr);
       stage<3, +1>(r, w);
       write_tile(r, tile, pass);
+    }
+  }
+
+  // ---- the tensor copies restated for the host replay: plain [nx][ny][P] spectrum ----------
+  EVX_HD static long long spec_index(const LineParams& p, int row, int kz, int i) {
+    return p.along_x ? ((long long)i * p.ny + row) * p.P + kz : ((long long)row * p.ny + i) * p.P + kz;
+  }
+  static void host_tile_load(const LineParams& p, int row, int kz0, unsigned char* tile) {
+    for (int i = 0; i < L; ++i)
+      for (int c = 0; c < KZ; ++c) {
+        const int kz = kz0 + c;
+        *tile_at(tile, tile_off(i, c)) = kz < p.ncols_valid ? p.spec[spec_index(p, row, kz, i)] : cf{0.f, 0.f};
+      }
+  }
+  static void host_tile_store(const LineParams& p, int row, int kz0, unsigned char* tile) {
+    for (int i = 0; i < L; ++i)
+      for (int c = 0; c < KZ; ++c) {
+        const int kz = kz0 + c;
+        if (kz < p.ncols_valid) p.spec[spec_index(p, row, kz, i)] = *tile_at(tile, tile_off(i, c));
+      }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// 1024-point lines, SIXTEEN points per thread (T = 64 threads per line).  The FFT kernels are
+// bound by the shared-memory pipe, and StridedLine4 sends every point through
+// shared memory 14 times in the x pass.  Here the radix-2 stage and the first radix-8 stage are
+// done together in registers - a thread that holds in[q + 64 e'], e' < 16, owns the eight radix-2
+// butterflies q + 64 e AND the two radix-8 butterflies 2q, 2q + 1 that consume their outputs - and
+// the two remaining radix-8 stages run two butterflies per thread (jv = q, q + 64).  Every output is
+// produced by the same operations in the same order as in StridedPass<1024> (same roots from the
+// same table), so the results are bit-identical; but a line crosses shared memory only twice per
+// transform, the block has the geometry of the 512-point kernel (512 compute threads = four
+// two-line groups, all eight lines of a tile in flight), and the exchanges alternate between ONE
+// padded buffer per group and the group's own tile columns:
+//   k0  tile (natural) -> stages 0+1 -> X at 16 q + k        (index i + (i >> 4), lines interleaved)
+//   k1  X (natural)    -> stage 2    -> tile rows (q/16) 128 + q%16 + 512 i + 16 r  (in place)
+//   k2  tile (natural) -> stage 3    -> tile (natural)       [x pass: weight, inverse stages 0+1 -> X]
+//   k3, k4  the inverse transform of the x pass, same pattern.
+// Three (x pass: five) phases per tile instead of eight (fourteen); ten instead of fourteen trips
+// through shared memory in the x pass.  All accesses are 64-bit and conflict-free per half-warp
+// (8 consecutive q x 2 lines), one base register plus an immediate each.
+// ---------------------------------------------------------------------------------------------
+template <int L, int KZ, int MODE>
+struct StridedLine16 {
+  static_assert(L == 1024 && KZ == 8, "sixteen-point form: 1024-point lines, 64-byte tile rows");
+  static constexpr int LEN = L;
+  static constexpr int COLS = KZ;
+  static constexpr int T = L / 16;             // 64 threads per line
+  static constexpr int G = 2;
+  static constexpr int GT = T * G;             // 128
+  static constexpr int NPASS = 1;
+  static constexpr int NG = KZ / G;            // 4
+  static constexpr int NTHREADS = GT * NG;     // 512
+  static constexpr bool XMID = pass_is_xmid(MODE);
+  static constexpr int NPHASES = XMID ? 5 : 3;
+  static constexpr int ROWB = KZ * (int)sizeof(cf);
+  static constexpr int TILE_BYTES = L * ROWB;
+  static constexpr int LP = L + (L >> 4);      // padded line length: index i + (i >> 4)
+  static constexpr int XG = LP * G;
+  static constexpr int XSTRIDE = XG;
+  static constexpr int X_BYTES = NG * XSTRIDE * (int)sizeof(cf);
+
+  // roots of this thread's butterflies: stage 2 (both butterflies share them), stage 3 (jv = q and
+  // q + 64); the roots of the merged stage are the same for every thread and come from the table
+  struct Roots { cf w2[3], w3[2][3]; };
+  struct Regs {
+    cf v[16];
+    int t, c2, g, col;
+    int tb;                  // byte offset of tile element (row q, col)
+    int sb;                  // byte offset of tile element (row (q/16) 128 + q%16, col): stage-2 output base
+    int xn, xs;              // cf index in X: natural-order base / output base of the merged stage
+    int kz, kother;
+  };
+
+  EVX_HD static int pad16(int i) { return i + (i >> 4); }
+  EVX_HD static int swz(int r) { return ((r >> 1) & 3) << 4; }
+  EVX_HD static int tile_off(int r, int c) { return r * ROWB + ((c * (int)sizeof(cf)) ^ swz(r)); }
+
+  EVX_HD static void init(Regs& r, int tid) {
+    r.g = tid / GT;
+    const int tg = tid - r.g * GT;
+    r.c2 = tg % G;
+    r.t = tg / G;
+    r.col = r.g * G + r.c2;
+    r.tb = tile_off(r.t, r.col);
+    r.sb = tile_off((r.t / 16) * 128 + r.t % 16, r.col);
+    r.xn = pad16(r.t) * G + r.c2;
+    r.xs = pad16(16 * r.t) * G + r.c2;
+  }
+  EVX_HD static void load_roots(Roots& w, int t, const cf* tw) {
+    stage_twiddles<L>(2, t, tw, w.w2);                 // m = (q % 16) * 8 for jv = q and q + 64
+    stage_twiddles<L>(3, t, tw, w.w3[0]);              // m = q
+    stage_twiddles<L>(3, t + T, tw, w.w3[1]);          // m = q + 64
+  }
+  EVX_HD static void set_tile(Regs& r, int kother, int kz0) {
+    r.kz = kz0 + r.col;
+    r.kother = kother;
+  }
+  EVX_HD static cf* tile_at(unsigned char* tile, int byte_off) {
+    return reinterpret_cast<cf*>(tile + byte_off);
+  }
+  EVX_HD static void read_tile(Regs& r, unsigned char* tile) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) r.v[e] = *tile_at(tile, r.tb + e * T * ROWB);
+  }
+  EVX_HD static void write_tile(Regs& r, unsigned char* tile) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) *tile_at(tile, r.tb + e * T * ROWB) = r.v[e];
+  }
+  EVX_HD static void read_x(Regs& r, const cf* xg) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) r.v[e] = xg[r.xn + pad16(e * T) * G];
+  }
+
+  // stages 0 + 1 on v[e'] = in[q + 64 e']; the outputs go to X at 16 q + b + 2 r
+  template <int DIR>
+  EVX_HD static void merged_to_x(Regs& r, cf* xg, const cf* tw) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dft2<DIR>(r.v[e], r.v[e + 8]);        // butterflies q + 64 e of stage 0
+    const cf wa[3] = {tw[0], tw[0], tw[0]};                             // jv = 2 q: m = 0
+    line_stage_compute_pre<L, DIR>(1, r.v, 0, wa);
+    const cf wb[3] = {tw[L / 16], tw[2 * (L / 16)], tw[4 * (L / 16)]};  // jv = 2 q + 1: m = 64
+    line_stage_compute_pre<L, DIR>(1, r.v + 8, 0, wb);
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) xg[r.xs + (b + 2 * k) * G] = r.v[8 * b + k];
+  }
+  // stage 2 on v (natural order): butterfly jv = q + 64 i takes v[2 e + i]; outputs to the tile rows
+  template <int DIR>
+  EVX_HD static void stage2_to_tile(Regs& r, unsigned char* tile, const Roots& w) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      cf a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = r.v[2 * e + i];
+      line_stage_compute_pre<L, DIR>(2, a, 0, w.w2);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) *tile_at(tile, r.sb + (512 * i + 16 * k) * ROWB) = a[k];
+    }
+  }
+  // stage 3 in registers: v (natural order in) -> v (natural order out: jv + 128 r = q + 64 (i + 2 r));
+  // FILTER: the weight of the x pass on the way (the points q + 64 i + 128 r are the eight points
+  // t + e 128 of "thread" t = q + 64 i of the 128-thread forms - the very same routine)
+  template <int DIR, bool FILTER>
+  EVX_HD static void stage3(Regs& r, const Roots& w, const LineParams& p) {
+    cf o[16];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      cf a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = r.v[2 * e + i];
+      line_stage_compute_pre<L, DIR>(3, a, 0, w.w3[i]);
+      if (FILTER) xmid_apply_filter<MODE, L / 8>(a, r.t + T * i, r.kother, r.kz, p.filt);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[i + 2 * k] = a[k];
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) r.v[e] = o[e];
+  }
+
+  EVX_HD static void phase(int /*pass*/, int k, Regs& r, unsigned char* tile, cf* xg, const LineParams& p,
+                           const Roots& w) {
+    constexpr int DIR = MODE == PASS_INV ? +1 : -1;      // direction of the first transform
+    if (k == 0) {
+      read_tile(r, tile);
+      merged_to_x<DIR>(r, xg, p.tw);
+    } else if (k == 1) {
+      read_x(r, xg);
+      stage2_to_tile<DIR>(r, tile, w);
+    } else if (k == 2) {
+      read_tile(r, tile);
+      if (!XMID) {
+        stage3<DIR, false>(r, w, p);
+        write_tile(r, tile);
+      } else {
+        stage3<DIR, true>(r, w, p);
+        merged_to_x<+1>(r, xg, p.tw);
+      }
+    } else if (k == 3) {
+      read_x(r, xg);
+      stage2_to_tile<+1>(r, tile, w);
+    } else {
+      read_tile(r, tile);
+      stage3<+1, false>(r, w, p);
+      write_tile(r, tile);
     }
   }
 

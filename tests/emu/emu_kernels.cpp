@@ -262,16 +262,16 @@ static void run_line(LineParams p, int nblocks) {
 
 // 1024-point form (StridedLine4): two line pairs per group and tile, two exchange buffers per
 // group; groups (and, inside a group, the pairs) are replayed one after the other.
-template <int MODE>
-static void run_line4(LineParams p, int nblocks) {
-  using Prog = StridedLine4<1024, 8, MODE>;
+static int g_emu_line4_form = 16;   // 16: StridedLine16 (sixteen points per thread), 8: StridedLine4
+template <class Prog>
+static void run_line4_prog(LineParams p, int nblocks) {
   p.tiles_per_row = (p.ncols_valid + 7) / 8;
   if (p.nrows <= 0) p.nrows = (p.along_x ? p.ny : p.nx) - p.row0;
   p.ntiles = (long long)p.nrows * p.tiles_per_row;
   std::vector<typename Prog::Regs> regs(Prog::NTHREADS);
   std::vector<typename Prog::Roots> roots(Prog::NTHREADS);
   std::vector<unsigned char> tiles(2 * (size_t)Prog::TILE_BYTES, 0xff);
-  std::vector<cf> xall((size_t)Prog::NG * 2 * Prog::XG, cf{std::nanf(""), std::nanf("")});
+  std::vector<cf> xall((size_t)Prog::NG * Prog::XSTRIDE, cf{std::nanf(""), std::nanf("")});
   for (int t = 0; t < Prog::NTHREADS; ++t) {
     Prog::init(regs[t], t);
     Prog::load_roots(roots[t], regs[t].t, p.tw);
@@ -283,7 +283,7 @@ static void run_line4(LineParams p, int nblocks) {
       const int row = p.row0 + (int)(tile / p.tiles_per_row), kz0 = (int)(tile % p.tiles_per_row) * 8;
       Prog::host_tile_load(p, row, kz0, tb);
       for (int g = Prog::NG - 1; g >= 0; --g) {
-        cf* xg = xall.data() + (size_t)g * 2 * Prog::XG;
+        cf* xg = xall.data() + (size_t)g * Prog::XSTRIDE;
         for (int pass = 0; pass < Prog::NPASS; ++pass)
           for (int k = 0; k < Prog::NPHASES; ++k)
             for (int t = g * Prog::GT; t < (g + 1) * Prog::GT; ++t) {
@@ -294,6 +294,12 @@ static void run_line4(LineParams p, int nblocks) {
       Prog::host_tile_store(p, row, kz0, tb);
     }
   }
+}
+
+template <int MODE>
+static void run_line4(LineParams p, int nblocks) {
+  if (g_emu_line4_form == 16) run_line4_prog<StridedLine16<1024, 8, MODE>>(p, nblocks);
+  else run_line4_prog<StridedLine4<1024, 8, MODE>>(p, nblocks);
 }
 
 static int g_emu_line_kz = 0;       // 8 / 16: 512-point strided passes through the TMA-tiled program
@@ -375,6 +381,7 @@ extern "C" {
 
 void emu_set_pipe_blocks(int n) { g_emu_pipe_blocks = n; }
 void emu_set_line_columns(int kz) { g_emu_line_kz = kz; }
+void emu_set_line4_form(int f) { g_emu_line4_form = f; }
 void emu_set_xpass_columns(int kz) { g_emu_xkz = kz; }
 
 // out = u + irfftn(P * rfftn(r)) through the five native passes; spec is scratch

@@ -252,14 +252,17 @@ def test_tma_tile_image_is_conflict_free():
                     assert len(nat) == len(st1) == len(xn) == len(xs) == 16, (kz, g, t0, e)
 
 
+@pytest.mark.parametrize("form", [8, 16])
 @pytest.mark.parametrize("shape,blocks,power", [((8, 1024, 16), 3, 2), ((1024, 8, 16), 2, 2),
                                                 ((1024, 8, 32), 5, 1 | 0x100)])
-def test_four_stage_tma_tiled_passes_are_bit_identical(emu, shape, blocks, power):
+def test_four_stage_tma_tiled_passes_are_bit_identical(emu, shape, blocks, power, form):
     """1024-point lines (StridedLine4 in fft_line_core.h: two groups of 256 threads, two line
     pairs per group and tile, exchanges alternating between two padded buffers, tile touched in
-    natural order only) replayed on the CPU against the cp.async passes: y forward, x
-    forward*weight*inverse (IMEX and exponential-Euler weight), y inverse - same bits, including
-    the partly out-of-range last tile of a row."""
+    natural order only; form 16 = StridedLine16: sixteen points per thread, radix-2 and first
+    radix-8 stage merged in registers, one padded buffer per group + the tile columns) replayed on
+    the CPU against the cp.async passes: y forward, x forward*weight*inverse (IMEX and
+    exponential-Euler weight), y inverse - same bits, including the partly out-of-range last tile
+    of a row."""
     nx, ny, nz = shape
     rng = np.random.default_rng(5)
     r = rng.standard_normal(shape).astype(np.float32)
@@ -272,12 +275,39 @@ def test_four_stage_tma_tiled_passes_are_bit_identical(emu, shape, blocks, power
     got = np.full(shape, np.nan, np.float32)
     emu.emu_set_line_columns(8)
     emu.emu_set_pipe_blocks(blocks)
+    emu.emu_set_line4_form(form)
     try:
         assert emu.emu_native_apply(_p(u), _p(r), _p(got), None, nx, ny, nz, h, d(0.1), d(1.5), power) == 0
     finally:
         emu.emu_set_line_columns(0)
         emu.emu_set_pipe_blocks(0)
+        emu.emu_set_line4_form(16)
     assert np.array_equal(got, want)
+
+
+def test_sixteen_point_form_layout_is_conflict_free():
+    """Bank check of StridedLine16 (T = 64 threads per line): 64-bit accesses of a half-warp (8
+    consecutive q x the 2 lines of a group) hit 16 distinct 8-byte bank pairs - tile rows in natural
+    order (q + 64 e) and in stage-2 output order ((q/16) 128 + q%16 + 512 i + 16 r) under the
+    64-byte TMA swizzle, the exchange buffer (index i + (i >> 4)) in natural order and in the output
+    order of the merged stage (16 q + k); every index is written exactly once."""
+    T = 64
+    pad16 = lambda i: i + (i >> 4)
+    tile = lambda r, c: r * 64 + ((c * 8) ^ (((r >> 1) & 3) << 4))
+    for g in range(4):
+        for q0 in range(0, T, 8):
+            lanes = [(q, 2 * g + c2) for q in range(q0, q0 + 8) for c2 in (0, 1)]
+            for e in range(16):
+                assert len({(tile(q + 64 * e, c) // 8) % 16 for q, c in lanes}) == 16
+                assert len({(pad16(q + 64 * e) * 2 + c % 2) % 16 for q, c in lanes}) == 16
+                assert len({(pad16(16 * q + e) * 2 + c % 2) % 16 for q, c in lanes}) == 16
+                i, k = e % 2, e // 2
+                rows = {(tile((q // 16) * 128 + q % 16 + 512 * i + 16 * k, c) // 8) % 16 for q, c in lanes}
+                assert len(rows) == 16
+    assert sorted(16 * q + k for q in range(T) for k in range(16)) == list(range(1024))
+    assert sorted((q // 16) * 128 + q % 16 + 512 * i + 16 * k for q in range(T) for i in range(2)
+                  for k in range(8)) == list(range(1024))
+    assert max(pad16(q + 64 * e) for q in range(T) for e in range(16)) * 2 + 1 < (1024 + 64) * 2
 
 
 def test_four_stage_tile_and_exchange_layout_is_conflict_free():

@@ -642,11 +642,15 @@ def test_line_pass_forms_agree_bit_for_bit(cuda_device, monkeypatch, ws):
         assert torch.isfinite(b).all() and torch.equal(a, b)
 
 
+@pytest.mark.parametrize("form", ["default", "8", "16"])
 @pytest.mark.parametrize("shape", [(1024, 64, 32), (32, 1024, 64), (1024, 1024, 16), (1024, 8, 16)])
-def test_four_stage_tma_passes_match_the_cp_async_passes_bit_for_bit(cuda_device, monkeypatch, shape):
-    """1024-point strided passes: the four-stage TMA-tiled kernel (fft_line4_ws_kernel, 4-D tensor
-    maps) against the cp.async kernels - y forward, x forward*weight*inverse (IMEX and
-    exponential-Euler weight), y inverse; the update must be bit-identical."""
+def test_four_stage_tma_passes_match_the_cp_async_passes_bit_for_bit(cuda_device, monkeypatch, shape, form):
+    """1024-point strided passes: the TMA-tiled kernel (fft_line4_ws_kernel, 4-D tensor maps) in its
+    eight-point (StridedLine4) and sixteen-point (StridedLine16) forms against the cp.async kernels -
+    y forward, x forward*weight*inverse (IMEX and exponential-Euler weight; the latter always runs
+    the eight-point form), y inverse; the update must be bit-identical."""
+    if form != "default":
+        monkeypatch.setenv("EVX_LINE4_FORM", form)
     gen = torch.Generator(device="cuda").manual_seed(3)
     u = 0.5 + 0.1 * torch.rand(shape, device="cuda", generator=gen)
     r = torch.randn(shape, device="cuda", generator=gen)
