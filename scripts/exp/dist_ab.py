@@ -20,13 +20,12 @@ if len(sys.argv) > 1 and "x" in sys.argv[1]:
     shape = tuple(int(v) for v in sys.argv[1].split("x"))
 variants = [
     ("ce4", dict(transport="ce", overlap_chunks=4), {}),
-    ("ce4_thin_edges", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "0.12,0.38,0.38,0.12"}),
+    ("ce4_mid4", dict(transport="ce", overlap_chunks=4, mid_chunks=4), {}),
     ("ce4_mid6", dict(transport="ce", overlap_chunks=4, mid_chunks=6), {}),
-    ("ce4_direct1", dict(transport="ce", overlap_chunks=4), {"direct": 1, "direct_mid": 1}),
-    ("ce4_direct_mid1", dict(transport="ce", overlap_chunks=4), {"direct": 0, "direct_mid": 1}),
-    ("ce4_last148", dict(transport="ce", overlap_chunks=4), {"EVX_CE_LAST_CTAS": "148"}),
-    ("ce4_last_dma", dict(transport="ce", overlap_chunks=4), {"EVX_CE_LAST_CTAS": "0"}),
-    ("ce6", dict(transport="ce", overlap_chunks=4, mid_chunks=6), {"EVX_CE_FWD_SPLIT": "1,1,1,1,1,1"}),
+    ("ce4_mid_dec", dict(transport="ce", overlap_chunks=4, mid_chunks=4), {"EVX_CE_MID_SPLIT": "0.3,0.3,0.25,0.15"}),
+    ("ce4_mid_dec5", dict(transport="ce", overlap_chunks=4, mid_chunks=4), {"EVX_CE_MID_SPLIT": "0.26,0.24,0.22,0.18,0.10"}),
+    ("ce4_fwd_b", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "0.10,0.40,0.40,0.10"}),
+    ("ce4_fwd_c", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "0.15,0.35,0.35,0.15"}),
 ]
 only = os.environ.get("EVX_AB_ONLY")
 if only:
