@@ -554,6 +554,14 @@ def run_ours(args):
         "kernels": {k: {"ms": v[0], "bytes_per_voxel": v[1],
                         "achieved_GBs": v[1] * nvox / (v[0] * 1e-3) / 1e9,
                         "frac": v[1] * nvox / (v[0] * 1e-3) / 1e9 / peak} for k, v in kernels.items()},
+        # second roofline of these kernels (not measured live: one ncu capture per round)
+        "shared_memory_pipe": {
+            "note": "the FFT kernels are bound by shared-memory wavefronts, not by HBM: every radix-8 "
+                    "exchange sends each spectrum point through shared memory twice",
+            "pct_of_peak": {"fft_chain forward": 77.0, "x pass (512-point lines)": 76.9,
+                            "fft_chain inverse": 58.1, "ch_rhs": 41.4},
+            "metric": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "source": "profiles/r02_ncu_smem_pipe.txt (ncu --set full, 512^3, one launch each)"},
     }
 
     if rank != 0:
