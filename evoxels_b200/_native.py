@@ -85,6 +85,8 @@ SIGNATURES = {
     "evx_copy_async": [_c_void_p, _c_void_p, ctypes.c_size_t, _c_void_p],
     "evx_copy2d_async": [_c_void_p, ctypes.c_size_t, _c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                          ctypes.c_size_t, _c_void_p],
+    "evx_copy_batch_async": [ctypes.POINTER(_c_void_p), ctypes.c_size_t, ctypes.POINTER(_c_void_p), ctypes.c_size_t,
+                             ctypes.c_size_t, ctypes.c_size_t, _c_int, _c_void_p],
     "evx_dist_forward_p2p_f32": [_c_void_p, _c_void_p, _c_void_p, ctypes.POINTER(_c_void_p), _c_void_p],
     "evx_dist_forward_chunk_p2p_f32": [_c_void_p, _c_void_p, _c_void_p, ctypes.POINTER(_c_void_p), _c_int,
                                        _c_int, _c_int, _c_void_p],
@@ -289,6 +291,17 @@ def copy_async(dst_ptr, src_ptr, nbytes, stream):
     """cudaMemcpyAsync between raw device pointers (local or mapped peer memory) on `stream`."""
     check(load_library().evx_copy_async(_c_void_p(int(dst_ptr)), _c_void_p(int(src_ptr)), int(nbytes),
                                         _c_void_p(stream.cuda_stream)), "evx_copy_async")
+
+
+def copy_batch_async(dst_ptrs, dpitch, src_ptrs, spitch, width_bytes, height, stream):
+    """The copies of one chunk to all peers as ONE unordered batch (the driver may spread them over
+    its copy engines); height 1 = contiguous regions."""
+    n = len(dst_ptrs)
+    d = (_c_void_p * n)(*[int(p) for p in dst_ptrs])
+    s = (_c_void_p * n)(*[int(p) for p in src_ptrs])
+    with torch.cuda.device(stream.device):
+        check(load_library().evx_copy_batch_async(d, int(dpitch), s, int(spitch), int(width_bytes), int(height),
+                                                  n, _c_void_p(stream.cuda_stream)), "evx_copy_batch_async")
 
 
 def copy2d_async(dst_ptr, dpitch, src_ptr, spitch, width_bytes, height, stream):

@@ -800,6 +800,35 @@ int evx_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
   if (!dst || !src) return EVX_ERR_ARG;
   return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
 }
+int evx_copy_batch_async(void* const* dst, size_t dpitch, const void* const* src, size_t spitch,
+                         size_t width_bytes, size_t height, int n, void* stream) {
+  if (!dst || !src || n < 1 || n > 8 || !width_bytes || !height || !stream) return EVX_ERR_ARG;
+  size_t fail = 0;
+  if (height == 1) {
+    void* d[8]; void* s[8]; size_t sz[8];
+    for (int i = 0; i < n; ++i) { d[i] = dst[i]; s[i] = const_cast<void*>(src[i]); sz[i] = width_bytes; }
+    cudaMemcpyAttributes attr = {};
+    attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    attr.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+    size_t idx = 0;
+    return (int)cudaMemcpyBatchAsync(d, s, sz, (size_t)n, &attr, &idx, 1, &fail, (cudaStream_t)stream);
+  }
+  cudaMemcpy3DBatchOp ops[8] = {};
+  for (int i = 0; i < n; ++i) {
+    ops[i].src.type = cudaMemcpyOperandTypePointer;
+    ops[i].src.op.ptr.ptr = const_cast<void*>(src[i]);
+    ops[i].src.op.ptr.rowLength = spitch;
+    ops[i].src.op.ptr.layerHeight = height;
+    ops[i].dst.type = cudaMemcpyOperandTypePointer;
+    ops[i].dst.op.ptr.ptr = dst[i];
+    ops[i].dst.op.ptr.rowLength = dpitch;
+    ops[i].dst.op.ptr.layerHeight = height;
+    ops[i].extent = make_cudaExtent(width_bytes, height, 1);
+    ops[i].srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    ops[i].flags = cudaMemcpyFlagPreferOverlapWithCompute;
+  }
+  return (int)cudaMemcpy3DBatchAsync((size_t)n, ops, &fail, 0, (cudaStream_t)stream);
+}
 int evx_copy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes,
                      size_t height, void* stream) {
   if (!dst || !src) return EVX_ERR_ARG;

@@ -301,6 +301,9 @@ class CudaOps:
     # (measured ~420 GB/s aggregate over 7 peers for contiguous regions, ~215 GB/s for the pitched
     # regions after the x pass).  0 = DMA for every chunk.
     last_chunk_ctas = int(os.environ.get("EVX_CE_LAST_CTAS", "24"))
+    # the DMA copies of a chunk as ONE unordered batch (cudaMemcpyBatchAsync): 1 = forward and x pass,
+    # 2 = forward only
+    batch_copies = int(os.environ.get("EVX_CE_BATCH", "0"))
     # hybrid transport: number of peers served by TMA stores from inside the y pass / x pass
     direct_peers = int(os.environ.get("EVX_CE_DIRECT", "0"))
     direct_peers_mid = int(os.environ.get("EVX_CE_DIRECT_MID", os.environ.get("EVX_CE_DIRECT", "0")))
@@ -403,6 +406,14 @@ class CudaOps:
                                      self.last_chunk_ctas if last else self.scatter_ctas, cs)
                 self._mark(f"fwd{i} scatter", cs)
                 continue
+            if self.batch_copies:
+                cs = copies[0]
+                cs.wait_event(done)
+                _native.copy_batch_async([b_ptrs[j] + me * blk + x0 * row for j in peers_], (x1 - x0) * row,
+                                         [a_ptr + j * blk + x0 * row for j in peers_], (x1 - x0) * row,
+                                         (x1 - x0) * row, 1, cs)
+                self._mark(f"fwd{i} batch", cs)
+                continue
             for j in peers_:
                 cs = copies[j]
                 cs.wait_event(done)
@@ -462,6 +473,18 @@ class CudaOps:
                                      (y1 - y0) * P * 8, nxl, pitch, pitch,
                                      self.last_chunk_ctas if last else self.scatter_ctas, cs)
                 self._mark(f"mid{i} scatter", cs)
+                continue
+            if self.batch_copies == 1:
+                cs = copies[0]
+                cs.wait_event(done)
+                if y1 - y0 == nyl:
+                    _native.copy_batch_async([a_ptrs[j] + me * blk for j in peers_], blk,
+                                             [b_ptr + j * blk for j in peers_], blk, blk, 1, cs)
+                else:
+                    _native.copy_batch_async([a_ptrs[j] + me * blk + y0 * P * 8 for j in peers_], pitch,
+                                             [b_ptr + j * blk + y0 * P * 8 for j in peers_], pitch,
+                                             (y1 - y0) * P * 8, nxl, cs)
+                self._mark(f"mid{i} batch", cs)
                 continue
             for j in peers_:
                 cs = copies[j]

@@ -264,6 +264,12 @@ int evx_dist_middle_chunk_p2p_f32(evx_dist_plan* plan, void* recv, void* const* 
  * (cudaMemcpyDefault) on `stream`. */
 int evx_dist_forward_chunk_f32(evx_dist_plan* plan, const float* r_local, void* spec, void* send,
                                void* self_block, int x0, int nxc, void* stream);
+/* n <= 8 copies of one chunk (region i: `height` rows of `width_bytes`, pitches dpitch / spitch;
+ * height 1 = contiguous) handed to the driver as ONE batch (cudaMemcpyBatchAsync /
+ * cudaMemcpy3DBatchAsync): the copies of a batch are unordered among themselves, so the driver may
+ * spread them over its copy engines instead of running them one after the other. */
+int evx_copy_batch_async(void* const* dst, size_t dpitch, const void* const* src, size_t spitch,
+                         size_t width_bytes, size_t height, int n, void* stream);
 int evx_dist_middle_chunk_f32(evx_dist_plan* plan, void* recv, void* self_block, int yl0, int nylc,
                               const double* h, double dt, double coef, int power, void* stream);
 /* One launch that copies n <= 8 pitched regions (rows x row_bytes; 16-byte aligned) src[i] ->

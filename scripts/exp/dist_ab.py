@@ -20,12 +20,10 @@ if len(sys.argv) > 1 and "x" in sys.argv[1]:
     shape = tuple(int(v) for v in sys.argv[1].split("x"))
 variants = [
     ("ce4", dict(transport="ce", overlap_chunks=4), {}),
-    ("ce4_mid4", dict(transport="ce", overlap_chunks=4, mid_chunks=4), {}),
-    ("ce4_mid6", dict(transport="ce", overlap_chunks=4, mid_chunks=6), {}),
-    ("ce4_mid_dec", dict(transport="ce", overlap_chunks=4, mid_chunks=4), {"EVX_CE_MID_SPLIT": "0.3,0.3,0.25,0.15"}),
-    ("ce4_mid_dec5", dict(transport="ce", overlap_chunks=4, mid_chunks=4), {"EVX_CE_MID_SPLIT": "0.26,0.24,0.22,0.18,0.10"}),
-    ("ce4_fwd_b", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "0.10,0.40,0.40,0.10"}),
-    ("ce4_fwd_c", dict(transport="ce", overlap_chunks=4), {"EVX_CE_FWD_SPLIT": "0.15,0.35,0.35,0.15"}),
+    ("ce4_batch_fwd", dict(transport="ce", overlap_chunks=4), {"batch": 2}),
+    ("ce4_batch_all", dict(transport="ce", overlap_chunks=4), {"batch": 1}),
+    ("ce4_batch_all_lastdma", dict(transport="ce", overlap_chunks=4), {"batch": 1, "EVX_CE_LAST_CTAS": "0"}),
+    ("ce4_again", dict(transport="ce", overlap_chunks=4), {}),
 ]
 only = os.environ.get("EVX_AB_ONLY")
 if only:
@@ -42,12 +40,23 @@ for name, kw, env in variants:
     st = DistributedCahnHilliardIMEX(shape, (1.0, 1.0, 1.0), 0.1, device=dev, **kw)
     if "EVX_CE_LAST_CTAS" in env:
         st.ops.last_chunk_ctas = int(env["EVX_CE_LAST_CTAS"])
+    if "batch" in attrs:
+        st.ops.batch_copies = attrs["batch"]
     if "direct" in attrs:
         st.ops.direct_peers, st.ops.direct_peers_mid = attrs["direct"], attrs["direct_mid"]
     u = u0.clone()
-    for _ in range(5):
-        u = st.step(u)
-    torch.cuda.synchronize()
+    try:
+        for _ in range(5):
+            u = st.step(u)
+        torch.cuda.synchronize()
+    except Exception as exc:                      # e.g. an API the driver refuses: same on every rank
+        if rank == 0:
+            print(name, "FAILED", repr(exc)[:300], flush=True)
+        out[name] = {"error": repr(exc)[:300]}
+        del st
+        torch.cuda.empty_cache()
+        dist.barrier()
+        continue
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
