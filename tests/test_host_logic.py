@@ -38,6 +38,15 @@ def test_library_exports_every_header_symbol():
 def test_argument_errors_are_reported_without_a_gpu():
     lib = _native.load_library()
     assert lib.evx_ch_rhs_f32(None, None, None, 4, 4, 4, None, 3.0, 1.0, None, None, None, None, None) == -1
+    # entry points of the chunked / hybrid distributed passes: null plan, null tables, empty batches
+    assert lib.evx_dist_middle_chunk_p2p_f32(None, None, None, 0, 1, None, 0.1, 1.0, 2, None) == -1
+    assert lib.evx_dist_forward_chunk_p2p_f32(None, None, None, None, 0, 1, 3, None) == -1
+    assert lib.evx_copy_batch_async(None, 0, None, 0, 16, 1, 1, None) == -1
+    import ctypes
+    one = (ctypes.c_void_p * 1)(1)
+    assert lib.evx_copy_batch_async(one, 16, one, 16, 16, 1, 9, ctypes.c_void_p(1)) == -1      # more than 8 regions
+    assert lib.evx_copy_batch_async(one, 16, one, 16, 0, 1, 1, ctypes.c_void_p(1)) == -1       # empty region
+    assert lib.evx_copy_batch_async(one, 16, one, 16, 16, 1, 1, None) == -1                    # legacy stream
     with pytest.raises(_native.NativeLibraryError):
         _native.check(-2, "probe")
 
